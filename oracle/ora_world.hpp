@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE -- CPU oracle (see ora_math.hpp header).
+// World state + one fixed step of the sequential stepper restated without EnTT:
+//   src/edyn/simulation/stepper_sequential.cpp:71-102  (order of phases)
+//   src/edyn/collision/broadphase.cpp:119-195, src/edyn/collision/narrowphase.cpp:21-40,
+//   include/edyn/util/collision_util.hpp:105-276, src/edyn/dynamics/solver.cpp:387-468,
+//   src/edyn/dynamics/island_solver.cpp:76-111,263-376,521-543.
+// Not restated (out of scope): restitution_solver (run both sides with
+// restitution iterations = 0 so restitution goes through the row rhs), sleeping (benchmarks set
+// sleeping_disabled), center_of_mass/origin offsets, contact_extras.
+#pragma once
+#include "ora_collide.hpp"
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace ora {
+
+enum body_kind : uint32_t { BK_DYNAMIC = 0, BK_KINEMATIC = 1, BK_STATIC = 2 };
+
+struct Body {
+    vec3 pos; quat orn;
+    vec3 linvel, angvel, dv, dw;
+    scalar inv_m;
+    mat3 inv_I, inv_IW;
+    vec3 gravity;
+    shape sh;
+    aabb bb;
+    uint32_t kind;
+    scalar friction, restitution;
+    bool rolling;            // rolling_tag: dynamic sphere/cylinder/capsule (util/rigidbody.cpp:120-130)
+    bool has_filter; uint64_t group, mask;
+    bool procedural() const { return kind == BK_DYNAMIC; }
+};
+
+struct Point {               // contact_point + _geometry + _material + _impulse (collision/contact_point.hpp:17-58)
+    vec3 pivotA, pivotB, normal, local_normal;
+    scalar distance;
+    uint32_t att;
+    scalar friction, restitution;
+    uint32_t lifetime;
+    scalar imp_n, imp_t[2];
+};
+
+struct Manifold {            // contact_manifold + state; pt[0] is the linked-list head (newest point)
+    uint32_t a, b;
+    uint32_t num;
+    Point pt[4];
+};
+
+struct Hinge {               // constraints/hinge_constraint.hpp:22-93 without limits/springs/torque
+    uint32_t a, b;
+    vec3 pivot[2];
+    mat3 frame[2];
+    scalar imp_lin[3], imp_hinge[2];
+};
+
+struct World {
+    scalar dt = scalar(1.0 / 60);
+    int vel_iters = 8, pos_iters = 3;          // context/settings.hpp:22-30
+    std::vector<Body> bodies;
+    std::vector<Manifold> manifolds;
+    std::vector<Hinge> hinges;
+    std::unordered_map<uint64_t, uint32_t> manifold_map;   // contact_manifold_map
+    std::unordered_set<uint64_t> exclusions;               // collision_exclusion (pair form)
+    std::vector<uint32_t> island;                           // label per body (min procedural id), ~0u if none
+    // Optional injected Gauss-Seidel order (see ora_api.cpp: ora_set_order).
+    bool use_order = false;
+    std::vector<uint32_t> hinge_order;
+    std::vector<uint64_t> manifold_order;                   // pair keys
+    int threads = 1;                                        // island-parallel solve (run_island_solver_seq_mt analogue)
+
+    static uint64_t key(uint32_t a, uint32_t b) { return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a; }
+
+    uint32_t add_body(const Body &b);
+    void refresh_body(uint32_t i);             // AABB + inv_IW from current transform
+    void broadphase();
+    void narrowphase();
+    void islands();
+    void solve();
+    void step() { broadphase(); narrowphase(); islands(); solve(); }
+    bool should_collide(uint32_t a, uint32_t b) const;
+};
+
+// Row-level helpers exposed for pinning against the reference's constraint_row.cpp
+struct Row {
+    vec3 J[4];
+    scalar eff_mass, rhs, lo, hi, impulse;
+};
+void prepare_row(Row &row, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
+                 scalar error, scalar erp, scalar restitution, vec3 vA, vec3 wA, vec3 vB, vec3 wB);
+scalar solve_row(Row &row, vec3 dvA, vec3 dwA, vec3 dvB, vec3 dwB);
+mat3 moment_of_inertia(const shape &sh, scalar mass);
+
+} // namespace ora

@@ -1,0 +1,284 @@
+"""TEST INFRASTRUCTURE -- ctypes front-end of the CPU oracle (oracle/liboracle.so) and, when it
+was built, of the real reference functions (oracle/_ref/libedyn_ref.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (edyn_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libedyn_ref.so")
+
+SH_SPHERE, SH_CAPSULE, SH_BOX, SH_PLANE, SH_NONE = 0, 2, 3, 6, 255
+DYNAMIC, KINEMATIC, STATIC = 0, 1, 2
+PH_BROAD, PH_NARROW, PH_ISLANDS, PH_SOLVE = 1, 2, 4, 8
+
+_f = np.float32
+_u = np.uint32
+
+
+def build(force=False):
+    """Compile the restatement (always) and oracle/_ref (only where /root/reference exists)."""
+    if force or not os.path.exists(ORACLE_SO) or os.path.isdir("/root/reference/src/edyn"):
+        subprocess.run(["make", "-s", "-C", HERE], check=True)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(x, dt, shape=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=dt))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.ora_create.restype = C.c_void_p
+        _lib.ora_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int]
+        _lib.ora_solve_row.restype = C.c_float
+        for name in ("ora_num_bodies", "ora_num_manifolds"):
+            getattr(_lib, name).restype = C.c_uint32
+    return _lib
+
+
+def ref():
+    """The real reference functions, or None when oracle/_ref was not built/shipped."""
+    global _ref
+    if _ref is None and os.path.exists(REF_SO):
+        _ref = C.CDLL(REF_SO)
+        _ref.ref_solve_row.restype = C.c_float
+    return _ref
+
+
+class PureFns:
+    """Pure-function surface shared by the restatement (prefix 'ora_') and the reference ('ref_')."""
+
+    def __init__(self, dll, prefix):
+        self.dll, self.p = dll, prefix
+
+    def _fn(self, name):
+        return getattr(self.dll, self.p + name)
+
+    def collide(self, kindA, pA, kindB, pB, posA, ornA, posB, ornB):
+        out = np.zeros((4, 10), _f)
+        att = np.zeros(4, _u)
+        args = [_arr(x, _f) for x in (pA, pB, posA, ornA, posB, ornB)]
+        n = self._fn("collide")(C.c_uint32(kindA), _ptr(args[0]), C.c_uint32(kindB), _ptr(args[1]), _ptr(args[2]),
+                                _ptr(args[3]), _ptr(args[4]), _ptr(args[5]), _ptr(out), _ptr(att))
+        return out[:n].copy(), att[:n].copy()
+
+    def shape_aabb(self, kind, p, pos, orn):
+        out = np.zeros(6, _f)
+        a = [_arr(x, _f) for x in (p, pos, orn)]
+        self._fn("shape_aabb")(C.c_uint32(kind), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(out))
+        return out
+
+    def integrate(self, q, w, dt):
+        out = np.zeros(4, _f)
+        a = [_arr(q, _f), _arr(w, _f)]
+        self._fn("integrate")(_ptr(a[0]), _ptr(a[1]), C.c_float(dt), _ptr(out))
+        return out
+
+    def plane_space(self, n):
+        p, q = np.zeros(3, _f), np.zeros(3, _f)
+        a = _arr(n, _f)
+        self._fn("plane_space")(_ptr(a), _ptr(p), _ptr(q))
+        return p, q
+
+    def intersect_line_aabb(self, p0, p1, mn, mx):
+        s = np.zeros(2, _f)
+        a = [_arr(x, _f) for x in (p0, p1, mn, mx)]
+        fn = self._fn("intersect_line_aabb")
+        fn.restype = C.c_int
+        n = fn(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(s))
+        return n, s
+
+    def closest_segment_segment(self, p1, q1, p2, q2):
+        out = np.zeros(16, _f)
+        d = C.c_float(0)
+        a = [_arr(x, _f) for x in (p1, q1, p2, q2)]
+        fn = self._fn("closest_segment_segment")
+        fn.restype = C.c_int
+        n = fn(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(out), C.byref(d))
+        return n, out, d.value
+
+    def maybe_add_points(self, pivA, pivB):
+        pivA, pivB = _arr(pivA, _f, (-1, 3)), _arr(pivB, _f, (-1, 3))
+        oa, ob = np.zeros((4, 3), _f), np.zeros((4, 3), _f)
+        fn = self._fn("maybe_add_points")
+        fn.restype = C.c_int
+        n = fn(C.c_uint32(len(pivA)), _ptr(pivA), _ptr(pivB), _ptr(oa), _ptr(ob))
+        return oa[:n].copy(), ob[:n].copy()
+
+    def moment_of_inertia(self, kind, p, mass):
+        out = np.zeros(9, _f)
+        a = _arr(p, _f)
+        self._fn("moment_of_inertia")(C.c_uint32(kind), _ptr(a), C.c_float(mass), _ptr(out))
+        return out.reshape(3, 3)
+
+    def inverse_symmetric(self, m):
+        out = np.zeros(9, _f)
+        a = _arr(m, _f)
+        self._fn("inverse_symmetric")(_ptr(a), _ptr(out))
+        return out.reshape(3, 3)
+
+    def world_inertia(self, orn, inv_I):
+        out = np.zeros(9, _f)
+        a = [_arr(orn, _f), _arr(inv_I, _f)]
+        self._fn("world_inertia")(_ptr(a[0]), _ptr(a[1]), _ptr(out))
+        return out.reshape(3, 3)
+
+    def prepare_row(self, J, inv_mA, inv_IA, inv_mB, inv_IB, error, erp, restitution, vels):
+        out = np.zeros(2, _f)
+        a = [_arr(J, _f), _arr(inv_IA, _f), _arr(inv_IB, _f), _arr(vels, _f)]
+        self._fn("prepare_row")(_ptr(a[0]), C.c_float(inv_mA), _ptr(a[1]), C.c_float(inv_mB), _ptr(a[2]),
+                                C.c_float(error), C.c_float(erp), C.c_float(restitution), _ptr(a[3]), _ptr(out))
+        return out
+
+    def solve_row(self, J, row5, dv12):
+        r = _arr(row5, _f).copy()
+        a = [_arr(J, _f), _arr(dv12, _f)]
+        fn = self._fn("solve_row")
+        fn.restype = C.c_float
+        d = fn(_ptr(a[0]), _ptr(r), _ptr(a[1]))
+        return np.float32(d), r
+
+
+def ora_fns():
+    return PureFns(lib(), "ora_")
+
+
+def ref_fns():
+    r = ref()
+    return PureFns(r, "ref_") if r is not None else None
+
+
+def ref_hinge_rows(pivotA, pivotB, axisA, axisB, posA, ornA, posB, ornB):
+    r = ref()
+    J = np.zeros(60, _f)
+    a = [_arr(x, _f) for x in (pivotA, pivotB, axisA, axisB, posA, ornA, posB, ornB)]
+    r.ref_hinge_rows.restype = C.c_int
+    n = r.ref_hinge_rows(*[_ptr(x) for x in a], _ptr(J))
+    return n, J.reshape(5, 4, 3)
+
+
+class OracleWorld:
+    """CPU restatement of one edyn registry stepped by stepper_sequential (see ora_world.hpp)."""
+
+    def __init__(self, dt=1.0 / 60, vel_iters=8, pos_iters=3, threads=1):
+        self.l = lib()
+        self.h = C.c_void_p(self.l.ora_create(C.c_float(dt), vel_iters, pos_iters, threads))
+        self.dt = dt
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.l.ora_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add_bodies(self, b):
+        """b: dict of arrays as produced by edyn_b200.scenes / edyn_b200.bodies_soa()."""
+        n = len(b["kind"])
+        a = dict(pos=_arr(b["pos"], _f, (n, 3)), orn=_arr(b["orn"], _f, (n, 4)), linvel=_arr(b["linvel"], _f, (n, 3)),
+                 angvel=_arr(b["angvel"], _f, (n, 3)), inv_mass=_arr(b["inv_mass"], _f, (n,)),
+                 inv_inertia=_arr(b["inv_inertia"], _f, (n, 9)), gravity=_arr(b["gravity"], _f, (n, 3)),
+                 kind=_arr(b["kind"], _u, (n,)), shape_kind=_arr(b["shape_kind"], _u, (n,)),
+                 shape_params=_arr(b["shape_params"], _f, (n, 4)), friction=_arr(b["friction"], _f, (n,)),
+                 restitution=_arr(b["restitution"], _f, (n,)))
+        grp = _arr(b["group"], np.uint64, (n,)) if "group" in b and b["group"] is not None else None
+        msk = _arr(b["mask"], np.uint64, (n,)) if "mask" in b and b["mask"] is not None else None
+        self.l.ora_add_bodies.restype = C.c_int
+        return self.l.ora_add_bodies(self.h, C.c_uint32(n), _ptr(a["pos"]), _ptr(a["orn"]), _ptr(a["linvel"]),
+                                     _ptr(a["angvel"]), _ptr(a["inv_mass"]), _ptr(a["inv_inertia"]), _ptr(a["gravity"]),
+                                     _ptr(a["kind"]), _ptr(a["shape_kind"]), _ptr(a["shape_params"]),
+                                     _ptr(a["friction"]), _ptr(a["restitution"]), _ptr(grp), _ptr(msk))
+
+    def add_hinges(self, a, b, pivotA, pivotB, axisA, axisB):
+        n = len(a)
+        arrs = [_arr(a, _u), _arr(b, _u), _arr(pivotA, _f, (n, 3)), _arr(pivotB, _f, (n, 3)), _arr(axisA, _f, (n, 3)),
+                _arr(axisB, _f, (n, 3))]
+        return self.l.ora_add_hinges(self.h, C.c_uint32(n), *[_ptr(x) for x in arrs])
+
+    def add_exclusions(self, a, b):
+        a, b = _arr(a, _u), _arr(b, _u)
+        self.l.ora_add_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))
+
+    def step(self, n=1):
+        self.l.ora_step(self.h, int(n))
+
+    def run_phases(self, mask):
+        self.l.ora_run_phases(self.h, C.c_uint32(mask))
+
+    @property
+    def num_bodies(self):
+        return int(self.l.ora_num_bodies(self.h))
+
+    def state(self):
+        n = self.num_bodies
+        out = dict(pos=np.zeros((n, 3), _f), orn=np.zeros((n, 4), _f), linvel=np.zeros((n, 3), _f),
+                   angvel=np.zeros((n, 3), _f), aabb=np.zeros((n, 6), _f), inv_IW=np.zeros((n, 9), _f))
+        self.l.ora_get_state(self.h, _ptr(out["pos"]), _ptr(out["orn"]), _ptr(out["linvel"]), _ptr(out["angvel"]),
+                             _ptr(out["aabb"]), _ptr(out["inv_IW"]))
+        return out
+
+    def set_state(self, pos, orn, linvel, angvel):
+        a = [_arr(pos, _f), _arr(orn, _f), _arr(linvel, _f), _arr(angvel, _f)]
+        self.l.ora_set_state(self.h, *[_ptr(x) for x in a])
+
+    def pairs(self):
+        m = int(self.l.ora_num_manifolds(self.h))
+        p = np.zeros((m, 2), _u)
+        if m:
+            self.l.ora_get_pairs(self.h, _ptr(p))
+        return p
+
+    def contacts(self):
+        m = int(self.l.ora_num_manifolds(self.h))
+        num = np.zeros(m, _u)
+        pts = np.zeros((m, 4, 18), _f)
+        u = np.zeros((m, 4, 2), _u)
+        if m:
+            self.l.ora_get_contacts(self.h, _ptr(num), _ptr(pts), _ptr(u))
+        return dict(pairs=self.pairs(), num=num, pts=pts, att=u[:, :, 0].copy(), lifetime=u[:, :, 1].copy())
+
+    def set_contacts(self, pairs, num, pts, att, lifetime=None):
+        pairs = _arr(pairs, _u, (-1, 2))
+        m = len(pairs)
+        num = _arr(num, _u, (m,))
+        pts = _arr(pts, _f, (m, 4, 18))
+        u = np.zeros((m, 4, 2), _u)
+        u[:, :, 0] = _arr(att, _u, (m, 4))
+        if lifetime is not None:
+            u[:, :, 1] = _arr(lifetime, _u, (m, 4))
+        self.l.ora_set_contacts(self.h, C.c_uint32(m), _ptr(pairs), _ptr(num), _ptr(pts), _ptr(u))
+
+    def islands(self):
+        lab = np.zeros(self.num_bodies, _u)
+        self.l.ora_get_islands(self.h, _ptr(lab))
+        return lab
+
+    def set_order(self, hinge_idx, pairs):
+        h = _arr(hinge_idx, _u)
+        p = _arr(pairs, _u, (-1, 2))
+        self.l.ora_set_order(self.h, C.c_uint32(len(h)), _ptr(h), C.c_uint32(len(p)), _ptr(p))
+
+    def clear_order(self):
+        self.l.ora_clear_order(self.h)

@@ -1,0 +1,146 @@
+// TEST INFRASTRUCTURE -- oracle/_ref: thin extern "C" wrappers over the REAL reference functions,
+// compiled in place from /root/reference by oracle/Makefile (no reference source is copied into
+// this repo).  Signatures match the ora_* pure functions of ora_api.cpp one to one, so tests can
+// diff the restatement against the reference bit for bit.
+#include <edyn/collision/collide.hpp>
+#include <edyn/collision/collision_result.hpp>
+#include <edyn/constraints/constraint_row.hpp>
+#include <edyn/constraints/constraint_row_options.hpp>
+#include <edyn/constraints/hinge_constraint.hpp>
+#include <edyn/constraints/constraint_body.hpp>
+#include <edyn/dynamics/moment_of_inertia.hpp>
+#include <edyn/dynamics/row_cache.hpp>
+#include <edyn/math/geom.hpp>
+#include <edyn/math/quaternion.hpp>
+#include <edyn/math/matrix3x3.hpp>
+#include <edyn/util/aabb_util.hpp>
+#include <cstring>
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+using namespace edyn;
+
+namespace {
+vector3 v3(const float *p) { return {p[0], p[1], p[2]}; }
+quaternion q4(const float *p) { return {p[0], p[1], p[2], p[3]}; }
+void put3(float *p, const vector3 &v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+void put4(float *p, const quaternion &q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
+matrix3x3 m9(const float *p) { return {vector3{p[0], p[1], p[2]}, vector3{p[3], p[4], p[5]}, vector3{p[6], p[7], p[8]}}; }
+void put9(float *p, const matrix3x3 &m) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) p[i * 3 + j] = m[i][j]; }
+
+// kinds follow shapes.hpp:23-37: sphere 0, capsule 2, box 3, plane 6
+template<typename F> void with_shape(uint32_t kind, const float *p, F f) {
+    switch (kind) {
+    case 0: f(sphere_shape{p[0]}); break;
+    case 2: { capsule_shape c; c.radius = p[0]; c.half_length = p[1]; c.axis = static_cast<coordinate_axis>(int(p[2])); f(c); break; }
+    case 3: f(box_shape{vector3{p[0], p[1], p[2]}}); break;
+    case 6: f(plane_shape{vector3{p[0], p[1], p[2]}, p[3]}); break;
+    default: break;
+    }
+}
+template<typename S> AABB aabb_of(const S &s, const vector3 &pos, const quaternion &orn) { return shape_aabb(s, pos, orn); }
+}
+
+REF_API int ref_collide(uint32_t kindA, const float *pA, uint32_t kindB, const float *pB, const float *posA, const float *ornA,
+                        const float *posB, const float *ornB, float *out10, uint32_t *att) {
+    collision_result result;
+    with_shape(kindA, pA, [&](auto &&shA) {
+        with_shape(kindB, pB, [&](auto &&shB) {
+            auto aabbA = aabb_of(shA, v3(posA), q4(ornA));
+            auto aabbB = aabb_of(shB, v3(posB), q4(ornB));
+            auto ctx = collision_context{v3(posA), q4(ornA), aabbA, v3(posB), q4(ornB), aabbB, collision_threshold};
+            collide(shA, shB, ctx, result);
+        });
+    });
+    for (size_t i = 0; i < result.num_points; ++i) {
+        auto &pt = result.point[i];
+        put3(out10 + 10 * i, pt.pivotA); put3(out10 + 10 * i + 3, pt.pivotB); put3(out10 + 10 * i + 6, pt.normal);
+        out10[10 * i + 9] = pt.distance;
+        att[i] = static_cast<uint32_t>(pt.normal_attachment);
+    }
+    return int(result.num_points);
+}
+
+REF_API void ref_shape_aabb(uint32_t kind, const float *p, const float *pos, const float *orn, float *out6) {
+    with_shape(kind, p, [&](auto &&sh) {
+        auto bb = aabb_of(sh, v3(pos), q4(orn));
+        put3(out6, bb.min); put3(out6 + 3, bb.max);
+    });
+}
+
+REF_API void ref_integrate(const float *q, const float *w, float dt, float *out4) { put4(out4, integrate(q4(q), v3(w), dt)); }
+
+REF_API void ref_plane_space(const float *n, float *p, float *q) { vector3 a, b; plane_space(v3(n), a, b); put3(p, a); put3(q, b); }
+
+REF_API int ref_intersect_line_aabb(const float *p0, const float *p1, const float *mn, const float *mx, float *s) {
+    return int(intersect_line_aabb(vector2{p0[0], p0[1]}, vector2{p1[0], p1[1]}, vector2{mn[0], mn[1]}, vector2{mx[0], mx[1]}, s[0], s[1]));
+}
+
+REF_API int ref_closest_segment_segment(const float *p1, const float *q1, const float *p2, const float *q2, float *out16, float *dist) {
+    scalar s, t, sp = 0, tp = 0; vector3 c1, c2, c1p{0, 0, 0}, c2p{0, 0, 0}; size_t np = 0;
+    *dist = closest_point_segment_segment(v3(p1), v3(q1), v3(p2), v3(q2), s, t, c1, c2, &np, &sp, &tp, &c1p, &c2p);
+    out16[0] = s; out16[1] = t; put3(out16 + 2, c1); put3(out16 + 5, c2);
+    out16[8] = sp; out16[9] = tp; put3(out16 + 10, c1p); put3(out16 + 13, c2p);
+    return int(np);
+}
+
+REF_API int ref_maybe_add_points(uint32_t n, const float *pivotA, const float *pivotB, float *outA, float *outB) {
+    collision_result r;
+    for (uint32_t i = 0; i < n; ++i) {
+        collision_result::collision_point p{};
+        p.pivotA = v3(pivotA + 3 * i); p.pivotB = v3(pivotB + 3 * i); p.normal = vector3_y;
+        p.distance = 0; p.normal_attachment = contact_normal_attachment::none;
+        r.maybe_add_point(p);
+    }
+    for (size_t i = 0; i < r.num_points; ++i) { put3(outA + 3 * i, r.point[i].pivotA); put3(outB + 3 * i, r.point[i].pivotB); }
+    return int(r.num_points);
+}
+
+REF_API void ref_moment_of_inertia(uint32_t kind, const float *p, float mass, float *out9) {
+    with_shape(kind, p, [&](auto &&sh) { put9(out9, moment_of_inertia(sh, mass)); });
+}
+REF_API void ref_inverse_symmetric(const float *m, float *out9) { put9(out9, inverse_matrix_symmetric(m9(m))); }
+REF_API void ref_world_inertia(const float *orn, const float *inv_I, float *out9) {
+    auto basis = to_matrix3x3(q4(orn));
+    put9(out9, basis * m9(inv_I) * transpose(basis));
+}
+
+REF_API void ref_prepare_row(const float *J, float inv_mA, const float *inv_IA, float inv_mB, const float *inv_IB, float error,
+                             float erp, float restitution, const float *vels12, float *out2) {
+    constraint_row row{};
+    for (int i = 0; i < 4; ++i) row.J[i] = v3(J + 3 * i);
+    row.inv_mA = inv_mA; row.inv_IA = m9(inv_IA); row.inv_mB = inv_mB; row.inv_IB = m9(inv_IB);
+    constraint_row_options opt{};
+    opt.error = error; opt.erp = erp; opt.restitution = restitution;
+    prepare_row(row, opt, v3(vels12), v3(vels12 + 3), v3(vels12 + 6), v3(vels12 + 9));
+    out2[0] = row.eff_mass; out2[1] = row.rhs;
+}
+
+REF_API float ref_solve_row(const float *J, float *row5, const float *dv12) {
+    constraint_row row{};
+    for (int i = 0; i < 4; ++i) row.J[i] = v3(J + 3 * i);
+    row.eff_mass = row5[0]; row.rhs = row5[1]; row.lower_limit = row5[2]; row.upper_limit = row5[3]; row.impulse = row5[4];
+    delta_linvel dvA{v3(dv12)}, dvB{v3(dv12 + 6)};
+    delta_angvel dwA{v3(dv12 + 3)}, dwB{v3(dv12 + 9)};
+    row.dvA = &dvA; row.dwA = &dwA; row.dvB = &dvB; row.dwB = &dwB;
+    float d = solve(row);
+    row5[4] = row.impulse;
+    return d;
+}
+
+// hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for
+// pivot/axes given in body space.  bodies: pos(3) orn(4) per body.
+REF_API int ref_hinge_rows(const float *pivotA, const float *pivotB, const float *axisA, const float *axisB,
+                           const float *posA, const float *ornA, const float *posB, const float *ornB, float *J60) {
+    hinge_constraint con{};
+    con.pivot[0] = v3(pivotA); con.pivot[1] = v3(pivotB);
+    con.set_axes(v3(axisA), v3(axisB));
+    constraint_row_prep_cache cache{};
+    cache.add_constraint();
+    constraint_body bA{v3(posA), v3(posA), q4(ornA), vector3_zero, vector3_zero, 1, matrix3x3_identity};
+    constraint_body bB{v3(posB), v3(posB), q4(ornB), vector3_zero, vector3_zero, 1, matrix3x3_identity};
+    con.prepare(cache, scalar(1.0 / 60), bA, bB);
+    int n = int(cache.num_rows);
+    for (int i = 0; i < n && i < 5; ++i) for (int k = 0; k < 4; ++k) put3(J60 + i * 12 + k * 3, cache.rows[i].row.J[k]);
+    return n;
+}

@@ -1,0 +1,4 @@
+// Declaration-level stand-in for EnTT 3.15 (see entt/entity/fwd.hpp in this shim).
+#pragma once
+#include <cstdint>
+namespace entt { using id_type = std::uint32_t; class any; }
