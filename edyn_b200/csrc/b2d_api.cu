@@ -1,0 +1,601 @@
+// C-ABI implementation (include/b2d.h): owns the device world, stages host SoA arrays in and out, and
+// enqueues the per-step kernel sequence that stands in for stepper_sequential::update's
+// bphase.update -> nphase.update -> island_manager.update -> solver.update
+// (/root/reference/src/edyn/simulation/stepper_sequential.cpp:82-91).
+// There is deliberately no CPU path: if CUDA is unavailable every entry point fails with B2D_ERR_CUDA.
+#include "../../include/b2d.h"
+#include "b2d_kernels.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+using namespace b2d;
+
+static std::string g_create_error;
+
+struct b2d_world {
+    b2d_config cfg{};
+    Dev d{};
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    std::string error;
+    int num_sms = 0;
+    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0;
+    void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
+    uint64_t launches = 0, steps = 0;
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_solve0 = nullptr, ev_solve1 = nullptr, ev_int0 = nullptr, ev_int1 = nullptr;
+    bool timed = false;
+    // host mirrors needed for grid sizing / exclusions
+    float max_extent = 0.0f;
+    std::vector<uint32_t> large;
+    std::vector<uint64_t> exclusions;
+    bool contacts_dirty = false;
+};
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { w->error = std::string(#call) + ": " + cudaGetErrorString(_e); return B2D_ERR_CUDA; } } while (0)
+
+template<typename T>
+static bool dalloc(b2d_world *w, T *&p, size_t n, int fill = 0) {
+    void *q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (cudaMalloc(&q, bytes) != cudaSuccess) { w->error = "cudaMalloc failed"; return false; }
+    cudaMemsetAsync(q, fill, bytes, w->stream);
+    w->allocs.push_back(q);
+    p = static_cast<T *>(q);
+    return true;
+}
+static uint32_t pow2_at_least(uint64_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+static int blocks_for(b2d_world *w, uint64_t n, int threads) {
+    uint64_t b = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)w->num_sms * 16;
+    return (int)std::max<uint64_t>(1, std::min(b, cap));
+}
+#define LAUNCH(kernel, n, threads, ...) do { kernel<<<blocks_for(w, (n), (threads)), (threads), 0, w->stream>>>(__VA_ARGS__); ++w->launches; } while (0)
+
+template<typename K, typename... Args>
+static cudaError_t coop_launch(b2d_world *w, K kernel, int blocks, int threads, Args... args) {
+    void *params[] = {(void *)&args...};
+    ++w->launches;
+    return cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(threads), params, 0, w->stream);
+}
+
+extern "C" {
+
+const char *b2d_last_error(const b2d_world *w) { return w ? w->error.c_str() : g_create_error.c_str(); }
+
+b2d_world *b2d_create(const b2d_config *cfg) {
+    if (!cfg || cfg->max_bodies == 0 || cfg->max_manifolds == 0) { g_create_error = "b2d_create: bad config"; return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "b2d_create: no CUDA device (there is no CPU fallback)"; return nullptr;
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { g_create_error = "b2d_create: cudaSetDevice failed"; return nullptr; }
+    b2d_world *w = new b2d_world();
+    w->cfg = *cfg;
+    if (w->cfg.fixed_dt <= 0) w->cfg.fixed_dt = 1.0f / 60.0f;
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cfg->device);
+    w->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { g_create_error = "b2d_create: device lacks cooperative launch"; delete w; return nullptr; }
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream"; delete w; return nullptr; }
+    for (cudaEvent_t *e : {&w->ev_step0, &w->ev_step1, &w->ev_solve0, &w->ev_solve1, &w->ev_int0, &w->ev_int1}) cudaEventCreate(e);
+
+    Dev &d = w->d;
+    const uint32_t NB = cfg->max_bodies, NM = cfg->max_manifolds, NH = std::max<uint32_t>(cfg->max_hinges, 1);
+    d.NB = NB; d.NM = NM; d.NH = NH; d.dt = w->cfg.fixed_dt;
+    d.nbodies = 0; d.nhinges = 0; d.nlarge = 0; d.cell = 1.0f; d.inv_cell = 1.0f;
+    bool ok = true;
+    ok = ok && dalloc(w, d.pos, NB) && dalloc(w, d.orn, NB) && dalloc(w, d.linvel, NB) && dalloc(w, d.angvel, NB);
+    ok = ok && dalloc(w, d.dvw, 2 * (size_t)NB) && dalloc(w, d.invI, 3 * (size_t)NB) && dalloc(w, d.invIW, 3 * (size_t)NB);
+    ok = ok && dalloc(w, d.grav, NB) && dalloc(w, d.shp, NB) && dalloc(w, d.bbmin, NB) && dalloc(w, d.bbmax, NB);
+    ok = ok && dalloc(w, d.flags, NB) && dalloc(w, d.mat, NB) && dalloc(w, d.group, NB) && dalloc(w, d.fmask, NB);
+    ok = ok && dalloc(w, d.cellkey, NB) && dalloc(w, d.cellkey_s, NB) && dalloc(w, d.cellbody, NB) && dalloc(w, d.cellbody_s, NB);
+    d.chash_size = pow2_at_least(2ull * NB);
+    ok = ok && dalloc(w, d.chash_key, d.chash_size, 0xFF) && dalloc(w, d.chash_val, d.chash_size);
+    ok = ok && dalloc(w, d.large_list, NB) && dalloc(w, d.newcount, NB) && dalloc(w, d.newoff, NB) && dalloc(w, d.newpairs, NM);
+    ok = ok && dalloc(w, d.free_flag, NM) && dalloc(w, d.free_rank, NM) && dalloc(w, d.free_list, NM);
+    d.mhash_size = pow2_at_least(2ull * NM);
+    ok = ok && dalloc(w, d.mhash_key, d.mhash_size, 0xFF) && dalloc(w, d.mhash_val, d.mhash_size);
+    d.xhash_size = 0; d.xhash_key = nullptr;
+    ok = ok && dalloc(w, d.mpair, NM) && dalloc(w, d.mstate, NM);
+    ok = ok && dalloc(w, d.pA, 4 * (size_t)NM) && dalloc(w, d.pB, 4 * (size_t)NM) && dalloc(w, d.pN, 4 * (size_t)NM);
+    ok = ok && dalloc(w, d.pL, 4 * (size_t)NM) && dalloc(w, d.pI, 4 * (size_t)NM);
+    ok = ok && dalloc(w, d.parent, NB) && dalloc(w, d.bmask, NB) && dalloc(w, d.jmask, NB) && dalloc(w, d.prop, NB) && dalloc(w, d.jprop, NB);
+    ok = ok && dalloc(w, d.ckey, NM) && dalloc(w, d.ckey_s, NM) && dalloc(w, d.cidx, NM) && dalloc(w, d.cidx_s, NM);
+    ok = ok && dalloc(w, d.hkey, NH) && dalloc(w, d.hkey_s, NH) && dalloc(w, d.hidx, NH) && dalloc(w, d.hidx_s, NH);
+    ok = ok && dalloc(w, d.isl_err, NB) && dalloc(w, d.isl_done, NB);
+    ok = ok && dalloc(w, d.hdr, NM) && dalloc(w, d.R0, 4 * (size_t)NM) && dalloc(w, d.R1, 4 * (size_t)NM) && dalloc(w, d.R2, 4 * (size_t)NM);
+    ok = ok && dalloc(w, d.R3, 4 * (size_t)NM) && dalloc(w, d.IMP, 4 * (size_t)NM);
+    ok = ok && dalloc(w, d.hpair, NH) && dalloc(w, d.hpivA, NH) && dalloc(w, d.hpivB, NH) && dalloc(w, d.hfA0, NH) && dalloc(w, d.hfA1, NH);
+    ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
+    ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
+    // hcolor must hold COLOR_NONE (0xFF as a 32-bit value), not 0xFFFFFFFF
+    if (ok) { std::vector<uint32_t> hc(NH, COLOR_NONE); cudaMemcpyAsync(d.hcolor, hc.data(), NH * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
+
+    // CUB temp storage: the largest of the sorts/scans used per step
+    size_t need = 0, t = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)NB, 0, 63, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, 8, w->stream); need = std::max(need, t);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
+    w->cub_tmp_bytes = need + 256;
+    void *tmp = nullptr;
+    if (ok && cudaMalloc(&tmp, w->cub_tmp_bytes) != cudaSuccess) ok = false;
+    w->cub_tmp = tmp; if (tmp) w->allocs.push_back(tmp);
+    w->stage_floats = (size_t)NB * 32 + (size_t)NM * 80;
+    float *st = nullptr;
+    if (ok && cudaMalloc(&st, w->stage_floats * sizeof(float)) != cudaSuccess) ok = false;
+    w->stage = st; if (st) w->allocs.push_back(st);
+
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, 256, 0); w->coop_blocks_color = std::max(1, per_sm) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, per_sm) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, per_sm) * w->num_sms;
+
+    if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
+        g_create_error = "b2d_create: device allocation failed: " + w->error;
+        b2d_destroy(w);
+        return nullptr;
+    }
+    return w;
+}
+
+void b2d_destroy(b2d_world *w) {
+    if (!w) return;
+    cudaSetDevice(w->cfg.device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    for (void *p : w->allocs) cudaFree(p);
+    for (cudaEvent_t e : {w->ev_step0, w->ev_step1, w->ev_solve0, w->ev_solve1, w->ev_int0, w->ev_int1}) if (e) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+void *b2d_stream(b2d_world *w) { return w ? (void *)w->stream : nullptr; }
+int b2d_sync(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; cudaSetDevice(w->cfg.device); CK(cudaStreamSynchronize(w->stream)); return B2D_OK; }
+
+// Bounding diameter of a shape: an upper bound of any AABB extent it can have.
+static float shape_diameter(uint32_t kind, const float *p) {
+    switch (kind) {
+    case B2D_SHAPE_SPHERE: return 2 * p[0];
+    case B2D_SHAPE_CAPSULE: return 2 * (p[0] + p[1]);
+    case B2D_SHAPE_BOX: return 2 * std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    default: return INFINITY;
+    }
+}
+
+int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
+    if (!w || !b) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    const uint32_t n = b->count, first = d.nbodies;
+    if (first + (uint64_t)n > d.NB) { w->error = "b2d_add_bodies: max_bodies exceeded"; return B2D_ERR_CAPACITY; }
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t sk = b->shape_kind[i];
+        if (!(sk == B2D_SHAPE_SPHERE || sk == B2D_SHAPE_CAPSULE || sk == B2D_SHAPE_BOX || sk == B2D_SHAPE_PLANE || sk == B2D_SHAPE_NONE)) {
+            w->error = "b2d_add_bodies: shape kind outside the hot-path scope (sphere, capsule, box, plane)"; return B2D_ERR_UNSUPPORTED;
+        }
+        if (sk == B2D_SHAPE_PLANE && b->kind[i] != B2D_STATIC) { w->error = "b2d_add_bodies: plane shapes must be static"; return B2D_ERR_UNSUPPORTED; }
+        if (b->kind[i] > B2D_STATIC) { w->error = "b2d_add_bodies: bad body kind"; return B2D_ERR_ARGUMENT; }
+    }
+    // Grid pitch: largest bounding diameter among the bodies that go into the grid.  Bodies much larger
+    // than the typical dynamic body (and all planes) are kept in a brute-force list instead.
+    double sum = 0; uint32_t cnt = 0;
+    for (uint32_t i = 0; i < n; ++i) if (b->kind[i] == B2D_DYNAMIC && b->shape_kind[i] != B2D_SHAPE_NONE) { sum += shape_diameter(b->shape_kind[i], b->shape_params + 4 * i); ++cnt; }
+    const float big = cnt ? float(4.0 * sum / cnt) : 1e30f;
+
+    std::vector<float4> pos(n), orn(n), lv(n), av(n), invI(3 * (size_t)n), grav(n), shp(n);
+    std::vector<uint32_t> flags(n); std::vector<float2> mat(n); std::vector<unsigned long long> grp(n), msk(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t kind = b->kind[i], sk = b->shape_kind[i];
+        const bool dyn = kind == B2D_DYNAMIC;
+        pos[i] = make_float4(b->pos[3 * i], b->pos[3 * i + 1], b->pos[3 * i + 2], dyn ? b->inv_mass[i] : 0.0f);
+        orn[i] = make_float4(b->orn[4 * i], b->orn[4 * i + 1], b->orn[4 * i + 2], b->orn[4 * i + 3]);
+        if (kind == B2D_STATIC) { lv[i] = av[i] = make_float4(0, 0, 0, 0); }
+        else { lv[i] = make_float4(b->linvel[3 * i], b->linvel[3 * i + 1], b->linvel[3 * i + 2], 0); av[i] = make_float4(b->angvel[3 * i], b->angvel[3 * i + 1], b->angvel[3 * i + 2], 0); }
+        for (int r = 0; r < 3; ++r) invI[3 * (size_t)i + r] = dyn ? make_float4(b->inv_inertia[9 * i + 3 * r], b->inv_inertia[9 * i + 3 * r + 1], b->inv_inertia[9 * i + 3 * r + 2], 0) : make_float4(0, 0, 0, 0);
+        grav[i] = make_float4(b->gravity[3 * i], b->gravity[3 * i + 1], b->gravity[3 * i + 2], 0);
+        shp[i] = make_float4(b->shape_params[4 * i], b->shape_params[4 * i + 1], b->shape_params[4 * i + 2], b->shape_params[4 * i + 3]);
+        uint32_t f = kind | (sk << F_SHAPE_SHIFT);
+        if (dyn && (sk == B2D_SHAPE_SPHERE || sk == B2D_SHAPE_CAPSULE)) f |= F_ROLLING;
+        unsigned long long g = b->group ? b->group[i] : ~0ULL, m = b->mask ? b->mask[i] : ~0ULL;
+        if (b->group && b->mask && !(g == ~0ULL && m == ~0ULL)) f |= F_FILTER;
+        if (sk != B2D_SHAPE_NONE) {
+            float diam = shape_diameter(sk, b->shape_params + 4 * i);
+            if (sk == B2D_SHAPE_PLANE || diam > big) { f |= F_LARGE; w->large.push_back(first + i); }
+            else w->max_extent = std::max(w->max_extent, diam);
+        }
+        flags[i] = f; mat[i] = make_float2(b->friction[i], b->restitution[i]); grp[i] = g; msk[i] = m;
+    }
+    if (w->large.size() > d.NB) { w->error = "large list overflow"; return B2D_ERR_CAPACITY; }
+    cudaStream_t s = w->stream;
+    CK(cudaMemcpyAsync(d.pos + first, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.orn + first, orn.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.linvel + first, lv.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.angvel + first, av.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.invI + 3 * (size_t)first, invI.data(), 3 * (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.grav + first, grav.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.shp + first, shp.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.flags + first, flags.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.mat + first, mat.data(), n * sizeof(float2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.group + first, grp.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.fmask + first, msk.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.large_list, w->large.data(), w->large.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    d.nbodies = first + n;
+    d.nlarge = (uint32_t)w->large.size();
+    d.cell = w->max_extent + 2 * BREAKING_THRESHOLD + 1e-3f;
+    d.inv_cell = 1.0f / d.cell;
+    LAUNCH(k_refresh_bodies, n, 256, d, first, n);
+    CK(cudaStreamSynchronize(s));
+    if (first_id) *first_id = first;
+    return B2D_OK;
+}
+
+static void plane_space_host(const float *n, float *p, float *q) {   // geom.cpp:730-754
+    if (std::fabs(n[2]) > 0.7071067811865475244f) {
+        float a = n[1] * n[1] + n[2] * n[2]; float k = 1.0f / std::sqrt(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k; q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        float a = n[0] * n[0] + n[1] * n[1]; float k = 1.0f / std::sqrt(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0; q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b, const float *pivA, const float *pivB,
+                   const float *axA, const float *axB) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    const uint32_t first = d.nhinges;
+    if (first + (uint64_t)n > w->cfg.max_hinges) { w->error = "b2d_add_hinges: max_hinges exceeded"; return B2D_ERR_CAPACITY; }
+    std::vector<uint2> pr(n); std::vector<float4> pa(n), pb(n), f0(n), f1(n), f2(n), g0(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (a[i] >= d.nbodies || b[i] >= d.nbodies) { w->error = "b2d_add_hinges: body id out of range"; return B2D_ERR_ARGUMENT; }
+        pr[i] = make_uint2(a[i], b[i]);
+        pa[i] = make_float4(pivA[3 * i], pivA[3 * i + 1], pivA[3 * i + 2], 0); pb[i] = make_float4(pivB[3 * i], pivB[3 * i + 1], pivB[3 * i + 2], 0);
+        float p[3], q[3];
+        plane_space_host(axA + 3 * i, p, q);       // set_axes, hinge_constraint.cpp:11-17
+        f0[i] = make_float4(axA[3 * i], axA[3 * i + 1], axA[3 * i + 2], 0); f1[i] = make_float4(p[0], p[1], p[2], 0); f2[i] = make_float4(q[0], q[1], q[2], 0);
+        g0[i] = make_float4(axB[3 * i], axB[3 * i + 1], axB[3 * i + 2], 0);
+    }
+    cudaStream_t s = w->stream;
+    CK(cudaMemcpyAsync(d.hpair + first, pr.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hpivA + first, pa.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hpivB + first, pb.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hfA0 + first, f0.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hfA1 + first, f1.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hfA2 + first, f2.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.hfB0 + first, g0.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d.himp + 5 * (size_t)first, 0, 5 * (size_t)n * sizeof(float), s));
+    CK(cudaStreamSynchronize(s));
+    d.nhinges = first + n;
+    return B2D_OK;
+}
+
+int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
+        w->exclusions.push_back((lo << 32) | hi);
+    }
+    uint32_t size = pow2_at_least(2ull * w->exclusions.size() + 2);
+    std::vector<unsigned long long> table(size, ~0ULL);
+    auto h64 = [](unsigned long long k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return (uint32_t)k; };
+    for (uint64_t k : w->exclusions) {
+        uint32_t h = h64(k) & (size - 1);
+        while (table[h] != ~0ULL && table[h] != k) h = (h + 1) & (size - 1);
+        table[h] = k;
+    }
+    unsigned long long *dev = nullptr;
+    if (!dalloc(w, dev, size)) return B2D_ERR_CUDA;
+    CK(cudaMemcpyAsync(dev, table.data(), size * sizeof(unsigned long long), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    d.xhash_key = dev; d.xhash_size = size;
+    return B2D_OK;
+}
+
+// ------------------------------------------------------------------ one step
+
+static int enqueue_broadphase(b2d_world *w) {
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    CK(cudaMemsetAsync(d.mhash_key, 0xFF, (size_t)d.mhash_size * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(d.chash_key, 0xFF, (size_t)d.chash_size * sizeof(unsigned long long), s));
+    LAUNCH(k_bp_separate, d.NM, 256, d);
+    size_t t = w->cub_tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.free_flag, d.free_rank, (int)d.NM, s)); ++w->launches;
+    LAUNCH(k_bp_free_list, d.NM, 256, d);
+    if (d.nbodies) {
+        LAUNCH(k_bp_cells, d.nbodies, 256, d);
+        t = w->cub_tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, 63, s)); w->launches += 4;
+        LAUNCH(k_bp_cell_starts, d.nbodies, 256, d);
+        LAUNCH(k_bp_pairs<false>, d.nbodies, 128, d);
+        t = w->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.newcount, d.newoff, (int)d.nbodies, s)); ++w->launches;
+        LAUNCH(k_bp_total, 1, 32, d);
+        LAUNCH(k_bp_pairs<true>, d.nbodies, 128, d);
+        LAUNCH(k_bp_append, d.NM, 256, d);
+        LAUNCH(k_bp_finish, 1, 32, d);
+    }
+    return B2D_OK;
+}
+static int enqueue_narrowphase(b2d_world *w) {
+    Dev &d = w->d;
+    LAUNCH(k_narrowphase, d.NM, 128, d);
+    return B2D_OK;
+}
+static int enqueue_islands(b2d_world *w) {
+    Dev &d = w->d;
+    CK(cudaMemsetAsync(&d.cnt->nislands, 0, sizeof(uint32_t), w->stream));
+    LAUNCH(k_cc_init, d.nbodies, 256, d);
+    LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d);
+    LAUNCH(k_cc_flatten, d.nbodies, 256, d);
+    return B2D_OK;
+}
+static int enqueue_solver(b2d_world *w) {
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    const int vi = (int)w->cfg.velocity_iterations, pi = (int)w->cfg.position_iterations;
+    LAUNCH(k_gravity, d.nbodies, 256, d);
+    int recolor = ((w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->contacts_dirty) ? 1 : 0;
+    w->contacts_dirty = false;
+    CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d, recolor));
+    LAUNCH(k_color_keys, d.NM, 256, d);
+    size_t t = w->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
+    t = w->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)d.NH, 0, 8, s)); w->launches += 3;
+    LAUNCH(k_color_offsets, d.NM, 256, d);
+    LAUNCH(k_color_fixup, 1, 32, d);
+    LAUNCH(k_prepare_contacts, d.NM, 256, d);
+    if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
+    cudaEventRecord(w->ev_solve0, s);
+    CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
+    cudaEventRecord(w->ev_solve1, s);
+    cudaEventRecord(w->ev_int0, s);
+    LAUNCH(k_integrate, d.nbodies, 256, d, pi == 0 ? 1 : 0);
+    cudaEventRecord(w->ev_int1, s);
+    LAUNCH(k_store_impulses, d.NM, 256, d);
+    if (pi > 0) {
+        CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
+        LAUNCH(k_finalize, d.nbodies, 256, d);
+    }
+    w->timed = true;
+    return B2D_OK;
+}
+
+int b2d_run_phases(b2d_world *w, uint32_t mask) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    int rc = B2D_OK;
+    if (mask & B2D_PHASE_BROAD) if ((rc = enqueue_broadphase(w))) return rc;
+    if (mask & B2D_PHASE_NARROW) if ((rc = enqueue_narrowphase(w))) return rc;
+    if (mask & B2D_PHASE_ISLANDS) if ((rc = enqueue_islands(w))) return rc;
+    if (mask & B2D_PHASE_SOLVE) if ((rc = enqueue_solver(w))) return rc;
+    CK(cudaGetLastError());
+    return B2D_OK;
+}
+
+int b2d_step(b2d_world *w, uint32_t num_steps) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    cudaEventRecord(w->ev_step0, w->stream);
+    for (uint32_t i = 0; i < num_steps; ++i) {
+        int rc = b2d_run_phases(w, B2D_PHASE_ALL);
+        if (rc) return rc;
+        ++w->steps;
+    }
+    cudaEventRecord(w->ev_step1, w->stream);
+    return B2D_OK;
+}
+
+// ------------------------------------------------------------------ state in / out
+
+int b2d_upload_state(b2d_world *w, const float *pos, const float *orn, const float *lv, const float *av) {
+    if (!w || !pos || !orn || !lv || !av) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d; const size_t n = d.nbodies; cudaStream_t s = w->stream;
+    float *sp = w->stage, *so = sp + 3 * n, *sl = so + 4 * n, *sa = sl + 3 * n;
+    CK(cudaMemcpyAsync(sp, pos, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(so, orn, 4 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sl, lv, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sa, av, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    LAUNCH(k_unpack_state, n, 256, d, sp, so, sl, sa, (uint32_t)n);
+    LAUNCH(k_refresh_bodies, n, 256, d, 0u, (uint32_t)n);
+    return B2D_OK;
+}
+
+int b2d_download_state(b2d_world *w, float *pos, float *orn, float *lv, float *av, float *bb, float *iw) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d; const size_t n = d.nbodies; cudaStream_t s = w->stream;
+    float *sp = w->stage, *so = sp + 3 * n, *sl = so + 4 * n, *sa = sl + 3 * n, *sb = sa + 3 * n, *si = sb + 6 * n;
+    LAUNCH(k_pack_state, n, 256, d, pos ? sp : nullptr, orn ? so : nullptr, lv ? sl : nullptr, av ? sa : nullptr, bb ? sb : nullptr, iw ? si : nullptr, (uint32_t)n);
+    if (pos) CK(cudaMemcpyAsync(pos, sp, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (orn) CK(cudaMemcpyAsync(orn, so, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (lv) CK(cudaMemcpyAsync(lv, sl, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (av) CK(cudaMemcpyAsync(av, sa, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (bb) CK(cudaMemcpyAsync(bb, sb, 6 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (iw) CK(cudaMemcpyAsync(iw, si, 9 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2D_OK;
+}
+
+static int fetch_counters(b2d_world *w, Counters &c) {
+    CK(cudaMemcpyAsync(&c, w->d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return B2D_OK;
+}
+
+// Host-side gather of the alive manifolds in slot order (the device arrays have holes).
+struct HostManifolds {
+    std::vector<uint2> pair; std::vector<uint32_t> state; std::vector<uint32_t> slots;
+};
+static int fetch_manifolds(b2d_world *w, HostManifolds &hm, uint32_t &hwm) {
+    Counters c; int rc = fetch_counters(w, c); if (rc) return rc;
+    hwm = c.hwm;
+    hm.pair.resize(hwm); hm.state.resize(hwm);
+    if (hwm) {
+        CK(cudaMemcpyAsync(hm.pair.data(), w->d.mpair, hwm * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(hm.state.data(), w->d.mstate, hwm * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    hm.slots.clear();
+    for (uint32_t m = 0; m < hwm; ++m) if (hm.state[m] & MS_ALIVE) hm.slots.push_back(m);
+    return B2D_OK;
+}
+
+int b2d_num_manifolds(b2d_world *w, uint32_t *n) {
+    if (!w || !n) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    HostManifolds hm; uint32_t hwm; int rc = fetch_manifolds(w, hm, hwm); if (rc) return rc;
+    *n = (uint32_t)hm.slots.size();
+    return B2D_OK;
+}
+
+int b2d_download_pairs(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint32_t *n) {
+    if (!w || !n) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    HostManifolds hm; uint32_t hwm; int rc = fetch_manifolds(w, hm, hwm); if (rc) return rc;
+    *n = (uint32_t)hm.slots.size();
+    if (*n > capacity) { w->error = "b2d_download_pairs: capacity too small"; return B2D_ERR_CAPACITY; }
+    for (uint32_t k = 0; k < *n; ++k) { pairs[2 * k] = hm.pair[hm.slots[k]].x; pairs[2 * k + 1] = hm.pair[hm.slots[k]].y; }
+    return B2D_OK;
+}
+
+int b2d_download_contacts(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint32_t *num, float *pt18, uint32_t *ptu2, uint32_t *n) {
+    if (!w || !n) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    HostManifolds hm; uint32_t hwm; int rc = fetch_manifolds(w, hm, hwm); if (rc) return rc;
+    *n = (uint32_t)hm.slots.size();
+    if (*n > capacity) { w->error = "b2d_download_contacts: capacity too small"; return B2D_ERR_CAPACITY; }
+    const Dev &d = w->d;
+    std::vector<float4> A(4 * (size_t)hwm), B(4 * (size_t)hwm), N(4 * (size_t)hwm), L(4 * (size_t)hwm), I(4 * (size_t)hwm);
+    for (int s = 0; s < 4 && hwm; ++s) {
+        size_t off = (size_t)s * d.NM, ho = (size_t)s * hwm;
+        CK(cudaMemcpyAsync(A.data() + ho, d.pA + off, hwm * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(B.data() + ho, d.pB + off, hwm * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(N.data() + ho, d.pN + off, hwm * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(L.data() + ho, d.pL + off, hwm * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(I.data() + ho, d.pI + off, hwm * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+    }
+    CK(cudaStreamSynchronize(w->stream));
+    for (uint32_t k = 0; k < *n; ++k) {
+        uint32_t m = hm.slots[k];
+        pairs[2 * k] = hm.pair[m].x; pairs[2 * k + 1] = hm.pair[m].y;
+        uint32_t np = hm.state[m] & MS_NPTS_MASK;
+        num[k] = np;
+        for (uint32_t s = 0; s < 4; ++s) {
+            float *f = pt18 + ((size_t)k * 4 + s) * 18; uint32_t *u = ptu2 + ((size_t)k * 4 + s) * 2;
+            if (s >= np) { std::memset(f, 0, 18 * sizeof(float)); u[0] = u[1] = 0; continue; }
+            size_t i = (size_t)s * hwm + m;
+            f[0] = A[i].x; f[1] = A[i].y; f[2] = A[i].z; f[3] = B[i].x; f[4] = B[i].y; f[5] = B[i].z;
+            f[6] = N[i].x; f[7] = N[i].y; f[8] = N[i].z; f[9] = L[i].x; f[10] = L[i].y; f[11] = L[i].z;
+            f[12] = A[i].w; f[13] = B[i].w; f[14] = N[i].w; f[15] = I[i].x; f[16] = I[i].y; f[17] = I[i].z;
+            uint32_t bits; std::memcpy(&bits, &L[i].w, 4);
+            u[0] = bits & 3u; u[1] = bits >> 2;
+        }
+    }
+    return B2D_OK;
+}
+
+int b2d_upload_contacts(b2d_world *w, uint32_t n, const uint32_t *pairs, const uint32_t *num, const float *pt18, const uint32_t *ptu2) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    if (n > d.NM) { w->error = "b2d_upload_contacts: max_manifolds exceeded"; return B2D_ERR_CAPACITY; }
+    std::vector<uint2> pr(n); std::vector<uint32_t> st(n);
+    std::vector<float4> A(4 * (size_t)n), B(4 * (size_t)n), N(4 * (size_t)n), L(4 * (size_t)n), I(4 * (size_t)n);
+    for (uint32_t k = 0; k < n; ++k) {
+        pr[k] = make_uint2(pairs[2 * k], pairs[2 * k + 1]);
+        if (num[k] > 4) { w->error = "b2d_upload_contacts: more than 4 points"; return B2D_ERR_ARGUMENT; }
+        st[k] = MS_ALIVE | (COLOR_NONE << MS_COLOR_SHIFT) | num[k];
+        for (uint32_t s = 0; s < 4; ++s) {
+            const float *f = pt18 + ((size_t)k * 4 + s) * 18; const uint32_t *u = ptu2 + ((size_t)k * 4 + s) * 2;
+            size_t i = (size_t)s * n + k;
+            uint32_t bits = (u[0] & 3u) | (u[1] << 2); float fb; std::memcpy(&fb, &bits, 4);
+            A[i] = make_float4(f[0], f[1], f[2], f[12]); B[i] = make_float4(f[3], f[4], f[5], f[13]);
+            N[i] = make_float4(f[6], f[7], f[8], f[14]); L[i] = make_float4(f[9], f[10], f[11], fb);
+            I[i] = make_float4(f[15], f[16], f[17], 0);
+        }
+    }
+    cudaStream_t s_ = w->stream;
+    CK(cudaMemsetAsync(d.mstate, 0, (size_t)d.NM * sizeof(uint32_t), s_));
+    if (n) {
+        CK(cudaMemcpyAsync(d.mpair, pr.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, s_));
+        CK(cudaMemcpyAsync(d.mstate, st.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s_));
+        for (int s = 0; s < 4; ++s) {
+            size_t off = (size_t)s * d.NM, ho = (size_t)s * n;
+            CK(cudaMemcpyAsync(d.pA + off, A.data() + ho, n * sizeof(float4), cudaMemcpyHostToDevice, s_));
+            CK(cudaMemcpyAsync(d.pB + off, B.data() + ho, n * sizeof(float4), cudaMemcpyHostToDevice, s_));
+            CK(cudaMemcpyAsync(d.pN + off, N.data() + ho, n * sizeof(float4), cudaMemcpyHostToDevice, s_));
+            CK(cudaMemcpyAsync(d.pL + off, L.data() + ho, n * sizeof(float4), cudaMemcpyHostToDevice, s_));
+            CK(cudaMemcpyAsync(d.pI + off, I.data() + ho, n * sizeof(float4), cudaMemcpyHostToDevice, s_));
+        }
+    }
+    CK(cudaMemcpyAsync(&d.cnt->hwm, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s_));
+    CK(cudaStreamSynchronize(s_));
+    w->contacts_dirty = true;
+    return B2D_OK;
+}
+
+int b2d_download_islands(b2d_world *w, uint32_t *label) {
+    if (!w || !label) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    CK(cudaMemcpyAsync(label, w->d.parent, w->d.nbodies * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return B2D_OK;
+}
+
+int b2d_download_solver_order(b2d_world *w, uint32_t *hinge_ids, uint32_t *nh, uint32_t *pairs, uint32_t *nm) {
+    if (!w || !nh || !nm) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Counters c; int rc = fetch_counters(w, c); if (rc) return rc;
+    const uint32_t na = c.nactive, nhh = c.hoff[MAX_COLORS];
+    if (na > *nm || nhh > *nh) { w->error = "b2d_download_solver_order: capacity too small"; return B2D_ERR_CAPACITY; }
+    std::vector<uint4> hdr(na), hh(nhh);
+    if (na) CK(cudaMemcpyAsync(hdr.data(), w->d.hdr, na * sizeof(uint4), cudaMemcpyDeviceToHost, w->stream));
+    if (nhh) CK(cudaMemcpyAsync(hh.data(), w->d.hhdr, nhh * sizeof(uint4), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (uint32_t i = 0; i < na; ++i) { pairs[2 * i] = hdr[i].x & 0x7FFFFFFFu; pairs[2 * i + 1] = hdr[i].y & 0x7FFFFFFFu; }
+    for (uint32_t i = 0; i < nhh; ++i) hinge_ids[i] = hh[i].z;
+    *nm = na; *nh = nhh;
+    return B2D_OK;
+}
+
+int b2d_download_hinge_impulses(b2d_world *w, float *imp5) {
+    if (!w || !imp5) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    CK(cudaMemcpyAsync(imp5, w->d.himp, 5 * (size_t)w->d.nhinges * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return B2D_OK;
+}
+
+int b2d_get_stats(b2d_world *w, b2d_stats *out) {
+    if (!w || !out) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    CK(cudaMemsetAsync(&d.cnt->npoints, 0, sizeof(uint32_t), w->stream));
+    LAUNCH(k_count_points, d.NM, 256, d); --w->launches;
+    Counters c; int rc = fetch_counters(w, c); if (rc) return rc;
+    HostManifolds hm; uint32_t hwm; rc = fetch_manifolds(w, hm, hwm); if (rc) return rc;
+    std::memset(out, 0, sizeof(*out));
+    out->bodies = d.nbodies; out->manifolds = (uint32_t)hm.slots.size(); out->contact_points = c.npoints; out->hinges = d.nhinges;
+    out->contact_colors = c.ncolors; out->hinge_colors = c.nhcolors; out->islands = c.nislands; out->manifold_high_water = c.hwm;
+    out->kernel_launches = w->launches; out->steps = w->steps; out->error_flags = c.err;
+    if (w->timed) {
+        cudaEventElapsedTime(&out->solve_ms, w->ev_solve0, w->ev_solve1);
+        cudaEventElapsedTime(&out->integrate_ms, w->ev_int0, w->ev_int1);
+        if (cudaEventQuery(w->ev_step1) == cudaSuccess) cudaEventElapsedTime(&out->last_step_ms, w->ev_step0, w->ev_step1);
+        cudaGetLastError();
+    }
+    return B2D_OK;
+}
+
+} // extern "C"

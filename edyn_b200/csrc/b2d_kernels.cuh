@@ -1,0 +1,988 @@
+// CUDA kernels of the per-step hot path (sm_100a).  One section per reference phase:
+//   broadphase   src/edyn/collision/broadphase.cpp:119-195      -> k_bp_*
+//   narrowphase  src/edyn/collision/narrowphase.cpp:21-40        -> k_narrowphase
+//   islands      src/edyn/simulation/island_manager.cpp:117-247  -> k_cc_*
+//   solver       src/edyn/dynamics/solver.cpp:387-468,
+//                src/edyn/dynamics/island_solver.cpp:76-111,263-376 -> k_gravity, k_color, k_prepare_*, k_solve,
+//                                                                      k_integrate, k_position, k_finalize
+// All kernels are grid-stride over device-side counts, so a step needs no host round trip.
+#pragma once
+#include "b2d_collide.cuh"
+#include "b2d_world.cuh"
+#include <cooperative_groups.h>
+
+namespace b2d {
+namespace cg = cooperative_groups;
+
+#define GRID_STRIDE(i, n) for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, _s = gridDim.x * blockDim.x; i < (n); i += _s)
+
+B2D_D uint32_t kind_of(uint32_t f) { return f & F_KIND_MASK; }
+B2D_D bool is_dynamic(uint32_t f) { return (f & F_KIND_MASK) == 0u; }
+B2D_D int shape_of(uint32_t f) { return (int)((f >> F_SHAPE_SHIFT) & 0xFFu); }
+B2D_D unsigned long long pair_key(uint32_t a, uint32_t b) {
+    return a < b ? ((unsigned long long)a << 32) | b : ((unsigned long long)b << 32) | a;
+}
+B2D_D uint32_t hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+constexpr unsigned long long EMPTY_KEY = ~0ULL;
+
+B2D_D void hash_insert(unsigned long long *keys, uint32_t *vals, uint32_t size, unsigned long long k, uint32_t v) {
+    uint32_t h = hash64(k) & (size - 1);
+    for (;;) {
+        unsigned long long prev = atomicCAS(&keys[h], EMPTY_KEY, k);
+        if (prev == EMPTY_KEY || prev == k) { if (vals) vals[h] = v; return; }
+        h = (h + 1) & (size - 1);
+    }
+}
+B2D_D bool hash_find(const unsigned long long *keys, const uint32_t *vals, uint32_t size, unsigned long long k, uint32_t &v) {
+    uint32_t h = hash64(k) & (size - 1);
+    for (;;) {
+        unsigned long long cur = keys[h];
+        if (cur == k) { if (vals) v = vals[h]; return true; }
+        if (cur == EMPTY_KEY) return false;
+        h = (h + 1) & (size - 1);
+    }
+}
+
+B2D_D box3 body_box(const Dev &d, uint32_t i) { box3 b; b.mn = mk3(d.bbmin[i]); b.mx = mk3(d.bbmax[i]); return b; }
+B2D_D m3 load_m3(const float4 *p, uint32_t i) { m3 m; m.r0 = mk3(p[3 * i]); m.r1 = mk3(p[3 * i + 1]); m.r2 = mk3(p[3 * i + 2]); return m; }
+B2D_D void store_invIW(const Dev &d, uint32_t i, const m3 &m, float inv_m) {
+    d.invIW[3 * i] = f4(m.r0, inv_m); d.invIW[3 * i + 1] = f4(m.r1, 0); d.invIW[3 * i + 2] = f4(m.r2, 0);
+}
+
+// ====================================================================== state staging
+
+// Refresh AABB (all shaped bodies) and inertia_world_inv (dynamic) from the current transform:
+// util/rigidbody.cpp:75-77,113 at creation; solver.cpp:453-465 after a resync.
+__global__ void k_refresh_bodies(Dev d, uint32_t first, uint32_t count) {
+    GRID_STRIDE(k, count) {
+        uint32_t i = first + k;
+        uint32_t f = d.flags[i];
+        v3 pos = mk3(d.pos[i]); q4 orn = mkq(d.orn[i]);
+        float inv_m = d.pos[i].w;
+        if (is_dynamic(f)) store_invIW(d, i, world_inertia(orn, load_m3(d.invI, i)), inv_m);
+        else store_invIW(d, i, m3_zero(), 0.0f);
+        int sk = shape_of(f);
+        if (sk != SH_NONE) { box3 bb = shape_aabb(sk, d.shp[i], pos, orn); d.bbmin[i] = f4(bb.mn, 0); d.bbmax[i] = f4(bb.mx, 0); }
+        d.dvw[2 * i] = make_float4(0, 0, 0, 0); d.dvw[2 * i + 1] = make_float4(0, 0, 0, 0);
+    }
+}
+
+// host float3/float4 packed arrays (staging buffer on device) -> float4 SoA
+__global__ void k_unpack_state(Dev d, const float *pos, const float *orn, const float *lv, const float *av, uint32_t n) {
+    GRID_STRIDE(i, n) {
+        float inv_m = d.pos[i].w;
+        d.pos[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], inv_m);
+        d.orn[i] = make_float4(orn[4 * i], orn[4 * i + 1], orn[4 * i + 2], orn[4 * i + 3]);
+        if (kind_of(d.flags[i]) != 2u) {
+            d.linvel[i] = make_float4(lv[3 * i], lv[3 * i + 1], lv[3 * i + 2], 0);
+            d.angvel[i] = make_float4(av[3 * i], av[3 * i + 1], av[3 * i + 2], 0);
+        }
+    }
+}
+__global__ void k_pack_state(Dev d, float *pos, float *orn, float *lv, float *av, float *bb, float *iw, uint32_t n) {
+    GRID_STRIDE(i, n) {
+        if (pos) { float4 p = d.pos[i]; pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z; }
+        if (orn) { float4 q = d.orn[i]; orn[4 * i] = q.x; orn[4 * i + 1] = q.y; orn[4 * i + 2] = q.z; orn[4 * i + 3] = q.w; }
+        if (lv) { float4 v = d.linvel[i]; lv[3 * i] = v.x; lv[3 * i + 1] = v.y; lv[3 * i + 2] = v.z; }
+        if (av) { float4 v = d.angvel[i]; av[3 * i] = v.x; av[3 * i + 1] = v.y; av[3 * i + 2] = v.z; }
+        if (bb) { float4 a = d.bbmin[i], b = d.bbmax[i]; bb[6 * i] = a.x; bb[6 * i + 1] = a.y; bb[6 * i + 2] = a.z; bb[6 * i + 3] = b.x; bb[6 * i + 4] = b.y; bb[6 * i + 5] = b.z; }
+        if (iw) { for (int r = 0; r < 3; ++r) { float4 m = d.invIW[3 * i + r]; iw[9 * i + 3 * r] = m.x; iw[9 * i + 3 * r + 1] = m.y; iw[9 * i + 3 * r + 2] = m.z; } }
+    }
+}
+
+// ====================================================================== broadphase
+
+constexpr float BP_OFFSET = -BREAKING_THRESHOLD;                 // m_aabb_offset, broadphase.hpp:15
+constexpr float BP_SEPARATION = -(BREAKING_THRESHOLD * 1.3f);    // -m_separation_threshold, broadphase.hpp:18
+
+// destroy_separated_manifolds (broadphase.cpp:119-134) + rebuild of the pair -> manifold hash
+// (contact_manifold_map) from the survivors + dead-slot flags for the free list.
+__global__ void k_bp_separate(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, d.NM) {
+        uint32_t flag = 0;
+        if (m < hwm) {
+            uint32_t st = d.mstate[m];
+            if (st & MS_ALIVE) {
+                uint2 p = d.mpair[m];
+                if (!intersect(inset(body_box(d, p.x), BP_SEPARATION), body_box(d, p.y))) {
+                    d.mstate[m] = COLOR_NONE << MS_COLOR_SHIFT;      // clear_contact_manifold + destroy
+                    flag = 1;
+                } else {
+                    hash_insert(d.mhash_key, d.mhash_val, d.mhash_size, pair_key(p.x, p.y), m);
+                }
+            } else flag = 1;
+        }
+        d.free_flag[m] = flag;
+    }
+}
+__global__ void k_bp_free_list(Dev d) {
+    GRID_STRIDE(m, d.NM) {
+        if (d.free_flag[m]) d.free_list[d.free_rank[m]] = m;
+        if (m == d.NM - 1) d.cnt->nfree = d.free_rank[m] + d.free_flag[m];
+    }
+}
+
+B2D_D unsigned long long cell_key_of(int cx, int cy, int cz) {
+    const int OFF = 1 << 20, MX = (1 << 21) - 1;
+    unsigned long long x = (unsigned long long)min(max(cx + OFF, 0), MX);
+    unsigned long long y = (unsigned long long)min(max(cy + OFF, 0), MX);
+    unsigned long long z = (unsigned long long)min(max(cz + OFF, 0), MX);
+    return (x << 42) | (y << 21) | z;
+}
+B2D_D void cell_of(const Dev &d, uint32_t i, int &cx, int &cy, int &cz) {
+    float4 a = d.bbmin[i], b = d.bbmax[i];
+    cx = (int)floorf((a.x + b.x) * 0.5f * d.inv_cell);
+    cy = (int)floorf((a.y + b.y) * 0.5f * d.inv_cell);
+    cz = (int)floorf((a.z + b.z) * 0.5f * d.inv_cell);
+}
+
+// Cell key per body.  Shapeless and "large" bodies get the all-ones key and sort to the end.
+__global__ void k_bp_cells(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t f = d.flags[i];
+        unsigned long long key = EMPTY_KEY;
+        if (shape_of(f) != SH_NONE && !(f & F_LARGE)) { int cx, cy, cz; cell_of(d, i, cx, cy, cz); key = cell_key_of(cx, cy, cz); }
+        d.cellkey[i] = key; d.cellbody[i] = i;
+    }
+}
+// First sorted index of every occupied cell -> hash table.
+__global__ void k_bp_cell_starts(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        unsigned long long k = d.cellkey_s[i];
+        if (k != EMPTY_KEY && (i == 0 || d.cellkey_s[i - 1] != k)) hash_insert(d.chash_key, d.chash_val, d.chash_size, k, i);
+    }
+}
+
+// should_collide_default, collision/should_collide.cpp:23-57 (exclusion list kept as a pair hash set)
+B2D_D bool should_collide(const Dev &d, uint32_t a, uint32_t fa, uint32_t b, uint32_t fb) {
+    bool ha = fa & F_FILTER, hb = fb & F_FILTER;
+    if (ha && hb) {
+        if ((d.group[a] & d.fmask[b]) == 0ULL || (d.group[b] & d.fmask[a]) == 0ULL) return false;
+    } else if (ha || hb) {
+        uint32_t f = ha ? a : b;
+        if (d.group[f] == 0ULL || d.fmask[f] == 0ULL) return false;
+    }
+    if (d.xhash_size) { uint32_t v; if (hash_find(d.xhash_key, nullptr, d.xhash_size, pair_key(a, b), v)) return false; }
+    return true;
+}
+
+// One query body A against one candidate j.  The reference creates a manifold when EITHER body's query
+// (its AABB inflated by 0.02) hits the other's AABB, whichever is iterated first (broadphase.cpp:183-194,
+// :136-155).  Each unordered pair is evaluated by exactly one thread: the one of the higher-id procedural
+// body (views are assumed to iterate newest-first), which therefore becomes body[0].
+B2D_D void bp_candidate(const Dev &d, uint32_t A, uint32_t fA, const box3 &bbA, const box3 &qA, uint32_t j,
+                        uint32_t &count, uint2 *out) {
+    if (j == A) return;
+    uint32_t fj = d.flags[j];
+    if (shape_of(fj) == SH_NONE) return;
+    bool pj = is_dynamic(fj);
+    if (pj && j > A) return;
+    box3 bbj = body_box(d, j);
+    uint32_t first = A, second = j;
+    if (pj) {
+        bool t1 = intersect(qA, bbj);
+        if (!t1) {
+            if (!intersect(inset(bbj, BP_OFFSET), bbA)) return;
+            first = j; second = A;
+        }
+    } else if (!intersect(qA, bbj)) return;
+    if (!should_collide(d, A, fA, j, fj)) return;
+    uint32_t v;
+    if (hash_find(d.mhash_key, d.mhash_val, d.mhash_size, pair_key(A, j), v)) return;
+    if (out) out[count] = make_uint2(first, second);
+    ++count;
+}
+
+template<bool FILL>
+__global__ void k_bp_pairs(Dev d) {
+    GRID_STRIDE(A, d.nbodies) {
+        uint32_t fA = d.flags[A];
+        uint32_t count = 0;
+        uint2 *out = nullptr;
+        if (FILL) { if (d.newcount[A] == 0) continue; out = d.newpairs + d.newoff[A]; }
+        if (is_dynamic(fA) && shape_of(fA) != SH_NONE) {
+            box3 bbA = body_box(d, A);
+            box3 qA = inset(bbA, BP_OFFSET);
+            if (!(fA & F_LARGE)) {
+                int cx, cy, cz; cell_of(d, A, cx, cy, cz);
+                for (int dx = -1; dx <= 1; ++dx) for (int dy = -1; dy <= 1; ++dy) for (int dz = -1; dz <= 1; ++dz) {
+                    unsigned long long key = cell_key_of(cx + dx, cy + dy, cz + dz);
+                    uint32_t start;
+                    if (!hash_find(d.chash_key, d.chash_val, d.chash_size, key, start)) continue;
+                    for (uint32_t k = start; k < d.nbodies && d.cellkey_s[k] == key; ++k)
+                        bp_candidate(d, A, fA, bbA, qA, d.cellbody_s[k], count, out);
+                }
+            } else {
+                for (uint32_t j = 0; j < d.nbodies; ++j) if (!(d.flags[j] & F_LARGE)) bp_candidate(d, A, fA, bbA, qA, j, count, out);
+            }
+            for (uint32_t k = 0; k < d.nlarge; ++k) bp_candidate(d, A, fA, bbA, qA, d.large_list[k], count, out);
+        }
+        if (!FILL) d.newcount[A] = count;
+    }
+}
+__global__ void k_bp_total(Dev d) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t n = d.nbodies;
+        d.cnt->nnew = n ? d.newoff[n - 1] + d.newcount[n - 1] : 0;
+    }
+}
+// make_contact_manifold (util/constraint_util.cpp:67-102): slots come from the free list first.
+__global__ void k_bp_append(Dev d) {
+    const uint32_t nnew = d.cnt->nnew, nfree = d.cnt->nfree, hwm = d.cnt->hwm;
+    GRID_STRIDE(k, nnew) {
+        uint32_t slot = k < nfree ? d.free_list[k] : hwm + (k - nfree);
+        if (slot >= d.NM) { atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
+        d.mpair[slot] = d.newpairs[k];
+        d.mstate[slot] = MS_ALIVE | (COLOR_NONE << MS_COLOR_SHIFT);
+    }
+}
+__global__ void k_bp_finish(Dev d) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Counters &c = *d.cnt;
+        if (c.nnew > c.nfree) c.hwm = min(d.NM, c.hwm + (c.nnew - c.nfree));
+    }
+}
+
+// ====================================================================== narrowphase
+
+B2D_D unsigned lbits(float4 pl) { return __float_as_uint(pl.w); }
+
+// collision_util.cpp:233-255
+B2D_D int find_nearest_contact(v3 cpA, v3 cpB, const CResult &res) {
+    float shortest = CACHING_THRESHOLD * CACHING_THRESHOLD;
+    int nearest = res.num;
+    for (int i = 0; i < res.num; ++i) {
+        float dA = length_sqr(res.pt[i].pivotA - cpA);
+        float dB = length_sqr(res.pt[i].pivotB - cpB);
+        if (dA < shortest) { shortest = dA; nearest = i; }
+        if (dB < shortest) { shortest = dB; nearest = i; }
+    }
+    return nearest;
+}
+// collision_util.cpp:257-280 (uses result.pivotA for either body, like the reference)
+B2D_D int find_nearest_contact_rolling(const CResult &res, v3 cp_pivot, v3 origin, q4 orn, v3 angvel, float dt) {
+    int nearest = res.num;
+    q4 prev_orn = integrate(orn, angvel, -dt);
+    v3 prev_pivot = to_world(cp_pivot, origin, prev_orn);
+    float shortest = CACHING_THRESHOLD * CACHING_THRESHOLD;
+    for (int i = 0; i < res.num; ++i) {
+        v3 pA = to_world(res.pt[i].pivotA, origin, orn);
+        float ds = distance_sqr(pA, prev_pivot);
+        if (ds < shortest) { shortest = ds; nearest = i; }
+    }
+    return nearest;
+}
+
+struct MPoint {   // one persisted contact point in registers
+    v3 pivotA, pivotB, normal, local_normal;
+    float distance, friction, restitution;
+    unsigned att, lifetime;
+    v3 imp;
+};
+B2D_D void load_point(const Dev &d, uint32_t m, int s, MPoint &p) {
+    size_t i = (size_t)s * d.NM + m;
+    float4 a = d.pA[i], b = d.pB[i], n = d.pN[i], l = d.pL[i], im = d.pI[i];
+    p.pivotA = mk3(a); p.distance = a.w; p.pivotB = mk3(b); p.friction = b.w; p.normal = mk3(n); p.restitution = n.w;
+    p.local_normal = mk3(l); unsigned u = __float_as_uint(l.w); p.att = u & 3u; p.lifetime = u >> 2;
+    p.imp = mk3(im);
+}
+B2D_D void store_point(const Dev &d, uint32_t m, int s, const MPoint &p) {
+    size_t i = (size_t)s * d.NM + m;
+    d.pA[i] = f4(p.pivotA, p.distance); d.pB[i] = f4(p.pivotB, p.friction); d.pN[i] = f4(p.normal, p.restitution);
+    d.pL[i] = f4(p.local_normal, __uint_as_float((p.att & 3u) | (p.lifetime << 2)));
+    d.pI[i] = f4(p.imp, 0);
+}
+// merge_point, collision_util.cpp:205-231
+B2D_D void merge_point(const CPoint &rp, MPoint &cp, q4 ornA, q4 ornB) {
+    cp.pivotA = rp.pivotA; cp.pivotB = rp.pivotB; cp.normal = rp.normal; cp.distance = rp.distance; cp.att = rp.att;
+    if (rp.att != ATT_NONE) cp.local_normal = rotate(conjugate(rp.att == ATT_A ? ornA : ornB), rp.normal);
+    else cp.local_normal = mk3(0, 0, 0);
+}
+// create_contact_point, collision_util.cpp:319-395; mixing dynamics/material_mixing.hpp:12-18
+B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float2 matB) {
+    MPoint cp;
+    cp.pivotA = rp.pivotA; cp.pivotB = rp.pivotB; cp.normal = rp.normal; cp.att = rp.att; cp.distance = rp.distance;
+    if (rp.att != ATT_NONE) cp.local_normal = rotate(conjugate(rp.att == ATT_A ? ornA : ornB), rp.normal);
+    else cp.local_normal = mk3(0, 0, 0);
+    cp.friction = sqrtf(matA.x * matB.x);
+    cp.restitution = fminf(matA.y, matB.y);
+    cp.lifetime = 0; cp.imp = mk3(0, 0, 0);
+    return cp;
+}
+
+// One thread per manifold: update_contact_distances (collision_util.cpp:28-45), detect_collision (:440-475),
+// process_collision (collision_util.hpp:105-276, sequential flavour of narrowphase.hpp:62-84).
+__global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, hwm) {
+        uint32_t st = d.mstate[m];
+        if (!(st & MS_ALIVE)) continue;
+        uint2 pr = d.mpair[m];
+        const uint32_t a = pr.x, b = pr.y;
+        const uint32_t fa = d.flags[a], fb = d.flags[b];
+        const v3 posA = mk3(d.pos[a]), posB = mk3(d.pos[b]);
+        const q4 ornA = mkq(d.orn[a]), ornB = mkq(d.orn[b]);
+        int num = (int)(st & MS_NPTS_MASK);
+        MPoint P[4];
+        for (int s = 0; s < num; ++s) {
+            load_point(d, m, s, P[s]);
+            v3 pAw = to_world(P[s].pivotA, posA, ornA), pBw = to_world(P[s].pivotB, posB, ornB);
+            P[s].distance = dot(P[s].normal, pAw - pBw);
+        }
+        CResult res; res.num = 0;
+        if (intersect(inset(body_box(d, a), -BREAKING_THRESHOLD), body_box(d, b))) {
+            CCtx ctx; ctx.posA = posA; ctx.ornA = ornA; ctx.posB = posB; ctx.ornB = ornB; ctx.threshold = COLLISION_THRESHOLD;
+            collide(shape_of(fa), d.shp[a], shape_of(fb), d.shp[b], ctx, res);
+        }
+        // ---- merge with persisted points
+        bool merged[4] = {false, false, false, false};
+        const bool rollA = fa & F_ROLLING, rollB = fb & F_ROLLING;
+        int i = 0;
+        while (i < num) {
+            MPoint &cp = P[i];
+            ++cp.lifetime;
+            int nearest = find_nearest_contact(cp.pivotA, cp.pivotB, res);
+            if (nearest == res.num && rollA) nearest = find_nearest_contact_rolling(res, cp.pivotA, posA, ornA, mk3(d.angvel[a]), d.dt);
+            if (nearest == res.num && rollB) nearest = find_nearest_contact_rolling(res, cp.pivotB, posB, ornB, mk3(d.angvel[b]), d.dt);
+            bool remove = false;
+            if (nearest < res.num && !merged[nearest]) { merge_point(res.pt[nearest], cp, ornA, ornB); merged[nearest] = true; }
+            else {                                          // should_remove_point, collision_util.cpp:397-413
+                v3 pA = to_world(cp.pivotA, posA, ornA), pB = to_world(cp.pivotB, posB, ornB);
+                v3 dd = pA - pB;
+                float nd = dot(dd, cp.normal);
+                v3 td = dd - nd * cp.normal;
+                remove = nd > BREAKING_THRESHOLD || length_sqr(td) > BREAKING_THRESHOLD * BREAKING_THRESHOLD;
+            }
+            if (remove) { for (int k = i + 1; k < num; ++k) P[k - 1] = P[k]; --num; }
+            else ++i;
+        }
+        bool all = true;
+        for (int k = 0; k < res.num; ++k) all = all && merged[k];
+        if (!all) {
+            CPoint L[4]; int ent[4] = {-1, -1, -1, -1}; int type[4] = {INS_NONE, INS_NONE, INS_NONE, INS_NONE};
+            int num_points = num;
+            if (num_points > 0) {
+                for (int k = 0; k < num; ++k) { L[k].pivotA = P[k].pivotA; L[k].pivotB = P[k].pivotB; L[k].normal = P[k].normal; L[k].distance = P[k].distance; L[k].att = ATT_NONE; ent[k] = k; }
+            } else {
+                num_points = 1; L[0] = res.pt[0]; type[0] = INS_APPEND; merged[0] = true;
+            }
+            for (int k = 0; k < res.num; ++k) {
+                if (merged[k]) continue;
+                v3 piv[4];
+                for (int j = 0; j < num_points; ++j) piv[j] = L[j].pivotA;
+                int idx;
+                int t = insertion_point_index(piv, num_points, res.pt[k].pivotA, idx);
+                if (t == INS_NONE) {
+                    for (int j = 0; j < num_points; ++j) piv[j] = L[j].pivotB;
+                    t = insertion_point_index(piv, num_points, res.pt[k].pivotB, idx);
+                }
+                if (t != INS_NONE && idx >= 0 && idx < 4) { L[idx] = res.pt[k]; type[idx] = t; }
+            }
+            const float2 matA = d.mat[a], matB = d.mat[b];
+            MPoint created[4]; int n_created = 0;
+            bool alive[4] = {true, true, true, true};
+            for (int k = 0; k < num_points; ++k) {
+                if (type[k] == INS_APPEND) created[n_created++] = create_point(L[k], ornA, ornB, matA, matB);
+                else if (type[k] == INS_SIMILAR) {
+                    if (ent[k] < 0) created[n_created++] = create_point(L[k], ornA, ornB, matA, matB);
+                    else merge_point(L[k], P[ent[k]], ornA, ornB);
+                } else if (type[k] == INS_REPLACE) {
+                    if (ent[k] >= 0) alive[ent[k]] = false;
+                    created[n_created++] = create_point(L[k], ornA, ornB, matA, matB);
+                }
+            }
+            MPoint Q[4]; int w = 0;
+            for (int k = n_created - 1; k >= 0; --k) Q[w++] = created[k];      // newest point = list head
+            for (int k = 0; k < num; ++k) if (alive[k] && w < 4) Q[w++] = P[k];
+            num = w;
+            for (int k = 0; k < num; ++k) P[k] = Q[k];
+        }
+        for (int s = 0; s < num; ++s) store_point(d, m, s, P[s]);
+        d.mstate[m] = (st & ~MS_NPTS_MASK) | (uint32_t)num;
+    }
+}
+
+// ====================================================================== islands (connected components)
+
+// Union-find with atomic hooking (roots hook onto smaller ids, so every component ends labelled by its
+// smallest body id).  Only procedural nodes connect (core/entity_graph.hpp:303-307); every manifold is an
+// edge even with zero points (make_contact_manifold adds a null_constraint edge), plus every joint.
+B2D_D uint32_t cc_find(uint32_t *parent, uint32_t x) {
+    uint32_t p = parent[x];
+    while (p != x) { uint32_t gp = parent[p]; if (gp != p) parent[x] = gp; x = p; p = parent[x]; }
+    return x;
+}
+B2D_D void cc_union(uint32_t *parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = cc_find(parent, a); b = cc_find(parent, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+__global__ void k_cc_init(Dev d) { GRID_STRIDE(i, d.nbodies) d.parent[i] = i; }
+__global__ void k_cc_union(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, hwm + d.nhinges) {
+        uint2 p;
+        if (m < hwm) { if (!(d.mstate[m] & MS_ALIVE)) continue; p = d.mpair[m]; }
+        else p = d.hpair[m - hwm];
+        if (is_dynamic(d.flags[p.x]) && is_dynamic(d.flags[p.y])) cc_union(d.parent, p.x, p.y);
+    }
+}
+__global__ void k_cc_flatten(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        if (is_dynamic(d.flags[i])) { uint32_t r = cc_find(d.parent, i); d.parent[i] = r; if (r == i) atomicAdd(&d.cnt->nislands, 1u); }
+        else d.parent[i] = 0xFFFFFFFFu;
+    }
+}
+
+// ====================================================================== solver: gravity, colouring
+
+// apply_gravity, sys/apply_gravity.hpp:12-17
+__global__ void k_gravity(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        if (!is_dynamic(d.flags[i])) continue;
+        v3 v = mk3(d.linvel[i]); v += mk3(d.grav[i]) * d.dt;
+        d.linvel[i] = f4(v, 0);
+    }
+}
+
+// Deterministic greedy colouring of the constraint graph (manifolds and hinges coloured independently:
+// they are solved in separate passes).  Colours persist across steps; only new constraints enter the
+// rounds below.  A constraint wins a round when it holds the smallest id on both of its dynamic bodies,
+// then takes the lowest colour unused on either body.  Cooperative launch (grid-wide barriers).
+__global__ void __launch_bounds__(256) k_color(Dev d, int recolor) {
+    cg::grid_group grid = cg::this_grid();
+    Counters &c = *d.cnt;
+    const uint32_t hwm = c.hwm;
+    const uint32_t total = hwm + d.nhinges;
+    GRID_STRIDE(i, d.nbodies) { d.bmask[i] = 0ULL; d.jmask[i] = 0ULL; d.prop[i] = ~0ULL; d.jprop[i] = ~0ULL; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { c.remaining[0] = 0; c.remaining[1] = 0; }
+    grid.sync();
+    GRID_STRIDE(k, total) {
+        if (k < hwm) {
+            uint32_t st = d.mstate[k];
+            if (!(st & MS_ALIVE)) continue;
+            if (recolor) { st |= MS_COLOR_MASK; d.mstate[k] = st; }
+            uint32_t col = (st >> MS_COLOR_SHIFT) & 0xFFu;
+            if (col == COLOR_NONE) continue;
+            uint2 p = d.mpair[k];
+            if (is_dynamic(d.flags[p.x])) atomicOr(&d.bmask[p.x], 1ULL << col);
+            if (is_dynamic(d.flags[p.y])) atomicOr(&d.bmask[p.y], 1ULL << col);
+        } else {
+            uint32_t h = k - hwm;
+            if (recolor) d.hcolor[h] = COLOR_NONE;
+            uint32_t col = d.hcolor[h];
+            if (col == COLOR_NONE) continue;
+            uint2 p = d.hpair[h];
+            if (is_dynamic(d.flags[p.x])) atomicOr(&d.jmask[p.x], 1ULL << col);
+            if (is_dynamic(d.flags[p.y])) atomicOr(&d.jmask[p.y], 1ULL << col);
+        }
+    }
+    grid.sync();
+    for (uint32_t round = 0;; ++round) {
+        const unsigned long long stamp = (unsigned long long)(0x7FFFFFFFu - round) << 32;
+        GRID_STRIDE(k, total) {
+            bool isM = k < hwm;
+            uint2 p; unsigned long long *prop;
+            if (isM) { uint32_t st = d.mstate[k]; if (!(st & MS_ALIVE) || ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[k]; prop = d.prop; }
+            else { uint32_t h = k - hwm; if (d.hcolor[h] != COLOR_NONE) continue; p = d.hpair[h]; prop = d.jprop; }
+            unsigned long long v = stamp | (isM ? k : k - hwm);
+            if (is_dynamic(d.flags[p.x])) atomicMin(&prop[p.x], v);
+            if (is_dynamic(d.flags[p.y])) atomicMin(&prop[p.y], v);
+        }
+        grid.sync();
+        GRID_STRIDE(k, total) {
+            bool isM = k < hwm;
+            uint2 p; unsigned long long *prop, *mask;
+            if (isM) { uint32_t st = d.mstate[k]; if (!(st & MS_ALIVE) || ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[k]; prop = d.prop; mask = d.bmask; }
+            else { uint32_t h = k - hwm; if (d.hcolor[h] != COLOR_NONE) continue; p = d.hpair[h]; prop = d.jprop; mask = d.jmask; }
+            unsigned long long v = stamp | (isM ? k : k - hwm);
+            bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
+            bool win = (!da || prop[p.x] == v) && (!db || prop[p.y] == v);
+            if (win) {
+                unsigned long long used = (da ? mask[p.x] : 0ULL) | (db ? mask[p.y] : 0ULL);
+                unsigned long long freeb = ~used;
+                uint32_t col = freeb ? (uint32_t)(__ffsll((long long)freeb) - 1) : (MAX_COLORS - 1);
+                if (!freeb) atomicOr(&c.err, ERR_COLOR_OVERFLOW);
+                if (da) atomicOr(&mask[p.x], 1ULL << col);
+                if (db) atomicOr(&mask[p.y], 1ULL << col);
+                if (isM) d.mstate[k] = (d.mstate[k] & ~MS_COLOR_MASK) | (col << MS_COLOR_SHIFT);
+                else d.hcolor[k - hwm] = col;
+            } else atomicAdd(&c.remaining[round & 1], 1u);
+        }
+        grid.sync();
+        uint32_t rem = c.remaining[round & 1];
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.remaining[(round + 1) & 1] = 0;
+        if (rem == 0) break;
+        grid.sync();
+    }
+}
+
+// Sort keys: colour for constraints that have rows this step, 0xFF otherwise.
+__global__ void k_color_keys(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, d.NM) {
+        unsigned char key = 0xFF;
+        if (m < hwm) { uint32_t st = d.mstate[m]; if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) key = (unsigned char)((st >> MS_COLOR_SHIFT) & 0xFFu); }
+        d.ckey[m] = key; d.cidx[m] = m;
+    }
+    GRID_STRIDE(h, d.NH) {
+        unsigned char key = 0xFF;
+        if (h < d.nhinges) { uint2 p = d.hpair[h]; if (is_dynamic(d.flags[p.x]) || is_dynamic(d.flags[p.y])) key = (unsigned char)d.hcolor[h]; }
+        d.hkey[h] = key; d.hidx[h] = h;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < MAX_COLORS + 2) { d.cnt->coff[threadIdx.x] = 0xFFFFFFFFu; d.cnt->hoff[threadIdx.x] = 0xFFFFFFFFu; }
+}
+__global__ void k_color_offsets(Dev d) {
+    GRID_STRIDE(i, d.NM) {
+        unsigned char k = d.ckey_s[i];
+        if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->coff[k == 0xFF ? MAX_COLORS : k] = i;
+    }
+    GRID_STRIDE(i, d.NH) {
+        unsigned char k = d.hkey_s[i];
+        if (i == 0 || d.hkey_s[i - 1] != k) d.cnt->hoff[k == 0xFF ? MAX_COLORS : k] = i;
+    }
+}
+__global__ void k_color_fixup(Dev d) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Counters &c = *d.cnt;
+    if (c.coff[MAX_COLORS] == 0xFFFFFFFFu) c.coff[MAX_COLORS] = d.NM;
+    if (c.hoff[MAX_COLORS] == 0xFFFFFFFFu) c.hoff[MAX_COLORS] = d.NH;
+    c.coff[MAX_COLORS + 1] = c.coff[MAX_COLORS]; c.hoff[MAX_COLORS + 1] = c.hoff[MAX_COLORS];
+    uint32_t nc = 0, nh = 0;
+    for (int k = MAX_COLORS - 1; k >= 0; --k) {
+        if (c.coff[k] == 0xFFFFFFFFu) c.coff[k] = c.coff[k + 1]; else if (!nc) nc = k + 1;
+        if (c.hoff[k] == 0xFFFFFFFFu) c.hoff[k] = c.hoff[k + 1]; else if (!nh) nh = k + 1;
+    }
+    c.ncolors = nc; c.nhcolors = nh; c.nactive = c.coff[MAX_COLORS];
+}
+
+// ====================================================================== solver: row preparation
+
+struct SBody { v3 v, w; float inv_m; m3 inv_I; bool proc; };
+// constraint_body + row masses, solver.cpp:101-147: dynamic -> (inv_m, inv_IW, v, w); kinematic -> (0, 0, v, w);
+// static -> zeros.
+B2D_D SBody solver_body(const Dev &d, uint32_t i, uint32_t f) {
+    SBody s;
+    s.proc = is_dynamic(f);
+    if (s.proc) { float4 r0 = d.invIW[3 * i]; s.inv_m = r0.w; s.inv_I.r0 = mk3(r0); s.inv_I.r1 = mk3(d.invIW[3 * i + 1]); s.inv_I.r2 = mk3(d.invIW[3 * i + 2]); }
+    else { s.inv_m = 0; s.inv_I = m3_zero(); }
+    if (kind_of(f) == 2u) { s.v = mk3(0, 0, 0); s.w = mk3(0, 0, 0); } else { s.v = mk3(d.linvel[i]); s.w = mk3(d.angvel[i]); }
+    return s;
+}
+// get_effective_mass / prepare_row, util/constraint_util.cpp:137-146, constraints/constraint_row.cpp:6-22
+B2D_D float eff_mass(v3 J0, v3 J1, v3 J2, v3 J3, const SBody &A, const SBody &B) {
+    float s = dot(J0, J0) * A.inv_m + dot(A.inv_I * J1, J1) + dot(J2, J2) * B.inv_m + dot(B.inv_I * J3, J3);
+    return 1.0f / s;
+}
+B2D_D float rel_speed(v3 J0, v3 J1, v3 J2, v3 J3, v3 vA, v3 wA, v3 vB, v3 wB) {
+    return dot(J0, vA) + dot(J1, wA) + dot(J2, vB) + dot(J3, wB);
+}
+
+// contact_constraint::prepare (contact_constraint.cpp:15-56) + prepare_row per sorted manifold; rows are
+// written in colour order so the solve kernel streams them.  Row storage keeps (n, rA, rB) and rebuilds the
+// Jacobian in registers: 84 B/point instead of the reference's 312 B (constraint_row + _friction).
+__global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
+    const uint32_t n = d.cnt->nactive;
+    GRID_STRIDE(i, n) {
+        uint32_t m = d.cidx_s[i];
+        uint2 pr = d.mpair[m];
+        uint32_t npts = d.mstate[m] & MS_NPTS_MASK;
+        uint32_t fa = d.flags[pr.x], fb = d.flags[pr.y];
+        SBody A = solver_body(d, pr.x, fa), B = solver_body(d, pr.y, fb);
+        v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
+        q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
+        d.hdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), npts, m);
+        for (uint32_t s = 0; s < npts; ++s) {
+            size_t mi = (size_t)s * d.NM + m, ri = (size_t)s * d.NM + i;
+            float4 a4 = d.pA[mi], b4 = d.pB[mi], n4 = d.pN[mi], im = d.pI[mi];
+            v3 normal = mk3(n4);
+            v3 pAw = to_world(mk3(a4), posA, ornA), pBw = to_world(mk3(b4), posB, ornB);
+            v3 rA = pAw - posA, rB = pBw - posB;
+            v3 J1 = cross(rA, normal), J2 = -normal, J3 = -cross(rB, normal);
+            float em = eff_mass(normal, J1, J2, J3, A, B);
+            float error = 0.0f;
+            if (a4.w > 0) error = a4.w / d.dt;
+            float relvel = rel_speed(normal, J1, J2, J3, A.v, A.w, B.v, B.w);
+            float rhs = -(error * 0.2f + relvel * (1.0f + n4.w));
+            v3 t, u; plane_space(normal, t, u);
+            v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
+            v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
+            float em_t = eff_mass(t, T1, T2, T3, A, B), em_u = eff_mass(u, U1, U2, U3, A, B);
+            float rhs_t = -rel_speed(t, T1, T2, T3, A.v, A.w, B.v, B.w), rhs_u = -rel_speed(u, U1, U2, U3, A.v, A.w, B.v, B.w);
+            d.R0[ri] = f4(normal, rhs); d.R1[ri] = f4(rA, em); d.R2[ri] = f4(rB, b4.w);
+            d.R3[ri] = make_float4(em_t, em_u, rhs_t, rhs_u);
+            d.IMP[ri] = make_float4(im.x, im.y, im.z, 0);
+        }
+    }
+}
+
+// hinge_constraint::prepare, hinge_constraint.cpp:26-69 (no limits / springs / torque rows)
+__global__ void k_prepare_hinges(Dev d) {
+    const uint32_t n = d.cnt->hoff[MAX_COLORS];
+    GRID_STRIDE(i, n) {
+        uint32_t h = d.hidx_s[i];
+        uint2 pr = d.hpair[h];
+        uint32_t fa = d.flags[pr.x], fb = d.flags[pr.y];
+        SBody A = solver_body(d, pr.x, fa), B = solver_body(d, pr.y, fb);
+        v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
+        q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
+        v3 rA = to_world(mk3(d.hpivA[h]), posA, ornA) - posA;
+        v3 rB = to_world(mk3(d.hpivB[h]), posB, ornB) - posB;
+        v3 p = rotate(ornA, mk3(d.hfA1[h])), q = rotate(ornA, mk3(d.hfA2[h]));
+        float em[5], rhs[5];
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v3 e = axis_vec(k);
+            // rows of skew(r): (0,-z,y), (z,0,-x), (-y,x,0)  matrix3x3.hpp:243-249
+            v3 sa = k == 0 ? mk3(0, -rA.z, rA.y) : (k == 1 ? mk3(rA.z, 0, -rA.x) : mk3(-rA.y, rA.x, 0));
+            v3 sb = k == 0 ? mk3(0, -rB.z, rB.y) : (k == 1 ? mk3(rB.z, 0, -rB.x) : mk3(-rB.y, rB.x, 0));
+            v3 J1 = -sa, J2 = -e, J3 = sb;
+            em[k] = eff_mass(e, J1, J2, J3, A, B);
+            rhs[k] = -(0.0f * 0.2f + rel_speed(e, J1, J2, J3, A.v, A.w, B.v, B.w) * (1.0f + 0.0f));
+        }
+        const v3 z = mk3(0, 0, 0);
+        em[3] = eff_mass(z, p, z, -p, A, B); rhs[3] = -(0.0f * 0.2f + rel_speed(z, p, z, -p, A.v, A.w, B.v, B.w) * (1.0f + 0.0f));
+        em[4] = eff_mass(z, q, z, -q, A, B); rhs[4] = -(0.0f * 0.2f + rel_speed(z, q, z, -q, A.v, A.w, B.v, B.w) * (1.0f + 0.0f));
+        const float *imp = d.himp + 5 * (size_t)h;
+        float4 *R = d.HR + 7 * (size_t)i;
+        R[0] = f4(rA, em[0]); R[1] = f4(rB, em[1]); R[2] = f4(p, em[2]); R[3] = f4(q, em[3]);
+        R[4] = make_float4(em[4], rhs[0], rhs[1], rhs[2]);
+        R[5] = make_float4(rhs[3], rhs[4], imp[0], imp[1]);
+        R[6] = make_float4(imp[2], imp[3], imp[4], 0);
+        d.hhdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), h, 0);
+    }
+}
+
+// ====================================================================== solver: velocity iterations
+
+struct VBody { v3 dv, dw; float inv_m; m3 inv_I; uint32_t id; bool proc; };
+B2D_D void vb_load(const Dev &d, uint32_t tag, VBody &b) {
+    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
+    if (b.proc) {
+        b.dv = mk3(d.dvw[2 * b.id]); b.dw = mk3(d.dvw[2 * b.id + 1]);
+        float4 r0 = d.invIW[3 * b.id]; b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * b.id + 1]); b.inv_I.r2 = mk3(d.invIW[3 * b.id + 2]);
+    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); }
+}
+B2D_D void vb_store(const Dev &d, const VBody &b) {
+    if (b.proc) { d.dvw[2 * b.id] = f4(b.dv, 0); d.dvw[2 * b.id + 1] = f4(b.dw, 0); }
+}
+// apply_row_impulse, constraint_row.cpp:24-32
+B2D_D void apply_imp(VBody &A, VBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float imp) {
+    A.dv += A.inv_m * J0 * imp;
+    B.dv += B.inv_m * J2 * imp;
+    A.dw += A.inv_I * J1 * imp;
+    B.dw += B.inv_I * J3 * imp;
+}
+// friction flavour keeps the reference's A-lin, A-ang, B-lin, B-ang order (constraint_row_friction.cpp:47-53)
+B2D_D void apply_imp_f(VBody &A, VBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float imp) {
+    A.dv += A.inv_m * J0 * imp;
+    A.dw += A.inv_I * J1 * imp;
+    B.dv += B.inv_m * J2 * imp;
+    B.dw += B.inv_I * J3 * imp;
+}
+// solve(constraint_row&), constraint_row.cpp:38-57
+B2D_D float solve_row(float rhs, float em, float lo, float hi, float &impulse, float delta_relvel) {
+    float delta = (rhs - delta_relvel) * em;
+    float imp = impulse + delta;
+    if (imp < lo) { delta = lo - impulse; impulse = lo; }
+    else if (imp > hi) { delta = hi - impulse; impulse = hi; }
+    else impulse = imp;
+    return delta;
+}
+
+B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm) {
+    uint4 hd = d.hhdr[i];
+    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
+    float4 *R = d.HR + 7 * (size_t)i;
+    float4 r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6];
+    v3 rA = mk3(r0), rB = mk3(r1), p = mk3(r2), q = mk3(r3);
+    float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x};
+    float rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
+    float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
+    #pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        v3 J0, J1, J2, J3;
+        if (k < 3) {
+            J0 = axis_vec(k);
+            v3 sa = k == 0 ? mk3(0, -rA.z, rA.y) : (k == 1 ? mk3(rA.z, 0, -rA.x) : mk3(-rA.y, rA.x, 0));
+            v3 sb = k == 0 ? mk3(0, -rB.z, rB.y) : (k == 1 ? mk3(rB.z, 0, -rB.x) : mk3(-rB.y, rB.x, 0));
+            J1 = -sa; J2 = -J0; J3 = sb;
+        } else { v3 ax = k == 3 ? p : q; J0 = mk3(0, 0, 0); J1 = ax; J2 = mk3(0, 0, 0); J3 = -ax; }
+        float delta;
+        if (warm) delta = imp[k];
+        else delta = solve_row(rhs[k], em[k], -SCALAR_MAX, SCALAR_MAX, imp[k], rel_speed(J0, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
+        apply_imp(A, B, J0, J1, J2, J3, delta);
+    }
+    if (!warm) { R[5] = make_float4(r5.x, r5.y, imp[0], imp[1]); R[6] = make_float4(imp[2], imp[3], imp[4], 0); }
+    vb_store(d, A); vb_store(d, B);
+}
+
+B2D_D void normal_pass(const Dev &d, uint32_t i, bool warm) {
+    uint4 hd = d.hdr[i];
+    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
+    for (uint32_t s = 0; s < hd.z; ++s) {
+        size_t ri = (size_t)s * d.NM + i;
+        float4 r0 = d.R0[ri], r1 = d.R1[ri], r2 = d.R2[ri], im = d.IMP[ri];
+        v3 n = mk3(r0), rA = mk3(r1), rB = mk3(r2);
+        v3 J1 = cross(rA, n), J2 = -n, J3 = -cross(rB, n);
+        float delta;
+        if (warm) delta = im.x;
+        else {
+            delta = solve_row(r0.w, r1.w, 0.0f, LARGE, im.x, rel_speed(n, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
+            d.IMP[ri] = im;
+        }
+        apply_imp(A, B, n, J1, J2, J3, delta);
+    }
+    vb_store(d, A); vb_store(d, B);
+}
+
+// solve_friction, constraint_row_friction.cpp:11-54: both tangent candidates from one delta-velocity snapshot,
+// clamped to the circle of radius mu * lambda_n (lambda_n of THIS iteration).
+B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm) {
+    uint4 hd = d.hdr[i];
+    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
+    for (uint32_t s = 0; s < hd.z; ++s) {
+        size_t ri = (size_t)s * d.NM + i;
+        float4 r0 = d.R0[ri], r1 = d.R1[ri], r2 = d.R2[ri], r3 = d.R3[ri], im = d.IMP[ri];
+        v3 n = mk3(r0), rA = mk3(r1), rB = mk3(r2);
+        v3 t, u; plane_space(n, t, u);
+        v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
+        v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
+        float d0, d1;
+        if (warm) { d0 = im.y; d1 = im.z; }
+        else {
+            d0 = (r3.z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r3.x;
+            d1 = (r3.w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r3.y;
+            float i0 = im.y + d0, i1 = im.z + d1;
+            float len_sqr = i0 * i0 + i1 * i1;
+            float max_len = r2.w * im.x;
+            if (len_sqr > max_len * max_len) {
+                float len = sqrtf(len_sqr);
+                if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
+                d0 = i0 - im.y; d1 = i1 - im.z;
+            }
+            im.y = i0; im.z = i1;
+            d.IMP[ri] = im;
+        }
+        apply_imp_f(A, B, t, T1, T2, T3, d0);
+        apply_imp_f(A, B, u, U1, U2, U3, d1);
+    }
+    vb_store(d, A); vb_store(d, B);
+}
+
+// Persistent cooperative kernel: warm start + N velocity iterations (island_solver.cpp:76-111).  Inside one
+// iteration: hinge rows, then contact normal rows, then friction pairs -- constraint-type major like
+// pack_rows (island_solver.cpp:162-175) -- each as a sequence of colours separated by grid barriers.
+// Constraints of one colour touch disjoint dynamic bodies, so the parallel pass equals the sequential
+// Gauss-Seidel sweep in (colour, slot) order; b2d_download_solver_order() exports that order.
+__global__ void __launch_bounds__(256) k_solve(Dev d, int iters) {
+    cg::grid_group grid = cg::this_grid();
+    const Counters &c = *d.cnt;
+    const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    for (int it = -1; it < iters; ++it) {
+        const bool warm = it < 0;
+        for (uint32_t col = 0; col < nh; ++col) {
+            const uint32_t b = c.hoff[col], e = c.hoff[col + 1];
+            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) hinge_pass(d, i, warm);
+            grid.sync();
+        }
+        for (uint32_t col = 0; col < nc; ++col) {
+            const uint32_t b = c.coff[col], e = c.coff[col + 1];
+            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) normal_pass(d, i, warm);
+            grid.sync();
+        }
+        for (uint32_t col = 0; col < nc; ++col) {
+            const uint32_t b = c.coff[col], e = c.coff[col + 1];
+            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) friction_pass(d, i, warm);
+            grid.sync();
+        }
+    }
+}
+
+// assign_applied_impulses (island_solver.cpp:232-248): rows -> warm-start cache of the constraints.
+__global__ void k_store_impulses(Dev d) {
+    const uint32_t n = d.cnt->nactive, nh = d.cnt->hoff[MAX_COLORS];
+    GRID_STRIDE(i, n) {
+        uint4 hd = d.hdr[i];
+        for (uint32_t s = 0; s < hd.z; ++s) d.pI[(size_t)s * d.NM + hd.w] = d.IMP[(size_t)s * d.NM + i];
+    }
+    GRID_STRIDE(i, nh) {
+        uint4 hd = d.hhdr[i];
+        const float4 *R = d.HR + 7 * (size_t)i;
+        float4 r5 = R[5], r6 = R[6];
+        float *imp = d.himp + 5 * (size_t)hd.z;
+        imp[0] = r5.z; imp[1] = r5.w; imp[2] = r6.x; imp[3] = r6.y; imp[4] = r6.z;
+    }
+}
+
+// ====================================================================== integration and refresh
+
+// integrate_velocities (island_solver.cpp:358-376); with refresh != 0 also update_aabbs + update_inertias
+// (solver.cpp:453-465) fused in, used when no position iterations run in between.
+__global__ void __launch_bounds__(256) k_integrate(Dev d, int refresh) {
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t f = d.flags[i];
+        if (!is_dynamic(f)) continue;
+        float4 p4 = d.pos[i];
+        v3 v = mk3(d.linvel[i]), w = mk3(d.angvel[i]);
+        v += mk3(d.dvw[2 * i]); w += mk3(d.dvw[2 * i + 1]);
+        v3 pos = mk3(p4); pos += v * d.dt;
+        q4 orn = integrate(mkq(d.orn[i]), w, d.dt);
+        d.linvel[i] = f4(v, 0); d.angvel[i] = f4(w, 0);
+        d.pos[i] = f4(pos, p4.w); d.orn[i] = f4(orn);
+        d.dvw[2 * i] = make_float4(0, 0, 0, 0); d.dvw[2 * i + 1] = make_float4(0, 0, 0, 0);
+        if (refresh) {
+            store_invIW(d, i, world_inertia(orn, load_m3(d.invI, i)), p4.w);
+            int sk = shape_of(f);
+            if (sk != SH_NONE) { box3 bb = shape_aabb(sk, d.shp[i], pos, orn); d.bbmin[i] = f4(bb.mn, 0); d.bbmax[i] = f4(bb.mx, 0); }
+        }
+    }
+}
+// update_aabbs (dynamic + kinematic) and update_inertias (dynamic), solver.cpp:453-465
+__global__ void __launch_bounds__(256) k_finalize(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t f = d.flags[i];
+        if (kind_of(f) == 2u) continue;
+        float4 p4 = d.pos[i];
+        v3 pos = mk3(p4); q4 orn = mkq(d.orn[i]);
+        int sk = shape_of(f);
+        if (sk != SH_NONE) { box3 bb = shape_aabb(sk, d.shp[i], pos, orn); d.bbmin[i] = f4(bb.mn, 0); d.bbmax[i] = f4(bb.mx, 0); }
+        if (is_dynamic(f)) store_invIW(d, i, world_inertia(orn, load_m3(d.invI, i)), p4.w);
+    }
+}
+
+// ====================================================================== position iterations
+
+struct PBody { v3 pos; q4 orn; float inv_m; m3 inv_IW, inv_I; uint32_t id; bool proc; };
+B2D_D void pb_load(const Dev &d, uint32_t id, PBody &b) {
+    b.id = id; b.proc = is_dynamic(d.flags[id]);
+    float4 p4 = d.pos[id];
+    b.pos = mk3(p4); b.orn = mkq(d.orn[id]);
+    if (b.proc) { b.inv_m = p4.w; b.inv_IW = load_m3(d.invIW, id); b.inv_I = load_m3(d.invI, id); }
+    else { b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero(); }
+}
+B2D_D void pb_store(const Dev &d, const PBody &b) {
+    if (!b.proc) return;
+    d.pos[b.id] = f4(b.pos, b.inv_m); d.orn[b.id] = f4(b.orn);
+    store_invIW(d, b.id, b.inv_IW, b.inv_m);
+}
+// position_solver::solve, dynamics/position_solver.hpp:16-51.  Non-procedural bodies are left untouched
+// (the reference only re-normalises their unit orientation).
+B2D_D void position_solve(PBody &A, PBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float error, float &max_error) {
+    float s = dot(J0, J0) * A.inv_m + dot(A.inv_IW * J1, J1) + dot(J2, J2) * B.inv_m + dot(B.inv_IW * J3, J3);
+    float em = 1.0f / s;
+    float corr = error * 0.2f * em;
+    if (A.proc) {
+        A.pos += A.inv_m * J0 * corr;
+        v3 ac = A.inv_IW * J1 * corr;
+        A.orn = A.orn + quat_derivative(A.orn, ac);
+        A.orn = normalize(A.orn);
+        A.inv_IW = world_inertia(A.orn, A.inv_I);
+    }
+    if (B.proc) {
+        B.pos += B.inv_m * J2 * corr;
+        v3 ac = B.inv_IW * J3 * corr;
+        B.orn = B.orn + quat_derivative(B.orn, ac);
+        B.orn = normalize(B.orn);
+        B.inv_IW = world_inertia(B.orn, B.inv_I);
+    }
+    max_error = fmaxf(fabsf(error), max_error);
+}
+B2D_D uint32_t island_of(const Dev &d, uint32_t a, uint32_t b) { uint32_t l = d.parent[a]; return l != 0xFFFFFFFFu ? l : d.parent[b]; }
+
+// contact_constraint::solve_position, contact_constraint.cpp:58-90
+B2D_D void contact_position(const Dev &d, uint32_t i) {
+    uint4 hd = d.hdr[i];
+    uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, m = hd.w;
+    uint32_t isl = island_of(d, a, b);
+    if (d.isl_done[isl]) return;
+    PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
+    float max_error = 0.0f;
+    for (uint32_t s = 0; s < hd.z; ++s) {
+        size_t mi = (size_t)s * d.NM + m;
+        float4 a4 = d.pA[mi], b4 = d.pB[mi], n4 = d.pN[mi], l4 = d.pL[mi];
+        v3 pAw = to_world(mk3(a4), A.pos, A.orn), pBw = to_world(mk3(b4), B.pos, B.orn);
+        unsigned att = __float_as_uint(l4.w) & 3u;
+        v3 normal = mk3(n4);
+        if (att == ATT_A) normal = rotate(A.orn, mk3(l4)); else if (att == ATT_B) normal = rotate(B.orn, mk3(l4));
+        float dist = dot(pAw - pBw, normal);
+        v3 rA = pAw - A.pos, rB = pBw - B.pos;
+        d.pN[mi] = f4(normal, n4.w); d.pA[mi] = f4(mk3(a4), dist);
+        if (dist > -EPS) continue;
+        position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
+    }
+    pb_store(d, A); pb_store(d, B);
+    if (max_error > 0.0f) atomicMax(&d.isl_err[isl], __float_as_uint(max_error));
+}
+// hinge_constraint::solve_position, hinge_constraint.cpp:180-213
+B2D_D void hinge_position(const Dev &d, uint32_t i) {
+    uint4 hd = d.hhdr[i];
+    uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, h = hd.z;
+    uint32_t isl = island_of(d, a, b);
+    if (d.isl_done[isl]) return;
+    PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
+    float max_error = 0.0f;
+    v3 axisA = rotate(A.orn, mk3(d.hfA0[h])), axisB = rotate(B.orn, mk3(d.hfB0[h]));
+    v3 p, q; plane_space(axisA, p, q);
+    v3 u = cross(axisA, axisB);
+    const v3 z = mk3(0, 0, 0);
+    { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
+    { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
+    v3 pivotA = to_world(mk3(d.hpivA[h]), A.pos, A.orn), pivotB = to_world(mk3(d.hpivB[h]), B.pos, B.orn);
+    v3 dir = pivotA - pivotB;
+    float e = length(dir);
+    if (e > EPS) {
+        dir /= e;
+        v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+        position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
+    }
+    pb_store(d, A); pb_store(d, B);
+    if (max_error > 0.0f) atomicMax(&d.isl_err[isl], __float_as_uint(max_error));
+}
+
+// <= N position iterations, each island stopping once its max error drops below 0.005
+// (island_solver.cpp:263-353, :538-543).  Same colouring as the velocity solve; cooperative launch.
+__global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
+    cg::grid_group grid = cg::this_grid();
+    const Counters &c = *d.cnt;
+    const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    GRID_STRIDE(i, d.nbodies) { d.isl_err[i] = 0; d.isl_done[i] = 0; }
+    grid.sync();
+    for (int it = 0; it < iters; ++it) {
+        for (uint32_t col = 0; col < nh; ++col) {
+            const uint32_t b = c.hoff[col], e = c.hoff[col + 1];
+            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) hinge_position(d, i);
+            grid.sync();
+        }
+        for (uint32_t col = 0; col < nc; ++col) {
+            const uint32_t b = c.coff[col], e = c.coff[col + 1];
+            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) contact_position(d, i);
+            grid.sync();
+        }
+        if (it + 1 < iters) {
+            GRID_STRIDE(i, d.nbodies) {
+                if (d.parent[i] == i) { if (__uint_as_float(d.isl_err[i]) < 0.005f) d.isl_done[i] = 1; d.isl_err[i] = 0; }
+            }
+            grid.sync();
+        }
+    }
+}
+
+// ====================================================================== statistics
+__global__ void k_count_points(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    uint32_t local = 0;
+    GRID_STRIDE(m, hwm) { uint32_t st = d.mstate[m]; if (st & MS_ALIVE) local += st & MS_NPTS_MASK; }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.cnt->npoints, local);
+}
+
+} // namespace b2d

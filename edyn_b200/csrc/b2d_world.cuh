@@ -1,0 +1,114 @@
+// Device-resident world: SoA layout in HBM.  All per-body and per-contact arrays are
+// float4 so every access is one 16 B vector load; manifold point arrays are slot-major
+// (index = slot * max_manifolds + manifold) so a warp reading slot s of 32 consecutive manifolds
+// touches 512 contiguous bytes.
+#pragma once
+#include "b2d_math.cuh"
+
+namespace b2d {
+
+// flags word per body
+constexpr uint32_t F_KIND_MASK = 3u;          // 0 dynamic, 1 kinematic, 2 static (B2D_DYNAMIC..)
+constexpr uint32_t F_SHAPE_SHIFT = 4;         // bits 4..11 shape kind
+constexpr uint32_t F_ROLLING = 1u << 12;      // rolling_tag (util/rigidbody.cpp:120-130)
+constexpr uint32_t F_FILTER = 1u << 13;       // has collision_filter
+constexpr uint32_t F_LARGE = 1u << 14;        // larger than a broadphase cell: brute-force list
+
+// mstate word per manifold slot
+constexpr uint32_t MS_NPTS_MASK = 7u;
+constexpr uint32_t MS_ALIVE = 1u << 7;
+constexpr uint32_t MS_COLOR_SHIFT = 8;        // bits 8..15 colour, 0xFF = none
+constexpr uint32_t MS_COLOR_MASK = 0xFFu << MS_COLOR_SHIFT;
+constexpr uint32_t COLOR_NONE = 0xFFu;
+constexpr int MAX_COLORS = 64;
+
+constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
+constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
+constexpr uint32_t ERR_LARGE_CAPACITY = 4u;
+
+struct Counters {
+    uint32_t hwm;            // manifold slots in use are [0, hwm)
+    uint32_t nfree;          // dead slots below hwm this step
+    uint32_t nnew;           // pairs found this step
+    uint32_t nactive;        // manifolds with >= 1 point, i.e. rows in the solver arrays
+    uint32_t ncolors;        // contact colours in use
+    uint32_t nhcolors;       // hinge colours in use
+    uint32_t err;
+    uint32_t remaining[2];   // colouring loop: uncoloured constraints, double buffered per round
+    uint32_t npoints;        // contact points (statistics)
+    uint32_t nislands;
+    uint32_t pad;
+    uint32_t coff[MAX_COLORS + 2];   // start of each contact colour in the sorted arrays
+    uint32_t hoff[MAX_COLORS + 2];   // same for hinges
+};
+
+struct Dev {
+    uint32_t NB, NM, NH;           // capacities
+    uint32_t nbodies, nhinges, nlarge;   // host-known counts
+    float dt;
+    float cell, inv_cell;          // broadphase grid pitch
+
+    // ---- bodies
+    float4 *pos;       // xyz position, w inv_mass
+    float4 *orn;
+    float4 *linvel, *angvel;
+    float4 *dvw;       // [2*i] delta_linvel, [2*i+1] delta_angvel
+    float4 *invI;      // 3 rows, body space
+    float4 *invIW;     // 3 rows, world space; row0.w = inv_mass (0 unless dynamic)
+    float4 *grav;
+    float4 *shp;
+    float4 *bbmin, *bbmax;
+    uint32_t *flags;
+    float2 *mat;       // friction, restitution
+    unsigned long long *group, *fmask;
+
+    // ---- broadphase scratch
+    unsigned long long *cellkey, *cellkey_s;
+    uint32_t *cellbody, *cellbody_s;
+    unsigned long long *chash_key; uint32_t *chash_val; uint32_t chash_size;
+    uint32_t *large_list;
+    uint32_t *newcount, *newoff;
+    uint2 *newpairs;
+    uint32_t *free_flag, *free_rank, *free_list;
+    unsigned long long *mhash_key; uint32_t *mhash_val; uint32_t mhash_size;
+    unsigned long long *xhash_key; uint32_t xhash_size;    // exclusion pairs (0 = none)
+
+    // ---- manifolds (slot-major point arrays)
+    uint2 *mpair;
+    uint32_t *mstate;
+    float4 *pA;        // pivotA xyz, distance
+    float4 *pB;        // pivotB xyz, friction
+    float4 *pN;        // normal xyz, restitution
+    float4 *pL;        // local_normal xyz, bits(att | lifetime << 2)
+    float4 *pI;        // normal impulse, friction impulse[2], unused
+
+    // ---- islands / colouring
+    uint32_t *parent;
+    unsigned long long *bmask, *jmask;      // colours in use per body (contacts / hinges)
+    unsigned long long *prop, *jprop;
+    unsigned char *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
+    unsigned char *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
+    uint32_t *isl_err; uint32_t *isl_done;
+
+    // ---- solver rows, colour-sorted order (index = slot * NM + sorted position)
+    uint4 *hdr;        // body a, body b, npts, manifold slot
+    float4 *R0;        // normal xyz, rhs_n
+    float4 *R1;        // rA xyz, eff_mass_n
+    float4 *R2;        // rB xyz, friction
+    float4 *R3;        // eff_mass_t0, eff_mass_t1, rhs_t0, rhs_t1
+    float4 *IMP;       // impulse n, t0, t1
+
+    // ---- hinges
+    uint2 *hpair;
+    float4 *hpivA, *hpivB;       // pivot in body space
+    float4 *hfA0, *hfA1, *hfA2;  // frame[0] columns (axis, p, q)
+    float4 *hfB0;                // frame[1] column 0 (axis)
+    float *himp;                 // 5 per hinge
+    uint32_t *hcolor;
+    float4 *HR;                  // 7 float4 per sorted hinge: rA|eff0, rB|eff1, p|eff2, q|eff3, (eff4,rhs0,rhs1,rhs2), (rhs3,rhs4,imp0,imp1), (imp2,imp3,imp4,0)
+    uint4 *hhdr;                 // a, b, hinge id, 0
+
+    Counters *cnt;
+};
+
+} // namespace b2d

@@ -1,0 +1,228 @@
+"""Python host adapter over the C ABI (include/b2d.h).
+
+Mirrors the reference's lifecycle surface for the sequential stepper
+(include/edyn/edyn.hpp:66-186, src/edyn/edyn.cpp:73-301):
+    attach(config) -> World           edyn::attach(registry, config)
+    make_rigidbody(world, def)        edyn::make_rigidbody(registry, def)
+    make_hinge(world, a, b, ...)      edyn::make_constraint<hinge_constraint>(...) + set_axes
+    exclude_collision(world, a, b)    edyn::exclude_collision
+    step_simulation(world)            edyn::step_simulation(registry, t)   (one fixed step)
+    update(world, dt_elapsed)         edyn::update(registry, time)         (accumulator, <= max_steps)
+    set_solver_velocity_iterations... edyn::set_solver_velocity_iterations
+All compute happens in libb2d.so on the GPU; nothing here touches oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2DError, Bodies, Config, Stats
+from .rigidbody import RigidBodyDef, bodies_soa
+
+f32, u32 = np.float32, np.uint32
+
+PH_BROAD, PH_NARROW, PH_ISLANDS, PH_SOLVE, PH_ALL = 1, 2, 4, 8, 15
+FLAG_RECOLOR_EACH_STEP = 1
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(x, dt, shape=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=dt))
+    return a.reshape(shape) if shape is not None else a
+
+
+class World:
+    """One device-resident world (one entt::registry's worth of rigid bodies)."""
+
+    def __init__(self, max_bodies, max_manifolds=None, max_hinges=0, device=0, fixed_dt=1.0 / 60,
+                 velocity_iterations=8, position_iterations=3, flags=0, gravity=(0.0, -9.8, 0.0)):
+        self.l = _lib.lib()
+        if max_manifolds is None:
+            max_manifolds = max(1024, 8 * max_bodies)
+        self.cfg = Config(device, max_bodies, max_manifolds, max_hinges, fixed_dt, velocity_iterations,
+                          position_iterations, flags)
+        h = self.l.b2d_create(C.byref(self.cfg))
+        if not h:
+            raise B2DError(self.l.b2d_last_error(None).decode())
+        self.h = C.c_void_p(h)
+        self.gravity = tuple(gravity)
+        self.fixed_dt = fixed_dt
+        self.num_bodies = 0
+        self.num_hinges = 0
+        self.max_manifolds = max_manifolds
+        self._accum = 0.0
+        self.max_steps_per_update = 10          # settings.max_steps_per_update
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.b2d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2DError(f"b2d error {rc}: {self.l.b2d_last_error(self.h).decode()}")
+
+    # -- construction
+    def add_bodies(self, soa: dict) -> int:
+        n = len(soa["kind"])
+        keep = dict(pos=_c(soa["pos"], f32, (n, 3)), orn=_c(soa["orn"], f32, (n, 4)), linvel=_c(soa["linvel"], f32, (n, 3)),
+                    angvel=_c(soa["angvel"], f32, (n, 3)), inv_mass=_c(soa["inv_mass"], f32, (n,)),
+                    inv_inertia=_c(soa["inv_inertia"], f32, (n, 9)), gravity=_c(soa["gravity"], f32, (n, 3)),
+                    kind=_c(soa["kind"], u32, (n,)), shape_kind=_c(soa["shape_kind"], u32, (n,)),
+                    shape_params=_c(soa["shape_params"], f32, (n, 4)), friction=_c(soa["friction"], f32, (n,)),
+                    restitution=_c(soa["restitution"], f32, (n,)))
+        grp = _c(soa["group"], np.uint64, (n,)) if soa.get("group") is not None else None
+        msk = _c(soa["mask"], np.uint64, (n,)) if soa.get("mask") is not None else None
+        b = Bodies(n, *[_p(keep[k]) for k in ("pos", "orn", "linvel", "angvel", "inv_mass", "inv_inertia", "gravity",
+                                               "kind", "shape_kind", "shape_params", "friction", "restitution")],
+                   _p(grp), _p(msk))
+        first = C.c_uint32(0)
+        self._check(self.l.b2d_add_bodies(self.h, C.byref(b), C.byref(first)))
+        self.num_bodies += n
+        return first.value
+
+    def add_hinges(self, a, b, pivot_a, pivot_b, axis_a, axis_b):
+        n = len(a)
+        arr = [_c(a, u32), _c(b, u32), _c(pivot_a, f32, (n, 3)), _c(pivot_b, f32, (n, 3)), _c(axis_a, f32, (n, 3)), _c(axis_b, f32, (n, 3))]
+        self._check(self.l.b2d_add_hinges(self.h, C.c_uint32(n), *[_p(x) for x in arr]))
+        self.num_hinges += n
+
+    def add_exclusions(self, a, b):
+        a, b = _c(a, u32), _c(b, u32)
+        self._check(self.l.b2d_add_exclusions(self.h, C.c_uint32(len(a)), _p(a), _p(b)))
+
+    # -- stepping
+    def step(self, n=1):
+        self._check(self.l.b2d_step(self.h, C.c_uint32(n)))
+
+    def run_phases(self, mask):
+        self._check(self.l.b2d_run_phases(self.h, C.c_uint32(mask)))
+
+    def sync(self):
+        self._check(self.l.b2d_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.l.b2d_stream(self.h)
+
+    # -- state
+    def upload_state(self, pos, orn, linvel, angvel):
+        n = self.num_bodies
+        a = [_c(pos, f32, (n, 3)), _c(orn, f32, (n, 4)), _c(linvel, f32, (n, 3)), _c(angvel, f32, (n, 3))]
+        self._check(self.l.b2d_upload_state(self.h, *[_p(x) for x in a]))
+        self._keep = a
+
+    def download_state(self, aabb=True, inv_IW=False, out=None):
+        n = self.num_bodies
+        o = out or dict(pos=np.zeros((n, 3), f32), orn=np.zeros((n, 4), f32), linvel=np.zeros((n, 3), f32), angvel=np.zeros((n, 3), f32))
+        if aabb and "aabb" not in o:
+            o["aabb"] = np.zeros((n, 6), f32)
+        if inv_IW and "inv_IW" not in o:
+            o["inv_IW"] = np.zeros((n, 9), f32)
+        self._check(self.l.b2d_download_state(self.h, _p(o["pos"]), _p(o["orn"]), _p(o["linvel"]), _p(o["angvel"]),
+                                              _p(o.get("aabb")), _p(o.get("inv_IW"))))
+        return o
+
+    def pairs(self):
+        cap = self.max_manifolds
+        p = np.zeros((cap, 2), u32)
+        n = C.c_uint32(0)
+        self._check(self.l.b2d_download_pairs(self.h, C.c_uint32(cap), _p(p), C.byref(n)))
+        return p[:n.value].copy()
+
+    def contacts(self):
+        m = C.c_uint32(0)
+        self._check(self.l.b2d_num_manifolds(self.h, C.byref(m)))
+        cap = max(1, m.value)
+        pairs, num = np.zeros((cap, 2), u32), np.zeros(cap, u32)
+        pts, u = np.zeros((cap, 4, 18), f32), np.zeros((cap, 4, 2), u32)
+        n = C.c_uint32(0)
+        self._check(self.l.b2d_download_contacts(self.h, C.c_uint32(cap), _p(pairs), _p(num), _p(pts), _p(u), C.byref(n)))
+        k = n.value
+        return dict(pairs=pairs[:k], num=num[:k], pts=pts[:k], att=u[:k, :, 0].copy(), lifetime=u[:k, :, 1].copy())
+
+    def upload_contacts(self, pairs, num, pts, att, lifetime=None):
+        pairs = _c(pairs, u32, (-1, 2))
+        m = len(pairs)
+        num, pts = _c(num, u32, (m,)), _c(pts, f32, (m, 4, 18))
+        u = np.zeros((m, 4, 2), u32)
+        u[:, :, 0] = _c(att, u32, (m, 4))
+        if lifetime is not None:
+            u[:, :, 1] = _c(lifetime, u32, (m, 4))
+        self._check(self.l.b2d_upload_contacts(self.h, C.c_uint32(m), _p(pairs), _p(num), _p(pts), _p(u)))
+
+    def islands(self):
+        lab = np.zeros(self.num_bodies, u32)
+        self._check(self.l.b2d_download_islands(self.h, _p(lab)))
+        return lab
+
+    def solver_order(self):
+        hi = np.zeros(max(1, self.num_hinges), u32)
+        pr = np.zeros((self.max_manifolds, 2), u32)
+        nh, nm = C.c_uint32(len(hi)), C.c_uint32(len(pr))
+        self._check(self.l.b2d_download_solver_order(self.h, _p(hi), C.byref(nh), _p(pr), C.byref(nm)))
+        return hi[:nh.value].copy(), pr[:nm.value].copy()
+
+    def hinge_impulses(self):
+        imp = np.zeros((max(1, self.num_hinges), 5), f32)
+        self._check(self.l.b2d_download_hinge_impulses(self.h, _p(imp)))
+        return imp[:self.num_hinges]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.l.b2d_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+# ----------------------------------------------------------------------------- edyn-style free functions
+
+def attach(max_bodies, **kw) -> World:
+    """edyn::attach(registry, init_config) for execution_mode::sequential (src/edyn/edyn.cpp:73-141)."""
+    return World(max_bodies, **kw)
+
+
+def detach(world: World):
+    world.close()
+
+
+def make_rigidbody(world: World, definition) -> int:
+    """edyn::make_rigidbody (src/edyn/util/rigidbody.cpp:47-185).  Accepts one def or a list (batch_rigidbodies)."""
+    defs = [definition] if isinstance(definition, RigidBodyDef) else list(definition)
+    return world.add_bodies(bodies_soa(defs, world.gravity))
+
+
+def make_hinge(world: World, body_a, body_b, pivot_a, pivot_b, axis_a, axis_b):
+    """edyn::make_constraint<hinge_constraint> + pivot + set_axes (src/edyn/constraints/hinge_constraint.cpp:11-17)."""
+    world.add_hinges([body_a], [body_b], [pivot_a], [pivot_b], [axis_a], [axis_b])
+    return world.num_hinges - 1
+
+
+def exclude_collision(world: World, a, b):
+    world.add_exclusions([a], [b])
+
+
+def step_simulation(world: World):
+    """edyn::step_simulation(registry, t): exactly one fixed step (stepper_sequential.cpp:121-147)."""
+    world.step(1)
+
+
+def update(world: World, elapsed: float) -> int:
+    """edyn::update(registry, time): accumulate wall time, run floor(acc / fixed_dt) steps capped by
+    max_steps_per_update (stepper_sequential.cpp:45-65).  Returns the number of steps taken."""
+    world._accum += elapsed
+    n = int(world._accum / world.fixed_dt)
+    world._accum -= n * world.fixed_dt
+    n = min(n, world.max_steps_per_update)
+    if n:
+        world.step(n)
+    return n

@@ -1,0 +1,164 @@
+/*
+ * b2d.h -- C ABI of the B200-native Edyn step ("b2d" = B200 dynamics).
+ *
+ * Drop-in boundary.  The reference has no FFI; its boundary is
+ * four C++ objects called in fixed order from
+ *     edyn::stepper_sequential::update / step_simulation
+ *         /root/reference/src/edyn/simulation/stepper_sequential.cpp:71-102, :121-147
+ *             bphase.update(mt)        src/edyn/collision/broadphase.cpp:177
+ *             nphase.update(mt)        src/edyn/collision/narrowphase.cpp:21
+ *             m_island_manager.update  src/edyn/simulation/island_manager.cpp:533
+ *             m_solver.update(mt)      src/edyn/dynamics/solver.cpp:387
+ * A device world is "a simulation_worker whose registry lives in HBM": the host adapter
+ * (edyn_b200/csrc/host/edyn_adapter.hpp for C++17/EnTT users, edyn_b200/world.py for Python) stages
+ * components into the SoA arrays below, calls b2d_step(), and reads results back.
+ *
+ * Every function returns 0 on success or a negative b2d_status; b2d_last_error() gives the text.
+ * Unsupported content is an error, never a CPU fallback.  All pointers are HOST pointers
+ * (pinned memory recommended); arrays are densely packed float / uint32_t / uint64_t.
+ * One world per registry; calls on one world are not re-entrant.
+ */
+#ifndef B2D_H
+#define B2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* shape_index values of the reference (include/edyn/shapes/shapes.hpp:23-37). */
+#define B2D_SHAPE_SPHERE  0u
+#define B2D_SHAPE_CAPSULE 2u
+#define B2D_SHAPE_BOX     3u
+#define B2D_SHAPE_PLANE   6u
+#define B2D_SHAPE_NONE    255u
+
+/* rigidbody_kind (include/edyn/util/rigidbody.hpp): dynamic_tag / kinematic_tag / static_tag. */
+#define B2D_DYNAMIC   0u
+#define B2D_KINEMATIC 1u
+#define B2D_STATIC    2u
+
+/* contact_normal_attachment (include/edyn/collision/contact_normal_attachment.hpp:16-20). */
+#define B2D_ATTACH_NONE 0u
+#define B2D_ATTACH_A    1u
+#define B2D_ATTACH_B    2u
+
+/* b2d_run_phases() mask: the four calls of stepper_sequential.cpp:82-91. */
+#define B2D_PHASE_BROAD   1u
+#define B2D_PHASE_NARROW  2u
+#define B2D_PHASE_ISLANDS 4u
+#define B2D_PHASE_SOLVE   8u
+#define B2D_PHASE_ALL     15u
+
+typedef enum b2d_status {
+    B2D_OK = 0,
+    B2D_ERR_CUDA = -1,         /* a CUDA runtime call failed */
+    B2D_ERR_CAPACITY = -2,     /* max_bodies / max_manifolds / max_hinges exceeded */
+    B2D_ERR_UNSUPPORTED = -3,  /* shape / constraint / setting outside the hot-path scope */
+    B2D_ERR_ARGUMENT = -4
+} b2d_status;
+
+typedef struct b2d_world b2d_world;
+
+/* edyn::init_config + settings (include/edyn/edyn.hpp:39-60, include/edyn/context/settings.hpp:21-57). */
+typedef struct b2d_config {
+    int32_t  device;               /* CUDA ordinal */
+    uint32_t max_bodies;
+    uint32_t max_manifolds;        /* device-resident contact manifolds (4 point slots each) */
+    uint32_t max_hinges;
+    float    fixed_dt;             /* settings.fixed_dt, default 1/60 */
+    uint32_t velocity_iterations;  /* settings.num_solver_velocity_iterations, default 8 */
+    uint32_t position_iterations;  /* settings.num_solver_position_iterations, default 3 */
+    uint32_t flags;                /* B2D_FLAG_* */
+} b2d_config;
+
+#define B2D_FLAG_RECOLOR_EACH_STEP 1u  /* recompute the constraint colouring from scratch every step */
+
+/* make_rigidbody() output for n bodies (src/edyn/util/rigidbody.cpp:47-185), SoA.
+ * inv_inertia = inertia_inv component, row-major 3x3 in body space (ignored unless dynamic).
+ * gravity = gravity component (zero if absent).  group/mask may be NULL (= no collision_filter). */
+typedef struct b2d_bodies {
+    uint32_t count;
+    const float *pos;          /* 3n  position */
+    const float *orn;          /* 4n  orientation x,y,z,w */
+    const float *linvel;       /* 3n */
+    const float *angvel;       /* 3n */
+    const float *inv_mass;     /* n   mass_inv */
+    const float *inv_inertia;  /* 9n  inertia_inv */
+    const float *gravity;      /* 3n */
+    const uint32_t *kind;      /* n   B2D_DYNAMIC.. */
+    const uint32_t *shape_kind;/* n   B2D_SHAPE_.. */
+    const float *shape_params; /* 4n  sphere{r} capsule{r,half_length,axis} box{half_extents} plane{n,constant} */
+    const float *friction;     /* n   material.friction */
+    const float *restitution;  /* n   material.restitution */
+    const uint64_t *group;     /* n or NULL  collision_filter.group */
+    const uint64_t *mask;      /* n or NULL  collision_filter.mask */
+} b2d_bodies;
+
+/* profile_counters + profile_timers analogue (include/edyn/context/profile.hpp:8-27). */
+typedef struct b2d_stats {
+    uint32_t bodies, manifolds, contact_points, hinges;
+    uint32_t contact_colors, hinge_colors, islands, manifold_high_water;
+    uint64_t kernel_launches;      /* kernels launched by this world since creation */
+    uint64_t steps;
+    float last_step_ms;            /* CUDA-event time of the last b2d_step() call */
+    float solve_ms;                /* CUDA-event time of the velocity-solve kernel inside it (last step) */
+    float integrate_ms;            /* ... of the integrate kernel */
+    uint32_t error_flags;          /* device-side overflow flags, 0 if none */
+} b2d_stats;
+
+b2d_world  *b2d_create(const b2d_config *cfg);
+void        b2d_destroy(b2d_world *w);
+const char *b2d_last_error(const b2d_world *w);   /* w may be NULL: error of the last failed b2d_create */
+
+/* Appends bodies; ids are consecutive, *first_id receives the id of bodies[0]. */
+int b2d_add_bodies(b2d_world *w, const b2d_bodies *bodies, uint32_t *first_id);
+/* make_constraint<hinge_constraint> + set_axes (src/edyn/constraints/hinge_constraint.cpp:11-17). */
+int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b,
+                   const float *pivot_a, const float *pivot_b, const float *axis_a, const float *axis_b);
+/* exclude_collision (src/edyn/util/exclude_collision.cpp): pairs that never collide. */
+int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
+
+/* n fixed steps: broadphase -> narrowphase -> islands -> solve/integrate (step_simulation semantics). */
+int b2d_step(b2d_world *w, uint32_t num_steps);
+/* Selected phases of ONE step, in stepper order (parity tests of individual phases). */
+int b2d_run_phases(b2d_world *w, uint32_t phase_mask);
+
+/* Overwrite position/orientation/linvel/angvel of ALL bodies from host arrays (full resync after the
+ * user wrote components directly); AABB and inertia_world_inv are refreshed as solver.cpp:453-465 does. */
+int b2d_upload_state(b2d_world *w, const float *pos, const float *orn, const float *linvel, const float *angvel);
+/* Any output may be NULL.  aabb: 6 floats per body (min, max); inv_inertia_world: 9 per body. */
+int b2d_download_state(b2d_world *w, float *pos, float *orn, float *linvel, float *angvel,
+                       float *aabb, float *inv_inertia_world);
+
+/* Contact manifolds (contact_manifold / contact_point*, include/edyn/collision/contact_point.hpp:17-58).
+ * pairs: 2 uint32 per manifold (body[0], body[1]).  num: points per manifold.  Per point slot
+ * (4 per manifold, list order, slot 0 = newest): pt18 = pivotA(3) pivotB(3) normal(3) local_normal(3)
+ * distance friction restitution normal_impulse friction_impulse[2]; pt_u2 = {normal_attachment, lifetime}. */
+int b2d_num_manifolds(b2d_world *w, uint32_t *n);
+int b2d_download_pairs(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint32_t *n);
+int b2d_download_contacts(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint32_t *num,
+                          float *pt18, uint32_t *pt_u2, uint32_t *n);
+/* Replaces all manifolds (solver-only and narrowphase-only parity tests; EnTT -> device mirroring). */
+int b2d_upload_contacts(b2d_world *w, uint32_t n, const uint32_t *pairs, const uint32_t *num,
+                        const float *pt18, const uint32_t *pt_u2);
+
+/* island_resident analogue: label[i] = smallest body id of i's island, 0xFFFFFFFF for static/kinematic. */
+int b2d_download_islands(b2d_world *w, uint32_t *label);
+/* The sequential Gauss-Seidel order equivalent to the device's coloured solve in the last step:
+ * hinge ids, then manifold body pairs.  Capacities in *nh / *nm on entry, counts on exit. */
+int b2d_download_solver_order(b2d_world *w, uint32_t *hinge_ids, uint32_t *nh, uint32_t *pairs, uint32_t *nm);
+/* applied_impulse.linear[3], .hinge[2] per hinge (constraints/hinge_constraint.hpp:63-70). */
+int b2d_download_hinge_impulses(b2d_world *w, float *imp5);
+
+int b2d_get_stats(b2d_world *w, b2d_stats *out);
+/* Blocks until all queued device work of this world has finished. */
+int b2d_sync(b2d_world *w);
+/* The CUDA stream (cudaStream_t) the world launches on, for event timing by the caller. */
+void *b2d_stream(b2d_world *w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2D_H */
