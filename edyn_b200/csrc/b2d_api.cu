@@ -29,7 +29,11 @@ struct b2d_world {
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
     uint64_t launches = 0, steps = 0;
-    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_solve0 = nullptr, ev_solve1 = nullptr, ev_int0 = nullptr, ev_int1 = nullptr;
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+    // ring of per-step event pairs around the solve and integrate kernels (averaged by b2d_get_stats)
+    static constexpr int RING = 256;
+    cudaEvent_t ev_solve0[RING] = {}, ev_solve1[RING] = {}, ev_int0[RING] = {}, ev_int1[RING] = {};
+    uint64_t timed_steps = 0;       // solver phases enqueued since the last b2d_reset_timers
     bool timed = false;
     // host mirrors needed for grid sizing / exclusions
     float max_extent = 0.0f;
@@ -84,7 +88,8 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     w->num_sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { g_create_error = "b2d_create: device lacks cooperative launch"; delete w; return nullptr; }
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream"; delete w; return nullptr; }
-    for (cudaEvent_t *e : {&w->ev_step0, &w->ev_step1, &w->ev_solve0, &w->ev_solve1, &w->ev_int0, &w->ev_int1}) cudaEventCreate(e);
+    cudaEventCreate(&w->ev_step0); cudaEventCreate(&w->ev_step1);
+    for (int i = 0; i < b2d_world::RING; ++i) { cudaEventCreate(&w->ev_solve0[i]); cudaEventCreate(&w->ev_solve1[i]); cudaEventCreate(&w->ev_int0[i]); cudaEventCreate(&w->ev_int1[i]); }
 
     Dev &d = w->d;
     const uint32_t NB = cfg->max_bodies, NM = cfg->max_manifolds, NH = std::max<uint32_t>(cfg->max_hinges, 1);
@@ -151,7 +156,9 @@ void b2d_destroy(b2d_world *w) {
     cudaSetDevice(w->cfg.device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (void *p : w->allocs) cudaFree(p);
-    for (cudaEvent_t e : {w->ev_step0, w->ev_step1, w->ev_solve0, w->ev_solve1, w->ev_int0, w->ev_int1}) if (e) cudaEventDestroy(e);
+    if (w->ev_step0) cudaEventDestroy(w->ev_step0);
+    if (w->ev_step1) cudaEventDestroy(w->ev_step1);
+    for (int i = 0; i < b2d_world::RING; ++i) for (cudaEvent_t e : {w->ev_solve0[i], w->ev_solve1[i], w->ev_int0[i], w->ev_int1[i]}) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
 }
@@ -355,12 +362,14 @@ static int enqueue_solver(b2d_world *w) {
     LAUNCH(k_color_fixup, 1, 32, d);
     LAUNCH(k_prepare_contacts, d.NM, 256, d);
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
-    cudaEventRecord(w->ev_solve0, s);
+    const int slot = (int)(w->timed_steps % b2d_world::RING);
+    cudaEventRecord(w->ev_solve0[slot], s);
     CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
-    cudaEventRecord(w->ev_solve1, s);
-    cudaEventRecord(w->ev_int0, s);
+    cudaEventRecord(w->ev_solve1[slot], s);
+    cudaEventRecord(w->ev_int0[slot], s);
     LAUNCH(k_integrate, d.nbodies, 256, d, pi == 0 ? 1 : 0);
-    cudaEventRecord(w->ev_int1, s);
+    cudaEventRecord(w->ev_int1[slot], s);
+    ++w->timed_steps;
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
         CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
@@ -589,13 +598,24 @@ int b2d_get_stats(b2d_world *w, b2d_stats *out) {
     out->bodies = d.nbodies; out->manifolds = (uint32_t)hm.slots.size(); out->contact_points = c.npoints; out->hinges = d.nhinges;
     out->contact_colors = c.ncolors; out->hinge_colors = c.nhcolors; out->islands = c.nislands; out->manifold_high_water = c.hwm;
     out->kernel_launches = w->launches; out->steps = w->steps; out->error_flags = c.err;
-    if (w->timed) {
-        cudaEventElapsedTime(&out->solve_ms, w->ev_solve0, w->ev_solve1);
-        cudaEventElapsedTime(&out->integrate_ms, w->ev_int0, w->ev_int1);
+    if (w->timed && w->timed_steps) {
+        // average over the steps since b2d_reset_timers (at most the ring size)
+        const uint64_t cnt = std::min<uint64_t>(w->timed_steps, b2d_world::RING);
+        double ss = 0, si = 0;
+        for (uint64_t k = 0; k < cnt; ++k) {
+            int slot = (int)((w->timed_steps - 1 - k) % b2d_world::RING);
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, w->ev_solve0[slot], w->ev_solve1[slot]);
+            cudaEventElapsedTime(&b, w->ev_int0[slot], w->ev_int1[slot]);
+            ss += a; si += b;
+        }
+        out->solve_ms = (float)(ss / cnt); out->integrate_ms = (float)(si / cnt);
         if (cudaEventQuery(w->ev_step1) == cudaSuccess) cudaEventElapsedTime(&out->last_step_ms, w->ev_step0, w->ev_step1);
         cudaGetLastError();
     }
     return B2D_OK;
 }
+
+int b2d_reset_timers(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; w->timed_steps = 0; return B2D_OK; }
 
 } // extern "C"

@@ -178,6 +178,9 @@ class World:
         self._check(self.l.b2d_download_hinge_impulses(self.h, _p(imp)))
         return imp[:self.num_hinges]
 
+    def reset_timers(self):
+        self._check(self.l.b2d_reset_timers(self.h))
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self.l.b2d_get_stats(self.h, C.byref(s)))

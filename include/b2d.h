@@ -103,8 +103,8 @@ typedef struct b2d_stats {
     uint64_t kernel_launches;      /* kernels launched by this world since creation */
     uint64_t steps;
     float last_step_ms;            /* CUDA-event time of the last b2d_step() call */
-    float solve_ms;                /* CUDA-event time of the velocity-solve kernel inside it (last step) */
-    float integrate_ms;            /* ... of the integrate kernel */
+    float solve_ms;                /* mean CUDA-event time of the velocity-solve kernel per step since b2d_reset_timers */
+    float integrate_ms;            /* ... of the integrate kernel (means cover at most the last 256 steps) */
     uint32_t error_flags;          /* device-side overflow flags, 0 if none */
 } b2d_stats;
 
@@ -153,6 +153,8 @@ int b2d_download_solver_order(b2d_world *w, uint32_t *hinge_ids, uint32_t *nh, u
 int b2d_download_hinge_impulses(b2d_world *w, float *imp5);
 
 int b2d_get_stats(b2d_world *w, b2d_stats *out);
+/* Restart the per-kernel timing averages reported by b2d_get_stats. */
+int b2d_reset_timers(b2d_world *w);
 /* Blocks until all queued device work of this world has finished. */
 int b2d_sync(b2d_world *w);
 /* The CUDA stream (cudaStream_t) the world launches on, for event timing by the caller. */
