@@ -69,6 +69,12 @@ static cudaError_t coop_launch(b2d_world *w, K kernel, int blocks, int threads, 
     return cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(threads), params, 0, w->stream);
 }
 
+template<int FN> static void launch_detect(b2d_world *w) {
+    Dev &d = w->d;
+    // heavy overloads (box-box, capsule-box) get a full grid; the others are short
+    LAUNCH(k_np_detect<FN>, d.NM, 128, d);
+}
+
 extern "C" {
 
 const char *b2d_last_error(const b2d_world *w) { return w ? w->error.c_str() : g_create_error.c_str(); }
@@ -110,7 +116,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     d.xhash_size = 0; d.xhash_key = nullptr;
     ok = ok && dalloc(w, d.mpair, NM) && dalloc(w, d.mstate, NM);
     ok = ok && dalloc(w, d.pA, 4 * (size_t)NM) && dalloc(w, d.pB, 4 * (size_t)NM) && dalloc(w, d.pN, 4 * (size_t)NM);
-    ok = ok && dalloc(w, d.pL, 4 * (size_t)NM) && dalloc(w, d.pI, 4 * (size_t)NM);
+    ok = ok && dalloc(w, d.pL, 4 * (size_t)NM) && dalloc(w, d.pI, 4 * (size_t)NM) && dalloc(w, d.npres, NM) && dalloc(w, d.clist, NM);
     ok = ok && dalloc(w, d.parent, NB) && dalloc(w, d.bmask, NB) && dalloc(w, d.jmask, NB) && dalloc(w, d.prop, NB) && dalloc(w, d.jprop, NB);
     ok = ok && dalloc(w, d.ckey, NM) && dalloc(w, d.ckey_s, NM) && dalloc(w, d.cidx, NM) && dalloc(w, d.cidx_s, NM);
     ok = ok && dalloc(w, d.hkey, NH) && dalloc(w, d.hkey_s, NH) && dalloc(w, d.hidx, NH) && dalloc(w, d.hidx_s, NH);
@@ -138,10 +144,12 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     if (ok && cudaMalloc(&st, w->stage_floats * sizeof(float)) != cudaSuccess) ok = false;
     w->stage = st; if (st) w->allocs.push_back(st);
 
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, 256, 0); w->coop_blocks_color = std::max(1, per_sm) * w->num_sms;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, per_sm) * w->num_sms;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, per_sm) * w->num_sms;
+    // Persistent kernels: co-resident grid, a few CTAs per SM (barrier cost grows with the CTA count).
+    int per_sm = 0, want = 2;
+    if (const char *e = getenv("B2D_COOP_BLOCKS_PER_SM")) want = std::max(1, atoi(e));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, 256, 0); w->coop_blocks_color = std::max(1, std::min(per_sm, want)) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, std::min(per_sm, want)) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
         g_create_error = "b2d_create: device allocation failed: " + w->error;
@@ -334,8 +342,15 @@ static int enqueue_broadphase(b2d_world *w) {
     return B2D_OK;
 }
 static int enqueue_narrowphase(b2d_world *w) {
-    Dev &d = w->d;
-    LAUNCH(k_narrowphase, d.NM, 128, d);
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    LAUNCH(k_np_keys, d.NM, 256, d);
+    size_t t = w->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
+    LAUNCH(k_np_offsets, d.NM, 256, d);
+    LAUNCH(k_np_fixup, 1, 32, d);
+    launch_detect<1>(w); launch_detect<2>(w); launch_detect<3>(w); launch_detect<4>(w); launch_detect<5>(w);
+    launch_detect<6>(w); launch_detect<7>(w); launch_detect<8>(w); launch_detect<9>(w);
+    LAUNCH(k_np_merge, d.NM, 128, d);
     return B2D_OK;
 }
 static int enqueue_islands(b2d_world *w) {
@@ -350,9 +365,16 @@ static int enqueue_solver(b2d_world *w) {
     Dev &d = w->d; cudaStream_t s = w->stream;
     const int vi = (int)w->cfg.velocity_iterations, pi = (int)w->cfg.position_iterations;
     LAUNCH(k_gravity, d.nbodies, 256, d);
-    int recolor = ((w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->contacts_dirty) ? 1 : 0;
+    const int recolor = ((w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->contacts_dirty) ? 1 : 0;
     w->contacts_dirty = false;
-    CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d, recolor));
+    CK(cudaMemsetAsync(&d.cnt->remaining[0], 0, 2 * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(&d.cnt->nlist, 0, 2 * sizeof(uint32_t), s));          // nlist + bar
+    CK(cudaMemsetAsync(d.bmask, 0, (size_t)d.nbodies * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(d.jmask, 0, (size_t)d.nbodies * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(d.prop, 0xFF, (size_t)d.nbodies * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(d.jprop, 0xFF, (size_t)d.nbodies * sizeof(unsigned long long), s));
+    LAUNCH(k_color_list, d.NM, 256, d, recolor);
+    CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d));
     LAUNCH(k_color_keys, d.NM, 256, d);
     size_t t = w->cub_tmp_bytes;
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
@@ -363,6 +385,7 @@ static int enqueue_solver(b2d_world *w) {
     LAUNCH(k_prepare_contacts, d.NM, 256, d);
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
     const int slot = (int)(w->timed_steps % b2d_world::RING);
+    CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
     cudaEventRecord(w->ev_solve0[slot], s);
     CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
     cudaEventRecord(w->ev_solve1[slot], s);
@@ -372,6 +395,7 @@ static int enqueue_solver(b2d_world *w) {
     ++w->timed_steps;
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
+        CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
         CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }

@@ -28,6 +28,24 @@ B2D_D uint32_t hash64(unsigned long long k) {
 }
 constexpr unsigned long long EMPTY_KEY = ~0ULL;
 
+// Grid-wide barrier for the persistent (cooperatively launched, hence co-resident) kernels: one release
+// atomic + acquire spin per CTA on a monotonic counter that the host zeroes before the launch.
+struct GridBarrier {
+    unsigned *ctr; unsigned target; unsigned nblocks;
+    __device__ __forceinline__ GridBarrier(unsigned *c) : ctr(c), target(0), nblocks(gridDim.x) {}
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += nblocks;
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            unsigned v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+        }
+        __syncthreads();
+    }
+};
+
 B2D_D void hash_insert(unsigned long long *keys, uint32_t *vals, uint32_t size, unsigned long long k, uint32_t v) {
     uint32_t h = hash64(k) & (size - 1);
     for (;;) {
@@ -314,29 +332,96 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
     return cp;
 }
 
-// One thread per manifold: update_contact_distances (collision_util.cpp:28-45), detect_collision (:440-475),
-// process_collision (collision_util.hpp:105-276, sequential flavour of narrowphase.hpp:62-84).
-__global__ void __launch_bounds__(128) k_narrowphase(Dev d) {
+// Narrowphase in three kernels:
+//   k_np_keys     pair-type key per manifold slot (static per slot), radix-sorted on the host side so that
+//   k_np_detect<FN> runs ONE collide() overload per launch over a contiguous range of the sorted list
+//                 (no intra-warp divergence between sphere/box/capsule code paths); the <= 4 result points go to
+//                 the solver-row arrays R0/R1/R2, which are idle in this phase;
+//   k_np_merge    update_contact_distances (collision_util.cpp:28-45) + process_collision
+//                 (collision_util.hpp:105-276, sequential flavour of narrowphase.hpp:62-84) per manifold.
+__global__ void k_np_keys(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, d.NM) {
+        unsigned char key = 0xFF;
+        if (m < hwm && (d.mstate[m] & MS_ALIVE)) {
+            uint2 pr = d.mpair[m];
+            int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
+            int fn = pair_fn(ka, kb);
+            if (!fn) fn = pair_fn(kb, ka);
+            key = (unsigned char)fn;
+        }
+        d.ckey[m] = key; d.cidx[m] = m;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 16) d.cnt->npoff[threadIdx.x] = 0xFFFFFFFFu;
+}
+__global__ void k_np_offsets(Dev d) {
+    GRID_STRIDE(i, d.NM) {
+        unsigned char k = d.ckey_s[i];
+        if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->npoff[k == 0xFF ? 10 : k] = i;
+    }
+}
+__global__ void k_np_fixup(Dev d) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Counters &c = *d.cnt;
+    if (c.npoff[10] == 0xFFFFFFFFu) c.npoff[10] = d.NM;
+    for (int k = 9; k >= 0; --k) if (c.npoff[k] == 0xFFFFFFFFu) c.npoff[k] = c.npoff[k + 1];
+}
+
+template<int FN>
+__global__ void __launch_bounds__(128) k_np_detect(Dev d) {
+    const uint32_t b = d.cnt->npoff[FN], e = d.cnt->npoff[FN + 1];
+    for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        const uint32_t m = d.cidx_s[i];
+        const uint2 pr = d.mpair[m];
+        const uint32_t fa = d.flags[pr.x], fb = d.flags[pr.y];
+        CResult res; res.num = 0;
+        // detect_collision's AABB gate, collision_util.cpp:444-474
+        if (intersect(inset(body_box(d, pr.x), -BREAKING_THRESHOLD), body_box(d, pr.y))) {
+            const int ka = shape_of(fa), kb = shape_of(fb);
+            CCtx ctx; ctx.threshold = COLLISION_THRESHOLD;
+            if (pair_fn(ka, kb) == FN) {
+                ctx.posA = mk3(d.pos[pr.x]); ctx.ornA = mkq(d.orn[pr.x]); ctx.posB = mk3(d.pos[pr.y]); ctx.ornB = mkq(d.orn[pr.y]);
+                run_pair(FN, d.shp[pr.x], d.shp[pr.y], ctx, res);
+            } else {                                    // swap_collide, collide.hpp:369-374
+                ctx.posA = mk3(d.pos[pr.y]); ctx.ornA = mkq(d.orn[pr.y]); ctx.posB = mk3(d.pos[pr.x]); ctx.ornB = mkq(d.orn[pr.x]);
+                run_pair(FN, d.shp[pr.y], d.shp[pr.x], ctx, res);
+                swap_result(res);
+            }
+        }
+        d.npres[m] = (unsigned char)res.num;
+        for (int s = 0; s < res.num; ++s) {
+            size_t ri = (size_t)s * d.NM + m;
+            d.R0[ri] = f4(res.pt[s].pivotA, res.pt[s].distance);
+            d.R1[ri] = f4(res.pt[s].pivotB, __uint_as_float(res.pt[s].att));
+            d.R2[ri] = f4(res.pt[s].normal, 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_np_merge(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, hwm) {
         uint32_t st = d.mstate[m];
         if (!(st & MS_ALIVE)) continue;
+        int num = (int)(st & MS_NPTS_MASK);
+        CResult res; res.num = d.npres[m];
+        if (num == 0 && res.num == 0) continue;
         uint2 pr = d.mpair[m];
         const uint32_t a = pr.x, b = pr.y;
         const uint32_t fa = d.flags[a], fb = d.flags[b];
         const v3 posA = mk3(d.pos[a]), posB = mk3(d.pos[b]);
         const q4 ornA = mkq(d.orn[a]), ornB = mkq(d.orn[b]);
-        int num = (int)(st & MS_NPTS_MASK);
+        for (int s = 0; s < res.num; ++s) {
+            size_t ri = (size_t)s * d.NM + m;
+            float4 r0 = d.R0[ri], r1 = d.R1[ri], r2 = d.R2[ri];
+            res.pt[s].pivotA = mk3(r0); res.pt[s].distance = r0.w; res.pt[s].pivotB = mk3(r1); res.pt[s].att = __float_as_uint(r1.w);
+            res.pt[s].normal = mk3(r2);
+        }
         MPoint P[4];
         for (int s = 0; s < num; ++s) {
             load_point(d, m, s, P[s]);
             v3 pAw = to_world(P[s].pivotA, posA, ornA), pBw = to_world(P[s].pivotB, posB, ornB);
             P[s].distance = dot(P[s].normal, pAw - pBw);
-        }
-        CResult res; res.num = 0;
-        if (intersect(inset(body_box(d, a), -BREAKING_THRESHOLD), body_box(d, b))) {
-            CCtx ctx; ctx.posA = posA; ctx.ornA = ornA; ctx.posB = posB; ctx.ornB = ornB; ctx.threshold = COLLISION_THRESHOLD;
-            collide(shape_of(fa), d.shp[a], shape_of(fb), d.shp[b], ctx, res);
         }
         // ---- merge with persisted points
         bool merged[4] = {false, false, false, false};
@@ -453,57 +538,66 @@ __global__ void k_gravity(Dev d) {
     }
 }
 
-// Deterministic greedy colouring of the constraint graph (manifolds and hinges coloured independently:
-// they are solved in separate passes).  Colours persist across steps; only new constraints enter the
-// rounds below.  A constraint wins a round when it holds the smallest id on both of its dynamic bodies,
-// then takes the lowest colour unused on either body.  Cooperative launch (grid-wide barriers).
-__global__ void __launch_bounds__(256) k_color(Dev d, int recolor) {
-    cg::grid_group grid = cg::this_grid();
-    Counters &c = *d.cnt;
-    const uint32_t hwm = c.hwm;
-    const uint32_t total = hwm + d.nhinges;
-    GRID_STRIDE(i, d.nbodies) { d.bmask[i] = 0ULL; d.jmask[i] = 0ULL; d.prop[i] = ~0ULL; d.jprop[i] = ~0ULL; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { c.remaining[0] = 0; c.remaining[1] = 0; }
-    grid.sync();
-    GRID_STRIDE(k, total) {
-        if (k < hwm) {
-            uint32_t st = d.mstate[k];
-            if (!(st & MS_ALIVE)) continue;
-            if (recolor) { st |= MS_COLOR_MASK; d.mstate[k] = st; }
-            uint32_t col = (st >> MS_COLOR_SHIFT) & 0xFFu;
-            if (col == COLOR_NONE) continue;
-            uint2 p = d.mpair[k];
+// Colours persist from step to step for constraints that keep producing rows, so in steady state only the few
+// manifolds that just gained their first point (and new hinges) enter the colouring rounds.  This pass
+// releases the colour of manifolds that lost all points, rebuilds the per-body "colours in use" masks from
+// the constraints that keep theirs (masks are zeroed by the host before the launch) and lists the uncoloured
+// ones.  With recolor != 0 everything is recoloured from scratch.
+__global__ void k_color_list(Dev d, int recolor) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(m, hwm) {
+        uint32_t st = d.mstate[m];
+        if (!(st & MS_ALIVE)) continue;
+        uint32_t col = (st >> MS_COLOR_SHIFT) & 0xFFu;
+        if (!(st & MS_NPTS_MASK) || recolor) {
+            if (col != COLOR_NONE) { st |= MS_COLOR_MASK; d.mstate[m] = st; col = COLOR_NONE; }
+            if (!(st & MS_NPTS_MASK)) continue;
+        }
+        if (col == COLOR_NONE) { uint32_t k = atomicAdd(&d.cnt->nlist, 1u); d.clist[k] = m; }
+        else {
+            uint2 p = d.mpair[m];
             if (is_dynamic(d.flags[p.x])) atomicOr(&d.bmask[p.x], 1ULL << col);
             if (is_dynamic(d.flags[p.y])) atomicOr(&d.bmask[p.y], 1ULL << col);
-        } else {
-            uint32_t h = k - hwm;
-            if (recolor) d.hcolor[h] = COLOR_NONE;
-            uint32_t col = d.hcolor[h];
-            if (col == COLOR_NONE) continue;
-            uint2 p = d.hpair[h];
-            if (is_dynamic(d.flags[p.x])) atomicOr(&d.jmask[p.x], 1ULL << col);
-            if (is_dynamic(d.flags[p.y])) atomicOr(&d.jmask[p.y], 1ULL << col);
         }
     }
-    grid.sync();
+    GRID_STRIDE(h, d.nhinges) {
+        if (recolor) d.hcolor[h] = COLOR_NONE;
+        uint32_t col = d.hcolor[h];
+        if (col == COLOR_NONE) continue;
+        uint2 p = d.hpair[h];
+        if (is_dynamic(d.flags[p.x])) atomicOr(&d.jmask[p.x], 1ULL << col);
+        if (is_dynamic(d.flags[p.y])) atomicOr(&d.jmask[p.y], 1ULL << col);
+    }
+}
+
+// Deterministic greedy colouring of the constraint graph (manifolds and hinges are coloured independently:
+// they are solved in separate passes).  Jones-Plassmann style rounds over the uncoloured constraints: one
+// takes the lowest colour unused on either of its dynamic bodies once it holds the smallest (hashed) priority
+// among the still uncoloured constraints on both bodies.  Priorities depend only on the slot index and the
+// inputs are the previous (deterministic) colouring, so the Gauss-Seidel order is reproducible run to run.
+__global__ void __launch_bounds__(256) k_color(Dev d) {
+    GridBarrier grid(&d.cnt->bar);
+    Counters &c = *d.cnt;
+    const uint32_t nlist = c.nlist;
+    const uint32_t total = nlist + d.nhinges;
     for (uint32_t round = 0;; ++round) {
-        const unsigned long long stamp = (unsigned long long)(0x7FFFFFFFu - round) << 32;
+        const unsigned long long stamp = (unsigned long long)(0xFFFFu - (round & 0xFFFFu)) << 48;
         GRID_STRIDE(k, total) {
-            bool isM = k < hwm;
-            uint2 p; unsigned long long *prop;
-            if (isM) { uint32_t st = d.mstate[k]; if (!(st & MS_ALIVE) || ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[k]; prop = d.prop; }
-            else { uint32_t h = k - hwm; if (d.hcolor[h] != COLOR_NONE) continue; p = d.hpair[h]; prop = d.jprop; }
-            unsigned long long v = stamp | (isM ? k : k - hwm);
+            const bool isM = k < nlist;
+            uint32_t id; uint2 p; unsigned long long *prop;
+            if (isM) { id = d.clist[k]; if (((d.mstate[id] >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[id]; prop = d.prop; }
+            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; }
+            unsigned long long v = stamp | ((unsigned long long)(hash64(id) & 0x3FFFFFu) << 26) | id;
             if (is_dynamic(d.flags[p.x])) atomicMin(&prop[p.x], v);
             if (is_dynamic(d.flags[p.y])) atomicMin(&prop[p.y], v);
         }
         grid.sync();
         GRID_STRIDE(k, total) {
-            bool isM = k < hwm;
-            uint2 p; unsigned long long *prop, *mask;
-            if (isM) { uint32_t st = d.mstate[k]; if (!(st & MS_ALIVE) || ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[k]; prop = d.prop; mask = d.bmask; }
-            else { uint32_t h = k - hwm; if (d.hcolor[h] != COLOR_NONE) continue; p = d.hpair[h]; prop = d.jprop; mask = d.jmask; }
-            unsigned long long v = stamp | (isM ? k : k - hwm);
+            const bool isM = k < nlist;
+            uint32_t id; uint2 p; unsigned long long *prop, *mask;
+            if (isM) { id = d.clist[k]; if (((d.mstate[id] >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[id]; prop = d.prop; mask = d.bmask; }
+            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; mask = d.jmask; }
+            unsigned long long v = stamp | ((unsigned long long)(hash64(id) & 0x3FFFFFu) << 26) | id;
             bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
             bool win = (!da || prop[p.x] == v) && (!db || prop[p.y] == v);
             if (win) {
@@ -513,8 +607,8 @@ __global__ void __launch_bounds__(256) k_color(Dev d, int recolor) {
                 if (!freeb) atomicOr(&c.err, ERR_COLOR_OVERFLOW);
                 if (da) atomicOr(&mask[p.x], 1ULL << col);
                 if (db) atomicOr(&mask[p.y], 1ULL << col);
-                if (isM) d.mstate[k] = (d.mstate[k] & ~MS_COLOR_MASK) | (col << MS_COLOR_SHIFT);
-                else d.hcolor[k - hwm] = col;
+                if (isM) d.mstate[id] = (d.mstate[id] & ~MS_COLOR_MASK) | (col << MS_COLOR_SHIFT);
+                else d.hcolor[id] = col;
             } else atomicAdd(&c.remaining[round & 1], 1u);
         }
         grid.sync();
@@ -725,57 +819,76 @@ B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm) {
     vb_store(d, A); vb_store(d, B);
 }
 
+// All row loads of a manifold are issued before the first dependent computation and all impulse stores after the
+// last one, so a 4-point manifold costs one memory round trip instead of four (the compiler cannot hoist loads
+// across the stores of a load-compute-store loop).
 B2D_D void normal_pass(const Dev &d, uint32_t i, bool warm) {
-    uint4 hd = d.hdr[i];
-    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
-    for (uint32_t s = 0; s < hd.z; ++s) {
+    const uint4 hd = d.hdr[i];
+    const uint32_t n = hd.z;
+    float4 r0[4], r1[4], r2[4], im[4];
+    #pragma unroll
+    for (int s = 0; s < 4; ++s) if (s < n) {
         size_t ri = (size_t)s * d.NM + i;
-        float4 r0 = d.R0[ri], r1 = d.R1[ri], r2 = d.R2[ri], im = d.IMP[ri];
-        v3 n = mk3(r0), rA = mk3(r1), rB = mk3(r2);
-        v3 J1 = cross(rA, n), J2 = -n, J3 = -cross(rB, n);
+        r0[s] = d.R0[ri]; r1[s] = d.R1[ri]; r2[s] = d.R2[ri]; im[s] = d.IMP[ri];
+    }
+    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
+    #pragma unroll
+    for (int s = 0; s < 4; ++s) if (s < n) {
+        v3 nrm = mk3(r0[s]), rA = mk3(r1[s]), rB = mk3(r2[s]);
+        v3 J1 = cross(rA, nrm), J2 = -nrm, J3 = -cross(rB, nrm);
         float delta;
-        if (warm) delta = im.x;
-        else {
-            delta = solve_row(r0.w, r1.w, 0.0f, LARGE, im.x, rel_speed(n, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
-            d.IMP[ri] = im;
-        }
-        apply_imp(A, B, n, J1, J2, J3, delta);
+        if (warm) delta = im[s].x;
+        else delta = solve_row(r0[s].w, r1[s].w, 0.0f, LARGE, im[s].x, rel_speed(nrm, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
+        apply_imp(A, B, nrm, J1, J2, J3, delta);
     }
     vb_store(d, A); vb_store(d, B);
+    if (!warm) {
+        #pragma unroll
+        for (int s = 0; s < 4; ++s) if (s < n) d.IMP[(size_t)s * d.NM + i] = im[s];
+    }
 }
 
 // solve_friction, constraint_row_friction.cpp:11-54: both tangent candidates from one delta-velocity snapshot,
 // clamped to the circle of radius mu * lambda_n (lambda_n of THIS iteration).
 B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm) {
-    uint4 hd = d.hdr[i];
-    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
-    for (uint32_t s = 0; s < hd.z; ++s) {
+    const uint4 hd = d.hdr[i];
+    const uint32_t n = hd.z;
+    float4 r0[4], r1[4], r2[4], r3[4], im[4];
+    #pragma unroll
+    for (int s = 0; s < 4; ++s) if (s < n) {
         size_t ri = (size_t)s * d.NM + i;
-        float4 r0 = d.R0[ri], r1 = d.R1[ri], r2 = d.R2[ri], r3 = d.R3[ri], im = d.IMP[ri];
-        v3 n = mk3(r0), rA = mk3(r1), rB = mk3(r2);
-        v3 t, u; plane_space(n, t, u);
+        r0[s] = d.R0[ri]; r1[s] = d.R1[ri]; r2[s] = d.R2[ri]; r3[s] = d.R3[ri]; im[s] = d.IMP[ri];
+    }
+    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
+    #pragma unroll
+    for (int s = 0; s < 4; ++s) if (s < n) {
+        v3 nrm = mk3(r0[s]), rA = mk3(r1[s]), rB = mk3(r2[s]);
+        v3 t, u; plane_space(nrm, t, u);
         v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
         v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
         float d0, d1;
-        if (warm) { d0 = im.y; d1 = im.z; }
+        if (warm) { d0 = im[s].y; d1 = im[s].z; }
         else {
-            d0 = (r3.z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r3.x;
-            d1 = (r3.w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r3.y;
-            float i0 = im.y + d0, i1 = im.z + d1;
+            d0 = (r3[s].z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r3[s].x;
+            d1 = (r3[s].w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r3[s].y;
+            float i0 = im[s].y + d0, i1 = im[s].z + d1;
             float len_sqr = i0 * i0 + i1 * i1;
-            float max_len = r2.w * im.x;
+            float max_len = r2[s].w * im[s].x;
             if (len_sqr > max_len * max_len) {
                 float len = sqrtf(len_sqr);
                 if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
-                d0 = i0 - im.y; d1 = i1 - im.z;
+                d0 = i0 - im[s].y; d1 = i1 - im[s].z;
             }
-            im.y = i0; im.z = i1;
-            d.IMP[ri] = im;
+            im[s].y = i0; im[s].z = i1;
         }
         apply_imp_f(A, B, t, T1, T2, T3, d0);
         apply_imp_f(A, B, u, U1, U2, U3, d1);
     }
     vb_store(d, A); vb_store(d, B);
+    if (!warm) {
+        #pragma unroll
+        for (int s = 0; s < 4; ++s) if (s < n) d.IMP[(size_t)s * d.NM + i] = im[s];
+    }
 }
 
 // Persistent cooperative kernel: warm start + N velocity iterations (island_solver.cpp:76-111).  Inside one
@@ -783,25 +896,48 @@ B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm) {
 // pack_rows (island_solver.cpp:162-175) -- each as a sequence of colours separated by grid barriers.
 // Constraints of one colour touch disjoint dynamic bodies, so the parallel pass equals the sequential
 // Gauss-Seidel sweep in (colour, slot) order; b2d_download_solver_order() exports that order.
+B2D_D void prefetch_L2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// Pass q of one iteration: hinge colours, then contact-normal colours, then friction colours.
+struct Pass { uint32_t b, e; int kind; };     // kind 0 hinge rows, 1 contact normal rows, 2 friction pairs
+B2D_D Pass get_pass(const Counters &c, uint32_t q, uint32_t nh, uint32_t nc) {
+    Pass p;
+    if (q < nh) { p.kind = 0; p.b = c.hoff[q]; p.e = c.hoff[q + 1]; }
+    else if (q < nh + nc) { p.kind = 1; p.b = c.coff[q - nh]; p.e = c.coff[q - nh + 1]; }
+    else { p.kind = 2; p.b = c.coff[q - nh - nc]; p.e = c.coff[q - nh - nc + 1]; }
+    return p;
+}
+// Rows never change during the solve and impulses are private to the thread that owns the constraint, so the
+// next pass's row data can be pulled towards L2 while this pass drains into the barrier; only the delta
+// velocities have to be read after it.
+B2D_D void prefetch_pass(const Dev &d, const Pass &p, uint32_t gtid) {
+    uint32_t i = p.b + gtid;
+    if (i >= p.e) return;
+    if (p.kind == 0) { const float4 *R = d.HR + 7 * (size_t)i; prefetch_L2(&d.hhdr[i]); prefetch_L2(R); prefetch_L2(R + 4); return; }
+    prefetch_L2(&d.hdr[i]);
+    #pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        size_t ri = (size_t)s * d.NM + i;
+        prefetch_L2(&d.R0[ri]); prefetch_L2(&d.R1[ri]); prefetch_L2(&d.R2[ri]); prefetch_L2(&d.IMP[ri]);
+        if (p.kind == 2) prefetch_L2(&d.R3[ri]);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_solve(Dev d, int iters) {
-    cg::grid_group grid = cg::this_grid();
+    GridBarrier grid(&d.cnt->bar);
     const Counters &c = *d.cnt;
     const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    const uint32_t npass = nh + 2 * nc;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (npass == 0) return;
     for (int it = -1; it < iters; ++it) {
         const bool warm = it < 0;
-        for (uint32_t col = 0; col < nh; ++col) {
-            const uint32_t b = c.hoff[col], e = c.hoff[col + 1];
-            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) hinge_pass(d, i, warm);
-            grid.sync();
-        }
-        for (uint32_t col = 0; col < nc; ++col) {
-            const uint32_t b = c.coff[col], e = c.coff[col + 1];
-            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) normal_pass(d, i, warm);
-            grid.sync();
-        }
-        for (uint32_t col = 0; col < nc; ++col) {
-            const uint32_t b = c.coff[col], e = c.coff[col + 1];
-            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) friction_pass(d, i, warm);
+        for (uint32_t q = 0; q < npass; ++q) {
+            const Pass p = get_pass(c, q, nh, nc);
+            if (p.kind == 0) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) hinge_pass(d, i, warm); }
+            else if (p.kind == 1) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) normal_pass(d, i, warm); }
+            else { for (uint32_t i = p.b + gtid; i < p.e; i += stride) friction_pass(d, i, warm); }
+            prefetch_pass(d, get_pass(c, q + 1 == npass ? 0 : q + 1, nh, nc), gtid);
             grid.sync();
         }
     }
@@ -951,7 +1087,7 @@ B2D_D void hinge_position(const Dev &d, uint32_t i) {
 // <= N position iterations, each island stopping once its max error drops below 0.005
 // (island_solver.cpp:263-353, :538-543).  Same colouring as the velocity solve; cooperative launch.
 __global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
-    cg::grid_group grid = cg::this_grid();
+    GridBarrier grid(&d.cnt->bar);
     const Counters &c = *d.cnt;
     const uint32_t nc = c.ncolors, nh = c.nhcolors;
     GRID_STRIDE(i, d.nbodies) { d.isl_err[i] = 0; d.isl_done[i] = 0; }

@@ -37,7 +37,9 @@ struct Counters {
     uint32_t remaining[2];   // colouring loop: uncoloured constraints, double buffered per round
     uint32_t npoints;        // contact points (statistics)
     uint32_t nislands;
-    uint32_t pad;
+    uint32_t nlist;          // colouring work list length
+    uint32_t bar;            // grid barrier counter (zeroed by the host before each persistent kernel)
+    uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
     uint32_t coff[MAX_COLORS + 2];   // start of each contact colour in the sorted arrays
     uint32_t hoff[MAX_COLORS + 2];   // same for hinges
 };
@@ -81,12 +83,14 @@ struct Dev {
     float4 *pN;        // normal xyz, restitution
     float4 *pL;        // local_normal xyz, bits(att | lifetime << 2)
     float4 *pI;        // normal impulse, friction impulse[2], unused
+    unsigned char *npres;   // narrowphase: number of result points per manifold (points parked in R0/R1/R2)
 
     // ---- islands / colouring
     uint32_t *parent;
     unsigned long long *bmask, *jmask;      // colours in use per body (contacts / hinges)
     unsigned long long *prop, *jprop;
     unsigned char *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
+    uint32_t *clist;             // colouring work list (manifold slots with points)
     unsigned char *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
     uint32_t *isl_err; uint32_t *isl_done;
 
