@@ -1,0 +1,196 @@
+"""Multi-GPU sharding of one scene across the ranks of a torch.distributed group.
+
+Simulation islands are independent for narrowphase -> solve -> integrate (reference docs/Design.md:205-209,
+src/edyn/dynamics/solver.cpp:408-428), so the unit of distribution is the island: every rank owns a set of whole
+islands plus a replica of the static bodies (multi_island_resident in the reference, comp/island.hpp:39-41).  There is
+no collective on the data path.  The only exchange is the broadphase one: each step every rank publishes the bounding
+box of the dynamic bodies it owns (6 floats, all_gather); two ranks whose boxes -- inflated by the broadphase margin --
+touch could grow a cross-rank contact and therefore a cross-rank island.  That event is detected and reported
+(`ShardedWorld.step` returns the offending rank pairs); moving the smaller island to the other rank (body migration)
+is the round-2 item listed in DESIGN.md section 8.
+
+Everything here is host/plumbing code: numpy for the partitioning, torch.distributed (NCCL on GPUs, gloo in the CPU
+tests) for the exchange.  The simulation itself runs in libb2d.so.
+"""
+import numpy as np
+
+from .rigidbody import DYNAMIC, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_NONE, SHAPE_PLANE, SHAPE_SPHERE
+
+MARGIN = 0.02 * 1.3            # manifold separation threshold, broadphase.hpp:18
+
+
+def _rotation_matrices(q):
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    s = 2.0 / (x * x + y * y + z * z + w * w)
+    R = np.empty((len(q), 3, 3), np.float64)
+    R[:, 0, 0] = 1 - s * (y * y + z * z); R[:, 0, 1] = s * (x * y - w * z); R[:, 0, 2] = s * (x * z + w * y)
+    R[:, 1, 0] = s * (x * y + w * z); R[:, 1, 1] = 1 - s * (x * x + z * z); R[:, 1, 2] = s * (y * z - w * x)
+    R[:, 2, 0] = s * (x * z - w * y); R[:, 2, 1] = s * (y * z + w * x); R[:, 2, 2] = 1 - s * (x * x + y * y)
+    return R
+
+
+def host_aabbs(b, idx):
+    """AABB half extents (util/aabb_util.cpp:42-88) of bodies `idx`, on the host, for partitioning only."""
+    kind, p = b["shape_kind"][idx], b["shape_params"][idx].astype(np.float64)
+    R = np.abs(_rotation_matrices(b["orn"][idx].astype(np.float64)))
+    half = np.zeros((len(idx), 3))
+    s, c, bx = kind == SHAPE_SPHERE, kind == SHAPE_CAPSULE, kind == SHAPE_BOX
+    half[s] = p[s, 0:1]
+    if c.any():
+        ax = p[c, 2].astype(np.int64)
+        half[c] = R[c][np.arange(c.sum()), :, ax] * p[c, 1:2] + p[c, 0:1]
+    half[bx] = np.einsum("nij,nj->ni", R[bx], p[bx, :3])
+    return half
+
+
+def initial_islands(scene, reach=MARGIN):
+    """Union-find over dynamic bodies whose AABBs, inflated by `reach`, intersect, plus all joints: the simulation
+    islands the first broadphase would produce (larger `reach` = merge bodies that are merely close).
+    Returns a label per body (smallest member id; -1 for non-dynamic bodies)."""
+    b = scene["bodies"]
+    n = len(b["kind"])
+    dyn = np.where((b["kind"] == DYNAMIC))[0]
+    parent = np.arange(n)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    def union(x, y):
+        rx, ry = find(x), find(y)
+        if rx != ry:
+            if rx < ry:
+                parent[ry] = rx
+            else:
+                parent[rx] = ry
+
+    if scene.get("hinges"):
+        for x, y in zip(scene["hinges"]["a"].tolist(), scene["hinges"]["b"].tolist()):
+            union(x, y)
+    shaped = dyn[b["shape_kind"][dyn] != SHAPE_NONE]
+    if len(shaped):
+        half = host_aabbs(b, shaped)
+        pos = b["pos"][shaped].astype(np.float64)
+        size = float(2 * half.max() + reach)
+        cell = np.floor(pos / size).astype(np.int64)
+        cells = {}
+        for i in range(len(shaped)):
+            cells.setdefault(tuple(cell[i]), []).append(i)
+        for key, members in cells.items():
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for dz in (-1, 0, 1):
+                        other = cells.get((key[0] + dx, key[1] + dy, key[2] + dz))
+                        if other is None:
+                            continue
+                        oth = np.asarray(other)
+                        for i in members:
+                            hit = np.all(np.abs(pos[oth] - pos[i]) <= half[oth] + half[i] + reach, axis=1)
+                            for j in oth[hit]:
+                                if j != i:
+                                    union(int(shaped[i]), int(shaped[j]))
+    lab = np.full(n, -1, np.int64)
+    for i in dyn:
+        lab[i] = find(i)
+    return lab
+
+
+def partition(scene, world_size, labels=None):
+    """Assign whole islands to ranks: islands ordered by centroid along x, cut into `world_size` runs of roughly equal
+    body count.  Static bodies go to every rank.  Returns owner[n] (rank, or -1 = replicated)."""
+    b = scene["bodies"]
+    lab = initial_islands(scene) if labels is None else labels
+    owner = np.full(len(lab), -1, np.int64)
+    ids = np.unique(lab[lab >= 0])
+    if len(ids) == 0:
+        return owner
+    cx = np.array([b["pos"][lab == i, 0].mean() for i in ids])
+    size = np.array([(lab == i).sum() for i in ids])
+    order = np.argsort(cx, kind="stable")
+    total, acc, rank = size.sum(), 0, 0
+    for k in order:
+        # move to the next rank once this one holds its share (never leave a later rank empty if islands remain)
+        if acc >= (rank + 1) * total / world_size and rank < world_size - 1:
+            rank += 1
+        owner[lab == ids[k]] = rank
+        acc += size[k]
+    return owner
+
+
+def shard(scene, rank, world_size, owner=None):
+    """The sub-scene rank `rank` simulates: its islands + replicated static bodies, hinges and exclusions remapped."""
+    b = scene["bodies"]
+    owner = partition(scene, world_size) if owner is None else owner
+    keep = np.where((owner == rank) | (owner < 0))[0]
+    remap = np.full(len(owner), -1, np.int64)
+    remap[keep] = np.arange(len(keep))
+    out = {k: (v[keep] if v is not None else None) for k, v in b.items()}
+    hinges = None
+    if scene.get("hinges"):
+        h = scene["hinges"]
+        sel = (owner[h["a"]] == rank)
+        hinges = {k: (remap[v[sel]].astype(np.uint32) if k in ("a", "b") else v[sel]) for k, v in h.items()}
+    excl = None
+    if scene.get("exclusions") is not None:
+        ea, eb = scene["exclusions"]
+        sel = (remap[ea] >= 0) & (remap[eb] >= 0)
+        excl = (remap[ea[sel]].astype(np.uint32), remap[eb[sel]].astype(np.uint32))
+    dyn = int(((owner == rank)).sum())
+    return dict(name=f"{scene['name']}@{rank}/{world_size}", bodies=out, hinges=hinges if hinges and len(hinges["a"]) else None,
+                exclusions=excl if excl is not None and len(excl[0]) else None, settings=scene["settings"], dynamic=dyn,
+                global_ids=keep)
+
+
+def overlapping_ranks(bounds, margin=MARGIN):
+    """bounds: (world_size, 6) array of min/max of each rank's dynamic bodies (NaN rows = rank owns nothing).
+    Returns the list of rank pairs whose boxes, inflated by `margin`, intersect."""
+    out = []
+    n = len(bounds)
+    for i in range(n):
+        for j in range(i + 1, n):
+            a, b = bounds[i], bounds[j]
+            if np.isnan(a).any() or np.isnan(b).any():
+                continue
+            if np.all(a[0:3] - margin <= b[3:6]) and np.all(a[3:6] + margin >= b[0:3]):
+                out.append((i, j))
+    return out
+
+
+class ShardedWorld:
+    """One rank's share of a scene + the per-step bounds exchange.  `dist` is torch.distributed (initialised) or None."""
+
+    def __init__(self, scene, rank, world_size, dist=None, device=0, **kw):
+        from .scenes import build_world
+        self.rank, self.world_size, self.dist = rank, world_size, dist
+        self.owner = partition(scene, world_size)
+        self.local = shard(scene, rank, world_size, self.owner)
+        self.world = build_world(self.local, device=device, **kw)
+        self.dynamic_local = np.where(self.local["bodies"]["kind"] == DYNAMIC)[0]
+
+    def local_bounds(self, aabb):
+        if len(self.dynamic_local) == 0:
+            return np.full(6, np.nan, np.float32)
+        a = aabb[self.dynamic_local]
+        return np.concatenate([a[:, 0:3].min(axis=0), a[:, 3:6].max(axis=0)]).astype(np.float32)
+
+    def exchange_bounds(self, bounds):
+        """all_gather of 6 floats per rank (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+        if self.dist is None or self.world_size == 1:
+            return bounds[None, :]
+        import torch
+        dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+        mine = torch.from_numpy(bounds.copy()).to(dev)
+        out = [torch.empty_like(mine) for _ in range(self.world_size)]
+        self.dist.all_gather(out, mine)
+        return torch.stack(out).cpu().numpy()
+
+    def step(self, n=1, check=True):
+        """n fixed steps on this rank's islands, then the cross-rank AABB exchange.  Returns the rank pairs whose
+        island groups came within the broadphase margin of each other (empty list = shards still independent)."""
+        self.world.step(n)
+        if not check:
+            return []
+        st = self.world.download_state(aabb=True)
+        return overlapping_ranks(self.exchange_bounds(self.local_bounds(st["aabb"])))

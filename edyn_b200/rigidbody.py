@@ -81,9 +81,13 @@ def moment_of_inertia(shape: Shape, mass) -> np.ndarray:
         cxx = f32(0.5) * cyl_mass * r * r
         cyz = f32(1) / f32(12) * cyl_mass * (f32(3) * r * r + length * length)
         sph_i = f32(0.4) * sph_mass * r * r
-        xx = sph_i + cxx
+        # the reference reads .x / .y of the cylinder inertia AFTER its own axis permutation
+        # (moment_of_inertia.cpp:27-44, :76-77); mirrored so the staged inertia_inv matches make_rigidbody
+        cyl = [cyz, cyz, cyz]
+        cyl[axis] = cxx
+        xx = sph_i + cyl[0]
         t = f32(4) * length + f32(3) * r
-        yy = sph_i + sph_mass * (t * t) / f32(64) + cyz
+        yy = sph_i + sph_mass * (t * t) / f32(64) + cyl[1]
         d = [yy, yy, yy]
         d[axis] = xx
         return np.diag(d).astype(f32)

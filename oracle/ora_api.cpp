@@ -181,7 +181,29 @@ void ora_set_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32_t nm,
 }
 void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; }
 
+int ora_should_collide(void *h, uint32_t a, uint32_t b) { return static_cast<World *>(h)->should_collide(a, b) ? 1 : 0; }
+
 // ------------------------------------------------------------------ pure functions (pinned against oracle/_ref)
+
+// The five Jacobians hinge_constraint::prepare builds (hinge_constraint.cpp:26-69), same layout as ref_hinge_rows.
+int ora_hinge_rows(const float *pivotA, const float *pivotB, const float *axisA, const float *axisB,
+                   const float *posA, const float *ornA, const float *posB, const float *ornB, float *J60) {
+    vec3 p, q;
+    plane_space(v3(axisA), p, q);
+    mat3 frameA = mat3_columns(v3(axisA), p, q);
+    vec3 pA = v3(posA), pB = v3(posB); quat qA = q4(ornA), qB = q4(ornB);
+    vec3 pivA = to_world(v3(pivotA), pA, qA), pivB = to_world(v3(pivotB), pB, qB);
+    vec3 rA = pivA - pA, rB = pivB - pB;
+    mat3 sA = {{{0, -rA.z, rA.y}, {rA.z, 0, -rA.x}, {-rA.y, rA.x, 0}}};
+    mat3 sB = {{{0, -rB.z, rB.y}, {rB.z, 0, -rB.x}, {-rB.y, rB.x, 0}}};
+    const vec3 I[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) { put3(J60 + i * 12, I[i]); put3(J60 + i * 12 + 3, -sA.row[i]); put3(J60 + i * 12 + 6, -I[i]); put3(J60 + i * 12 + 9, sB.row[i]); }
+    vec3 pq[2] = {rotate(qA, frameA.column(1)), rotate(qA, frameA.column(2))};
+    for (int i = 0; i < 2; ++i) { put3(J60 + (3 + i) * 12, vec3{0, 0, 0}); put3(J60 + (3 + i) * 12 + 3, pq[i]); put3(J60 + (3 + i) * 12 + 6, vec3{0, 0, 0}); put3(J60 + (3 + i) * 12 + 9, -pq[i]); }
+    (void)axisB;
+    return 5;
+}
+
 
 // out: per point 10 floats (pivotA, pivotB, normal, distance) + att.  Returns the number of points.
 int ora_collide(uint32_t kindA, const float *pA, uint32_t kindB, const float *pB, const float *posA, const float *ornA,

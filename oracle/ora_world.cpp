@@ -51,9 +51,12 @@ mat3 moment_of_inertia(const shape &sh, scalar mass) {
         scalar sph_mass = mass * sph_vol / total;
         scalar cxx = scalar(0.5) * cyl_mass * radius * radius;
         scalar cyz = scalar(1) / scalar(12) * cyl_mass * (scalar(3) * radius * radius + len * len);
+        // moment_of_inertia_solid_cylinder already permutes by axis (:27-44); the capsule code then reads .x/.y of
+        // that permuted vector (:76-77), which is kept as is for axis != x.
+        vec3 cyl{cyz, cyz, cyz}; cyl[axis] = cxx;
         scalar sph_i = scalar(0.4) * sph_mass * radius * radius;
-        scalar xx = sph_i + cxx;
-        scalar yy_zz = sph_i + sph_mass * square(scalar(4) * len + scalar(3) * radius) / scalar(64) + cyz;
+        scalar xx = sph_i + cyl.x;
+        scalar yy_zz = sph_i + sph_mass * square(scalar(4) * len + scalar(3) * radius) / scalar(64) + cyl.y;
         vec3 v{yy_zz, yy_zz, yy_zz}; v[axis] = xx;
         return diag(v);
     }
@@ -458,6 +461,7 @@ static void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scal
 
 void World::solve() {
     const uint32_t nb = uint32_t(bodies.size());
+    if (island.size() != bodies.size()) islands();
     // apply_gravity, sys/apply_gravity.hpp:12-17
     for (Body &b : bodies) if (b.kind == BK_DYNAMIC) b.linvel += b.gravity * dt;
 

@@ -169,12 +169,14 @@ def ref_fns():
     return PureFns(r, "ref_") if r is not None else None
 
 
-def ref_hinge_rows(pivotA, pivotB, axisA, axisB, posA, ornA, posB, ornB):
-    r = ref()
+def hinge_rows(which, pivotA, pivotB, axisA, axisB, posA, ornA, posB, ornB):
+    """which = 'ora' (restatement) or 'ref' (real reference): the 5 hinge Jacobians as (5, 4, 3)."""
+    dll = lib() if which == "ora" else ref()
+    fn = getattr(dll, which + "_hinge_rows")
     J = np.zeros(60, _f)
     a = [_arr(x, _f) for x in (pivotA, pivotB, axisA, axisB, posA, ornA, posB, ornB)]
-    r.ref_hinge_rows.restype = C.c_int
-    n = r.ref_hinge_rows(*[_ptr(x) for x in a], _ptr(J))
+    fn.restype = C.c_int
+    n = fn(*[_ptr(x) for x in a], _ptr(J))
     return n, J.reshape(5, 4, 3)
 
 
@@ -274,6 +276,10 @@ class OracleWorld:
         lab = np.zeros(self.num_bodies, _u)
         self.l.ora_get_islands(self.h, _ptr(lab))
         return lab
+
+    def should_collide(self, a, b):
+        self.l.ora_should_collide.restype = C.c_int
+        return bool(self.l.ora_should_collide(self.h, C.c_uint32(a), C.c_uint32(b)))
 
     def set_order(self, hinge_idx, pairs):
         h = _arr(hinge_idx, _u)

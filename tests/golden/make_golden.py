@@ -1,0 +1,158 @@
+"""Generates tests/golden/*.npz from the REAL reference functions (oracle/_ref/libedyn_ref.so, compiled in place
+from /root/reference by oracle/Makefile).  /root/reference does not exist on the GPU box, so the vectors are
+committed; re-run this script here to regenerate them:
+
+    python tests/golden/make_golden.py
+
+Every file holds seeded random inputs plus the reference's outputs for one function of the hot path.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+f32 = np.float32
+SPHERE, CAPSULE, BOX, PLANE = 0, 2, 3, 6
+
+
+def rq(rng):
+    q = rng.normal(size=4)
+    return (q / np.linalg.norm(q)).astype(f32)
+
+
+def shape_params(kind, rng):
+    if kind == SPHERE:
+        return np.array([0.2 + 0.25 * rng.random(), 0, 0, 0], f32)
+    if kind == CAPSULE:
+        return np.array([0.1 + 0.1 * rng.random(), 0.15 + 0.25 * rng.random(), float(rng.integers(3)), 0], f32)
+    if kind == BOX:
+        return np.concatenate([0.15 + 0.35 * rng.random(3), [0]]).astype(f32)
+    n = rng.normal(size=3) if rng.random() < 0.3 else np.array([0, 1, 0])
+    n = n / np.linalg.norm(n)
+    return np.array([n[0], n[1], n[2], 0.1 * rng.normal()], f32)
+
+
+def collide_cases(rng, count):
+    pairs = [(SPHERE, SPHERE), (SPHERE, PLANE), (BOX, PLANE), (CAPSULE, PLANE), (SPHERE, BOX), (CAPSULE, CAPSULE),
+             (CAPSULE, SPHERE), (CAPSULE, BOX), (BOX, BOX), (PLANE, SPHERE), (BOX, SPHERE), (BOX, CAPSULE),
+             (SPHERE, CAPSULE), (PLANE, BOX), (PLANE, CAPSULE)]
+    out = []
+    ident = np.array([0, 0, 0, 1], f32)
+    for ka, kb in pairs:
+        for it in range(count):
+            pA, pB = shape_params(ka, rng), shape_params(kb, rng)
+            posA, posB = (rng.random(3) * 0.8).astype(f32), (rng.random(3) * 0.8).astype(f32)
+            qa, qb = rq(rng), rq(rng)
+            if kb == PLANE:
+                posB, qb = np.zeros(3, f32), ident
+                posA = (pB[:3] * (pB[3] + 0.5 * rng.random()) + 0.3 * rng.normal(size=3) * (1 - np.abs(pB[:3]))).astype(f32)
+            if ka == PLANE:
+                posA, qa = np.zeros(3, f32), ident
+                posB = (pA[:3] * (pA[3] + 0.5 * rng.random()) + 0.3 * rng.normal(size=3) * (1 - np.abs(pA[:3]))).astype(f32)
+            if it % 3 == 0 and kb == BOX and ka in (BOX, CAPSULE):        # stacked / parallel: face-face, 4 points
+                qa = ident
+                qb = ident if it % 2 else rq(rng)
+                hA = pA[1] if ka == BOX else pA[0]
+                if ka == CAPSULE:
+                    pA[2] = 0.0
+                posB = (posA + np.array([0.1 * rng.random(), -(hA + pB[1]) + 0.005 * rng.normal(), 0.1 * rng.random()])).astype(f32)
+            if it % 3 == 1 and ka == CAPSULE and kb == CAPSULE:           # parallel capsules: 2 points
+                pA[2] = pB[2] = 0.0
+                qa = qb = ident
+                posB = (posA + np.array([0.2 * rng.normal(), pA[0] + pB[0] + 0.005 * rng.normal(), 0])).astype(f32)
+            out.append((ka, pA, kb, pB, posA, qa, posB, qb))
+    return out
+
+
+def main():
+    r = O.ref_fns()
+    if r is None:
+        raise SystemExit("oracle/_ref/libedyn_ref.so missing: run `make -C oracle` where /root/reference exists")
+    rng = np.random.default_rng(20260922)
+
+    # ---- collide(): 15 ordered shape pairs
+    cases = collide_cases(rng, 160)
+    n = len(cases)
+    kinds = np.zeros((n, 2), np.uint32)
+    params = np.zeros((n, 2, 4), f32)
+    poses = np.zeros((n, 2, 3), f32)
+    orns = np.zeros((n, 2, 4), f32)
+    num = np.zeros(n, np.uint32)
+    pts = np.zeros((n, 4, 10), f32)
+    att = np.zeros((n, 4), np.uint32)
+    for i, (ka, pA, kb, pB, posA, qa, posB, qb) in enumerate(cases):
+        kinds[i] = (ka, kb); params[i, 0], params[i, 1] = pA, pB
+        poses[i, 0], poses[i, 1] = posA, posB; orns[i, 0], orns[i, 1] = qa, qb
+        p, a = r.collide(ka, pA, kb, pB, posA, qa, posB, qb)
+        num[i] = len(p); pts[i, :len(p)] = p; att[i, :len(p)] = a
+    np.savez_compressed(os.path.join(HERE, "collide.npz"), kinds=kinds, params=params, pos=poses, orn=orns, num=num, pts=pts, att=att)
+    print("collide.npz:", n, "cases, point histogram", np.bincount(num, minlength=5).tolist())
+
+    # ---- shape AABBs
+    m = 600
+    k = rng.choice([SPHERE, CAPSULE, BOX], size=m).astype(np.uint32)
+    sp = np.stack([shape_params(int(x), rng) for x in k])
+    pos = rng.normal(size=(m, 3)).astype(f32) * 3
+    orn = np.stack([rq(rng) for _ in range(m)])
+    bb = np.stack([r.shape_aabb(int(k[i]), sp[i], pos[i], orn[i]) for i in range(m)])
+    planes = np.array([[0, 1, 0, 0], [1, 0, 0, -0.5], [-1, 0, 0, -35.5], [0, 0, 1, 0.25], [0, 0, -1, 2], [0, -1, 0, 1],
+                       [0.6, 0.8, 0, 0.3]], f32)
+    pbb = np.stack([r.shape_aabb(PLANE, p, [0, 0, 0], [0, 0, 0, 1]) for p in planes])
+    np.savez_compressed(os.path.join(HERE, "aabb.npz"), kind=k, params=sp, pos=pos, orn=orn, aabb=bb, planes=planes, plane_aabb=pbb)
+
+    # ---- quaternion integrate (both branches), world inertia, moment of inertia
+    q = np.stack([rq(rng) for _ in range(m)])
+    w = rng.normal(size=(m, 3)).astype(f32) * 4
+    w[: m // 6] *= f32(1e-4)                                           # Taylor branch (|w| < 1e-3)
+    dts = np.where(rng.random(m) < 0.5, 1.0 / 60, -1.0 / 60).astype(f32)
+    qo = np.stack([r.integrate(q[i], w[i], float(dts[i])) for i in range(m)])
+    invI = np.zeros((m, 9), f32)
+    moi = np.zeros((m, 9), f32)
+    mass = (0.5 + 10 * rng.random(m)).astype(f32)
+    for i in range(m):
+        I = r.moment_of_inertia(int(k[i]), sp[i], float(mass[i]))
+        moi[i] = I.reshape(9)
+        invI[i] = r.inverse_symmetric(I).reshape(9)
+    iw = np.stack([r.world_inertia(q[i], invI[i]).reshape(9) for i in range(m)])
+    np.savez_compressed(os.path.join(HERE, "body_math.npz"), q=q, w=w, dt=dts, q_out=qo, kind=k, params=sp, mass=mass, moi=moi,
+                        inv_inertia=invI, inv_inertia_world=iw)
+
+    # ---- constraint rows: prepare_row / solve (constraint_row.cpp), plane_space, hinge Jacobians
+    J = rng.normal(size=(m, 12)).astype(f32)
+    IA = np.stack([np.diag(1 + rng.random(3)).reshape(9) for _ in range(m)]).astype(f32)
+    IB = np.stack([np.diag(1 + rng.random(3)).reshape(9) for _ in range(m)]).astype(f32)
+    mA, mB = rng.random(m).astype(f32), rng.random(m).astype(f32)
+    mB[::5] = 0; IB[::5] = 0                                          # static second body
+    err, rest = rng.normal(size=m).astype(f32) * 0.1, (rng.random(m) * 0.5).astype(f32)
+    vel = rng.normal(size=(m, 12)).astype(f32)
+    prep = np.stack([r.prepare_row(J[i], mA[i], IA[i], mB[i], IB[i], err[i], 0.2, rest[i], vel[i]) for i in range(m)])
+    row5 = np.stack([prep[:, 0], prep[:, 1], np.where(rng.random(m) < 0.5, 0, -1e30).astype(f32),
+                     np.where(rng.random(m) < 0.5, 1e18, 0.05).astype(f32), (rng.normal(size=m) * 0.1).astype(f32)], axis=1).astype(f32)
+    dv = rng.normal(size=(m, 12)).astype(f32) * 0.3
+    sol = [r.solve_row(J[i], row5[i], dv[i]) for i in range(m)]
+    delta = np.array([s[0] for s in sol], f32)
+    imp = np.array([s[1][4] for s in sol], f32)
+    nrm = np.stack([x / np.linalg.norm(x) for x in rng.normal(size=(m, 3))]).astype(f32)
+    ps = np.stack([np.concatenate(r.plane_space(nrm[i])) for i in range(m)])
+    hin = np.zeros((100, 5, 4, 3), f32)
+    hpar = np.zeros((100, 26), f32)
+    for i in range(100):
+        piv = rng.normal(size=6).astype(f32) * 0.4
+        axA = nrm[i]; axB = nrm[i + 100]
+        pa, pb = rng.normal(size=3).astype(f32), rng.normal(size=3).astype(f32)
+        qa, qb = rq(rng), rq(rng)
+        hpar[i] = np.concatenate([piv, axA, axB, pa, qa, pb, qb])
+        _, hin[i] = O.hinge_rows("ref", piv[:3], piv[3:], axA, axB, pa, qa, pb, qb)
+    np.savez_compressed(os.path.join(HERE, "rows.npz"), J=J, inv_mA=mA, inv_IA=IA, inv_mB=mB, inv_IB=IB, error=err, restitution=rest,
+                        vel=vel, prepared=prep, row5=row5, dv=dv, delta=delta, impulse=imp, normal=nrm, plane_space=ps,
+                        hinge_params=hpar, hinge_J=hin)
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()

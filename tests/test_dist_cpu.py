@@ -1,0 +1,109 @@
+"""The N > 1 path on CPU: island-aware partitioning, sub-scene extraction and the per-step bounds exchange, with a real
+two-process torch.distributed group on the gloo backend (127.0.0.1)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+f32 = np.float32
+
+
+def test_partition_keeps_islands_whole(E):
+    from edyn_b200 import dist
+    scene = E.scenes.hinge_chains(6, 4)
+    lab = dist.initial_islands(scene)
+    n = scene["dynamic"]
+    chains = lab[:n].reshape(-1, 4)
+    assert (chains == chains[:, :1]).all(), "a chain is one island"
+    assert len(np.unique(chains[:, 0])) == 24
+    for ws in (2, 3, 4):
+        owner = dist.partition(scene, ws, lab)
+        assert (owner[n:] == -1).all(), "static bodies are replicated"
+        assert set(np.unique(owner[:n])) == set(range(ws))
+        o = owner[:n].reshape(-1, 4)
+        assert (o == o[:, :1]).all(), "an island never straddles two ranks"
+        counts = np.bincount(owner[:n], minlength=ws)
+        assert counts.max() - counts.min() <= 8
+        parts = [dist.shard(scene, r, ws, owner) for r in range(ws)]
+        assert sum(p["dynamic"] for p in parts) == n
+        gids = np.concatenate([p["global_ids"][p["bodies"]["kind"] == 0] for p in parts])
+        assert len(np.unique(gids)) == n, "every dynamic body is owned by exactly one rank"
+        for p in parts:
+            h = p["hinges"]
+            assert h is not None and (h["b"] - h["a"] == 1).all() and h["b"].max() < len(p["bodies"]["kind"])
+            assert len(h["a"]) == 3 * p["dynamic"] // 4
+            ea, eb = p["exclusions"]
+            assert len(ea) == len(h["a"])
+
+
+def test_initial_islands_follow_aabb_proximity(E):
+    from edyn_b200 import dist
+    scene = E.scenes.boxes_on_plane(3)          # 27 unit boxes at 1.1 pitch
+    lab = dist.initial_islands(scene)
+    n = scene["dynamic"]
+    assert len(np.unique(lab[:n])) == 27        # 0.1 gaps in every direction at t = 0: nothing within the 0.026 margin
+    lab = dist.initial_islands(scene, reach=0.25)
+    assert len(np.unique(lab[:n])) == 1
+
+
+def test_overlapping_ranks():
+    from edyn_b200 import dist
+    b = np.array([[0, 0, 0, 1, 1, 1], [1.01, 0, 0, 2, 1, 1], [5, 5, 5, 6, 6, 6], [np.nan] * 6], f32)
+    assert dist.overlapping_ranks(b) == [(0, 1)]
+    assert dist.overlapping_ranks(b, margin=0.001) == []
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, q):
+    import torch.distributed as dist_mod
+    import edyn_b200 as E
+    from edyn_b200 import dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist_mod.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scene = E.scenes.hinge_chains(4, 2)
+        owner = dist.partition(scene, world_size)
+        local = dist.shard(scene, rank, world_size, owner)
+        # stand-in for ShardedWorld without a GPU: same exchange code path, bounds computed from the initial positions
+        sw = dist.ShardedWorld.__new__(dist.ShardedWorld)
+        sw.rank, sw.world_size, sw.dist, sw.local = rank, world_size, dist_mod, local
+        sw.dynamic_local = np.where(local["bodies"]["kind"] == 0)[0]
+        pos = local["bodies"]["pos"]
+        aabb = np.concatenate([pos - 0.35, pos + 0.35], axis=1).astype(f32)
+        far = sw.exchange_bounds(sw.local_bounds(aabb))
+        hits_far = dist.overlapping_ranks(far)
+        # now pretend rank 1's islands drifted into rank 0's region
+        if rank == 1:
+            aabb[:, [0, 3]] -= aabb[sw.dynamic_local][:, 0].min() - 1.0
+        near = sw.exchange_bounds(sw.local_bounds(aabb))
+        q.put((rank, local["dynamic"], far.tolist(), hits_far, dist.overlapping_ranks(near)))
+    finally:
+        dist_mod.destroy_process_group()
+
+
+def test_bounds_exchange_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, n0, far0, hf0, hn0), (r1, n1, far1, hf1, hn1) = res
+    assert n0 + n1 == 32 and n0 == n1 == 16
+    assert far0 == far1, "all ranks see the same gathered bounds"
+    assert hf0 == hf1 == [], "disjoint shards: no cross-rank overlap"
+    assert hn0 == hn1 == [(0, 1)], "the drifted shard is detected on every rank"

@@ -1,0 +1,127 @@
+"""CPU-only checks of the boundary and the host logic: the C-ABI library loads and exports every symbol include/b2d.h
+declares, the product fails loudly without a GPU (no CPU fallback, no oracle import), scene generators and the
+make_rigidbody mirror produce what the reference would stage."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "b2d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2d_[a-z_]+)\s*\(", text)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from edyn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b2d.h but not exported by libb2d.so"
+    assert set(_lib.EXPORTS) == set(names), set(_lib.EXPORTS) ^ set(names)
+
+
+def test_abi_signatures_use_plain_c_types_only():
+    text = open(os.path.join(ROOT, "include", "b2d.h")).read()
+    assert "torch" not in text and "std::" not in text and "#include <stdint.h>" in text
+    assert 'extern "C"' in text
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device b2d_create must fail with a message; the Python adapter raises."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import edyn_b200 as E
+    with pytest.raises(E.B2DError, match="CUDA"):
+        E.World(16)
+
+
+def test_product_never_imports_the_oracle():
+    code = "import sys; import edyn_b200, edyn_b200.dist, edyn_b200.scenes; " \
+           "bad=[m for m in sys.modules if m.split('.')[0]=='oracle']; print(bad); sys.exit(1 if bad else 0)"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "edyn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_make_rigidbody_mirror(E, O):
+    """Component values staged for a dynamic box / sphere / capsule equal the oracle's (which is pinned to the reference)."""
+    o = O.ora_fns()
+    defs = [E.RigidBodyDef(shape=E.box_shape((0.5, 0.25, 0.125)), mass=3.0),
+            E.RigidBodyDef(shape=E.sphere_shape(0.3), mass=2.0),
+            E.RigidBodyDef(shape=E.capsule_shape(0.1, 0.25, 2), mass=1.5),
+            E.RigidBodyDef(kind=E.STATIC, shape=E.plane_shape((0, 1, 0), 0.0))]
+    soa = E.bodies_soa(defs)
+    for i, d in enumerate(defs[:3]):
+        I = o.moment_of_inertia(d.shape.kind, np.array(d.shape.params, f32), d.mass)
+        assert np.array_equal(soa["inv_inertia"][i].reshape(3, 3), o.inverse_symmetric(I))
+        assert soa["inv_mass"][i] == f32(1) / f32(d.mass)
+        assert np.array_equal(soa["gravity"][i], np.array([0, -9.8, 0], f32))
+    assert soa["inv_mass"][3] == 0 and not soa["gravity"][3].any() and soa["kind"][3] == E.STATIC
+
+
+def test_scene_generators(E):
+    s = E.scenes.boxes_on_plane(16)
+    assert s["dynamic"] == 4096 and len(s["bodies"]["kind"]) == 4097 and s["settings"]["velocity_iterations"] == 10
+    s = E.scenes.spheres_in_box(8, 2, 8)
+    assert s["dynamic"] == 128 and (s["bodies"]["kind"] == 2).sum() == 5
+    s = E.scenes.mixed_pile(6)
+    k = s["bodies"]["shape_kind"][:216]
+    assert set(np.unique(k)) == {0, 2, 3} and s["settings"]["velocity_iterations"] == 20
+    assert np.allclose(np.linalg.norm(s["bodies"]["orn"], axis=1), 1, atol=1e-6)
+    a = E.scenes.mixed_pile(6)["bodies"]["orn"]
+    assert np.array_equal(a, s["bodies"]["orn"]), "scene generation must be deterministic"
+    s = E.scenes.hinge_chains(3, 2)
+    assert s["dynamic"] == 24 and len(s["hinges"]["a"]) == 18 and len(s["exclusions"][0]) == 18
+    assert (s["hinges"]["b"] - s["hinges"]["a"] == 1).all()
+
+
+def test_oracle_is_deterministic_and_thread_count_independent(E, O):
+    scene = E.scenes.mixed_pile(5)
+
+    def run(threads):
+        w = O.OracleWorld(vel_iters=20, pos_iters=3, threads=threads)
+        w.add_bodies(scene["bodies"])
+        w.step(50)
+        return w.state()
+
+    a, b, c = run(1), run(1), run(4)
+    for k in ("pos", "orn", "linvel", "angvel"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+
+
+def test_oracle_injected_order_is_a_pure_permutation(E, O):
+    """Replaying the natural order through ora_set_order must not change anything (guards the order-injection path the
+    GPU parity tests rely on)."""
+    scene = E.scenes.boxes_on_plane(3, jitter=0.01)
+    a = O.OracleWorld(vel_iters=10, pos_iters=3); a.add_bodies(scene["bodies"])
+    b = O.OracleWorld(vel_iters=10, pos_iters=3); b.add_bodies(scene["bodies"])
+    for _ in range(80):
+        a.step(1)
+        b.run_phases(O.PH_BROAD | O.PH_NARROW | O.PH_ISLANDS)
+        c = b.contacts()
+        active = c["pairs"][c["num"] > 0][::-1]                 # natural order: newest manifold first
+        b.set_order([], active)
+        b.run_phases(O.PH_SOLVE)
+    sa, sb = a.state(), b.state()
+    for k in ("pos", "orn", "linvel", "angvel"):
+        assert np.array_equal(sa[k], sb[k]), k

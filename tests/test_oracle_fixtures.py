@@ -1,0 +1,112 @@
+"""CPU: the oracle restatement (and the product's host-side inertia code) against the committed golden vectors
+generated from the real reference functions (tests/golden/make_golden.py), and -- where oracle/_ref is present --
+against the reference library itself on fresh random inputs.  Integer/bit-level work must match exactly."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+f32 = np.float32
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_collide_matches_reference_vectors(O):
+    g = load("collide.npz")
+    o = O.ora_fns()
+    for i in range(len(g["num"])):
+        pts, att = o.collide(int(g["kinds"][i, 0]), g["params"][i, 0], int(g["kinds"][i, 1]), g["params"][i, 1],
+                             g["pos"][i, 0], g["orn"][i, 0], g["pos"][i, 1], g["orn"][i, 1])
+        n = int(g["num"][i])
+        assert len(pts) == n, f"case {i}: {len(pts)} points, reference {n}"
+        assert np.array_equal(pts, g["pts"][i, :n]), f"case {i} differs"
+        assert np.array_equal(att, g["att"][i, :n])
+
+
+def test_shape_aabb_matches_reference_vectors(O):
+    g = load("aabb.npz")
+    o = O.ora_fns()
+    for i in range(len(g["kind"])):
+        assert np.array_equal(o.shape_aabb(int(g["kind"][i]), g["params"][i], g["pos"][i], g["orn"][i]), g["aabb"][i])
+    for p, bb in zip(g["planes"], g["plane_aabb"]):
+        assert np.array_equal(o.shape_aabb(6, p, [0, 0, 0], [0, 0, 0, 1]), bb)
+
+
+def test_body_math_matches_reference_vectors(O, E):
+    g = load("body_math.npz")
+    o = O.ora_fns()
+    from edyn_b200 import rigidbody as rb
+    for i in range(len(g["q"])):
+        assert np.array_equal(o.integrate(g["q"][i], g["w"][i], float(g["dt"][i])), g["q_out"][i])
+        I = o.moment_of_inertia(int(g["kind"][i]), g["params"][i], float(g["mass"][i]))
+        assert np.array_equal(I.reshape(9), g["moi"][i])
+        assert np.array_equal(o.inverse_symmetric(I).reshape(9), g["inv_inertia"][i])
+        assert np.array_equal(o.world_inertia(g["q"][i], g["inv_inertia"][i]).reshape(9), g["inv_inertia_world"][i])
+        # the product's host adapter (make_rigidbody mirror) must stage the same inertia_inv
+        Ih = rb.moment_of_inertia(rb.Shape(int(g["kind"][i]), tuple(g["params"][i])), g["mass"][i])
+        assert np.array_equal(Ih.reshape(9), g["moi"][i]), f"host moment_of_inertia differs at {i}"
+        assert np.array_equal(rb.inverse_matrix_symmetric(Ih).reshape(9), g["inv_inertia"][i])
+
+
+def test_rows_match_reference_vectors(O):
+    g = load("rows.npz")
+    o = O.ora_fns()
+    for i in range(len(g["J"])):
+        out = o.prepare_row(g["J"][i], g["inv_mA"][i], g["inv_IA"][i], g["inv_mB"][i], g["inv_IB"][i], g["error"][i], 0.2,
+                            g["restitution"][i], g["vel"][i])
+        assert np.array_equal(out, g["prepared"][i])
+        d, r = o.solve_row(g["J"][i], g["row5"][i], g["dv"][i])
+        assert d == g["delta"][i] and r[4] == g["impulse"][i]
+        p, q = o.plane_space(g["normal"][i])
+        assert np.array_equal(np.concatenate([p, q]), g["plane_space"][i])
+    for i in range(len(g["hinge_J"])):
+        h = g["hinge_params"][i]
+        n, J = O.hinge_rows("ora", h[0:3], h[3:6], h[6:9], h[9:12], h[12:15], h[15:19], h[19:22], h[22:26])
+        assert n == 5 and np.array_equal(J, g["hinge_J"][i])
+
+
+def _rq(rng):
+    q = rng.normal(size=4)
+    return (q / np.linalg.norm(q)).astype(f32)
+
+
+def test_random_against_reference_library(O, ref):
+    """Fresh random inputs each run of the suite (seeded): restatement == reference, bit for bit."""
+    o = O.ora_fns()
+    rng = np.random.default_rng(7)
+    kinds = [0, 2, 3]
+    from tests.golden.make_golden import shape_params
+    for it in range(1500):
+        ka, kb = int(rng.choice(kinds)), int(rng.choice(kinds + [6]))
+        pA, pB = shape_params(ka, rng), shape_params(kb, rng)
+        posA, posB = (rng.random(3) * 0.7).astype(f32), (rng.random(3) * 0.7).astype(f32)
+        qa, qb = _rq(rng), _rq(rng)
+        if kb == 6:
+            posB, qb = np.zeros(3, f32), np.array([0, 0, 0, 1], f32)
+        a, b = o.collide(ka, pA, kb, pB, posA, qa, posB, qb), ref.collide(ka, pA, kb, pB, posA, qa, posB, qb)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (ka, kb, it)
+        a, b = o.collide(kb, pB, ka, pA, posB, qb, posA, qa), ref.collide(kb, pB, ka, pA, posB, qb, posA, qa)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (kb, ka, it)
+    for it in range(500):
+        p1, q1, p2, q2 = [rng.normal(size=3).astype(f32) for _ in range(4)]
+        if it % 4 == 0:
+            q2 = (p2 + (q1 - p1) * f32(rng.random() + 0.2)).astype(f32)          # parallel segments
+        a, b = o.closest_segment_segment(p1, q1, p2, q2), ref.closest_segment_segment(p1, q1, p2, q2)
+        assert a[0] == b[0] and a[2] == b[2]
+        k = 8 if b[0] < 2 else 16
+        assert np.array_equal(a[1][:k], b[1][:k])
+        pa = (rng.normal(size=(6, 3)) * 0.3).astype(f32)
+        pb = (rng.normal(size=(6, 3)) * 0.3).astype(f32)
+        if it % 3 == 0:
+            pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
+        a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_golden_generator_is_committed():
+    assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz"):
+        assert os.path.exists(os.path.join(GOLD, f))
