@@ -522,7 +522,14 @@ __global__ void k_cc_union(Dev d) {
 }
 __global__ void k_cc_flatten(Dev d) {
     GRID_STRIDE(i, d.nbodies) {
-        if (is_dynamic(d.flags[i])) { uint32_t r = cc_find(d.parent, i); d.parent[i] = r; if (r == i) atomicAdd(&d.cnt->nislands, 1u); }
+        if (is_dynamic(d.flags[i])) {
+            // read-only walk: a concurrent path-compressing find could overwrite another thread's final root with a
+            // stale grandparent; writing the root itself is harmless to walkers passing through i
+            uint32_t r = i, p = d.parent[r];
+            while (p != r) { r = p; p = d.parent[r]; }
+            d.parent[i] = r;
+            if (r == i) atomicAdd(&d.cnt->nislands, 1u);
+        }
         else d.parent[i] = 0xFFFFFFFFu;
     }
 }
