@@ -167,19 +167,44 @@ def run_device(args):
 
     scene = make_scene(args.workload, args.scale)
     n_dyn = scene["dynamic"]
+    if world_size > 1:
+        # weak scaling: rank r owns an island group of the same size, placed side by side along x
+        b = scene["bodies"]
+        p = b["pos"][b["kind"] == 0]
+        stride_x = float(p[:, 0].max() - p[:, 0].min()) + 20.0
+        b["pos"] = b["pos"].copy()
+        b["pos"][:, 0] += np.float32(rank * stride_x)
     w = E.scenes.build_world(scene, device=local_rank)
     w.step(SETTLE_STEPS)
     w.sync()
+    stream = torch.cuda.ExternalStream(w.stream, device=local_rank)
+    # cross-GPU AABB exchange: per step, bounds of the owned islands reduced on the device, all-gathered
+    # over NCCL, overlap-tested on the device; the hit counter is read once after the timed region
+    bounds = torch.zeros(6, dtype=torch.float32, device="cuda")
+    gathered = torch.zeros(world_size, 6, dtype=torch.float32, device="cuda")
+    hits = torch.zeros((), dtype=torch.int64, device="cuda")
+    margin = 0.026
+
+    def exchange():
+        if dist is None:
+            return
+        w.device_bounds(bounds.data_ptr())
+        torch.cuda.current_stream().wait_stream(stream)
+        dist.all_gather_into_tensor(gathered, bounds)
+        lo, hi = gathered[:, None, :3], gathered[:, None, 3:]
+        ov = ((lo - margin <= hi.transpose(0, 1)) & (hi + margin >= lo.transpose(0, 1))).all(dim=2)
+        hits.add_(ov.sum() - world_size)               # minus the diagonal
+        stream.wait_stream(torch.cuda.current_stream())
     st0 = w.stats()
     if st0["error_flags"]:
         raise SystemExit(f"device error flags {st0['error_flags']} after settling")
 
-    stream = torch.cuda.ExternalStream(w.stream, device=local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # ---------------- device-resident throughput ("value")
     for _ in range(args.warmup):
         w.step(1)
+        exchange()
     barrier()
     w.sync()
     w.reset_timers()
@@ -190,6 +215,7 @@ def run_device(args):
     e0.record(stream)
     for _ in range(args.steps):
         w.step(1)
+        exchange()
     e1.record(stream)
     w.sync()
     barrier()
@@ -267,7 +293,8 @@ def run_device(args):
                            "velocity_iterations": iters, "position_iterations": scene["settings"]["position_iterations"],
                            "settle_steps": SETTLE_STEPS, "manifolds": st["manifolds"], "contact_points": st["contact_points"],
                            "hinges": st["hinges"], "contact_colors": st["contact_colors"], "islands": st["islands"],
-                           "parallelism": f"islands sharded over {world_size} GPU(s), no data-path collective",
+                           "parallelism": f"islands sharded over {world_size} GPU(s); per-step NCCL all-gather of island-group bounds "
+                                          f"(24 B/rank), {int(hits.item())} cross-rank overlaps seen",
                            "l2": "working set (rows + bodies) exceeds the 126 MB L2; no explicit flush"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,

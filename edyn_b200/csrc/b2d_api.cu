@@ -642,4 +642,15 @@ int b2d_get_stats(b2d_world *w, b2d_stats *out) {
 
 int b2d_reset_timers(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; w->timed_steps = 0; return B2D_OK; }
 
+int b2d_device_bounds(b2d_world *w, float *device_out6) {
+    if (!w || !device_out6) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    LAUNCH(k_bounds_init, 1, 32, d);
+    LAUNCH(k_bounds_reduce, d.nbodies, 256, d);
+    LAUNCH(k_bounds_final, 1, 32, d, device_out6);
+    CK(cudaGetLastError());
+    return B2D_OK;
+}
+
 } // extern "C"

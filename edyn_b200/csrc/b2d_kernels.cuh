@@ -1119,6 +1119,35 @@ __global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
     }
 }
 
+// ====================================================================== multi-GPU: bounds of the owned islands
+
+// Bounding box of every dynamic body's AABB, reduced on the device into a caller-provided DEVICE buffer of 6 floats
+// (min xyz, max xyz) that the host adapter all-gathers over NCCL: the cross-GPU AABB-overlap exchange of SURVEY 8e at
+// rank granularity.  Floats are compared through an order-preserving int encoding so plain atomicMin/Max work.
+B2D_D int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+B2D_D float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+__global__ void k_bounds_init(Dev d) {
+    if (blockIdx.x == 0 && threadIdx.x < 6) d.cnt->bounds[threadIdx.x] = threadIdx.x < 3 ? f2ord(INFINITY) : f2ord(-INFINITY);
+}
+__global__ void k_bounds_reduce(Dev d) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t f = d.flags[i];
+        if (!is_dynamic(f) || shape_of(f) == SH_NONE) continue;
+        float4 a = d.bbmin[i], b = d.bbmax[i];
+        mn[0] = fminf(mn[0], a.x); mn[1] = fminf(mn[1], a.y); mn[2] = fminf(mn[2], a.z);
+        mx[0] = fmaxf(mx[0], b.x); mx[1] = fmaxf(mx[1], b.y); mx[2] = fmaxf(mx[2], b.z);
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&d.cnt->bounds[k], f2ord(mn[k])); atomicMax(&d.cnt->bounds[3 + k], f2ord(mx[k])); }
+    }
+}
+__global__ void k_bounds_final(Dev d, float *out6) {
+    if (blockIdx.x == 0 && threadIdx.x < 6) out6[threadIdx.x] = ord2f(d.cnt->bounds[threadIdx.x]);
+}
+
 // ====================================================================== statistics
 __global__ void k_count_points(Dev d) {
     const uint32_t hwm = d.cnt->hwm;

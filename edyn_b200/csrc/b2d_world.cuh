@@ -39,6 +39,7 @@ struct Counters {
     uint32_t nislands;
     uint32_t nlist;          // colouring work list length
     uint32_t bar;            // grid barrier counter (zeroed by the host before each persistent kernel)
+    int bounds[6];           // order-preserving int encoding of the min/max of all dynamic AABBs (multi-GPU exchange)
     uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
     uint32_t coff[MAX_COLORS + 2];   // start of each contact colour in the sorted arrays
     uint32_t hoff[MAX_COLORS + 2];   // same for hinges

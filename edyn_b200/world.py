@@ -178,6 +178,10 @@ class World:
         self._check(self.l.b2d_download_hinge_impulses(self.h, _p(imp)))
         return imp[:self.num_hinges]
 
+    def device_bounds(self, device_ptr):
+        """Enqueue the dynamic-AABB bounds reduction into 6 floats at `device_ptr` (an int device address)."""
+        self._check(self.l.b2d_device_bounds(self.h, C.c_void_p(device_ptr)))
+
     def reset_timers(self):
         self._check(self.l.b2d_reset_timers(self.h))
 

@@ -155,6 +155,10 @@ int b2d_download_hinge_impulses(b2d_world *w, float *imp5);
 int b2d_get_stats(b2d_world *w, b2d_stats *out);
 /* Restart the per-kernel timing averages reported by b2d_get_stats. */
 int b2d_reset_timers(b2d_world *w);
+/* Multi-GPU exchange: enqueue, on the world's stream, the reduction of all dynamic AABBs into
+ * device_out6 = {min xyz, max xyz} -- a DEVICE pointer (e.g. a buffer owned by the host framework) the adapter then all-gathers over
+ * NCCL to detect island groups of different ranks coming within the broadphase margin of each other. */
+int b2d_device_bounds(b2d_world *w, float *device_out6);
 /* Blocks until all queued device work of this world has finished. */
 int b2d_sync(b2d_world *w);
 /* The CUDA stream (cudaStream_t) the world launches on, for event timing by the caller. */
