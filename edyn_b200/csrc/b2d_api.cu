@@ -25,7 +25,8 @@ struct b2d_world {
     std::vector<void *> allocs;
     std::string error;
     int num_sms = 0;
-    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0;
+    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0, coop_blocks_df = 0;
+    bool barrier_solver = false;
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
     uint64_t launches = 0, steps = 0;
@@ -126,6 +127,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.hpair, NH) && dalloc(w, d.hpivA, NH) && dalloc(w, d.hpivB, NH) && dalloc(w, d.hfA0, NH) && dalloc(w, d.hfA1, NH);
     ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
     ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
+    ok = ok && dalloc(w, d.seq, NB) && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH);
     // hcolor must hold COLOR_NONE (0xFF as a 32-bit value), not 0xFFFFFFFF
     if (ok) { std::vector<uint32_t> hc(NH, COLOR_NONE); cudaMemcpyAsync(d.hcolor, hc.data(), NH * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 
@@ -150,6 +152,9 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, 256, 0); w->coop_blocks_color = std::max(1, std::min(per_sm, want)) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, std::min(per_sm, want)) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
+    // the dataflow solve wants every resident warp it can get (latency hiding, no barrier cost per CTA)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, 256, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
+    if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
         g_create_error = "b2d_create: device allocation failed: " + w->error;
@@ -386,8 +391,10 @@ static int enqueue_solver(b2d_world *w) {
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
     const int slot = (int)(w->timed_steps % b2d_world::RING);
     CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(d.seq, 0, (size_t)d.nbodies * sizeof(uint32_t), s));
     cudaEventRecord(w->ev_solve0[slot], s);
-    CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
+    if (w->barrier_solver) CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
+    else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, 256, d, vi));
     cudaEventRecord(w->ev_solve1[slot], s);
     cudaEventRecord(w->ev_int0[slot], s);
     LAUNCH(k_integrate, d.nbodies, 256, d, pi == 0 ? 1 : 0);

@@ -663,6 +663,11 @@ __global__ void k_color_fixup(Dev d) {
         if (c.hoff[k] == 0xFFFFFFFFu) c.hoff[k] = c.hoff[k + 1]; else if (!nh) nh = k + 1;
     }
     c.ncolors = nc; c.nhcolors = nh; c.nactive = c.coff[MAX_COLORS];
+    c.cchunk[0] = 0; c.hchunk[0] = 0;
+    for (int k = 0; k <= MAX_COLORS; ++k) {
+        c.cchunk[k + 1] = c.cchunk[k] + (k < (int)nc ? (c.coff[k + 1] - c.coff[k] + 31) / 32 : 0);
+        c.hchunk[k + 1] = c.hchunk[k] + (k < (int)nh ? (c.hoff[k + 1] - c.hoff[k] + 31) / 32 : 0);
+    }
 }
 
 // ====================================================================== solver: row preparation
@@ -701,6 +706,20 @@ __global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
         v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
         q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
         d.hdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), npts, m);
+        {   // dataflow tickets: per iteration a body sees its hinges (by colour), then its contact normals, then the
+            // friction pairs; colours are unique per body, so the rank of this manifold is a popcount
+            const uint32_t col = (d.mstate[m] >> MS_COLOR_SHIFT) & 0xFFu;
+            const unsigned long long below = (1ULL << col) - 1ULL;
+            uint32_t t[2];
+            const uint32_t ids[2] = {pr.x, pr.y};
+            #pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                unsigned long long bm = d.bmask[ids[k]], jm = d.jmask[ids[k]];
+                uint32_t kc = __popcll(bm), kh = __popcll(jm);
+                t[k] = (kh + 2 * kc) | ((kh + __popcll(bm & below)) << 8) | (kc << 16);
+            }
+            d.tkt[i] = make_uint2(t[0], t[1]);
+        }
         for (uint32_t s = 0; s < npts; ++s) {
             size_t mi = (size_t)s * d.NM + m, ri = (size_t)s * d.NM + i;
             float4 a4 = d.pA[mi], b4 = d.pB[mi], n4 = d.pN[mi], im = d.pI[mi];
@@ -759,21 +778,100 @@ __global__ void k_prepare_hinges(Dev d) {
         R[5] = make_float4(rhs[3], rhs[4], imp[0], imp[1]);
         R[6] = make_float4(imp[2], imp[3], imp[4], 0);
         d.hhdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), h, 0);
+        {
+            const unsigned long long below = (1ULL << d.hcolor[h]) - 1ULL;
+            uint32_t t[2];
+            const uint32_t ids[2] = {pr.x, pr.y};
+            #pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                unsigned long long bm = d.bmask[ids[k]], jm = d.jmask[ids[k]];
+                t[k] = (__popcll(jm) + 2 * __popcll(bm)) | (__popcll(jm & below) << 8);
+            }
+            d.htkt[i] = make_uint2(t[0], t[1]);
+        }
     }
 }
 
 // ====================================================================== solver: velocity iterations
 
+// ---- dataflow synchronisation: instead of a grid barrier per colour, every dynamic body carries a ticket counter.
+// A constraint pass may touch its two bodies when both counters equal the tickets computed for it in k_prepare_*
+// (position of this pass in the body's fixed sequence: iteration-major, then hinges / normals / frictions, then
+// colour); afterwards it bumps them.  The per-body order -- and therefore every bit of the result -- is the same as
+// in the barrier version, but a pass waits only for its own two predecessors (an L2 round trip) rather than for the
+// slowest CTA of the whole grid.
+B2D_D uint32_t ld_relaxed(const uint32_t *p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+B2D_D void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+B2D_D void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+struct Ticket { uint32_t a, b, ta, tb, mask; bool pa, pb, on; };
+// pass = (iteration + 1); kind: 0 hinge, 1 contact normal, 2 friction
+B2D_D Ticket ticket_of(uint32_t tagA, uint32_t tagB, uint2 tk, int pass, int kind, uint32_t mask) {
+    Ticket t;
+    t.on = pass >= 0; t.mask = mask;
+    t.pa = !(tagA & 0x80000000u); t.pb = !(tagB & 0x80000000u);
+    t.a = tagA & 0x7FFFFFFFu; t.b = tagB & 0x7FFFFFFFu;
+    const uint32_t SA = tk.x & 0xFFu, bA = (tk.x >> 8) & 0xFFu, kA = (tk.x >> 16) & 0xFFu;
+    const uint32_t SB = tk.y & 0xFFu, bB = (tk.y >> 8) & 0xFFu, kB = (tk.y >> 16) & 0xFFu;
+    t.ta = (uint32_t)pass * SA + bA + (kind == 2 ? kA : 0u);
+    t.tb = (uint32_t)pass * SB + bB + (kind == 2 ? kB : 0u);
+    return t;
+}
 struct VBody { v3 dv, dw; float inv_m; m3 inv_I; uint32_t id; bool proc; };
 B2D_D void vb_load(const Dev &d, uint32_t tag, VBody &b) {
     b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
     if (b.proc) {
-        b.dv = mk3(d.dvw[2 * b.id]); b.dw = mk3(d.dvw[2 * b.id + 1]);
+        b.dv = mk3(__ldcg(&d.dvw[2 * b.id])); b.dw = mk3(__ldcg(&d.dvw[2 * b.id + 1]));
         float4 r0 = d.invIW[3 * b.id]; b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * b.id + 1]); b.inv_I.r2 = mk3(d.invIW[3 * b.id + 2]);
     } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); }
 }
 B2D_D void vb_store(const Dev &d, const VBody &b) {
-    if (b.proc) { d.dvw[2 * b.id] = f4(b.dv, 0); d.dvw[2 * b.id + 1] = f4(b.dw, 0); }
+    if (b.proc) { __stcg(&d.dvw[2 * b.id], f4(b.dv, 0)); __stcg(&d.dvw[2 * b.id + 1], f4(b.dw, 0)); }
+}
+// Dataflow acquire / publish.  The delta-velocity record of a body (two float4 = one 32 B sector) carries the
+// body's ticket in BOTH .w lanes, so data and synchronisation travel in the same L2 transactions: a reader that
+// sees the expected ticket in both halves has a consistent record (16 B aligned vector stores are single
+// transactions; a torn pair is rejected by the double check) and needs no fence, a writer needs none either.
+B2D_D float4 ld_volatile4(const float4 *p) {
+    float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+B2D_D void st_volatile4(float4 *p, float4 v) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+B2D_D void vb_static(const Dev &d, uint32_t tag, VBody &b) {
+    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
+    b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0);
+    if (b.proc) { float4 r0 = d.invIW[3 * b.id]; b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * b.id + 1]); b.inv_I.r2 = mk3(d.invIW[3 * b.id + 2]); }
+    else { b.inv_m = 0; b.inv_I = m3_zero(); }
+}
+B2D_D bool vb_try(const Dev &d, VBody &b, uint32_t expect) {
+    float4 a = ld_volatile4(&d.dvw[2 * b.id]), w = ld_volatile4(&d.dvw[2 * b.id + 1]);
+    b.dv = mk3(a); b.dw = mk3(w);
+    return __float_as_uint(a.w) == expect && __float_as_uint(w.w) == expect;
+}
+// Lanes of a chunk become ready one by one; each lane solves as soon as ITS two bodies carry the expected tickets
+// (the ready subset runs the solve converged, the rest keep polling), so one late predecessor delays one constraint
+// and not the 31 others that happen to share its warp.
+B2D_D void acquire_begin(const Dev &d, const Ticket &t, uint32_t tagA, uint32_t tagB, VBody &A, VBody &B) {
+    if (!t.on) { vb_load(d, tagA, A); vb_load(d, tagB, B); return; }
+    vb_static(d, tagA, A); vb_static(d, tagB, B);
+}
+B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
+    if (!t.on) return true;
+    return (!A.proc || vb_try(d, A, t.ta)) & (!B.proc || vb_try(d, B, t.tb));
+}
+B2D_D bool acquire_more(const Dev &d, const Ticket &t, bool pending, bool progressed, uint32_t &spins) {
+    if (!t.on) return false;
+    if (!__any_sync(t.mask, pending)) return false;
+    if (!__any_sync(t.mask, progressed)) {
+        if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); return false; }      // never hang the GPU
+        if (spins > 64) __nanosleep(20);
+    }
+    return true;
+}
+B2D_D void bodies_publish(const Dev &d, const Ticket &t, const VBody &A, const VBody &B) {
+    if (!t.on) { vb_store(d, A); vb_store(d, B); return; }
+    if (A.proc) { st_volatile4(&d.dvw[2 * A.id], f4(A.dv, __uint_as_float(t.ta + 1))); st_volatile4(&d.dvw[2 * A.id + 1], f4(A.dw, __uint_as_float(t.ta + 1))); }
+    if (B.proc) { st_volatile4(&d.dvw[2 * B.id], f4(B.dv, __uint_as_float(t.tb + 1))); st_volatile4(&d.dvw[2 * B.id + 1], f4(B.dw, __uint_as_float(t.tb + 1))); }
 }
 // apply_row_impulse, constraint_row.cpp:24-32
 B2D_D void apply_imp(VBody &A, VBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float imp) {
@@ -799,15 +897,20 @@ B2D_D float solve_row(float rhs, float em, float lo, float hi, float &impulse, f
     return delta;
 }
 
-B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm) {
+B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
     uint4 hd = d.hhdr[i];
-    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
     float4 *R = d.HR + 7 * (size_t)i;
     float4 r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6];
+    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.htkt[i] : make_uint2(0, 0), pass, 0, mask);
+    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
+    bool pending = true; uint32_t spins = 0;
     v3 rA = mk3(r0), rB = mk3(r1), p = mk3(r2), q = mk3(r3);
     float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x};
     float rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
     float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
+    do {
+    const bool ok = pending && acquire_try(d, tk, A, B);
+    if (ok) {
     #pragma unroll
     for (int k = 0; k < 5; ++k) {
         v3 J0, J1, J2, J3;
@@ -822,88 +925,111 @@ B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm) {
         else delta = solve_row(rhs[k], em[k], -SCALAR_MAX, SCALAR_MAX, imp[k], rel_speed(J0, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
         apply_imp(A, B, J0, J1, J2, J3, delta);
     }
+    bodies_publish(d, tk, A, B);
     if (!warm) { R[5] = make_float4(r5.x, r5.y, imp[0], imp[1]); R[6] = make_float4(imp[2], imp[3], imp[4], 0); }
-    vb_store(d, A); vb_store(d, B);
+    pending = false;
+    }
+    if (!acquire_more(d, tk, pending, ok, spins)) break;
+    } while (true);
 }
 
-// All row loads of a manifold are issued before the first dependent computation and all impulse stores after the
-// last one, so a 4-point manifold costs one memory round trip instead of four (the compiler cannot hoist loads
-// across the stores of a load-compute-store loop).
-B2D_D void normal_pass(const Dev &d, uint32_t i, bool warm) {
+// Row loads are issued ahead of the dependent computation: slots 0 and 1 before the ticket wait / body loads,
+// slots 2 and 3 (box faces, ~15 % of manifolds) into the registers freed by slots 0 and 1 while those are being
+// solved.  Impulses are private to the owning thread and stored as soon as they are final.
+B2D_D void prefetch_L2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+struct NRow { float4 r0, r1, r2, im; };
+B2D_D NRow load_nrow(const Dev &d, size_t ri) { NRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.im = d.IMP[ri]; return r; }
+B2D_D void solve_nrow(const Dev &d, NRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
+    v3 nrm = mk3(r.r0), rA = mk3(r.r1), rB = mk3(r.r2);
+    v3 J1 = cross(rA, nrm), J2 = -nrm, J3 = -cross(rB, nrm);
+    float delta;
+    if (warm) delta = r.im.x;
+    else {
+        delta = solve_row(r.r0.w, r.r1.w, 0.0f, LARGE, r.im.x, rel_speed(nrm, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
+        d.IMP[ri] = r.im;
+    }
+    apply_imp(A, B, nrm, J1, J2, J3, delta);
+}
+B2D_D void normal_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
     const uint4 hd = d.hdr[i];
+    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.tkt[i] : make_uint2(0, 0), pass, 1, mask);
     const uint32_t n = hd.z;
-    float4 r0[4], r1[4], r2[4], im[4];
-    #pragma unroll
-    for (int s = 0; s < 4; ++s) if (s < n) {
-        size_t ri = (size_t)s * d.NM + i;
-        r0[s] = d.R0[ri]; r1[s] = d.R1[ri]; r2[s] = d.R2[ri]; im[s] = d.IMP[ri];
+    const size_t NM = d.NM;
+    NRow ra, rb;
+    ra = load_nrow(d, i);
+    if (n > 1) rb = load_nrow(d, NM + i);
+    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
+    bool pending = true; uint32_t spins = 0;
+    do {
+    const bool ok = pending && acquire_try(d, tk, A, B);
+    if (ok) {
+    solve_nrow(d, ra, i, A, B, warm);
+    if (n > 2) ra = load_nrow(d, 2 * NM + i);
+    if (n > 1) solve_nrow(d, rb, NM + i, A, B, warm);
+    if (n > 3) rb = load_nrow(d, 3 * NM + i);
+    if (n > 2) solve_nrow(d, ra, 2 * NM + i, A, B, warm);
+    if (n > 3) solve_nrow(d, rb, 3 * NM + i, A, B, warm);
+    bodies_publish(d, tk, A, B);
+    pending = false;
     }
-    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
-    #pragma unroll
-    for (int s = 0; s < 4; ++s) if (s < n) {
-        v3 nrm = mk3(r0[s]), rA = mk3(r1[s]), rB = mk3(r2[s]);
-        v3 J1 = cross(rA, nrm), J2 = -nrm, J3 = -cross(rB, nrm);
-        float delta;
-        if (warm) delta = im[s].x;
-        else delta = solve_row(r0[s].w, r1[s].w, 0.0f, LARGE, im[s].x, rel_speed(nrm, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
-        apply_imp(A, B, nrm, J1, J2, J3, delta);
-    }
-    vb_store(d, A); vb_store(d, B);
-    if (!warm) {
-        #pragma unroll
-        for (int s = 0; s < 4; ++s) if (s < n) d.IMP[(size_t)s * d.NM + i] = im[s];
-    }
+    if (!acquire_more(d, tk, pending, ok, spins)) break;
+    } while (true);
 }
 
 // solve_friction, constraint_row_friction.cpp:11-54: both tangent candidates from one delta-velocity snapshot,
 // clamped to the circle of radius mu * lambda_n (lambda_n of THIS iteration).
-B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm) {
-    const uint4 hd = d.hdr[i];
-    const uint32_t n = hd.z;
-    float4 r0[4], r1[4], r2[4], r3[4], im[4];
-    #pragma unroll
-    for (int s = 0; s < 4; ++s) if (s < n) {
-        size_t ri = (size_t)s * d.NM + i;
-        r0[s] = d.R0[ri]; r1[s] = d.R1[ri]; r2[s] = d.R2[ri]; r3[s] = d.R3[ri]; im[s] = d.IMP[ri];
-    }
-    VBody A, B; vb_load(d, hd.x, A); vb_load(d, hd.y, B);
-    #pragma unroll
-    for (int s = 0; s < 4; ++s) if (s < n) {
-        v3 nrm = mk3(r0[s]), rA = mk3(r1[s]), rB = mk3(r2[s]);
-        v3 t, u; plane_space(nrm, t, u);
-        v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
-        v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
-        float d0, d1;
-        if (warm) { d0 = im[s].y; d1 = im[s].z; }
-        else {
-            d0 = (r3[s].z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r3[s].x;
-            d1 = (r3[s].w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r3[s].y;
-            float i0 = im[s].y + d0, i1 = im[s].z + d1;
-            float len_sqr = i0 * i0 + i1 * i1;
-            float max_len = r2[s].w * im[s].x;
-            if (len_sqr > max_len * max_len) {
-                float len = sqrtf(len_sqr);
-                if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
-                d0 = i0 - im[s].y; d1 = i1 - im[s].z;
-            }
-            im[s].y = i0; im[s].z = i1;
+struct FRow { float4 r0, r1, r2, r3, im; };
+B2D_D FRow load_frow(const Dev &d, size_t ri) { FRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.r3 = d.R3[ri]; r.im = d.IMP[ri]; return r; }
+B2D_D void solve_frow(const Dev &d, FRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
+    v3 nrm = mk3(r.r0), rA = mk3(r.r1), rB = mk3(r.r2);
+    v3 t, u; plane_space(nrm, t, u);
+    v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
+    v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
+    float d0, d1;
+    if (warm) { d0 = r.im.y; d1 = r.im.z; }
+    else {
+        d0 = (r.r3.z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r.r3.x;
+        d1 = (r.r3.w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r.r3.y;
+        float i0 = r.im.y + d0, i1 = r.im.z + d1;
+        float len_sqr = i0 * i0 + i1 * i1;
+        float max_len = r.r2.w * r.im.x;
+        if (len_sqr > max_len * max_len) {
+            float len = sqrtf(len_sqr);
+            if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
+            d0 = i0 - r.im.y; d1 = i1 - r.im.z;
         }
-        apply_imp_f(A, B, t, T1, T2, T3, d0);
-        apply_imp_f(A, B, u, U1, U2, U3, d1);
+        r.im.y = i0; r.im.z = i1;
+        d.IMP[ri] = r.im;
     }
-    vb_store(d, A); vb_store(d, B);
-    if (!warm) {
-        #pragma unroll
-        for (int s = 0; s < 4; ++s) if (s < n) d.IMP[(size_t)s * d.NM + i] = im[s];
+    apply_imp_f(A, B, t, T1, T2, T3, d0);
+    apply_imp_f(A, B, u, U1, U2, U3, d1);
+}
+B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
+    const uint4 hd = d.hdr[i];
+    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.tkt[i] : make_uint2(0, 0), pass, 2, mask);
+    const uint32_t n = hd.z;
+    const size_t NM = d.NM;
+    FRow ra, rb;
+    ra = load_frow(d, i);
+    if (n > 1) rb = load_frow(d, NM + i);
+    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
+    bool pending = true; uint32_t spins = 0;
+    do {
+    const bool ok = pending && acquire_try(d, tk, A, B);
+    if (ok) {
+    solve_frow(d, ra, i, A, B, warm);
+    if (n > 2) ra = load_frow(d, 2 * NM + i);
+    if (n > 1) solve_frow(d, rb, NM + i, A, B, warm);
+    if (n > 3) rb = load_frow(d, 3 * NM + i);
+    if (n > 2) solve_frow(d, ra, 2 * NM + i, A, B, warm);
+    if (n > 3) solve_frow(d, rb, 3 * NM + i, A, B, warm);
+    bodies_publish(d, tk, A, B);
+    pending = false;
     }
+    if (!acquire_more(d, tk, pending, ok, spins)) break;
+    } while (true);
 }
 
-// Persistent cooperative kernel: warm start + N velocity iterations (island_solver.cpp:76-111).  Inside one
-// iteration: hinge rows, then contact normal rows, then friction pairs -- constraint-type major like
-// pack_rows (island_solver.cpp:162-175) -- each as a sequence of colours separated by grid barriers.
-// Constraints of one colour touch disjoint dynamic bodies, so the parallel pass equals the sequential
-// Gauss-Seidel sweep in (colour, slot) order; b2d_download_solver_order() exports that order.
-B2D_D void prefetch_L2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // Pass q of one iteration: hinge colours, then contact-normal colours, then friction colours.
 struct Pass { uint32_t b, e; int kind; };     // kind 0 hinge rows, 1 contact normal rows, 2 friction pairs
@@ -946,6 +1072,55 @@ __global__ void __launch_bounds__(256) k_solve(Dev d, int iters) {
             else { for (uint32_t i = p.b + gtid; i < p.e; i += stride) friction_pass(d, i, warm); }
             prefetch_pass(d, get_pass(c, q + 1 == npass ? 0 : q + 1, nh, nc), gtid);
             grid.sync();
+        }
+    }
+}
+
+// Dataflow flavour of k_solve (default): same passes, same per-body order, no grid barriers.  Work is dealt to warps
+// in 32-constraint chunks that never span two colours (so lanes of a warp never wait on each other), chunk j to warp
+// j mod W, each warp walking its chunks in increasing (iteration, type, colour) order.  The globally smallest
+// unfinished chunk therefore always has its predecessors done and its warp working on it: no deadlock as long as the
+// grid is co-resident (cooperative launch).  wait_ticket() additionally bails out after a bounded number of spins.
+// chunk j of a pass type -> (colour, first sorted index); `col` is a monotone cursor
+B2D_D uint32_t chunk_index(const uint32_t *chunk, const uint32_t *off, uint32_t j, uint32_t &col) {
+    while (j >= chunk[col + 1]) ++col;
+    return off[col] + (j - chunk[col]) * 32u;
+}
+__global__ void __launch_bounds__(256, 2) k_solve_df(Dev d, int iters) {
+    const Counters &c = *d.cnt;
+    const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t hchunks = c.hchunk[nh], cchunks = c.cchunk[nc];
+    for (int it = -1; it < iters; ++it) {
+        const bool warm = it < 0;
+        const int pass = it + 1;
+        { uint32_t col = 0;
+          for (uint32_t j = wid; j < hchunks; j += nw) {
+              const uint32_t i = chunk_index(c.hchunk, c.hoff, j, col) + lane;
+              const bool act = i < c.hoff[col + 1];
+              const uint32_t mask = __ballot_sync(0xffffffffu, act);
+              if (act) hinge_pass(d, i, warm, pass, mask);
+          } }
+        #pragma unroll 1
+        for (int kind = 1; kind <= 2; ++kind) {
+            uint32_t col = 0, pcol = 0;
+            for (uint32_t j = wid; j < cchunks; j += nw) {
+                const uint32_t i = chunk_index(c.cchunk, c.coff, j, col) + lane;
+                const bool act = i < c.coff[col + 1];
+                const uint32_t mask = __ballot_sync(0xffffffffu, act);
+                // pull this warp's next chunk (same pass type) towards L2 while the current one is being solved
+                if (j + nw < cchunks) {
+                    if (pcol < col) pcol = col;
+                    const uint32_t ni = chunk_index(c.cchunk, c.coff, j + nw, pcol) + lane;
+                    if (ni < c.coff[pcol + 1]) {
+                        prefetch_L2(&d.hdr[ni]); prefetch_L2(&d.tkt[ni]);
+                        prefetch_L2(&d.R0[ni]); prefetch_L2(&d.R1[ni]); prefetch_L2(&d.R2[ni]); prefetch_L2(&d.IMP[ni]);
+                        if (kind == 2) prefetch_L2(&d.R3[ni]);
+                    }
+                }
+                if (act) { if (kind == 1) normal_pass(d, i, warm, pass, mask); else friction_pass(d, i, warm, pass, mask); }
+            }
         }
     }
 }

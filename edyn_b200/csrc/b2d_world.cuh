@@ -25,6 +25,7 @@ constexpr int MAX_COLORS = 64;
 constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
 constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
 constexpr uint32_t ERR_LARGE_CAPACITY = 4u;
+constexpr uint32_t ERR_SOLVER_TIMEOUT = 8u;     // a dataflow wait exceeded its spin budget (would have been a hang)
 
 struct Counters {
     uint32_t hwm;            // manifold slots in use are [0, hwm)
@@ -43,6 +44,8 @@ struct Counters {
     uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
     uint32_t coff[MAX_COLORS + 2];   // start of each contact colour in the sorted arrays
     uint32_t hoff[MAX_COLORS + 2];   // same for hinges
+    uint32_t cchunk[MAX_COLORS + 2]; // prefix sum of ceil(colour size / 32): warp-sized chunks never span two colours
+    uint32_t hchunk[MAX_COLORS + 2];
 };
 
 struct Dev {
@@ -112,6 +115,10 @@ struct Dev {
     uint32_t *hcolor;
     float4 *HR;                  // 7 float4 per sorted hinge: rA|eff0, rB|eff1, p|eff2, q|eff3, (eff4,rhs0,rhs1,rhs2), (rhs3,rhs4,imp0,imp1), (imp2,imp3,imp4,0)
     uint4 *hhdr;                 // a, b, hinge id, 0
+
+    // ---- dataflow schedule of the velocity solve
+    uint32_t *seq;               // per body: number of constraint passes applied so far in this solve
+    uint2 *tkt, *htkt;           // per sorted constraint, per body side: S | base << 8 | k << 16 (see k_prepare_*)
 
     Counters *cnt;
 };
