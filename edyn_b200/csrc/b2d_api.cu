@@ -25,7 +25,7 @@ struct b2d_world {
     std::vector<void *> allocs;
     std::string error;
     int num_sms = 0;
-    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0, coop_blocks_df = 0;
+    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
     bool barrier_solver = false;
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
@@ -154,6 +154,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
     // the dataflow solve wants every resident warp it can get (latency hiding, no barrier cost per CTA)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, 256, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, 256, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
     if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
@@ -403,7 +404,8 @@ static int enqueue_solver(b2d_world *w) {
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
         CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
-        CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
+        if (w->barrier_solver) CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
+        else { CK(cudaMemsetAsync(d.seq, 0, (size_t)d.nbodies * sizeof(uint32_t), s)); CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, 256, d, pi)); }
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
     w->timed = true;

@@ -785,7 +785,7 @@ __global__ void k_prepare_hinges(Dev d) {
             #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 unsigned long long bm = d.bmask[ids[k]], jm = d.jmask[ids[k]];
-                t[k] = (__popcll(jm) + 2 * __popcll(bm)) | (__popcll(jm & below) << 8);
+                t[k] = (__popcll(jm) + 2 * __popcll(bm)) | (__popcll(jm & below) << 8) | (__popcll(bm) << 16);
             }
             d.htkt[i] = make_uint2(t[0], t[1]);
         }
@@ -1182,9 +1182,13 @@ __global__ void __launch_bounds__(256) k_finalize(Dev d) {
 struct PBody { v3 pos; q4 orn; float inv_m; m3 inv_IW, inv_I; uint32_t id; bool proc; };
 B2D_D void pb_load(const Dev &d, uint32_t id, PBody &b) {
     b.id = id; b.proc = is_dynamic(d.flags[id]);
-    float4 p4 = d.pos[id];
-    b.pos = mk3(p4); b.orn = mkq(d.orn[id]);
-    if (b.proc) { b.inv_m = p4.w; b.inv_IW = load_m3(d.invIW, id); b.inv_I = load_m3(d.invI, id); }
+    float4 p4 = __ldcg(&d.pos[id]);
+    b.pos = mk3(p4); b.orn = mkq(__ldcg(&d.orn[id]));
+    if (b.proc) {
+        b.inv_m = p4.w;
+        b.inv_IW.r0 = mk3(__ldcg(&d.invIW[3 * id])); b.inv_IW.r1 = mk3(__ldcg(&d.invIW[3 * id + 1])); b.inv_IW.r2 = mk3(__ldcg(&d.invIW[3 * id + 2]));
+        b.inv_I = load_m3(d.invI, id);
+    }
     else { b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero(); }
 }
 B2D_D void pb_store(const Dev &d, const PBody &b) {
@@ -1214,14 +1218,55 @@ B2D_D void position_solve(PBody &A, PBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float 
     }
     max_error = fmaxf(fabsf(error), max_error);
 }
+// Per-island max error, aggregated per warp first: in a pile every lane belongs to the same island and one atomic per
+// lane on a single address serialises the whole pass at the L2 atomic unit (0.9 ms per step at 262k bodies).
+B2D_D void island_error_max(const Dev &d, uint32_t isl, float err) {
+    const uint32_t active = __activemask();
+    const uint32_t grp = __match_any_sync(active, isl);
+    const uint32_t m = __reduce_max_sync(grp, __float_as_uint(err));
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(grp) - 1) && m) atomicMax(&d.isl_err[isl], m);
+}
 B2D_D uint32_t island_of(const Dev &d, uint32_t a, uint32_t b) { uint32_t l = d.parent[a]; return l != 0xFFFFFFFFu ? l : d.parent[b]; }
 
 // contact_constraint::solve_position, contact_constraint.cpp:58-90
-B2D_D void contact_position(const Dev &d, uint32_t i) {
+// Dataflow tickets of the position sweeps: per iteration a body sees its hinges, then its contacts (no friction
+// pass), so the schedule is the velocity one with S' = S - k_contacts.  Transforms do not fit a self-validating
+// record, hence a separate counter (d.seq) with release/acquire fences -- 3 iterations only, the hop cost is irrelevant.
+struct PTicket { uint32_t ta, tb, mask; bool on; };
+B2D_D PTicket pticket_of(uint2 tk, int it, uint32_t mask, bool on) {
+    PTicket t; t.on = on; t.mask = mask;
+    const uint32_t SA = (tk.x & 0xFFu) - ((tk.x >> 16) & 0xFFu), SB = (tk.y & 0xFFu) - ((tk.y >> 16) & 0xFFu);
+    t.ta = (uint32_t)it * SA + ((tk.x >> 8) & 0xFFu); t.tb = (uint32_t)it * SB + ((tk.y >> 8) & 0xFFu);
+    return t;
+}
+B2D_D void pticket_wait(const Dev &d, const PTicket &t, uint32_t a, bool pa, uint32_t b, bool pb) {
+    if (!t.on) return;
+    uint32_t spins = 0;
+    for (;;) {
+        bool ok = (!pa || ld_relaxed(&d.seq[a]) == t.ta) & (!pb || ld_relaxed(&d.seq[b]) == t.tb);
+        if (__all_sync(t.mask, ok)) break;
+        if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); break; }
+        if (spins > 16) __nanosleep(20);
+    }
+    fence_gpu();
+}
+B2D_D void pticket_release(const Dev &d, const PTicket &t, uint32_t a, bool pa, uint32_t b, bool pb) {
+    if (!t.on) return;
+    fence_gpu();
+    if (pa) st_relaxed(&d.seq[a], t.ta + 1);
+    if (pb) st_relaxed(&d.seq[b], t.tb + 1);
+}
+
+B2D_D void contact_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask = 0xffffffffu, bool df = false) {
     uint4 hd = d.hdr[i];
     uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, m = hd.w;
     uint32_t isl = island_of(d, a, b);
-    if (d.isl_done[isl]) return;
+    // all constraints of a finished island skip together (and keep skipping), so their tickets stay consistent
+    const bool skip = d.isl_done[isl] != 0;
+    const PTicket tk = pticket_of(df ? d.tkt[i] : make_uint2(0, 0), it, __ballot_sync(mask, !skip), df);
+    if (skip) return;
+    const bool pa = !(hd.x >> 31), pb = !(hd.y >> 31);
+    pticket_wait(d, tk, a, pa, b, pb);
     PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
     float max_error = 0.0f;
     for (uint32_t s = 0; s < hd.z; ++s) {
@@ -1238,14 +1283,19 @@ B2D_D void contact_position(const Dev &d, uint32_t i) {
         position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
     }
     pb_store(d, A); pb_store(d, B);
-    if (max_error > 0.0f) atomicMax(&d.isl_err[isl], __float_as_uint(max_error));
+    pticket_release(d, tk, a, pa, b, pb);
+    island_error_max(d, isl, max_error);
 }
 // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
-B2D_D void hinge_position(const Dev &d, uint32_t i) {
+B2D_D void hinge_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask = 0xffffffffu, bool df = false) {
     uint4 hd = d.hhdr[i];
     uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, h = hd.z;
     uint32_t isl = island_of(d, a, b);
-    if (d.isl_done[isl]) return;
+    const bool skip = d.isl_done[isl] != 0;
+    const PTicket tk = pticket_of(df ? d.htkt[i] : make_uint2(0, 0), it, __ballot_sync(mask, !skip), df);
+    if (skip) return;
+    const bool pa = !(hd.x >> 31), pb = !(hd.y >> 31);
+    pticket_wait(d, tk, a, pa, b, pb);
     PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
     float max_error = 0.0f;
     v3 axisA = rotate(A.orn, mk3(d.hfA0[h])), axisB = rotate(B.orn, mk3(d.hfB0[h]));
@@ -1263,7 +1313,8 @@ B2D_D void hinge_position(const Dev &d, uint32_t i) {
         position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
     }
     pb_store(d, A); pb_store(d, B);
-    if (max_error > 0.0f) atomicMax(&d.isl_err[isl], __float_as_uint(max_error));
+    pticket_release(d, tk, a, pa, b, pb);
+    island_error_max(d, isl, max_error);
 }
 
 // <= N position iterations, each island stopping once its max error drops below 0.005
@@ -1286,6 +1337,42 @@ __global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
             grid.sync();
         }
         if (it + 1 < iters) {
+            GRID_STRIDE(i, d.nbodies) {
+                if (d.parent[i] == i) { if (__uint_as_float(d.isl_err[i]) < 0.005f) d.isl_done[i] = 1; d.isl_err[i] = 0; }
+            }
+            grid.sync();
+        }
+    }
+}
+
+// Dataflow flavour (default): colours inside an iteration are ordered by per-body tickets instead of grid barriers;
+// only the per-island convergence test between iterations still needs the whole grid (2 barriers per iteration).
+__global__ void __launch_bounds__(256) k_position_df(Dev d, int iters) {
+    GridBarrier grid(&d.cnt->bar);
+    const Counters &c = *d.cnt;
+    const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t hchunks = c.hchunk[nh], cchunks = c.cchunk[nc];
+    GRID_STRIDE(i, d.nbodies) { d.isl_err[i] = 0; d.isl_done[i] = 0; }
+    grid.sync();
+    for (int it = 0; it < iters; ++it) {
+        { uint32_t col = 0;
+          for (uint32_t j = wid; j < hchunks; j += nw) {
+              const uint32_t i = chunk_index(c.hchunk, c.hoff, j, col) + lane;
+              const bool act = i < c.hoff[col + 1];
+              const uint32_t mask = __ballot_sync(0xffffffffu, act);
+              if (act) hinge_position(d, i, it, mask, true);
+          } }
+        { uint32_t col = 0;
+          for (uint32_t j = wid; j < cchunks; j += nw) {
+              const uint32_t i = chunk_index(c.cchunk, c.coff, j, col) + lane;
+              const bool act = i < c.coff[col + 1];
+              const uint32_t mask = __ballot_sync(0xffffffffu, act);
+              if (act) contact_position(d, i, it, mask, true);
+          } }
+        if (it + 1 < iters) {
+            grid.sync();
             GRID_STRIDE(i, d.nbodies) {
                 if (d.parent[i] == i) { if (__uint_as_float(d.isl_err[i]) < 0.005f) d.isl_done[i] = 1; d.isl_err[i] = 0; }
             }
