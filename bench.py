@@ -264,8 +264,14 @@ def run_device(args):
     algo_bytes = (iters + 0.75) * (BYTES_PER_POINT_ITER * st["contact_points"] + BYTES_PER_HINGE_ITER * st["hinges"])
     achieved = algo_bytes / (st["solve_ms"] * 1e-3) / 1e9 if st["solve_ms"] > 0 else 0.0
     integ_gbs = BYTES_PER_BODY_INTEGRATE * n_dyn / (st["integrate_ms"] * 1e-3) / 1e9 if st["integrate_ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_solve", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath) and args.scale == 1.0:
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload:
+            traffic = tj["k_solve"]["dram_bytes_read"] + tj["k_solve"]["dram_bytes_write"]     # ncu --set full capture, per launch
+    roofline = {"bound": "hbm", "kernel": "k_solve_df", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": st["solve_ms"], "kernel_share_of_step": st["solve_ms"] / (ms / args.steps),
                 "integrate": {"kernel": "k_integrate", "achieved": integ_gbs, "frac": integ_gbs / peak, "kernel_ms": st["integrate_ms"]}}
 
