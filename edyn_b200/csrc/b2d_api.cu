@@ -134,7 +134,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     // CUB temp storage: the largest of the sorts/scans used per step
     size_t need = 0, t = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)NB, 0, 63, w->stream); need = std::max(need, t);
-    cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, 8, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, 9, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
     w->cub_tmp_bytes = need + 256;
@@ -383,7 +383,7 @@ static int enqueue_solver(b2d_world *w) {
     CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d));
     LAUNCH(k_color_keys, d.NM, 256, d);
     size_t t = w->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 9, s)); w->launches += 3;
     t = w->cub_tmp_bytes;
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)d.NH, 0, 8, s)); w->launches += 3;
     LAUNCH(k_color_offsets, d.NM, 256, d);
@@ -649,6 +649,14 @@ int b2d_get_stats(b2d_world *w, b2d_stats *out) {
     return B2D_OK;
 }
 
+// development aid: raw copy of the device counters block
+int b2d_debug_counters(b2d_world *w, void *out, uint32_t bytes) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    CK(cudaStreamSynchronize(w->stream));
+    CK(cudaMemcpy(out, w->d.cnt, std::min<size_t>(bytes, sizeof(Counters)), cudaMemcpyDeviceToHost));
+    return B2D_OK;
+}
 int b2d_reset_timers(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; w->timed_steps = 0; return B2D_OK; }
 
 int b2d_device_bounds(b2d_world *w, float *device_out6) {

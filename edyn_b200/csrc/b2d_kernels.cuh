@@ -342,13 +342,13 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
 __global__ void k_np_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, d.NM) {
-        unsigned char key = 0xFF;
+        unsigned short key = 0xFF;
         if (m < hwm && (d.mstate[m] & MS_ALIVE)) {
             uint2 pr = d.mpair[m];
             int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
             int fn = pair_fn(ka, kb);
             if (!fn) fn = pair_fn(kb, ka);
-            key = (unsigned char)fn;
+            key = (unsigned short)fn;
         }
         d.ckey[m] = key; d.cidx[m] = m;
     }
@@ -356,7 +356,7 @@ __global__ void k_np_keys(Dev d) {
 }
 __global__ void k_np_offsets(Dev d) {
     GRID_STRIDE(i, d.NM) {
-        unsigned char k = d.ckey_s[i];
+        unsigned short k = d.ckey_s[i];
         if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->npoff[k == 0xFF ? 10 : k] = i;
     }
 }
@@ -630,8 +630,10 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
 __global__ void k_color_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, d.NM) {
-        unsigned char key = 0xFF;
-        if (m < hwm) { uint32_t st = d.mstate[m]; if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) key = (unsigned char)((st >> MS_COLOR_SHIFT) & 0xFFu); }
+        // sort key: colour, then point count -- chunks of 32 manifolds then run the same number of row solves in
+        // every lane, and single-point manifolds publish their bodies without waiting for four-point neighbours
+        unsigned short key = 0x100;
+        if (m < hwm) { uint32_t st = d.mstate[m]; if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) key = (unsigned short)((((st >> MS_COLOR_SHIFT) & 0x3Fu) << 2) | ((st & MS_NPTS_MASK) - 1u)); }
         d.ckey[m] = key; d.cidx[m] = m;
     }
     GRID_STRIDE(h, d.NH) {
@@ -643,8 +645,8 @@ __global__ void k_color_keys(Dev d) {
 }
 __global__ void k_color_offsets(Dev d) {
     GRID_STRIDE(i, d.NM) {
-        unsigned char k = d.ckey_s[i];
-        if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->coff[k == 0xFF ? MAX_COLORS : k] = i;
+        unsigned short k = d.ckey_s[i] >> 2;
+        if (i == 0 || (d.ckey_s[i - 1] >> 2) != k) d.cnt->coff[k >= MAX_COLORS ? MAX_COLORS : k] = i;
     }
     GRID_STRIDE(i, d.NH) {
         unsigned char k = d.hkey_s[i];

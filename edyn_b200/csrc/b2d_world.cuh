@@ -46,6 +46,7 @@ struct Counters {
     uint32_t hoff[MAX_COLORS + 2];   // same for hinges
     uint32_t cchunk[MAX_COLORS + 2]; // prefix sum of ceil(colour size / 32): warp-sized chunks never span two colours
     uint32_t hchunk[MAX_COLORS + 2];
+    unsigned long long dbg[16];  // development counters (B2D_DF_PROFILE builds only)
 };
 
 struct Dev {
@@ -93,7 +94,7 @@ struct Dev {
     uint32_t *parent;
     unsigned long long *bmask, *jmask;      // colours in use per body (contacts / hinges)
     unsigned long long *prop, *jprop;
-    unsigned char *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
+    unsigned short *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
     uint32_t *clist;             // colouring work list (manifold slots with points)
     unsigned char *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
     uint32_t *isl_err; uint32_t *isl_done;
