@@ -952,9 +952,8 @@ B2D_D void solve_nrow(const Dev &d, NRow &r, size_t ri, VBody &A, VBody &B, bool
     }
     apply_imp(A, B, nrm, J1, J2, J3, delta);
 }
-B2D_D void normal_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
-    const uint4 hd = d.hdr[i];
-    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.tkt[i] : make_uint2(0, 0), pass, 1, mask);
+B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
+    const Ticket tk = ticket_of(hd.x, hd.y, tk2, pass, 1, mask);
     const uint32_t n = hd.z;
     const size_t NM = d.NM;
     NRow ra, rb;
@@ -1006,9 +1005,8 @@ B2D_D void solve_frow(const Dev &d, FRow &r, size_t ri, VBody &A, VBody &B, bool
     apply_imp_f(A, B, t, T1, T2, T3, d0);
     apply_imp_f(A, B, u, U1, U2, U3, d1);
 }
-B2D_D void friction_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
-    const uint4 hd = d.hdr[i];
-    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.tkt[i] : make_uint2(0, 0), pass, 2, mask);
+B2D_D void friction_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
+    const Ticket tk = ticket_of(hd.x, hd.y, tk2, pass, 2, mask);
     const uint32_t n = hd.z;
     const size_t NM = d.NM;
     FRow ra, rb;
@@ -1070,8 +1068,8 @@ __global__ void __launch_bounds__(256) k_solve(Dev d, int iters) {
         for (uint32_t q = 0; q < npass; ++q) {
             const Pass p = get_pass(c, q, nh, nc);
             if (p.kind == 0) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) hinge_pass(d, i, warm); }
-            else if (p.kind == 1) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) normal_pass(d, i, warm); }
-            else { for (uint32_t i = p.b + gtid; i < p.e; i += stride) friction_pass(d, i, warm); }
+            else if (p.kind == 1) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) normal_pass(d, i, d.hdr[i], make_uint2(0, 0), warm); }
+            else { for (uint32_t i = p.b + gtid; i < p.e; i += stride) friction_pass(d, i, d.hdr[i], make_uint2(0, 0), warm); }
             prefetch_pass(d, get_pass(c, q + 1 == npass ? 0 : q + 1, nh, nc), gtid);
             grid.sync();
         }
@@ -1089,39 +1087,50 @@ B2D_D uint32_t chunk_index(const uint32_t *chunk, const uint32_t *off, uint32_t 
     return off[col] + (j - chunk[col]) * 32u;
 }
 __global__ void __launch_bounds__(256, 2) k_solve_df(Dev d, int iters) {
+    // colour tables live in shared memory: every chunk walk reads them, and a global read costs an L2 round trip
+    __shared__ uint32_t s_coff[MAX_COLORS + 2], s_cchunk[MAX_COLORS + 2], s_hoff[MAX_COLORS + 2], s_hchunk[MAX_COLORS + 2];
     const Counters &c = *d.cnt;
+    if (threadIdx.x < MAX_COLORS + 2) {
+        s_coff[threadIdx.x] = c.coff[threadIdx.x]; s_cchunk[threadIdx.x] = c.cchunk[threadIdx.x];
+        s_hoff[threadIdx.x] = c.hoff[threadIdx.x]; s_hchunk[threadIdx.x] = c.hchunk[threadIdx.x];
+    }
     const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t hchunks = c.hchunk[nh], cchunks = c.cchunk[nc];
+    const uint32_t hchunks = s_hchunk[nh], cchunks = s_cchunk[nc];
+    // The header and ticket words of this warp's NEXT contact chunk are fetched one chunk ahead into registers (they
+    // are the same for every pass and both row types), so a chunk starts polling its bodies without first waiting for
+    // its own header; the rows of the next chunk are pulled towards L2 at the same time.
+    uint32_t ncol = 0, ni = 0; bool nact = false; uint4 nhd = make_uint4(0, 0, 0, 0); uint2 ntk = make_uint2(0, 0);
+    if (wid < cchunks) {
+        ni = chunk_index(s_cchunk, s_coff, wid, ncol) + lane; nact = ni < s_coff[ncol + 1];
+        if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; }
+    }
     for (int it = -1; it < iters; ++it) {
         const bool warm = it < 0;
         const int pass = it + 1;
         { uint32_t col = 0;
           for (uint32_t j = wid; j < hchunks; j += nw) {
-              const uint32_t i = chunk_index(c.hchunk, c.hoff, j, col) + lane;
-              const bool act = i < c.hoff[col + 1];
+              const uint32_t i = chunk_index(s_hchunk, s_hoff, j, col) + lane;
+              const bool act = i < s_hoff[col + 1];
               const uint32_t mask = __ballot_sync(0xffffffffu, act);
               if (act) hinge_pass(d, i, warm, pass, mask);
           } }
         #pragma unroll 1
         for (int kind = 1; kind <= 2; ++kind) {
-            uint32_t col = 0, pcol = 0;
             for (uint32_t j = wid; j < cchunks; j += nw) {
-                const uint32_t i = chunk_index(c.cchunk, c.coff, j, col) + lane;
-                const bool act = i < c.coff[col + 1];
-                const uint32_t mask = __ballot_sync(0xffffffffu, act);
-                // pull this warp's next chunk (same pass type) towards L2 while the current one is being solved
-                if (j + nw < cchunks) {
-                    if (pcol < col) pcol = col;
-                    const uint32_t ni = chunk_index(c.cchunk, c.coff, j + nw, pcol) + lane;
-                    if (ni < c.coff[pcol + 1]) {
-                        prefetch_L2(&d.hdr[ni]); prefetch_L2(&d.tkt[ni]);
-                        prefetch_L2(&d.R0[ni]); prefetch_L2(&d.R1[ni]); prefetch_L2(&d.R2[ni]); prefetch_L2(&d.IMP[ni]);
-                        if (kind == 2) prefetch_L2(&d.R3[ni]);
-                    }
+                const uint32_t i = ni; const bool act = nact; const uint4 hd = nhd; const uint2 tk2 = ntk;
+                uint32_t jn = j + nw;
+                if (jn >= cchunks) { jn = wid; ncol = 0; }
+                ni = chunk_index(s_cchunk, s_coff, jn, ncol) + lane; nact = ni < s_coff[ncol + 1];
+                if (nact) {
+                    nhd = d.hdr[ni]; ntk = d.tkt[ni];
+                    prefetch_L2(&d.R0[ni]); prefetch_L2(&d.R1[ni]); prefetch_L2(&d.R2[ni]); prefetch_L2(&d.IMP[ni]);
+                    if (kind == 2 || jn == wid) prefetch_L2(&d.R3[ni]);
                 }
-                if (act) { if (kind == 1) normal_pass(d, i, warm, pass, mask); else friction_pass(d, i, warm, pass, mask); }
+                const uint32_t mask = __ballot_sync(0xffffffffu, act);
+                if (act) { if (kind == 1) normal_pass(d, i, hd, tk2, warm, pass, mask); else friction_pass(d, i, hd, tk2, warm, pass, mask); }
             }
         }
     }
