@@ -4,7 +4,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2d.so")
+LIB_PATH = os.environ.get("B2D_LIB") or os.path.join(HERE, "libb2d.so")     # B2D_LIB: development builds
 SRC = os.path.join(HERE, "csrc", "b2d_api.cu")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -107,7 +107,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.dvw, 2 * (size_t)NB) && dalloc(w, d.invI, 3 * (size_t)NB) && dalloc(w, d.invIW, 3 * (size_t)NB);
     ok = ok && dalloc(w, d.grav, NB) && dalloc(w, d.shp, NB) && dalloc(w, d.bbmin, NB) && dalloc(w, d.bbmax, NB);
     ok = ok && dalloc(w, d.flags, NB) && dalloc(w, d.mat, NB) && dalloc(w, d.group, NB) && dalloc(w, d.fmask, NB);
-    ok = ok && dalloc(w, d.cellkey, NB) && dalloc(w, d.cellkey_s, NB) && dalloc(w, d.cellbody, NB) && dalloc(w, d.cellbody_s, NB);
+    ok = ok && dalloc(w, d.cellkey, NB) && dalloc(w, d.cellkey_s, NB) && dalloc(w, d.cellbody, NB) && dalloc(w, d.cellbody_s, NB) && dalloc(w, d.brank, NB);
     d.chash_size = pow2_at_least(2ull * NB);
     ok = ok && dalloc(w, d.chash_key, d.chash_size, 0xFF) && dalloc(w, d.chash_val, d.chash_size);
     ok = ok && dalloc(w, d.large_list, NB) && dalloc(w, d.newcount, NB) && dalloc(w, d.newoff, NB) && dalloc(w, d.newpairs, NM);
@@ -134,7 +134,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     // CUB temp storage: the largest of the sorts/scans used per step
     size_t need = 0, t = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)NB, 0, 63, w->stream); need = std::max(need, t);
-    cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, 9, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, COLOR_KEY_BITS, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
     w->cub_tmp_bytes = need + 256;
@@ -383,7 +383,7 @@ static int enqueue_solver(b2d_world *w) {
     CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d));
     LAUNCH(k_color_keys, d.NM, 256, d);
     size_t t = w->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 9, s)); w->launches += 3;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, COLOR_KEY_BITS, s)); w->launches += 3;
     t = w->cub_tmp_bytes;
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)d.NH, 0, 8, s)); w->launches += 3;
     LAUNCH(k_color_offsets, d.NM, 256, d);

@@ -144,12 +144,25 @@ __global__ void k_bp_free_list(Dev d) {
     }
 }
 
+#ifndef B2D_MORTON_CELLS
+#define B2D_MORTON_CELLS 0       // measured: Z-order cells are no better for the solver and slower for the pair search
+#endif
 B2D_D unsigned long long cell_key_of(int cx, int cy, int cz) {
     const int OFF = 1 << 20, MX = (1 << 21) - 1;
     unsigned long long x = (unsigned long long)min(max(cx + OFF, 0), MX);
     unsigned long long y = (unsigned long long)min(max(cy + OFF, 0), MX);
     unsigned long long z = (unsigned long long)min(max(cz + OFF, 0), MX);
+#if B2D_MORTON_CELLS
+    // Z-order: bodies that are neighbours in the sorted cell list are neighbours in space (the colour sort reuses the rank)
+    auto spread = [](unsigned long long v) {
+        v = (v | (v << 32)) & 0x1F00000000FFFFULL; v = (v | (v << 16)) & 0x1F0000FF0000FFULL;
+        v = (v | (v << 8)) & 0x100F00F00F00F00FULL; v = (v | (v << 4)) & 0x10C30C30C30C30C3ULL;
+        v = (v | (v << 2)) & 0x1249249249249249ULL; return v;
+    };
+    return (spread(x) << 2) | (spread(y) << 1) | spread(z);
+#else
     return (x << 42) | (y << 21) | z;
+#endif
 }
 B2D_D void cell_of(const Dev &d, uint32_t i, int &cx, int &cy, int &cz) {
     float4 a = d.bbmin[i], b = d.bbmax[i];
@@ -172,6 +185,7 @@ __global__ void k_bp_cell_starts(Dev d) {
     GRID_STRIDE(i, d.nbodies) {
         unsigned long long k = d.cellkey_s[i];
         if (k != EMPTY_KEY && (i == 0 || d.cellkey_s[i - 1] != k)) hash_insert(d.chash_key, d.chash_val, d.chash_size, k, i);
+        d.brank[d.cellbody_s[i]] = i;
     }
 }
 
@@ -342,13 +356,13 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
 __global__ void k_np_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, d.NM) {
-        unsigned short key = 0xFF;
+        uint32_t key = 0xFF;
         if (m < hwm && (d.mstate[m] & MS_ALIVE)) {
             uint2 pr = d.mpair[m];
             int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
             int fn = pair_fn(ka, kb);
             if (!fn) fn = pair_fn(kb, ka);
-            key = (unsigned short)fn;
+            key = (uint32_t)fn;
         }
         d.ckey[m] = key; d.cidx[m] = m;
     }
@@ -356,7 +370,7 @@ __global__ void k_np_keys(Dev d) {
 }
 __global__ void k_np_offsets(Dev d) {
     GRID_STRIDE(i, d.NM) {
-        unsigned short k = d.ckey_s[i];
+        uint32_t k = d.ckey_s[i];
         if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->npoff[k == 0xFF ? 10 : k] = i;
     }
 }
@@ -630,10 +644,20 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
 __global__ void k_color_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, d.NM) {
-        // sort key: colour, then point count -- chunks of 32 manifolds then run the same number of row solves in
-        // every lane, and single-point manifolds publish their bodies without waiting for four-point neighbours
-        unsigned short key = 0x100;
-        if (m < hwm) { uint32_t st = d.mstate[m]; if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) key = (unsigned short)((((st >> MS_COLOR_SHIFT) & 0x3Fu) << 2) | ((st & MS_NPTS_MASK) - 1u)); }
+        // sort key: colour, then point count (a chunk of 32 manifolds runs the same number of row solves in every
+        // lane), then the spatial rank of the manifold's dynamic body (lanes of a chunk touch neighbouring bodies, whose
+        // predecessors finish at about the same time and whose records share L2 sectors)
+        uint32_t key = 1u << (COLOR_KEY_BITS - 1);
+        if (m < hwm) {
+            uint32_t st = d.mstate[m];
+            if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) {
+                const uint2 pr = d.mpair[m];
+                const uint32_t fa = d.flags[pr.x];
+                const uint32_t b = (is_dynamic(fa) && !(fa & F_LARGE)) ? pr.x : pr.y;
+                const uint32_t sp = (uint32_t)(((unsigned long long)d.brank[b] << COLOR_KEY_SPATIAL_BITS) / d.nbodies);
+                key = (((st >> MS_COLOR_SHIFT) & 0x3Fu) << (COLOR_KEY_SPATIAL_BITS + 2)) | (((st & MS_NPTS_MASK) - 1u) << COLOR_KEY_SPATIAL_BITS) | sp;
+            }
+        }
         d.ckey[m] = key; d.cidx[m] = m;
     }
     GRID_STRIDE(h, d.NH) {
@@ -645,8 +669,8 @@ __global__ void k_color_keys(Dev d) {
 }
 __global__ void k_color_offsets(Dev d) {
     GRID_STRIDE(i, d.NM) {
-        unsigned short k = d.ckey_s[i] >> 2;
-        if (i == 0 || (d.ckey_s[i - 1] >> 2) != k) d.cnt->coff[k >= MAX_COLORS ? MAX_COLORS : k] = i;
+        uint32_t k = d.ckey_s[i] >> (COLOR_KEY_SPATIAL_BITS + 2);
+        if (i == 0 || (d.ckey_s[i - 1] >> (COLOR_KEY_SPATIAL_BITS + 2)) != k) d.cnt->coff[k >= MAX_COLORS ? MAX_COLORS : k] = i;
     }
     GRID_STRIDE(i, d.NH) {
         unsigned char k = d.hkey_s[i];
@@ -861,8 +885,24 @@ B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
     if (!t.on) return true;
     return (!A.proc || vb_try(d, A, t.ta)) & (!B.proc || vb_try(d, B, t.tb));
 }
+#ifdef B2D_DF_PROFILE
+// Development build (-DB2D_DF_PROFILE, tools/dbg4.py): per-warp cycle accounting of the dataflow solver, flushed once per
+// warp into Counters::dbg -- [0]/[1] cycles in poll iterations without/with progress, [2]/[3] their counts, [4] chunk
+// passes, [5] total cycles, [6] warps.
+__shared__ unsigned long long s_prof[8][8];
+__shared__ long long s_prof_t[8];
+#endif
 B2D_D bool acquire_more(const Dev &d, const Ticket &t, bool pending, bool progressed, uint32_t &spins) {
     if (!t.on) return false;
+#ifdef B2D_DF_PROFILE
+    {
+        const bool prog = __any_sync(t.mask, progressed);
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(t.mask) - 1)) {
+            const uint32_t w = threadIdx.x >> 5; const long long now = clock64();
+            s_prof[w][prog ? 1 : 0] += (unsigned long long)(now - s_prof_t[w]); s_prof[w][prog ? 3 : 2] += 1; s_prof_t[w] = now;
+        }
+    }
+#endif
     if (!__any_sync(t.mask, pending)) return false;
     if (!__any_sync(t.mask, progressed)) {
         if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); return false; }      // never hang the GPU
@@ -1107,6 +1147,11 @@ __global__ void __launch_bounds__(256, 2) k_solve_df(Dev d, int iters) {
         ni = chunk_index(s_cchunk, s_coff, wid, ncol) + lane; nact = ni < s_coff[ncol + 1];
         if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; }
     }
+#ifdef B2D_DF_PROFILE
+    if (lane < 8) s_prof[threadIdx.x >> 5][lane] = 0;
+    const long long t_begin = clock64();
+    __syncwarp();
+#endif
     for (int it = -1; it < iters; ++it) {
         const bool warm = it < 0;
         const int pass = it + 1;
@@ -1130,10 +1175,22 @@ __global__ void __launch_bounds__(256, 2) k_solve_df(Dev d, int iters) {
                     if (kind == 2 || jn == wid) prefetch_L2(&d.R3[ni]);
                 }
                 const uint32_t mask = __ballot_sync(0xffffffffu, act);
+#ifdef B2D_DF_PROFILE
+                __syncwarp(); if (lane == 0) { s_prof_t[threadIdx.x >> 5] = clock64(); s_prof[threadIdx.x >> 5][4] += 1; } __syncwarp();
+#endif
                 if (act) { if (kind == 1) normal_pass(d, i, hd, tk2, warm, pass, mask); else friction_pass(d, i, hd, tk2, warm, pass, mask); }
             }
         }
     }
+#ifdef B2D_DF_PROFILE
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t w = threadIdx.x >> 5;
+        for (int k = 0; k < 5; ++k) atomicAdd(&d.cnt->dbg[k], s_prof[w][k]);
+        atomicAdd(&d.cnt->dbg[5], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&d.cnt->dbg[6], 1ULL);
+    }
+#endif
 }
 
 // assign_applied_impulses (island_solver.cpp:232-248): rows -> warm-start cache of the constraints.

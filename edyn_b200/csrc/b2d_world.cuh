@@ -21,6 +21,11 @@ constexpr uint32_t MS_COLOR_SHIFT = 8;        // bits 8..15 colour, 0xFF = none
 constexpr uint32_t MS_COLOR_MASK = 0xFFu << MS_COLOR_SHIFT;
 constexpr uint32_t COLOR_NONE = 0xFFu;
 constexpr int MAX_COLORS = 64;
+#ifndef B2D_SPATIAL_BITS
+#define B2D_SPATIAL_BITS 16
+#endif
+constexpr int COLOR_KEY_SPATIAL_BITS = B2D_SPATIAL_BITS;                  // colour-sort key: colour(6) | points-1 (2) | spatial rank
+constexpr int COLOR_KEY_BITS = 6 + 2 + COLOR_KEY_SPATIAL_BITS + 1;      // + the 'inactive' bit on top
 
 constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
 constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
@@ -72,6 +77,7 @@ struct Dev {
     // ---- broadphase scratch
     unsigned long long *cellkey, *cellkey_s;
     uint32_t *cellbody, *cellbody_s;
+    uint32_t *brank;                     // position of every body in the sorted cell order (spatial rank)
     unsigned long long *chash_key; uint32_t *chash_val; uint32_t chash_size;
     uint32_t *large_list;
     uint32_t *newcount, *newoff;
@@ -94,7 +100,7 @@ struct Dev {
     uint32_t *parent;
     unsigned long long *bmask, *jmask;      // colours in use per body (contacts / hinges)
     unsigned long long *prop, *jprop;
-    unsigned short *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
+    uint32_t *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
     uint32_t *clist;             // colouring work list (manifold slots with points)
     unsigned char *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
     uint32_t *isl_err; uint32_t *isl_done;
