@@ -842,13 +842,20 @@ B2D_D Ticket ticket_of(uint32_t tagA, uint32_t tagB, uint2 tk, int pass, int kin
     t.tb = (uint32_t)pass * SB + bB + (kind == 2 ? kB : 0u);
     return t;
 }
-struct VBody { v3 dv, dw; float inv_m; m3 inv_I; uint32_t id; bool proc; };
+// ptxas recycles the unused lanes of a 128-bit load as scratch registers straight away, and the write-after-write hazard
+// then parks the warp until the load has landed -- in front of the ticket poll.  keep() pins such a lane as live up to
+// the point where the rest of the vector is consumed.
+B2D_D void keep(float x) { asm volatile("" :: "f"(x)); }
+B2D_D void keep(uint32_t x) { asm volatile("" :: "r"(x)); }
+struct VBody { v3 dv, dw; float inv_m; m3 inv_I; uint32_t id; bool proc; float pad1, pad2; };
+B2D_D void keep(const VBody &b) { keep(b.pad1); keep(b.pad2); }
 B2D_D void vb_load(const Dev &d, uint32_t tag, VBody &b) {
     b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
     if (b.proc) {
         b.dv = mk3(__ldcg(&d.dvw[2 * b.id])); b.dw = mk3(__ldcg(&d.dvw[2 * b.id + 1]));
-        float4 r0 = d.invIW[3 * b.id]; b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * b.id + 1]); b.inv_I.r2 = mk3(d.invIW[3 * b.id + 2]);
-    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); }
+        float4 r0 = d.invIW[3 * b.id], r1 = d.invIW[3 * b.id + 1], r2 = d.invIW[3 * b.id + 2];
+        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2); b.pad1 = r1.w; b.pad2 = r2.w;
+    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); b.pad1 = b.pad2 = 0; }
 }
 B2D_D void vb_store(const Dev &d, const VBody &b) {
     if (b.proc) { __stcg(&d.dvw[2 * b.id], f4(b.dv, 0)); __stcg(&d.dvw[2 * b.id + 1], f4(b.dw, 0)); }
@@ -866,8 +873,10 @@ B2D_D void st_volatile4(float4 *p, float4 v) {
 B2D_D void vb_static(const Dev &d, uint32_t tag, VBody &b) {
     b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
     b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0);
-    if (b.proc) { float4 r0 = d.invIW[3 * b.id]; b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * b.id + 1]); b.inv_I.r2 = mk3(d.invIW[3 * b.id + 2]); }
-    else { b.inv_m = 0; b.inv_I = m3_zero(); }
+    if (b.proc) {
+        float4 r0 = d.invIW[3 * b.id], r1 = d.invIW[3 * b.id + 1], r2 = d.invIW[3 * b.id + 2];
+        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2); b.pad1 = r1.w; b.pad2 = r2.w;
+    } else { b.inv_m = 0; b.inv_I = m3_zero(); b.pad1 = b.pad2 = 0; }
 }
 B2D_D bool vb_try(const Dev &d, VBody &b, uint32_t expect) {
     float4 a = ld_volatile4(&d.dvw[2 * b.id]), w = ld_volatile4(&d.dvw[2 * b.id + 1]);
@@ -998,12 +1007,14 @@ B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2
     const size_t NM = d.NM;
     NRow ra, rb;
     ra = load_nrow(d, i);
-    if (n > 1) rb = load_nrow(d, NM + i);
+    rb = load_nrow(d, n > 1 ? NM + i : i);          // unconditional: a predicated load drags a zero-fill + WAW wait along
     VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
     bool pending = true; uint32_t spins = 0;
     do {
     const bool ok = pending && acquire_try(d, tk, A, B);
     if (ok) {
+    keep(A); keep(B); keep(hd.w); keep(ra.r2.w); keep(ra.im.y); keep(ra.im.z); keep(ra.im.w);
+    keep(rb.r2.w); keep(rb.im.y); keep(rb.im.z); keep(rb.im.w);
     solve_nrow(d, ra, i, A, B, warm);
     if (n > 2) ra = load_nrow(d, 2 * NM + i);
     if (n > 1) solve_nrow(d, rb, NM + i, A, B, warm);
@@ -1051,12 +1062,14 @@ B2D_D void friction_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 t
     const size_t NM = d.NM;
     FRow ra, rb;
     ra = load_frow(d, i);
-    if (n > 1) rb = load_frow(d, NM + i);
+    rb = load_frow(d, n > 1 ? NM + i : i);
     VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
     bool pending = true; uint32_t spins = 0;
     do {
     const bool ok = pending && acquire_try(d, tk, A, B);
     if (ok) {
+    keep(A); keep(B); keep(hd.w); keep(ra.r0.w); keep(ra.r1.w); keep(ra.im.w);
+    keep(rb.r0.w); keep(rb.r1.w); keep(rb.im.w);
     solve_frow(d, ra, i, A, B, warm);
     if (n > 2) ra = load_frow(d, 2 * NM + i);
     if (n > 1) solve_frow(d, rb, NM + i, A, B, warm);
