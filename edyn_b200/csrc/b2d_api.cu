@@ -127,7 +127,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.hpair, NH) && dalloc(w, d.hpivA, NH) && dalloc(w, d.hpivB, NH) && dalloc(w, d.hfA0, NH) && dalloc(w, d.hfA1, NH);
     ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
     ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
-    ok = ok && dalloc(w, d.seq, NB) && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH);
+    ok = ok && dalloc(w, d.seq, NB) && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH) && dalloc(w, d.pisl, NM) && dalloc(w, d.hisl, NH) && dalloc(w, d.prec, 3 * NB);
     // hcolor must hold COLOR_NONE (0xFF as a 32-bit value), not 0xFFFFFFFF
     if (ok) { std::vector<uint32_t> hc(NH, COLOR_NONE); cudaMemcpyAsync(d.hcolor, hc.data(), NH * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 
@@ -363,8 +363,10 @@ static int enqueue_islands(b2d_world *w) {
     Dev &d = w->d;
     CK(cudaMemsetAsync(&d.cnt->nislands, 0, sizeof(uint32_t), w->stream));
     LAUNCH(k_cc_init, d.nbodies, 256, d);
-    LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d);
-    LAUNCH(k_cc_flatten, d.nbodies, 256, d);
+    LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d, 0);
+    LAUNCH(k_cc_flatten, d.nbodies, 256, d, 0);
+    LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d, 1);
+    LAUNCH(k_cc_flatten, d.nbodies, 256, d, 1);
     return B2D_OK;
 }
 static int enqueue_solver(b2d_world *w) {
@@ -405,7 +407,7 @@ static int enqueue_solver(b2d_world *w) {
     if (pi > 0) {
         CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
         if (w->barrier_solver) CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
-        else { CK(cudaMemsetAsync(d.seq, 0, (size_t)d.nbodies * sizeof(uint32_t), s)); CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, 256, d, pi)); }
+        else CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, 256, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
     w->timed = true;

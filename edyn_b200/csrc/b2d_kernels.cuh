@@ -525,16 +525,24 @@ B2D_D void cc_union(uint32_t *parent, uint32_t a, uint32_t b) {
     }
 }
 __global__ void k_cc_init(Dev d) { GRID_STRIDE(i, d.nbodies) d.parent[i] = i; }
-__global__ void k_cc_union(Dev d) {
+// Two rounds: a quarter of the edges is hooked first and the forest flattened; in a dense contact graph that already
+// joins most of every island, so the remaining edges mostly find parent[a] == parent[b] with two plain reads and never
+// reach the find / compare-and-swap path (which otherwise funnels the whole grid through the root of a giant island).
+__global__ void k_cc_union(Dev d, int round) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, hwm + d.nhinges) {
         uint2 p;
-        if (m < hwm) { if (!(d.mstate[m] & MS_ALIVE)) continue; p = d.mpair[m]; }
-        else p = d.hpair[m - hwm];
-        if (is_dynamic(d.flags[p.x]) && is_dynamic(d.flags[p.y])) cc_union(d.parent, p.x, p.y);
+        if (m < hwm) {
+            if (((m & 3u) == 0u) != (round == 0)) continue;
+            if (!(d.mstate[m] & MS_ALIVE)) continue;
+            p = d.mpair[m];
+        } else { if (round != 0) continue; p = d.hpair[m - hwm]; }
+        if (!is_dynamic(d.flags[p.x]) || !is_dynamic(d.flags[p.y])) continue;
+        if (round != 0 && d.parent[p.x] == d.parent[p.y]) continue;
+        cc_union(d.parent, p.x, p.y);
     }
 }
-__global__ void k_cc_flatten(Dev d) {
+__global__ void k_cc_flatten(Dev d, int last) {
     GRID_STRIDE(i, d.nbodies) {
         if (is_dynamic(d.flags[i])) {
             // read-only walk: a concurrent path-compressing find could overwrite another thread's final root with a
@@ -542,9 +550,9 @@ __global__ void k_cc_flatten(Dev d) {
             uint32_t r = i, p = d.parent[r];
             while (p != r) { r = p; p = d.parent[r]; }
             d.parent[i] = r;
-            if (r == i) atomicAdd(&d.cnt->nislands, 1u);
+            if (last && r == i) atomicAdd(&d.cnt->nislands, 1u);
         }
-        else d.parent[i] = 0xFFFFFFFFu;
+        else if (last) d.parent[i] = 0xFFFFFFFFu;
     }
 }
 
@@ -745,6 +753,7 @@ __global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
                 t[k] = (kh + 2 * kc) | ((kh + __popcll(bm & below)) << 8) | (kc << 16);
             }
             d.tkt[i] = make_uint2(t[0], t[1]);
+            { const uint32_t l = d.parent[pr.x]; d.pisl[i] = l != 0xFFFFFFFFu ? l : d.parent[pr.y]; }
         }
         for (uint32_t s = 0; s < npts; ++s) {
             size_t mi = (size_t)s * d.NM + m, ri = (size_t)s * d.NM + i;
@@ -814,6 +823,7 @@ __global__ void k_prepare_hinges(Dev d) {
                 t[k] = (__popcll(jm) + 2 * __popcll(bm)) | (__popcll(jm & below) << 8) | (__popcll(bm) << 16);
             }
             d.htkt[i] = make_uint2(t[0], t[1]);
+            { const uint32_t l = d.parent[pr.x]; d.hisl[i] = l != 0xFFFFFFFFu ? l : d.parent[pr.y]; }
         }
     }
 }
@@ -864,11 +874,15 @@ B2D_D void vb_store(const Dev &d, const VBody &b) {
 // body's ticket in BOTH .w lanes, so data and synchronisation travel in the same L2 transactions: a reader that
 // sees the expected ticket in both halves has a consistent record (16 B aligned vector stores are single
 // transactions; a torn pair is rejected by the double check) and needs no fence, a writer needs none either.
+#ifndef B2D_LD_POLL
+#define B2D_LD_POLL "ld.relaxed.gpu.global.v4.f32"     // gpu scope is all the protocol needs (.volatile = relaxed.sys)
+#define B2D_ST_POLL "st.relaxed.gpu.global.v4.f32"
+#endif
 B2D_D float4 ld_volatile4(const float4 *p) {
-    float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+    float4 v; asm volatile(B2D_LD_POLL " {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
 }
 B2D_D void st_volatile4(float4 *p, float4 v) {
-    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile(B2D_ST_POLL " [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 B2D_D void vb_static(const Dev &d, uint32_t tag, VBody &b) {
     b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
@@ -1260,9 +1274,9 @@ __global__ void __launch_bounds__(256) k_finalize(Dev d) {
 
 // ====================================================================== position iterations
 
-struct PBody { v3 pos; q4 orn; float inv_m; m3 inv_IW, inv_I; uint32_t id; bool proc; };
+struct PBody { v3 pos; q4 orn; float inv_m; m3 inv_IW, inv_I; uint32_t id; bool proc; bool fresh; };   // fresh: corrected in this solve
 B2D_D void pb_load(const Dev &d, uint32_t id, PBody &b) {
-    b.id = id; b.proc = is_dynamic(d.flags[id]);
+    b.id = id; b.proc = is_dynamic(d.flags[id]); b.fresh = false;
     float4 p4 = __ldcg(&d.pos[id]);
     b.pos = mk3(p4); b.orn = mkq(__ldcg(&d.orn[id]));
     if (b.proc) {
@@ -1288,14 +1302,14 @@ B2D_D void position_solve(PBody &A, PBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float 
         v3 ac = A.inv_IW * J1 * corr;
         A.orn = A.orn + quat_derivative(A.orn, ac);
         A.orn = normalize(A.orn);
-        A.inv_IW = world_inertia(A.orn, A.inv_I);
+        A.inv_IW = world_inertia(A.orn, A.inv_I); A.fresh = true;
     }
     if (B.proc) {
         B.pos += B.inv_m * J2 * corr;
         v3 ac = B.inv_IW * J3 * corr;
         B.orn = B.orn + quat_derivative(B.orn, ac);
         B.orn = normalize(B.orn);
-        B.inv_IW = world_inertia(B.orn, B.inv_I);
+        B.inv_IW = world_inertia(B.orn, B.inv_I); B.fresh = true;
     }
     max_error = fmaxf(fabsf(error), max_error);
 }
@@ -1428,36 +1442,189 @@ __global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
 
 // Dataflow flavour (default): colours inside an iteration are ordered by per-body tickets instead of grid barriers;
 // only the per-island convergence test between iterations still needs the whole grid (2 barriers per iteration).
-__global__ void __launch_bounds__(256) k_position_df(Dev d, int iters) {
+#ifndef B2D_POS_MIN_BLOCKS
+#define B2D_POS_MIN_BLOCKS 1
+#endif
+// ---- dataflow flavour of the position iterations (default).  Same idea as k_solve_df: what a constraint needs from a
+// body AND the body's ticket travel in the same 16-byte vectors, so a poll that sees the expected ticket in all three
+// vectors of a record already holds a consistent position / orientation and no fence or separate counter is needed.
+// The record does not carry the world-space inverse inertia: a body that was corrected at least once in this solve
+// ("fresh") has inv_IW == world_inertia(orn, inv_I) exactly (position_solve recomputes it that way), so the reader
+// recomputes it from the orientation; an untouched body still uses the tensor of the previous step (the reference
+// refreshes inertia only after the position iterations, solver.cpp:453-465), read from d.invIW.
+struct PRec { float4 p0, p1, p2; };
+B2D_D void prec_issue(const Dev &d, uint32_t id, PRec &r) {
+    const float4 *p = d.prec + 3 * (size_t)id;
+    r.p0 = ld_volatile4(p); r.p1 = ld_volatile4(p + 1); r.p2 = ld_volatile4(p + 2);
+}
+B2D_D bool prec_ok(const PRec &r, uint32_t t) {
+    return __float_as_uint(r.p0.w) == t && __float_as_uint(r.p1.w) == t && __float_as_uint(r.p2.w) == t;
+}
+B2D_D void prec_take(const PRec &r, PBody &b, const m3 &stale) {
+    b.pos = mk3(r.p0); b.orn.x = r.p1.x; b.orn.y = r.p1.y; b.orn.z = r.p1.z; b.orn.w = r.p2.x;
+    b.fresh = r.p2.y != 0.0f;
+    b.inv_IW = b.fresh ? world_inertia(b.orn, b.inv_I) : stale;
+}
+B2D_D void prec_publish(const Dev &d, const PBody &b, uint32_t t) {
+    float4 *p = d.prec + 3 * (size_t)b.id;
+    const float tf = __uint_as_float(t);
+    st_volatile4(p, f4(b.pos, tf)); st_volatile4(p + 1, make_float4(b.orn.x, b.orn.y, b.orn.z, tf)); st_volatile4(p + 2, make_float4(b.orn.w, b.fresh ? 1.0f : 0.0f, 0.0f, tf));
+}
+// everything of a body that does not change during the solve; `stale` = inverse world inertia of the previous step
+B2D_D void pb_begin(const Dev &d, uint32_t id, bool proc, PBody &b, m3 &stale) {
+    b.id = id; b.proc = proc; b.fresh = false;
+    if (proc) {
+        const float4 r0 = d.invIW[3 * id], r1 = d.invIW[3 * id + 1], r2 = d.invIW[3 * id + 2];
+        b.inv_m = r0.w; stale.r0 = mk3(r0); stale.r1 = mk3(r1); stale.r2 = mk3(r2);
+        b.inv_I = load_m3(d.invI, id);
+    } else {
+        b.pos = mk3(d.pos[id]); b.orn = mkq(d.orn[id]);
+        b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero(); stale = m3_zero();
+    }
+}
+// One chunk of position constraints.  `work` runs the constraint on (A, B) and returns its max error.
+template<typename Work>
+B2D_D void position_chunk_df(const Dev &d, uint32_t tagA, uint32_t tagB, uint2 tk2, uint32_t isl, int it, uint32_t mask, Work work) {
+    const uint32_t a = tagA & 0x7FFFFFFFu, b = tagB & 0x7FFFFFFFu;
+    const bool pa = !(tagA >> 31), pb = !(tagB >> 31);
+    // all constraints of a finished island skip together (and keep skipping), so their tickets stay consistent
+    const bool skip = __ldcg(&d.isl_done[isl]) != 0;
+    PBody A, B; m3 staleA, staleB;
+    pb_begin(d, a, pa, A, staleA); pb_begin(d, b, pb, B, staleB);
+    const uint32_t live = __ballot_sync(mask, !skip);
+    if (skip) return;
+    const PTicket tk = pticket_of(tk2, it, live, true);
+    bool pending = true; uint32_t spins = 0;
+    do {
+        PRec ra, rb;
+        if (pa) prec_issue(d, a, ra);
+        if (pb) prec_issue(d, b, rb);
+        const bool ok = (!pa || prec_ok(ra, tk.ta)) & (!pb || prec_ok(rb, tk.tb));
+        if (ok) {
+            if (pa) prec_take(ra, A, staleA);
+            if (pb) prec_take(rb, B, staleB);
+            const float max_error = work(A, B);
+            if (pa) prec_publish(d, A, tk.ta + 1);
+            if (pb) prec_publish(d, B, tk.tb + 1);
+            island_error_max(d, isl, max_error);
+            pending = false;
+        }
+        if (!__any_sync(live, pending)) break;
+        if (!__any_sync(live, ok)) {
+            if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); break; }      // never hang the GPU
+            if (spins > 64) __nanosleep(20);
+        }
+    } while (true);
+}
+// contact_constraint::solve_position, contact_constraint.cpp:58-90
+B2D_D void contact_position_df(const Dev &d, uint4 hd, uint2 tk2, uint32_t isl, int it, uint32_t mask) {
+    const uint32_t m = hd.w, n = hd.z;
+    const size_t NM = d.NM;
+    // slot 0 of the manifold is in flight while the tickets are polled
+    const float4 a0 = d.pA[m], b0 = d.pB[m], n0 = d.pN[m], l0 = d.pL[m];
+    position_chunk_df(d, hd.x, hd.y, tk2, isl, it, mask, [&](PBody &A, PBody &B) {
+        float max_error = 0.0f;
+        float4 a4 = a0, b4 = b0, n4 = n0, l4 = l0;
+        for (uint32_t s = 0; s < n; ++s) {
+            const size_t mi = (size_t)s * NM + m;
+            if (s) { a4 = d.pA[mi]; b4 = d.pB[mi]; n4 = d.pN[mi]; l4 = d.pL[mi]; }
+            v3 pAw = to_world(mk3(a4), A.pos, A.orn), pBw = to_world(mk3(b4), B.pos, B.orn);
+            unsigned att = __float_as_uint(l4.w) & 3u;
+            v3 normal = mk3(n4);
+            if (att == ATT_A) normal = rotate(A.orn, mk3(l4)); else if (att == ATT_B) normal = rotate(B.orn, mk3(l4));
+            float dist = dot(pAw - pBw, normal);
+            v3 rA = pAw - A.pos, rB = pBw - B.pos;
+            d.pN[mi] = f4(normal, n4.w); d.pA[mi] = f4(mk3(a4), dist);
+            if (dist > -EPS) continue;
+            position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
+        }
+        return max_error;
+    });
+}
+// hinge_constraint::solve_position, hinge_constraint.cpp:180-213
+B2D_D void hinge_position_df(const Dev &d, uint4 hd, uint2 tk2, uint32_t isl, int it, uint32_t mask) {
+    const uint32_t h = hd.z;
+    const v3 fA0 = mk3(d.hfA0[h]), fB0 = mk3(d.hfB0[h]), pvA = mk3(d.hpivA[h]), pvB = mk3(d.hpivB[h]);
+    position_chunk_df(d, hd.x, hd.y, tk2, isl, it, mask, [&](PBody &A, PBody &B) {
+        float max_error = 0.0f;
+        v3 axisA = rotate(A.orn, fA0), axisB = rotate(B.orn, fB0);
+        v3 p, q; plane_space(axisA, p, q);
+        v3 u = cross(axisA, axisB);
+        const v3 z = mk3(0, 0, 0);
+        { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
+        { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
+        v3 pivotA = to_world(pvA, A.pos, A.orn), pivotB = to_world(pvB, B.pos, B.orn);
+        v3 dir = pivotA - pivotB;
+        float e = length(dir);
+        if (e > EPS) {
+            dir /= e;
+            v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+            position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
+        }
+        return max_error;
+    });
+}
+__global__ void __launch_bounds__(256, B2D_POS_MIN_BLOCKS) k_position_df(Dev d, int iters) {
+    __shared__ uint32_t s_coff[MAX_COLORS + 2], s_cchunk[MAX_COLORS + 2], s_hoff[MAX_COLORS + 2], s_hchunk[MAX_COLORS + 2];
     GridBarrier grid(&d.cnt->bar);
     const Counters &c = *d.cnt;
+    if (threadIdx.x < MAX_COLORS + 2) {
+        s_coff[threadIdx.x] = c.coff[threadIdx.x]; s_cchunk[threadIdx.x] = c.cchunk[threadIdx.x];
+        s_hoff[threadIdx.x] = c.hoff[threadIdx.x]; s_hchunk[threadIdx.x] = c.hchunk[threadIdx.x];
+    }
     const uint32_t nc = c.ncolors, nh = c.nhcolors;
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t hchunks = c.hchunk[nh], cchunks = c.cchunk[nc];
-    GRID_STRIDE(i, d.nbodies) { d.isl_err[i] = 0; d.isl_done[i] = 0; }
+    const uint32_t hchunks = s_hchunk[nh], cchunks = s_cchunk[nc];
+    GRID_STRIDE(i, d.nbodies) {
+        d.isl_err[i] = 0; d.isl_done[i] = 0;
+        if (is_dynamic(d.flags[i])) {
+            const float4 p4 = d.pos[i], o4 = d.orn[i];
+            float4 *r = d.prec + 3 * (size_t)i;
+            r[0] = make_float4(p4.x, p4.y, p4.z, 0.0f); r[1] = make_float4(o4.x, o4.y, o4.z, 0.0f); r[2] = make_float4(o4.w, 0.0f, 0.0f, 0.0f);
+        }
+    }
+    // header, ticket and island words of this warp's next contact chunk are fetched one chunk ahead (as in k_solve_df)
+    uint32_t ncol = 0, ni = 0, nisl = 0; bool nact = false; uint4 nhd = make_uint4(0, 0, 0, 0); uint2 ntk = make_uint2(0, 0);
+    if (wid < cchunks) {
+        ni = chunk_index(s_cchunk, s_coff, wid, ncol) + lane; nact = ni < s_coff[ncol + 1];
+        if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; }
+    }
     grid.sync();
     for (int it = 0; it < iters; ++it) {
         { uint32_t col = 0;
           for (uint32_t j = wid; j < hchunks; j += nw) {
-              const uint32_t i = chunk_index(c.hchunk, c.hoff, j, col) + lane;
-              const bool act = i < c.hoff[col + 1];
+              const uint32_t i = chunk_index(s_hchunk, s_hoff, j, col) + lane;
+              const bool act = i < s_hoff[col + 1];
               const uint32_t mask = __ballot_sync(0xffffffffu, act);
-              if (act) hinge_position(d, i, it, mask, true);
+              if (act) hinge_position_df(d, d.hhdr[i], d.htkt[i], d.hisl[i], it, mask);
           } }
-        { uint32_t col = 0;
-          for (uint32_t j = wid; j < cchunks; j += nw) {
-              const uint32_t i = chunk_index(c.cchunk, c.coff, j, col) + lane;
-              const bool act = i < c.coff[col + 1];
-              const uint32_t mask = __ballot_sync(0xffffffffu, act);
-              if (act) contact_position(d, i, it, mask, true);
-          } }
+        for (uint32_t j = wid; j < cchunks; j += nw) {
+            const bool act = nact; const uint4 hd = nhd; const uint2 tk2 = ntk; const uint32_t isl = nisl;
+            uint32_t jn = j + nw;
+            if (jn >= cchunks) { jn = wid; ncol = 0; }
+            ni = chunk_index(s_cchunk, s_coff, jn, ncol) + lane; nact = ni < s_coff[ncol + 1];
+            if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; }
+            const uint32_t mask = __ballot_sync(0xffffffffu, act);
+            if (act) contact_position_df(d, hd, tk2, isl, it, mask);
+        }
         if (it + 1 < iters) {
             grid.sync();
             GRID_STRIDE(i, d.nbodies) {
                 if (d.parent[i] == i) { if (__uint_as_float(d.isl_err[i]) < 0.005f) d.isl_done[i] = 1; d.isl_err[i] = 0; }
             }
             grid.sync();
+        }
+    }
+    grid.sync();
+    GRID_STRIDE(i, d.nbodies) {
+        if (is_dynamic(d.flags[i])) {
+            const float4 *r = d.prec + 3 * (size_t)i;
+            const float4 r0 = __ldcg(r), r1 = __ldcg(r + 1), r2 = __ldcg(r + 2);
+            if (r2.y != 0.0f) {        // corrected at least once
+                d.pos[i] = make_float4(r0.x, r0.y, r0.z, d.pos[i].w); d.orn[i] = make_float4(r1.x, r1.y, r1.z, r2.x);
+            }
         }
     }
 }

@@ -125,6 +125,8 @@ struct Dev {
 
     // ---- dataflow schedule of the velocity solve
     uint32_t *seq;               // per body: number of constraint passes applied so far in this solve
+    uint32_t *pisl, *hisl;       // per sorted constraint: island label (position solver early exit)
+    float4 *prec;                // position solver: 3 float4 per body, (pos,t) (orn.xyz,t) (orn.w,fresh,0,t)
     uint2 *tkt, *htkt;           // per sorted constraint, per body side: S | base << 8 | k << 16 (see k_prepare_*)
 
     Counters *cnt;
