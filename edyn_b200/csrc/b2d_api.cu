@@ -127,7 +127,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.hpair, NH) && dalloc(w, d.hpivA, NH) && dalloc(w, d.hpivB, NH) && dalloc(w, d.hfA0, NH) && dalloc(w, d.hfA1, NH);
     ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
     ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
-    ok = ok && dalloc(w, d.seq, NB) && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH) && dalloc(w, d.pisl, NM) && dalloc(w, d.hisl, NH) && dalloc(w, d.prec, 3 * NB);
+    ok = ok && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH) && dalloc(w, d.pisl, NM) && dalloc(w, d.hisl, NH) && dalloc(w, d.prec, 3 * NB);
     // hcolor must hold COLOR_NONE (0xFF as a 32-bit value), not 0xFFFFFFFF
     if (ok) { std::vector<uint32_t> hc(NH, COLOR_NONE); cudaMemcpyAsync(d.hcolor, hc.data(), NH * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 
@@ -254,6 +254,24 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
     LAUNCH(k_refresh_bodies, n, 256, d, first, n);
     CK(cudaStreamSynchronize(s));
     if (first_id) *first_id = first;
+    return B2D_OK;
+}
+
+int b2d_remove_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
+    if (!w || (n && !ids)) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    for (uint32_t k = 0; k < n; ++k) if (ids[k] >= d.nbodies) { w->error = "b2d_remove_bodies: body id out of range"; return B2D_ERR_ARGUMENT; }
+    if (!n) return B2D_OK;
+    cudaStream_t s = w->stream;
+    uint32_t *dev_ids = nullptr;
+    CK(cudaMallocAsync(&dev_ids, n * sizeof(uint32_t), s));
+    CK(cudaMemcpyAsync(dev_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    LAUNCH(k_remove_bodies, n, 256, d, dev_ids, n);
+    if (d.nhinges) LAUNCH(k_remove_hinges, d.nhinges, 256, d);
+    CK(cudaFreeAsync(dev_ids, s));
+    CK(cudaStreamSynchronize(s));
+    w->contacts_dirty = true;
     return B2D_OK;
 }
 
@@ -394,7 +412,6 @@ static int enqueue_solver(b2d_world *w) {
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
     const int slot = (int)(w->timed_steps % b2d_world::RING);
     CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(d.seq, 0, (size_t)d.nbodies * sizeof(uint32_t), s));
     cudaEventRecord(w->ev_solve0[slot], s);
     if (w->barrier_solver) CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
     else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, 256, d, vi));

@@ -118,6 +118,26 @@ constexpr float BP_SEPARATION = -(BREAKING_THRESHOLD * 1.3f);    // -m_separatio
 
 // destroy_separated_manifolds (broadphase.cpp:119-134) + rebuild of the pair -> manifold hash
 // (contact_manifold_map) from the survivors + dead-slot flags for the free list.
+// registry.destroy(body): the node leaves the broadphase trees (broadphase.cpp:54-68) and the entity graph together
+// with every edge attached to it (island_manager.cpp:47-66).  Ids are not recycled: the slot turns into a static,
+// shapeless body; its manifolds are freed by the next k_bp_separate, its joints are parked on the dead body itself.
+__global__ void k_remove_bodies(Dev d, const uint32_t *ids, uint32_t n) {
+    GRID_STRIDE(k, n) {
+        const uint32_t i = ids[k];
+        d.flags[i] = 2u | ((uint32_t)SH_NONE << F_SHAPE_SHIFT) | F_REMOVED;
+        d.linvel[i] = make_float4(0, 0, 0, 0); d.angvel[i] = make_float4(0, 0, 0, 0);
+        d.dvw[2 * i] = make_float4(0, 0, 0, 0); d.dvw[2 * i + 1] = make_float4(0, 0, 0, 0);
+        d.pos[i].w = 0.0f;
+        store_invIW(d, i, m3_zero(), 0.0f);
+    }
+}
+__global__ void k_remove_hinges(Dev d) {
+    GRID_STRIDE(h, d.nhinges) {
+        const uint2 p = d.hpair[h];
+        const bool ra = d.flags[p.x] & F_REMOVED, rb = d.flags[p.y] & F_REMOVED;
+        if (ra || rb) { const uint32_t dead = ra ? p.x : p.y; d.hpair[h] = make_uint2(dead, dead); d.hcolor[h] = COLOR_NONE; }
+    }
+}
 __global__ void k_bp_separate(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, d.NM) {
@@ -126,7 +146,8 @@ __global__ void k_bp_separate(Dev d) {
             uint32_t st = d.mstate[m];
             if (st & MS_ALIVE) {
                 uint2 p = d.mpair[m];
-                if (!intersect(inset(body_box(d, p.x), BP_SEPARATION), body_box(d, p.y))) {
+                // a destroyed body takes its graph edges with it (island_manager.cpp:47-66)
+                if (((d.flags[p.x] | d.flags[p.y]) & F_REMOVED) || !intersect(inset(body_box(d, p.x), BP_SEPARATION), body_box(d, p.y))) {
                     d.mstate[m] = COLOR_NONE << MS_COLOR_SHIFT;      // clear_contact_manifold + destroy
                     flag = 1;
                 } else {
@@ -1325,8 +1346,7 @@ B2D_D uint32_t island_of(const Dev &d, uint32_t a, uint32_t b) { uint32_t l = d.
 
 // contact_constraint::solve_position, contact_constraint.cpp:58-90
 // Dataflow tickets of the position sweeps: per iteration a body sees its hinges, then its contacts (no friction
-// pass), so the schedule is the velocity one with S' = S - k_contacts.  Transforms do not fit a self-validating
-// record, hence a separate counter (d.seq) with release/acquire fences -- 3 iterations only, the hop cost is irrelevant.
+// pass), so the schedule is the velocity one with S' = S - k_contacts.
 struct PTicket { uint32_t ta, tb, mask; bool on; };
 B2D_D PTicket pticket_of(uint2 tk, int it, uint32_t mask, bool on) {
     PTicket t; t.on = on; t.mask = mask;
@@ -1334,34 +1354,15 @@ B2D_D PTicket pticket_of(uint2 tk, int it, uint32_t mask, bool on) {
     t.ta = (uint32_t)it * SA + ((tk.x >> 8) & 0xFFu); t.tb = (uint32_t)it * SB + ((tk.y >> 8) & 0xFFu);
     return t;
 }
-B2D_D void pticket_wait(const Dev &d, const PTicket &t, uint32_t a, bool pa, uint32_t b, bool pb) {
-    if (!t.on) return;
-    uint32_t spins = 0;
-    for (;;) {
-        bool ok = (!pa || ld_relaxed(&d.seq[a]) == t.ta) & (!pb || ld_relaxed(&d.seq[b]) == t.tb);
-        if (__all_sync(t.mask, ok)) break;
-        if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); break; }
-        if (spins > 16) __nanosleep(20);
-    }
-    fence_gpu();
-}
-B2D_D void pticket_release(const Dev &d, const PTicket &t, uint32_t a, bool pa, uint32_t b, bool pb) {
-    if (!t.on) return;
-    fence_gpu();
-    if (pa) st_relaxed(&d.seq[a], t.ta + 1);
-    if (pb) st_relaxed(&d.seq[b], t.tb + 1);
-}
 
-B2D_D void contact_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask = 0xffffffffu, bool df = false) {
+// barrier flavour (k_position): colours are separated by grid barriers, bodies are read and written in place
+B2D_D void contact_position(const Dev &d, uint32_t i) {
     uint4 hd = d.hdr[i];
     uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, m = hd.w;
     uint32_t isl = island_of(d, a, b);
     // all constraints of a finished island skip together (and keep skipping), so their tickets stay consistent
     const bool skip = d.isl_done[isl] != 0;
-    const PTicket tk = pticket_of(df ? d.tkt[i] : make_uint2(0, 0), it, __ballot_sync(mask, !skip), df);
     if (skip) return;
-    const bool pa = !(hd.x >> 31), pb = !(hd.y >> 31);
-    pticket_wait(d, tk, a, pa, b, pb);
     PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
     float max_error = 0.0f;
     for (uint32_t s = 0; s < hd.z; ++s) {
@@ -1378,19 +1379,15 @@ B2D_D void contact_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask 
         position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
     }
     pb_store(d, A); pb_store(d, B);
-    pticket_release(d, tk, a, pa, b, pb);
     island_error_max(d, isl, max_error);
 }
 // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
-B2D_D void hinge_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask = 0xffffffffu, bool df = false) {
+B2D_D void hinge_position(const Dev &d, uint32_t i) {
     uint4 hd = d.hhdr[i];
     uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, h = hd.z;
     uint32_t isl = island_of(d, a, b);
     const bool skip = d.isl_done[isl] != 0;
-    const PTicket tk = pticket_of(df ? d.htkt[i] : make_uint2(0, 0), it, __ballot_sync(mask, !skip), df);
     if (skip) return;
-    const bool pa = !(hd.x >> 31), pb = !(hd.y >> 31);
-    pticket_wait(d, tk, a, pa, b, pb);
     PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
     float max_error = 0.0f;
     v3 axisA = rotate(A.orn, mk3(d.hfA0[h])), axisB = rotate(B.orn, mk3(d.hfB0[h]));
@@ -1408,7 +1405,6 @@ B2D_D void hinge_position(const Dev &d, uint32_t i, int it = 0, uint32_t mask = 
         position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
     }
     pb_store(d, A); pb_store(d, B);
-    pticket_release(d, tk, a, pa, b, pb);
     island_error_max(d, isl, max_error);
 }
 

@@ -13,6 +13,7 @@ constexpr uint32_t F_SHAPE_SHIFT = 4;         // bits 4..11 shape kind
 constexpr uint32_t F_ROLLING = 1u << 12;      // rolling_tag (util/rigidbody.cpp:120-130)
 constexpr uint32_t F_FILTER = 1u << 13;       // has collision_filter
 constexpr uint32_t F_LARGE = 1u << 14;        // larger than a broadphase cell: brute-force list
+constexpr uint32_t F_REMOVED = 1u << 15;      // destroyed (b2d_remove_bodies): static, shapeless, its manifolds and joints die
 
 // mstate word per manifold slot
 constexpr uint32_t MS_NPTS_MASK = 7u;
@@ -124,7 +125,6 @@ struct Dev {
     uint4 *hhdr;                 // a, b, hinge id, 0
 
     // ---- dataflow schedule of the velocity solve
-    uint32_t *seq;               // per body: number of constraint passes applied so far in this solve
     uint32_t *pisl, *hisl;       // per sorted constraint: island label (position solver early exit)
     float4 *prec;                // position solver: 3 float4 per body, (pos,t) (orn.xyz,t) (orn.w,fresh,0,t)
     uint2 *tkt, *htkt;           // per sorted constraint, per body side: S | base << 8 | k << 16 (see k_prepare_*)

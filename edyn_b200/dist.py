@@ -5,9 +5,9 @@ src/edyn/dynamics/solver.cpp:408-428), so the unit of distribution is the island
 islands plus a replica of the static bodies (multi_island_resident in the reference, comp/island.hpp:39-41).  There is
 no collective on the data path.  The only exchange is the broadphase one: each step every rank publishes the bounding
 box of the dynamic bodies it owns (6 floats, all_gather); two ranks whose boxes -- inflated by the broadphase margin --
-touch could grow a cross-rank contact and therefore a cross-rank island.  That event is detected and reported
-(`ShardedWorld.step` returns the offending rank pairs); moving the smaller island to the other rank (body migration)
-is the round-2 item listed in DESIGN.md section 8.
+touch could grow a cross-rank contact and therefore a cross-rank island.  That event is detected
+(`ShardedWorld.step` returns the offending rank pairs) and resolved by body migration: the islands of the higher rank
+that reach into the lower rank's box move there (`ShardedWorld.migrate`), so an island never spans two GPUs.
 
 Everything here is host/plumbing code: numpy for the partitioning, torch.distributed (NCCL on GPUs, gloo in the CPU
 tests) for the exchange.  The simulation itself runs in libb2d.so.
@@ -158,16 +158,40 @@ def overlapping_ranks(bounds, margin=MARGIN):
     return out
 
 
-class ShardedWorld:
-    """One rank's share of a scene + the per-step bounds exchange.  `dist` is torch.distributed (initialised) or None."""
+def boxes_touch(a, b, margin=MARGIN):
+    """a: (n, 6) AABBs, b: one (6,) box; closed-interval intersection with `a` inflated by margin (geom.cpp:762-770)."""
+    return np.all(a[:, 0:3] - margin <= b[3:6], axis=1) & np.all(a[:, 3:6] + margin >= b[0:3], axis=1)
 
-    def __init__(self, scene, rank, world_size, dist=None, device=0, **kw):
-        from .scenes import build_world
+
+class ShardedWorld:
+    """One rank's share of a scene, the per-step bounds exchange and island migration.
+
+    `dist` is torch.distributed (initialised) or None.  `world_factory(scene, device=..., **kw)` builds the rank's
+    world (default: the device world of scenes.build_world; the CPU tests inject an oracle-backed stand-in).
+
+    Migration (mirrors merge_islands' "move into the other island", island_manager.cpp:297-350): when the
+    boxes of two ranks come within the broadphase margin, the higher rank hands every island of its own that reaches
+    into the lower rank's box over to it -- body definitions with their current state, the joints between them and
+    their contact manifolds (points, lifetimes and warm-start impulses) -- and destroys its copies.  Bodies are named
+    by scene-global ids on the wire; static bodies are replicated, so a manifold against the ground keeps its partner.
+    The transfer is one all_gather_object (sizes first, then payloads: NCCL on GPUs, gloo on CPU) and only happens on
+    the steps where `overlapping_ranks` is non-empty."""
+
+    def __init__(self, scene, rank, world_size, dist=None, device=0, world_factory=None, **kw):
+        if world_factory is None:
+            from .scenes import build_world as world_factory
         self.rank, self.world_size, self.dist = rank, world_size, dist
         self.owner = partition(scene, world_size)
         self.local = shard(scene, rank, world_size, self.owner)
-        self.world = build_world(self.local, device=device, **kw)
+        # any rank may end up owning every island: capacity for the whole scene
+        kw.setdefault("max_bodies", len(self.owner))
+        kw.setdefault("max_hinges", len(scene["hinges"]["a"]) if scene.get("hinges") else 0)
+        self.world = world_factory(self.local, device=device, **kw)
+        self.global_of_local = [int(g) for g in self.local["global_ids"]]
+        self.local_of_global = {g: l for l, g in enumerate(self.global_of_local)}
+        self.next_global = len(self.owner)              # ids for bodies created later (none yet): keep unique per scene
         self.dynamic_local = np.where(self.local["bodies"]["kind"] == DYNAMIC)[0]
+        self.migrated_in = self.migrated_out = 0
 
     def local_bounds(self, aabb):
         if len(self.dynamic_local) == 0:
@@ -186,11 +210,101 @@ class ShardedWorld:
         self.dist.all_gather(out, mine)
         return torch.stack(out).cpu().numpy()
 
-    def step(self, n=1, check=True):
+    # ------------------------------------------------------------------ migration
+    def _select_outgoing(self, pairs, bounds, st):
+        """Per destination rank: local ids of the islands this rank hands over (it is the higher rank of the pair)."""
+        dests = sorted(i for i, j in pairs if j == self.rank)
+        if not dests or len(self.dynamic_local) == 0:
+            return {}
+        lab = self.world.islands().astype(np.int64)
+        dyn = self.dynamic_local
+        out, taken = {}, np.zeros(len(lab), bool)
+        for dst in dests:
+            hit = boxes_touch(st["aabb"][dyn], bounds[dst])
+            isl = np.unique(lab[dyn[hit]])
+            sel = dyn[np.isin(lab[dyn], isl) & ~taken[dyn]]
+            if len(sel):
+                out[dst] = sel
+                taken[sel] = True
+        return out
+
+    def _pack(self, ids, st, contacts):
+        """Everything rank `dst` needs to continue simulating bodies `ids` (local ids), in scene-global naming."""
+        w = self.world
+        gol = np.asarray(self.global_of_local, np.int64)
+        defs = w.body_defs(ids)
+        for k in ("pos", "orn", "linvel", "angvel"):
+            defs[k] = st[k][ids].copy()
+        msg = dict(gid=gol[ids], defs=defs, hinges=None, contacts=None)
+        sel = np.zeros(w.num_bodies, bool); sel[ids] = True
+        h = w.hinge_defs()
+        if h is not None:
+            m = w.hinge_alive & sel[h["a"]] & sel[h["b"]]
+            if m.any():
+                msg["hinges"] = {k: (gol[v[m]] if k in ("a", "b") else v[m].copy()) for k, v in h.items()}
+        if len(contacts["pairs"]):
+            pr = contacts["pairs"].astype(np.int64)
+            m = sel[pr[:, 0]] | sel[pr[:, 1]]
+            if m.any():
+                msg["contacts"] = dict(pairs=gol[pr[m]], num=contacts["num"][m].copy(), pts=contacts["pts"][m].copy(),
+                                       att=contacts["att"][m].copy(), lifetime=contacts["lifetime"][m].copy())
+        return msg
+
+    def _unpack(self, msg):
+        w = self.world
+        first = w.add_bodies(msg["defs"])
+        n = len(msg["gid"])
+        for k, g in enumerate(msg["gid"].tolist()):
+            self.local_of_global[g] = first + k
+        self.global_of_local.extend(int(g) for g in msg["gid"])
+        new_ids = np.arange(first, first + n)
+        self.dynamic_local = np.concatenate([self.dynamic_local, new_ids[msg["defs"]["kind"] == DYNAMIC]])
+        to_local = np.vectorize(self.local_of_global.__getitem__, otypes=[np.uint32])
+        if msg["hinges"] is not None:
+            h = msg["hinges"]
+            w.add_hinges(to_local(h["a"]), to_local(h["b"]), h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
+        return n, (None if msg["contacts"] is None else dict(msg["contacts"], pairs=to_local(msg["contacts"]["pairs"])))
+
+    def migrate(self, pairs, bounds, st):
+        """Collective: every rank of the group must call it on the same step (they all see the same `pairs`)."""
+        out = self._select_outgoing(pairs, bounds, st)
+        outbox = {}
+        if out:
+            contacts = self.world.contacts()
+            for dst, ids in out.items():
+                outbox[dst] = self._pack(ids, st, contacts)
+            gone = np.concatenate(list(out.values()))
+            self.world.remove_bodies(gone)
+            self.dynamic_local = np.setdiff1d(self.dynamic_local, gone)
+            self.migrated_out += len(gone)
+        boxes = [None] * self.world_size
+        self.dist.all_gather_object(boxes, outbox)
+        incoming = [boxes[src][self.rank] for src in range(self.world_size) if boxes[src] and self.rank in boxes[src]]
+        if not incoming:
+            return 0
+        mine = self.world.contacts()
+        parts = [mine]
+        got = 0
+        for msg in incoming:
+            n, c = self._unpack(msg)
+            got += n
+            if c is not None:
+                parts.append(c)
+        if len(parts) > 1:
+            self.world.upload_contacts(*[np.concatenate([p[k] for p in parts]) for k in ("pairs", "num", "pts", "att", "lifetime")])
+        self.migrated_in += got
+        return got
+
+    def step(self, n=1, check=True, migrate=True):
         """n fixed steps on this rank's islands, then the cross-rank AABB exchange.  Returns the rank pairs whose
-        island groups came within the broadphase margin of each other (empty list = shards still independent)."""
+        island groups came within the broadphase margin of each other (empty list = shards still independent); with
+        `migrate` the offending islands have changed rank by the time the call returns."""
         self.world.step(n)
         if not check:
             return []
         st = self.world.download_state(aabb=True)
-        return overlapping_ranks(self.exchange_bounds(self.local_bounds(st["aabb"])))
+        bounds = self.exchange_bounds(self.local_bounds(st["aabb"]))
+        pairs = overlapping_ranks(bounds)
+        if pairs and migrate and self.dist is not None and self.world_size > 1:
+            self.migrate(pairs, bounds, st)
+        return pairs

@@ -94,6 +94,23 @@ def boxes_on_plane(side=16, jitter=0.0):
                 settings=dict(velocity_iterations=10, position_iterations=3))
 
 
+def approaching_stacks(height=2, gap=0.6, speed=3.0):
+    """Two stacks of unit boxes sliding towards each other on a plane: two islands that merge into one after a few
+    steps.  Exercises the cross-GPU case of SURVEY 8e (an island changes rank) and manifold / warm-start transfer."""
+    ys = 0.5 + np.arange(height, dtype=f32)
+    left = np.stack([np.zeros(height, f32), ys, np.zeros(height, f32)], axis=1)
+    right = left + np.array([1.0 + gap, 0, 0], f32)
+    pos = np.concatenate([left, right]).astype(f32)
+    n = len(pos)
+    dyn = (pos, _identity(n), np.full(n, SHAPE_BOX, np.uint32), np.tile(np.array([0.5, 0.5, 0.5, 0], f32), (n, 1)),
+           np.full(n, DYNAMIC, np.uint32))
+    b = _assemble(*_join(dyn, _planes([((0, 1, 0), 0.0)])))
+    b["linvel"][:height, 0] = speed
+    b["linvel"][height:n, 0] = -speed
+    return dict(name=f"approaching_stacks_{height}", bodies=b, hinges=None, exclusions=None, dynamic=n,
+                settings=dict(velocity_iterations=10, position_iterations=3))
+
+
 def _box_walls(x1, z1, height):
     """Floor plane y = 0 plus four static wall slabs around [-0.5, x1] x [-0.5, z1].
 
@@ -169,14 +186,15 @@ def hinge_chains(chains_x=512, chains_z=512, links=4):
                 settings=dict(velocity_iterations=10, position_iterations=3))
 
 
-def build_world(scene, device=0, max_manifolds=None, flags=0, **override):
-    """Create a device world holding `scene` (edyn_b200.World)."""
+def build_world(scene, device=0, max_manifolds=None, flags=0, max_bodies=None, max_hinges=None, **override):
+    """Create a device world holding `scene` (edyn_b200.World).  max_bodies / max_hinges reserve room for bodies that
+    arrive later (island migration)."""
     from .world import World
     b = scene["bodies"]
-    n = len(b["kind"])
+    n = max(len(b["kind"]), max_bodies or 0)
     st = dict(scene["settings"])
     st.update(override)
-    nh = len(scene["hinges"]["a"]) if scene["hinges"] else 0
+    nh = max(len(scene["hinges"]["a"]) if scene["hinges"] else 0, max_hinges or 0)
     w = World(n, max_manifolds=max_manifolds or max(4096, 10 * n), max_hinges=nh, device=device,
               velocity_iterations=st["velocity_iterations"], position_iterations=st["position_iterations"], flags=flags)
     w.add_bodies(b)

@@ -52,6 +52,9 @@ class World:
         self.fixed_dt = fixed_dt
         self.num_bodies = 0
         self.num_hinges = 0
+        self._defs, self._hinges = [], []
+        self.removed = np.zeros(max_bodies, bool)
+        self.hinge_alive = np.zeros(0, bool)
         self.max_manifolds = max_manifolds
         self._accum = 0.0
         self.max_steps_per_update = 10          # settings.max_steps_per_update
@@ -89,13 +92,42 @@ class World:
         first = C.c_uint32(0)
         self._check(self.l.b2d_add_bodies(self.h, C.byref(b), C.byref(first)))
         self.num_bodies += n
+        # host copy of the immutable definition (mass, shape, material, filter): what island migration ships to a peer
+        keep["group"] = grp if grp is not None else np.full(n, ~np.uint64(0), np.uint64)
+        keep["mask"] = msk if msk is not None else np.full(n, ~np.uint64(0), np.uint64)
+        keep["has_filter"] = np.full(n, grp is not None and msk is not None, bool)
+        self._defs.append(keep)
         return first.value
+
+    def body_defs(self, ids):
+        """Definition arrays (as passed to add_bodies) of bodies `ids`; state fields are the creation-time ones."""
+        ids = np.asarray(ids, np.int64)
+        if len(self._defs) > 1:
+            self._defs = [{k: np.concatenate([d[k] for d in self._defs]) for k in self._defs[0]}]
+        d = self._defs[0]
+        return {k: v[ids].copy() for k, v in d.items()}
+
+    def remove_bodies(self, ids):
+        """registry.destroy(body): the bodies, their manifolds and their joints leave the simulation; ids are not reused."""
+        ids = _c(ids, u32)
+        self._check(self.l.b2d_remove_bodies(self.h, _p(ids), C.c_uint32(len(ids))))
+        self.removed[ids] = True
+        if self._hinges:
+            h = self.hinge_defs()
+            self.hinge_alive &= ~(self.removed[h["a"]] | self.removed[h["b"]])
 
     def add_hinges(self, a, b, pivot_a, pivot_b, axis_a, axis_b):
         n = len(a)
         arr = [_c(a, u32), _c(b, u32), _c(pivot_a, f32, (n, 3)), _c(pivot_b, f32, (n, 3)), _c(axis_a, f32, (n, 3)), _c(axis_b, f32, (n, 3))]
         self._check(self.l.b2d_add_hinges(self.h, C.c_uint32(n), *[_p(x) for x in arr]))
         self.num_hinges += n
+        self._hinges.append(dict(zip(("a", "b", "pivot_a", "pivot_b", "axis_a", "axis_b"), arr)))
+        self.hinge_alive = np.concatenate([self.hinge_alive, np.ones(n, bool)])
+
+    def hinge_defs(self):
+        if len(self._hinges) > 1:
+            self._hinges = [{k: np.concatenate([h[k] for h in self._hinges]) for k in self._hinges[0]}]
+        return self._hinges[0] if self._hinges else None
 
     def add_exclusions(self, a, b):
         a, b = _c(a, u32), _c(b, u32)

@@ -117,6 +117,11 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *bodies, uint32_t *first_id);
 /* make_constraint<hinge_constraint> + set_axes (src/edyn/constraints/hinge_constraint.cpp:11-17). */
 int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b,
                    const float *pivot_a, const float *pivot_b, const float *axis_a, const float *axis_b);
+/* registry.destroy(body): the body leaves the broadphase (src/edyn/collision/broadphase.cpp:54-68) and the entity graph
+ * together with every manifold and joint attached to it (src/edyn/simulation/island_manager.cpp:47-66).  Ids are not
+ * recycled; state downloads keep reporting the slot (as a static body without shape).  Used by island migration
+ * between GPUs. */
+int b2d_remove_bodies(b2d_world *w, const uint32_t *body_ids, uint32_t n);
 /* exclude_collision (src/edyn/util/exclude_collision.cpp): pairs that never collide. */
 int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
 

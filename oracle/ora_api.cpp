@@ -68,6 +68,11 @@ int ora_add_hinges(void *h, uint32_t n, const uint32_t *a, const uint32_t *b, co
     return first;
 }
 
+void ora_remove_bodies(void *h, uint32_t n, const uint32_t *ids) {
+    World &w = *static_cast<World *>(h);
+    for (uint32_t i = 0; i < n; ++i) if (ids[i] < w.bodies.size()) w.remove_body(ids[i]);
+}
+
 void ora_add_exclusions(void *h, uint32_t n, const uint32_t *a, const uint32_t *b) {
     World &w = *static_cast<World *>(h);
     for (uint32_t i = 0; i < n; ++i) w.exclusions.insert(World::key(a[i], b[i]));

@@ -136,6 +136,30 @@ static inline uint64_t cell_key(int64_t x, int64_t y, int64_t z) {
     return (uint64_t(x & 0x1FFFFF) << 42) | (uint64_t(y & 0x1FFFFF) << 21) | uint64_t(z & 0x1FFFFF);
 }
 
+// registry.destroy(entity) of a rigid body: its tree node goes (broadphase.cpp:54-68) and island_manager's
+// on_destroy<graph_node> destroys every edge entity attached to the node -- contact manifolds and constraints
+// (island_manager.cpp:47-66).  Indices stay stable here: the slot becomes a static body without a shape, a joint that
+// loses a body is parked on the dead slot (neither end procedural: it is never prepared or solved again).
+void World::remove_body(uint32_t i) {
+    Body &b = bodies[i];
+    b.kind = BK_STATIC; b.sh.kind = SH_NONE;
+    b.linvel = b.angvel = b.dv = b.dw = vec3{0, 0, 0};
+    b.inv_m = 0; b.inv_I = b.inv_IW = mat3_zero();
+    size_t w = 0;
+    for (size_t k = 0; k < manifolds.size(); ++k) {
+        if (manifolds[k].a == i || manifolds[k].b == i) continue;
+        if (w != k) manifolds[w] = manifolds[k];
+        ++w;
+    }
+    if (w != manifolds.size()) {
+        manifolds.resize(w);
+        manifold_map.clear();
+        for (uint32_t k = 0; k < manifolds.size(); ++k) manifold_map[key(manifolds[k].a, manifolds[k].b)] = k;
+    }
+    for (Hinge &h : hinges) if (h.a == i || h.b == i) { h.a = h.b = i; }
+    if (i < island.size()) island[i] = ~0u;
+}
+
 void World::broadphase() {
     // destroy_separated_manifolds, broadphase.cpp:119-134; threshold broadphase.hpp:18
     const scalar sep_thr = BREAKING_THRESHOLD * scalar(1.3);

@@ -72,6 +72,7 @@ struct World {
     static uint64_t key(uint32_t a, uint32_t b) { return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a; }
 
     uint32_t add_body(const Body &b);
+    void remove_body(uint32_t i);              // registry.destroy(body): broadphase.cpp:54-68, island_manager.cpp:47-66
     void refresh_body(uint32_t i);             // AABB + inv_IW from current transform
     void broadphase();
     void narrowphase();

@@ -219,6 +219,10 @@ class OracleWorld:
                 _arr(axisB, _f, (n, 3))]
         return self.l.ora_add_hinges(self.h, C.c_uint32(n), *[_ptr(x) for x in arrs])
 
+    def remove_bodies(self, ids):
+        ids = _arr(ids, _u)
+        self.l.ora_remove_bodies(self.h, C.c_uint32(len(ids)), _ptr(ids))
+
     def add_exclusions(self, a, b):
         a, b = _arr(a, _u), _arr(b, _u)
         self.l.ora_add_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))

@@ -107,3 +107,61 @@ def test_bounds_exchange_gloo_world_size_2():
     assert far0 == far1, "all ranks see the same gathered bounds"
     assert hf0 == hf1 == [], "disjoint shards: no cross-rank overlap"
     assert hn0 == hn1 == [(0, 1)], "the drifted shard is detected on every rank"
+
+
+def _migration_worker(rank, world_size, port, q):
+    import torch.distributed as dist_mod
+    import edyn_b200 as E
+    from edyn_b200 import dist
+    from tests._oracle_world import OracleBackedWorld
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist_mod.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scene = E.scenes.approaching_stacks(height=2, gap=0.6, speed=3.0)
+        sw = dist.ShardedWorld(scene, rank, world_size, dist_mod, world_factory=OracleBackedWorld)
+        owned0 = len(sw.dynamic_local)
+        first_hit = None
+        for k in range(40):
+            pairs = sw.step(1)
+            if pairs and first_hit is None:
+                first_hit = k
+        st = sw.world.download_state()
+        gids = np.asarray(sw.global_of_local)[sw.dynamic_local]
+        q.put((rank, owned0, first_hit, sw.migrated_in, sw.migrated_out, gids.tolist(), st["pos"][sw.dynamic_local].tolist(),
+               len(sw.world.contacts()["pairs"])))
+    finally:
+        dist_mod.destroy_process_group()
+
+
+def test_island_migration_gloo_world_size_2(E):
+    """Two stacks owned by two ranks slide into each other: the higher rank hands its island over, and the merged
+    simulation on rank 0 tracks the single-world run of the same scene."""
+    import torch.multiprocessing as mp
+    from tests._oracle_world import OracleBackedWorld
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migration_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, own0, hit0, in0, out0, gid0, pos0, nc0), (_, own1, hit1, in1, out1, gid1, pos1, nc1) = res
+    assert own0 == own1 == 2
+    assert hit0 == hit1 and hit0 is not None and hit0 > 0, "both ranks see the overlap on the same step"
+    assert (in0, out0, in1, out1) == (2, 0, 0, 2), "rank 1's island moved to rank 0, nothing else moved"
+    assert sorted(gid0) == [0, 1, 2, 3] and gid1 == [] and nc1 == 0
+    assert nc0 >= 4, "ground contacts of both stacks plus the stack-stack contacts live on rank 0"
+    # single-world run of the same scene (same oracle): same bodies by global id
+    scene = E.scenes.approaching_stacks(height=2, gap=0.6, speed=3.0)
+    ref = OracleBackedWorld(scene)
+    ref.step(40)
+    want = ref.download_state()["pos"][:4]
+    got = np.zeros((4, 3), f32)
+    got[np.asarray(gid0)] = np.asarray(pos0, f32)
+    # body ids (hence pair and Gauss-Seidel order) differ after the move, so the runs agree to solver tolerance, not bitwise
+    assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
+    assert np.abs(got[:, 0].mean() - want[:, 0].mean()) < 1e-3
