@@ -41,6 +41,7 @@ struct b2d_world {
     std::vector<uint32_t> large;
     std::vector<uint64_t> exclusions;
     bool contacts_dirty = false;
+    uint64_t updates = 0;             // island updates so far (sleep timestamps)
 };
 
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { w->error = std::string(#call) + ": " + cudaGetErrorString(_e); return B2D_ERR_CUDA; } } while (0)
@@ -128,6 +129,11 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
     ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
     ok = ok && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH) && dalloc(w, d.pisl, NM) && dalloc(w, d.hisl, NH) && dalloc(w, d.prec, 3 * NB);
+    d.sleeping = (cfg->flags & B2D_FLAG_SLEEPING) ? 1u : 0u;
+    if (d.sleeping) {
+        ok = ok && dalloc(w, d.prev_label, NB, 0xFF) && dalloc(w, d.isl_size, NB) && dalloc(w, d.size_new, NB) && dalloc(w, d.isl_flags, NB)
+                && dalloc(w, d.contributor, NB) && dalloc(w, d.heir, NB) && dalloc(w, d.isl_ts, NB) && dalloc(w, d.ts_new, NB);
+    }
     // hcolor must hold COLOR_NONE (0xFF as a 32-bit value), not 0xFFFFFFFF
     if (ok) { std::vector<uint32_t> hc(NH, COLOR_NONE); cudaMemcpyAsync(d.hcolor, hc.data(), NH * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream); cudaStreamSynchronize(w->stream); }
 
@@ -269,9 +275,38 @@ int b2d_remove_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
     CK(cudaMemcpyAsync(dev_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     LAUNCH(k_remove_bodies, n, 256, d, dev_ids, n);
     if (d.nhinges) LAUNCH(k_remove_hinges, d.nhinges, 256, d);
+    // destroying a node queues its island for wake-up (island_manager.cpp:74-97); restated coarsely: everybody wakes
+    if (d.sleeping) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies);
     CK(cudaFreeAsync(dev_ids, s));
     CK(cudaStreamSynchronize(s));
     w->contacts_dirty = true;
+    return B2D_OK;
+}
+
+int b2d_wake_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
+    if (!w) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    cudaStream_t s = w->stream;
+    if (!ids) { if (d.nbodies) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies); CK(cudaStreamSynchronize(s)); return B2D_OK; }
+    for (uint32_t k = 0; k < n; ++k) if (ids[k] >= d.nbodies) { w->error = "b2d_wake_bodies: body id out of range"; return B2D_ERR_ARGUMENT; }
+    if (!n) return B2D_OK;
+    uint32_t *dev_ids = nullptr;
+    CK(cudaMallocAsync(&dev_ids, n * sizeof(uint32_t), s));
+    CK(cudaMemcpyAsync(dev_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    LAUNCH(k_wake_bodies, n, 256, d, (const uint32_t *)dev_ids, n);
+    CK(cudaFreeAsync(dev_ids, s));
+    CK(cudaStreamSynchronize(s));
+    return B2D_OK;
+}
+
+int b2d_download_sleeping(b2d_world *w, uint32_t *asleep) {
+    if (!w || !asleep) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    CK(cudaMemcpyAsync(asleep, d.flags, d.nbodies * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (uint32_t i = 0; i < d.nbodies; ++i) asleep[i] = (asleep[i] & F_SLEEPING) ? 1u : 0u;
     return B2D_OK;
 }
 
@@ -385,6 +420,23 @@ static int enqueue_islands(b2d_world *w) {
     LAUNCH(k_cc_flatten, d.nbodies, 256, d, 0);
     LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d, 1);
     LAUNCH(k_cc_flatten, d.nbodies, 256, d, 1);
+    const uint64_t j = w->updates++;                                 // island_manager::update calls so far
+    if (d.sleeping && d.nbodies) {
+        // m_last_time inside put_islands_to_sleep is the time of the PREVIOUS update (island_manager.cpp:538, :611-613);
+        // update j happens at j * fixed_dt, attach time 0
+        const double last_time = j ? double(j - 1) * double(w->cfg.fixed_dt) : 0.0;
+        cudaStream_t s = w->stream;
+        CK(cudaMemsetAsync(d.size_new, 0, d.nbodies * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(d.isl_flags, 0, d.nbodies * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(d.contributor, 0, d.nbodies * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(d.heir, 0, d.nbodies * sizeof(unsigned long long), s));
+        LAUNCH(k_sleep_gather, d.nbodies, 256, d);
+        LAUNCH(k_sleep_heirs, d.nbodies, 256, d);
+        LAUNCH(k_sleep_decide, d.nbodies, 256, d, last_time);
+        LAUNCH(k_sleep_apply, d.nbodies, 256, d);
+        std::swap(d.isl_size, d.size_new);
+        std::swap(d.isl_ts, d.ts_new);
+    }
     return B2D_OK;
 }
 static int enqueue_solver(b2d_world *w) {

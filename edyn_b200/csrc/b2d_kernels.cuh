@@ -17,7 +17,10 @@ namespace cg = cooperative_groups;
 #define GRID_STRIDE(i, n) for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, _s = gridDim.x * blockDim.x; i < (n); i += _s)
 
 B2D_D uint32_t kind_of(uint32_t f) { return f & F_KIND_MASK; }
-B2D_D bool is_dynamic(uint32_t f) { return (f & F_KIND_MASK) == 0u; }
+// "dynamic" on the per-step path = procedural AND awake (every reference view there is exclude_sleeping_disabled);
+// a sleeping body behaves like a static one until its island wakes.  is_procedural() is for the island bookkeeping.
+B2D_D bool is_dynamic(uint32_t f) { return (f & (F_KIND_MASK | F_SLEEPING)) == 0u; }
+B2D_D bool is_procedural(uint32_t f) { return (f & F_KIND_MASK) == 0u; }
 B2D_D int shape_of(uint32_t f) { return (int)((f >> F_SHAPE_SHIFT) & 0xFFu); }
 B2D_D unsigned long long pair_key(uint32_t a, uint32_t b) {
     return a < b ? ((unsigned long long)a << 32) | b : ((unsigned long long)b << 32) | a;
@@ -380,6 +383,7 @@ __global__ void k_np_keys(Dev d) {
         uint32_t key = 0xFF;
         if (m < hwm && (d.mstate[m] & MS_ALIVE)) {
             uint2 pr = d.mpair[m];
+            if (!is_dynamic(d.flags[pr.x]) && !is_dynamic(d.flags[pr.y])) { d.ckey[m] = key; d.cidx[m] = m; continue; }   // sleeping manifold (narrowphase.cpp:31)
             int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
             int fn = pair_fn(ka, kb);
             if (!fn) fn = pair_fn(kb, ka);
@@ -444,6 +448,7 @@ __global__ void __launch_bounds__(128) k_np_merge(Dev d) {
         uint2 pr = d.mpair[m];
         const uint32_t a = pr.x, b = pr.y;
         const uint32_t fa = d.flags[a], fb = d.flags[b];
+        if (!is_dynamic(fa) && !is_dynamic(fb)) continue;          // sleeping manifold (npres is stale): points, lifetimes untouched
         const v3 posA = mk3(d.pos[a]), posB = mk3(d.pos[b]);
         const q4 ornA = mkq(d.orn[a]), ornB = mkq(d.orn[b]);
         for (int s = 0; s < res.num; ++s) {
@@ -558,14 +563,14 @@ __global__ void k_cc_union(Dev d, int round) {
             if (!(d.mstate[m] & MS_ALIVE)) continue;
             p = d.mpair[m];
         } else { if (round != 0) continue; p = d.hpair[m - hwm]; }
-        if (!is_dynamic(d.flags[p.x]) || !is_dynamic(d.flags[p.y])) continue;
+        if (!is_procedural(d.flags[p.x]) || !is_procedural(d.flags[p.y])) continue;
         if (round != 0 && d.parent[p.x] == d.parent[p.y]) continue;
         cc_union(d.parent, p.x, p.y);
     }
 }
 __global__ void k_cc_flatten(Dev d, int last) {
     GRID_STRIDE(i, d.nbodies) {
-        if (is_dynamic(d.flags[i])) {
+        if (is_procedural(d.flags[i])) {
             // read-only walk: a concurrent path-compressing find could overwrite another thread's final root with a
             // stale grandparent; writing the root itself is harmless to walkers passing through i
             uint32_t r = i, p = d.parent[r];
@@ -575,6 +580,70 @@ __global__ void k_cc_flatten(Dev d, int last) {
         }
         else if (last) d.parent[i] = 0xFFFFFFFFu;
     }
+}
+
+// ---- island sleeping: wake_up_islands + put_islands_to_sleep (island_manager.cpp:524-539, :568-623) on labels that are
+// recomputed every step.  island::sleep_timestamp follows the island the way merge_islands (:303-316, biggest
+// constituent survives) and split_islands (:431-447, biggest part keeps the entity) move it: a new island takes the
+// timestamp of its biggest previous constituent O (procedural-body count, ties to the smaller label) iff it is also
+// O's biggest heir.  An island with an awake and a sleeping member was just joined by a new edge: everybody wakes
+// (insert_to_island -> wake_up_island, :257-295).  isl_flags: 1 any awake, 2 any fast, 4 falls asleep now.
+constexpr float PI_F = 3.1415926535897932384626433832795029f;   // math/constants.hpp
+constexpr float SLEEP_LIN2 = 0.005f * 0.005f;                      // config/constants.hpp:41-42
+constexpr float SLEEP_ANG2 = (PI_F / 48.0f) * (PI_F / 48.0f);
+__global__ void k_sleep_gather(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        const uint32_t f = d.flags[i];
+        if (!is_procedural(f)) continue;
+        const uint32_t r = d.parent[i];
+        atomicAdd(&d.size_new[r], 1u);
+        uint32_t bits = (f & F_SLEEPING) ? 0u : 1u;
+        const v3 v = mk3(d.linvel[i]), w = mk3(d.angvel[i]);
+        if (length_sqr(v) > SLEEP_LIN2 || length_sqr(w) > SLEEP_ANG2) bits |= 2u;
+        if (bits) atomicOr(&d.isl_flags[r], bits);
+        const uint32_t o = d.prev_label[i];
+        if (o != 0xFFFFFFFFu) atomicMax(&d.contributor[r], ((unsigned long long)d.isl_size[o] << 32) | (unsigned long long)(~o));
+    }
+}
+__global__ void k_sleep_heirs(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        if (!is_procedural(d.flags[i])) continue;
+        const uint32_t o = d.prev_label[i], r = d.parent[i];
+        if (o != 0xFFFFFFFFu) atomicMax(&d.heir[o], ((unsigned long long)d.size_new[r] << 32) | (unsigned long long)(~r));
+    }
+}
+__global__ void k_sleep_decide(Dev d, double last_time) {
+    GRID_STRIDE(r, d.nbodies) {
+        double ts = -1.0;
+        const uint32_t fl = d.isl_flags[r];
+        if (d.size_new[r] && (fl & 1u)) {                      // sleeping islands are not visited (exclude_sleeping_disabled)
+            const unsigned long long c = d.contributor[r];
+            if (c) {
+                const uint32_t o = ~(uint32_t)(c & 0xFFFFFFFFull);
+                if (~(uint32_t)(d.heir[o] & 0xFFFFFFFFull) == r) ts = d.isl_ts[o];
+            }
+            if (!(fl & 2u)) {
+                if (ts < 0) ts = last_time;
+                else if (last_time - ts > 2.0) { d.isl_flags[r] = fl | 4u; ts = -1.0; }      // island_time_to_sleep
+            } else ts = -1.0;
+        }
+        d.ts_new[r] = ts;
+    }
+}
+__global__ void k_sleep_apply(Dev d) {
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t f = d.flags[i];
+        if (!is_procedural(f)) { d.prev_label[i] = 0xFFFFFFFFu; continue; }
+        const uint32_t r = d.parent[i], fl = d.isl_flags[r];
+        if (fl & 1u) f &= ~F_SLEEPING;
+        if (fl & 4u) { f |= F_SLEEPING; d.linvel[i] = make_float4(0, 0, 0, 0); d.angvel[i] = make_float4(0, 0, 0, 0); }     // put_to_sleep, :541-566
+        d.flags[i] = f;
+        d.prev_label[i] = r;
+    }
+}
+// wake_up_entity (util/island_util.cpp): the island follows at the next island update
+__global__ void k_wake_bodies(Dev d, const uint32_t *ids, uint32_t n) {
+    GRID_STRIDE(k, n) { const uint32_t i = ids ? ids[k] : k; d.flags[i] &= ~F_SLEEPING; }
 }
 
 // ====================================================================== solver: gravity, colouring
@@ -603,20 +672,26 @@ __global__ void k_color_list(Dev d, int recolor) {
             if (col != COLOR_NONE) { st |= MS_COLOR_MASK; d.mstate[m] = st; col = COLOR_NONE; }
             if (!(st & MS_NPTS_MASK)) continue;
         }
+        const uint2 p = d.mpair[m];
+        const bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
+        if (!da && !db) {          // sleeping: drops its colour, takes a fresh one when the island wakes
+            if (col != COLOR_NONE) d.mstate[m] = st | MS_COLOR_MASK;
+            continue;
+        }
         if (col == COLOR_NONE) { uint32_t k = atomicAdd(&d.cnt->nlist, 1u); d.clist[k] = m; }
         else {
-            uint2 p = d.mpair[m];
-            if (is_dynamic(d.flags[p.x])) atomicOr(&d.bmask[p.x], 1ULL << col);
-            if (is_dynamic(d.flags[p.y])) atomicOr(&d.bmask[p.y], 1ULL << col);
+            if (da) atomicOr(&d.bmask[p.x], 1ULL << col);
+            if (db) atomicOr(&d.bmask[p.y], 1ULL << col);
         }
     }
     GRID_STRIDE(h, d.nhinges) {
-        if (recolor) d.hcolor[h] = COLOR_NONE;
+        uint2 p = d.hpair[h];
+        const bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
+        if (recolor || (!da && !db)) d.hcolor[h] = COLOR_NONE;
         uint32_t col = d.hcolor[h];
         if (col == COLOR_NONE) continue;
-        uint2 p = d.hpair[h];
-        if (is_dynamic(d.flags[p.x])) atomicOr(&d.jmask[p.x], 1ULL << col);
-        if (is_dynamic(d.flags[p.y])) atomicOr(&d.jmask[p.y], 1ULL << col);
+        if (da) atomicOr(&d.jmask[p.x], 1ULL << col);
+        if (db) atomicOr(&d.jmask[p.y], 1ULL << col);
     }
 }
 
@@ -636,7 +711,7 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
             const bool isM = k < nlist;
             uint32_t id; uint2 p; unsigned long long *prop;
             if (isM) { id = d.clist[k]; if (((d.mstate[id] >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[id]; prop = d.prop; }
-            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; }
+            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; if (!is_dynamic(d.flags[p.x]) && !is_dynamic(d.flags[p.y])) continue; }
             unsigned long long v = stamp | ((unsigned long long)(hash64(id) & 0x3FFFFFu) << 26) | id;
             if (is_dynamic(d.flags[p.x])) atomicMin(&prop[p.x], v);
             if (is_dynamic(d.flags[p.y])) atomicMin(&prop[p.y], v);
@@ -646,7 +721,7 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
             const bool isM = k < nlist;
             uint32_t id; uint2 p; unsigned long long *prop, *mask;
             if (isM) { id = d.clist[k]; if (((d.mstate[id] >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) continue; p = d.mpair[id]; prop = d.prop; mask = d.bmask; }
-            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; mask = d.jmask; }
+            else { id = k - nlist; if (d.hcolor[id] != COLOR_NONE) continue; p = d.hpair[id]; prop = d.jprop; mask = d.jmask; if (!is_dynamic(d.flags[p.x]) && !is_dynamic(d.flags[p.y])) continue; }
             unsigned long long v = stamp | ((unsigned long long)(hash64(id) & 0x3FFFFFu) << 26) | id;
             bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
             bool win = (!da || prop[p.x] == v) && (!db || prop[p.y] == v);
@@ -679,7 +754,7 @@ __global__ void k_color_keys(Dev d) {
         uint32_t key = 1u << (COLOR_KEY_BITS - 1);
         if (m < hwm) {
             uint32_t st = d.mstate[m];
-            if ((st & MS_ALIVE) && (st & MS_NPTS_MASK)) {
+            if ((st & MS_ALIVE) && (st & MS_NPTS_MASK) && ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) {      // uncoloured = sleeping
                 const uint2 pr = d.mpair[m];
                 const uint32_t fa = d.flags[pr.x];
                 const uint32_t b = (is_dynamic(fa) && !(fa & F_LARGE)) ? pr.x : pr.y;
@@ -1639,7 +1714,7 @@ __global__ void k_bounds_reduce(Dev d) {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     GRID_STRIDE(i, d.nbodies) {
         uint32_t f = d.flags[i];
-        if (!is_dynamic(f) || shape_of(f) == SH_NONE) continue;
+        if (!is_procedural(f) || shape_of(f) == SH_NONE) continue;
         float4 a = d.bbmin[i], b = d.bbmax[i];
         mn[0] = fminf(mn[0], a.x); mn[1] = fminf(mn[1], a.y); mn[2] = fminf(mn[2], a.z);
         mx[0] = fmaxf(mx[0], b.x); mx[1] = fmaxf(mx[1], b.y); mx[2] = fmaxf(mx[2], b.z);

@@ -13,6 +13,7 @@ constexpr uint32_t F_SHAPE_SHIFT = 4;         // bits 4..11 shape kind
 constexpr uint32_t F_ROLLING = 1u << 12;      // rolling_tag (util/rigidbody.cpp:120-130)
 constexpr uint32_t F_FILTER = 1u << 13;       // has collision_filter
 constexpr uint32_t F_LARGE = 1u << 14;        // larger than a broadphase cell: brute-force list
+constexpr uint32_t F_SLEEPING = 1u << 16;     // sleeping_tag: excluded from every per-step view until its island wakes
 constexpr uint32_t F_REMOVED = 1u << 15;      // destroyed (b2d_remove_bodies): static, shapeless, its manifolds and joints die
 
 // mstate word per manifold slot
@@ -125,6 +126,11 @@ struct Dev {
     uint4 *hhdr;                 // a, b, hinge id, 0
 
     // ---- dataflow schedule of the velocity solve
+    // island sleeping (island_manager.cpp:541-623); arrays are indexed by body id, island data sits at the root's id
+    uint32_t sleeping;                   // enabled (B2D_FLAG_SLEEPING)
+    uint32_t *prev_label, *isl_size, *size_new, *isl_flags;
+    unsigned long long *contributor, *heir;
+    double *isl_ts, *ts_new;
     uint32_t *pisl, *hisl;       // per sorted constraint: island label (position solver early exit)
     float4 *prec;                // position solver: 3 float4 per body, (pos,t) (orn.xyz,t) (orn.w,fresh,0,t)
     uint2 *tkt, *htkt;           // per sorted constraint, per body side: S | base << 8 | k << 16 (see k_prepare_*)

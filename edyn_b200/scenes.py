@@ -111,6 +111,17 @@ def approaching_stacks(height=2, gap=0.6, speed=3.0):
                 settings=dict(velocity_iterations=10, position_iterations=3))
 
 
+def sleep_and_wake(drop_height=55.0):
+    """A box resting on a plane (asleep after 2 s) and a second one dropped from `drop_height` that lands on it ~1.3 s
+    later and wakes it; both then fall asleep together.  Exercises island sleeping (island_manager.cpp:541-623)."""
+    pos = np.array([[0, 0.5, 0], [0.2, drop_height, 0.1]], f32)
+    dyn = (pos, _identity(2), np.full(2, SHAPE_BOX, np.uint32), np.tile(np.array([0.5, 0.5, 0.5, 0], f32), (2, 1)),
+           np.full(2, DYNAMIC, np.uint32))
+    b = _assemble(*_join(dyn, _planes([((0, 1, 0), 0.0)])))
+    return dict(name="sleep_and_wake", bodies=b, hinges=None, exclusions=None, dynamic=2,
+                settings=dict(velocity_iterations=10, position_iterations=3))
+
+
 def _box_walls(x1, z1, height):
     """Floor plane y = 0 plus four static wall slabs around [-0.5, x1] x [-0.5, z1].
 

@@ -23,6 +23,7 @@ f32, u32 = np.float32, np.uint32
 
 PH_BROAD, PH_NARROW, PH_ISLANDS, PH_SOLVE, PH_ALL = 1, 2, 4, 8, 15
 FLAG_RECOLOR_EACH_STEP = 1
+FLAG_SLEEPING = 2                # island sleeping; off = every body is sleeping_disabled (benchmark configurations)
 
 
 def _p(a):
@@ -98,6 +99,19 @@ class World:
         keep["has_filter"] = np.full(n, grp is not None and msk is not None, bool)
         self._defs.append(keep)
         return first.value
+
+    def wake_bodies(self, ids=None):
+        """edyn::wake_up_entity; ids=None wakes everything."""
+        if ids is None:
+            self._check(self.l.b2d_wake_bodies(self.h, None, C.c_uint32(0)))
+        else:
+            ids = _c(ids, u32)
+            self._check(self.l.b2d_wake_bodies(self.h, _p(ids), C.c_uint32(len(ids))))
+
+    def sleeping(self):
+        out = np.zeros(max(1, self.num_bodies), u32)
+        self._check(self.l.b2d_download_sleeping(self.h, _p(out)))
+        return out[:self.num_bodies].astype(bool)
 
     def body_defs(self, ids):
         """Definition arrays (as passed to add_bodies) of bodies `ids`; state fields are the creation-time ones."""

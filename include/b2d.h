@@ -74,6 +74,8 @@ typedef struct b2d_config {
 } b2d_config;
 
 #define B2D_FLAG_RECOLOR_EACH_STEP 1u  /* recompute the constraint colouring from scratch every step */
+#define B2D_FLAG_SLEEPING 2u           /* island sleeping (src/edyn/simulation/island_manager.cpp:541-623).  Off = every
+                                          body carries sleeping_disabled_tag, as the benchmark configurations prescribe */
 
 /* make_rigidbody() output for n bodies (src/edyn/util/rigidbody.cpp:47-185), SoA.
  * inv_inertia = inertia_inv component, row-major 3x3 in body space (ignored unless dynamic).
@@ -122,6 +124,10 @@ int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint3
  * recycled; state downloads keep reporting the slot (as a static body without shape).  Used by island migration
  * between GPUs. */
 int b2d_remove_bodies(b2d_world *w, const uint32_t *body_ids, uint32_t n);
+/* wake_up_entity (src/edyn/util/island_util.cpp): clears sleeping_tag; the body's island follows at the next island
+ * update.  ids == NULL wakes every body.  b2d_download_sleeping: 1 per body that carries sleeping_tag. */
+int b2d_wake_bodies(b2d_world *w, const uint32_t *body_ids, uint32_t n);
+int b2d_download_sleeping(b2d_world *w, uint32_t *asleep);
 /* exclude_collision (src/edyn/util/exclude_collision.cpp): pairs that never collide. */
 int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
 

@@ -73,6 +73,17 @@ void ora_remove_bodies(void *h, uint32_t n, const uint32_t *ids) {
     for (uint32_t i = 0; i < n; ++i) if (ids[i] < w.bodies.size()) w.remove_body(ids[i]);
 }
 
+void ora_set_sleeping(void *h, int enabled) { static_cast<World *>(h)->sleeping_enabled = enabled != 0; }
+// wake_up_entity (util/island_util.cpp): the island follows at the next island update
+void ora_wake_bodies(void *h, uint32_t n, const uint32_t *ids) {
+    World &w = *static_cast<World *>(h);
+    for (uint32_t i = 0; i < n; ++i) if (ids[i] < w.bodies.size()) w.wake_body(ids[i]);
+}
+void ora_get_sleeping(void *h, uint32_t *asleep) {
+    World &w = *static_cast<World *>(h);
+    for (size_t i = 0; i < w.bodies.size(); ++i) asleep[i] = w.bodies[i].asleep ? 1u : 0u;
+}
+
 void ora_add_exclusions(void *h, uint32_t n, const uint32_t *a, const uint32_t *b) {
     World &w = *static_cast<World *>(h);
     for (uint32_t i = 0; i < n; ++i) w.exclusions.insert(World::key(a[i], b[i]));

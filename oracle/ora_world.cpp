@@ -158,6 +158,7 @@ void World::remove_body(uint32_t i) {
     }
     for (Hinge &h : hinges) if (h.a == i || h.b == i) { h.a = h.b = i; }
     if (i < island.size()) island[i] = ~0u;
+    for (Body &o : bodies) o.asleep = false;       // on_destroy<island_resident> queues the island for wake-up (:74-97); restated coarsely
 }
 
 void World::broadphase() {
@@ -168,7 +169,9 @@ void World::broadphase() {
         size_t w = 0;
         for (size_t i = 0; i < manifolds.size(); ++i) {
             const Manifold &m = manifolds[i];
-            if (!intersect(inset(bodies[m.a].bb, sep_off), bodies[m.b].bb)) continue;
+            // view<contact_manifold>(exclude_sleeping_disabled), broadphase.cpp:121: a sleeping manifold is left alone
+            const bool sleeping = !bodies[m.a].awake() && !bodies[m.b].awake();
+            if (!sleeping && !intersect(inset(bodies[m.a].bb, sep_off), bodies[m.b].bb)) continue;
             if (w != i) manifolds[w] = manifolds[i];
             ++w;
         }
@@ -222,7 +225,7 @@ void World::broadphase() {
     // newest-first: descending index.  This fixes which body becomes body[0].
     for (uint32_t ii = n; ii-- > 0;) {
         const Body &A = bodies[ii];
-        if (!A.procedural() || A.sh.kind == SH_NONE) continue;
+        if (!A.awake() || A.sh.kind == SH_NONE) continue;         // view<AABB, procedural_tag>(exclude_sleeping_disabled)
         const aabb q = inset(A.bb, off);
         cand.clear();
         auto test = [&](uint32_t j) {
@@ -397,6 +400,7 @@ void World::narrowphase() {
     parallel_for(threads, manifolds.size(), [&](size_t mi) {
         Manifold &m = manifolds[mi];
         const Body &A = bodies[m.a], &B = bodies[m.b];
+        if (!A.awake() && !B.awake()) return;                     // narrowphase.cpp:31 excludes sleeping manifolds
         // update_contact_distances, collision_util.cpp:28-45
         for (size_t k = 0; k < m.num; ++k) {
             Point &cp = m.pt[k];
@@ -430,6 +434,69 @@ void World::islands() {
     for (const Hinge &h : hinges) unite(h.a, h.b);
     island.assign(n, ~0u);
     for (uint32_t i = 0; i < n; ++i) if (bodies[i].procedural()) island[i] = find(i);
+    update_sleep();
+}
+
+// wake_up_islands + put_islands_to_sleep (island_manager.cpp:524-539, :568-623) over labels that are recomputed every
+// step instead of incrementally maintained island entities:
+//  * an island with an awake and a sleeping member has just been joined by a new edge -> insert_to_island ->
+//    wake_up_island (:257-295): everybody wakes;
+//  * island::sleep_timestamp follows the island entity.  merge_islands keeps the biggest constituent (:303-316),
+//    split_islands keeps the original entity for the biggest part (:431-447); restated on labels: a new island takes
+//    the timestamp of its biggest previous constituent O (procedural-body count, ties to the smaller label) iff it is
+//    also O's biggest heir, otherwise it starts without one;
+//  * could_go_to_sleep (:575-603): no member faster than 0.005 m/s or pi/48 rad/s; put_islands_to_sleep (:605-623)
+//    with m_last_time = time of the PREVIOUS update (set at :538), time of update j = j * fixed_dt, attach time 0.
+void World::update_sleep() {
+    const uint32_t n = uint32_t(bodies.size());
+    const uint64_t j = updates++;
+    if (!sleeping_enabled) return;
+    prev_island.resize(n, ~0u); isl_size.resize(n, 0); isl_sleep_ts.resize(n, -1.0);
+    const double last_time = j ? double(j - 1) * double(dt) : 0.0;
+    std::vector<uint32_t> size_new(n, 0);
+    std::vector<uint8_t> any_awake(n, 0), any_fast(n, 0);
+    std::vector<uint64_t> contributor(n, 0), heir(n, 0);
+    const scalar lin2 = scalar(0.005) * scalar(0.005), ang2 = (PI / scalar(48)) * (PI / scalar(48));
+    for (uint32_t i = 0; i < n; ++i) {
+        const Body &b = bodies[i];
+        if (!b.procedural()) continue;
+        const uint32_t r = island[i];
+        ++size_new[r];
+        if (!b.asleep) any_awake[r] = 1;
+        if (length_sqr(b.linvel) > lin2 || length_sqr(b.angvel) > ang2) any_fast[r] = 1;
+        const uint32_t o = prev_island[i];
+        if (o != ~0u) contributor[r] = std::max(contributor[r], (uint64_t(isl_size[o]) << 32) | uint64_t(~o));
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!bodies[i].procedural()) continue;
+        const uint32_t o = prev_island[i], r = island[i];
+        if (o != ~0u) heir[o] = std::max(heir[o], (uint64_t(size_new[r]) << 32) | uint64_t(~r));
+    }
+    std::vector<double> ts_new(n, -1.0);
+    std::vector<uint8_t> sleep_now(n, 0);
+    for (uint32_t r = 0; r < n; ++r) {
+        if (!size_new[r] || !any_awake[r]) continue;              // sleeping islands are not visited (exclude_sleeping_disabled)
+        double ts = -1.0;
+        if (contributor[r]) {
+            const uint32_t o = ~uint32_t(contributor[r] & 0xFFFFFFFFu);
+            if (~uint32_t(heir[o] & 0xFFFFFFFFu) == r) ts = isl_sleep_ts[o];
+        }
+        if (!any_fast[r]) {
+            if (ts < 0) ts = last_time;
+            else if (last_time - ts > 2.0) { sleep_now[r] = 1; ts = -1.0; }
+        } else ts = -1.0;
+        ts_new[r] = ts;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        Body &b = bodies[i];
+        if (!b.procedural()) { prev_island[i] = ~0u; continue; }
+        const uint32_t r = island[i];
+        if (any_awake[r]) b.asleep = false;
+        if (sleep_now[r]) { b.asleep = true; b.linvel = b.angvel = vec3{0, 0, 0}; }       // put_to_sleep, :541-566
+        prev_island[i] = r;
+    }
+    isl_size = size_new;
+    isl_sleep_ts = ts_new;
 }
 
 // ------------------------------------------------------------------ solver
@@ -449,7 +516,7 @@ struct IslandWork {
 
 static SBody solver_body(const Body &b) {
     SBody s;
-    s.proc = b.procedural();
+    s.proc = b.awake();
     if (s.proc) { s.inv_m = b.inv_m; s.inv_I = b.inv_IW; } else { s.inv_m = 0; s.inv_I = mat3_zero(); }
     if (b.kind == BK_STATIC) { s.v = s.w = vec3{0, 0, 0}; } else { s.v = b.linvel; s.w = b.angvel; }
     return s;
@@ -457,7 +524,7 @@ static SBody solver_body(const Body &b) {
 
 // position_solver::solve, dynamics/position_solver.hpp:16-51
 static void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error) {
-    const bool pA = A.procedural(), pB = B.procedural();
+    const bool pA = A.awake(), pB = B.awake();
     const scalar inv_mA = pA ? A.inv_m : 0, inv_mB = pB ? B.inv_m : 0;
     mat3 zero = mat3_zero();
     const mat3 &inv_IA = pA ? A.inv_IW : zero;
@@ -487,26 +554,26 @@ void World::solve() {
     const uint32_t nb = uint32_t(bodies.size());
     if (island.size() != bodies.size()) islands();
     // apply_gravity, sys/apply_gravity.hpp:12-17
-    for (Body &b : bodies) if (b.kind == BK_DYNAMIC) b.linvel += b.gravity * dt;
+    for (Body &b : bodies) if (b.awake()) b.linvel += b.gravity * dt;
 
     // Group constraints per island in Gauss-Seidel order.
     std::unordered_map<uint32_t, uint32_t> isl_index;
     std::vector<IslandWork> work;
     auto island_of = [&](uint32_t a, uint32_t b) -> IslandWork & {
-        uint32_t lab = bodies[a].procedural() ? island[a] : island[b];
+        uint32_t lab = bodies[a].awake() ? island[a] : island[b];
         auto it = isl_index.find(lab);
         if (it == isl_index.end()) { it = isl_index.emplace(lab, uint32_t(work.size())).first; work.emplace_back(); }
         return work[it->second];
     };
-    for (uint32_t i = 0; i < nb; ++i) if (bodies[i].procedural()) island_of(i, i).bodies.push_back(i);
+    for (uint32_t i = 0; i < nb; ++i) if (bodies[i].awake()) island_of(i, i).bodies.push_back(i);
     if (use_order) {
         for (uint32_t h : hinge_order)
-            if (bodies[hinges[h].a].procedural() || bodies[hinges[h].b].procedural()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
+            if (bodies[hinges[h].a].awake() || bodies[hinges[h].b].awake()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
         for (uint64_t k : manifold_order) {
             auto it = manifold_map.find(k);
             if (it == manifold_map.end()) continue;
             const Manifold &m = manifolds[it->second];
-            if (!bodies[m.a].procedural() && !bodies[m.b].procedural()) continue;
+            if (!bodies[m.a].awake() && !bodies[m.b].awake()) continue;
             IslandWork &w = island_of(m.a, m.b);
             for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(it->second, p);
         }
@@ -514,11 +581,11 @@ void World::solve() {
         // Natural order: constraint-type major (hinge before contact, constraints/constraint.hpp:23-34),
         // newest-first inside a type (assumed EnTT order), list order inside a manifold.
         for (uint32_t h = uint32_t(hinges.size()); h-- > 0;)
-            if (bodies[hinges[h].a].procedural() || bodies[hinges[h].b].procedural()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
+            if (bodies[hinges[h].a].awake() || bodies[hinges[h].b].awake()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
         for (uint32_t mi = uint32_t(manifolds.size()); mi-- > 0;) {
             const Manifold &m = manifolds[mi];
             if (m.num == 0) continue;
-            if (!bodies[m.a].procedural() && !bodies[m.b].procedural()) continue;
+            if (!bodies[m.a].awake() && !bodies[m.b].awake()) continue;
             IslandWork &w = island_of(m.a, m.b);
             for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(mi, p);
         }
@@ -588,11 +655,11 @@ void World::solve() {
         (void)first_contact_row;
 
         vec3 dummy_dv{0, 0, 0}, dummy_dw{0, 0, 0};
-        auto DV = [&](uint32_t i) -> vec3 & { return bodies[i].procedural() ? bodies[i].dv : dummy_dv; };
-        auto DW = [&](uint32_t i) -> vec3 & { return bodies[i].procedural() ? bodies[i].dw : dummy_dw; };
-        auto MA = [&](uint32_t i) { return bodies[i].procedural() ? bodies[i].inv_m : scalar(0); };
+        auto DV = [&](uint32_t i) -> vec3 & { return bodies[i].awake() ? bodies[i].dv : dummy_dv; };
+        auto DW = [&](uint32_t i) -> vec3 & { return bodies[i].awake() ? bodies[i].dw : dummy_dw; };
+        auto MA = [&](uint32_t i) { return bodies[i].awake() ? bodies[i].inv_m : scalar(0); };
         mat3 zero = mat3_zero();
-        auto IA = [&](uint32_t i) -> const mat3 & { return bodies[i].procedural() ? bodies[i].inv_IW : zero; };
+        auto IA = [&](uint32_t i) -> const mat3 & { return bodies[i].awake() ? bodies[i].inv_IW : zero; };
 
         auto apply = [&](const SRow &sr, scalar imp) {       // apply_row_impulse, constraint_row.cpp:24-32
             DV(sr.a) += MA(sr.a) * sr.r.J[0] * imp;

@@ -29,7 +29,9 @@ struct Body {
     scalar friction, restitution;
     bool rolling;            // rolling_tag: dynamic sphere/cylinder/capsule (util/rigidbody.cpp:120-130)
     bool has_filter; uint64_t group, mask;
+    bool asleep = false;     // sleeping_tag (island_manager.cpp:541-566): excluded from every per-step view
     bool procedural() const { return kind == BK_DYNAMIC; }
+    bool awake() const { return kind == BK_DYNAMIC && !asleep; }
 };
 
 struct Point {               // contact_point + _geometry + _material + _impulse (collision/contact_point.hpp:17-58)
@@ -63,6 +65,15 @@ struct World {
     std::unordered_map<uint64_t, uint32_t> manifold_map;   // contact_manifold_map
     std::unordered_set<uint64_t> exclusions;               // collision_exclusion (pair form)
     std::vector<uint32_t> island;                           // label per body (min procedural id), ~0u if none
+    // Sleeping (island_manager.cpp:541-623, thresholds config/constants.hpp:41-48).  Off by default = every body
+    // carries sleeping_disabled_tag, which is what the benchmark configurations prescribe.
+    bool sleeping_enabled = false;
+    uint64_t updates = 0;                                   // island_manager::update calls so far
+    std::vector<uint32_t> prev_island;                      // label of the previous update (~0u: none)
+    std::vector<uint32_t> isl_size;                         // per previous label: number of procedural bodies
+    std::vector<double> isl_sleep_ts;                       // per previous label: island::sleep_timestamp, < 0 = unset
+    void update_sleep();
+    void wake_body(uint32_t i) { bodies[i].asleep = false; }
     // Optional injected Gauss-Seidel order (see ora_api.cpp: ora_set_order).
     bool use_order = false;
     std::vector<uint32_t> hinge_order;
@@ -78,7 +89,7 @@ struct World {
     void narrowphase();
     void islands();
     void solve();
-    void step() { broadphase(); narrowphase(); islands(); solve(); }
+    void step() { broadphase(); narrowphase(); islands(); solve(); }      // islands() ends with update_sleep()
     bool should_collide(uint32_t a, uint32_t b) const;
 };
 

@@ -223,6 +223,18 @@ class OracleWorld:
         ids = _arr(ids, _u)
         self.l.ora_remove_bodies(self.h, C.c_uint32(len(ids)), _ptr(ids))
 
+    def set_sleeping(self, enabled=True):
+        self.l.ora_set_sleeping(self.h, int(bool(enabled)))
+
+    def wake_bodies(self, ids):
+        ids = _arr(ids, _u)
+        self.l.ora_wake_bodies(self.h, C.c_uint32(len(ids)), _ptr(ids))
+
+    def sleeping(self):
+        out = np.zeros(self.num_bodies, _u)
+        self.l.ora_get_sleeping(self.h, _ptr(out))
+        return out.astype(bool)
+
     def add_exclusions(self, a, b):
         a, b = _arr(a, _u), _arr(b, _u)
         self.l.ora_add_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))

@@ -139,3 +139,50 @@ def test_island_migration_two_gpus(gpu, E):
     got[np.asarray(gid0)] = np.asarray(pos0, f32)
     # body ids (hence pair and Gauss-Seidel order) differ after the move: solver-tolerance agreement, not bitwise
     assert np.abs(got - want).max() < 5e-3, np.abs(got - want).max()
+
+
+SLEEP_SCENES = {
+    "sleep_and_wake": (lambda E: E.scenes.sleep_and_wake(), 400),
+    "boxes_27": (lambda E: E.scenes.boxes_on_plane(3, jitter=0.01), 190),
+    "approaching_stacks": (lambda E: E.scenes.approaching_stacks(height=2), 240),
+}
+
+
+@pytest.mark.parametrize("name", list(SLEEP_SCENES))
+def test_island_sleeping_matches_oracle(gpu, E, O, name):
+    """B2D_FLAG_SLEEPING: sleep timestamps, put_to_sleep and wake-up on the device in lock step with the oracle's
+    restatement of island_manager.cpp:524-623 -- sleeping flags, pair lists, islands and state every step."""
+    make, steps = SLEEP_SCENES[name]
+    scene = make(E)
+    w = E.scenes.build_world(scene, flags=E.world.FLAG_SLEEPING)
+    o = _make_oracle(O, scene)
+    o.set_sleeping(True)
+    n = scene["dynamic"]
+    slept = woke = 0
+    prev = np.zeros(n, bool)
+    for s in range(steps):
+        w.run_phases(E.world.PH_BROAD); o.run_phases(O.PH_BROAD)
+        assert _pairset(w.pairs()) == _pairset(o.pairs()), f"step {s}: broadphase pair lists differ"
+        w.run_phases(E.world.PH_NARROW | E.world.PH_ISLANDS); o.run_phases(O.PH_NARROW | O.PH_ISLANDS)
+        assert np.array_equal(w.islands(), o.islands()), f"step {s}: island partition differs"
+        gs, os_ = w.sleeping(), o.sleeping()
+        assert np.array_equal(gs, os_), f"step {s}: sleeping flags differ: {np.where(gs != os_)[0][:8]}"
+        slept += int((gs[:n] & ~prev).sum()); woke += int((~gs[:n] & prev).sum()); prev = gs[:n].copy()
+        w.run_phases(E.world.PH_SOLVE)
+        hi, pr = w.solver_order()
+        o.set_order(hi, pr)
+        o.run_phases(O.PH_SOLVE)
+        g, c = w.download_state(), o.state()
+        for k in ("pos", "orn", "linvel", "angvel"):
+            assert np.abs(g[k] - c[k]).max() <= 1e-5, f"step {s}: {k}"
+        o.set_state(g["pos"], g["orn"], g["linvel"], g["angvel"])
+        gc = w.contacts()
+        o.set_contacts(gc["pairs"], gc["num"], gc["pts"], gc["att"], gc["lifetime"])
+    assert w.stats()["error_flags"] == 0
+    assert slept >= (3 if name == "sleep_and_wake" else n), f"{name}: only {slept} fall-asleep events"
+    if name == "sleep_and_wake":
+        assert woke == 1
+    # wake_up_entity
+    w.wake_bodies([0]); o.wake_bodies([0])
+    w.run_phases(E.world.PH_ISLANDS); o.run_phases(O.PH_ISLANDS)
+    assert np.array_equal(w.sleeping(), o.sleeping()) and not w.sleeping()[0]

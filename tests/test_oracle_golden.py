@@ -127,3 +127,43 @@ def test_hello_world_rests_on_plane(O, E):
     assert abs(st["pos"][0, 1] - 0.5) < 1e-3
     assert np.abs(st["linvel"][0]).max() < 1e-3
     assert c["num"].tolist() == [4]
+
+
+def test_island_sleeping_and_wake_up(E, O):
+    """put_islands_to_sleep / wake_up_island restated (island_manager.cpp:524-623): a resting box falls asleep after
+    island_time_to_sleep = 2 s below the velocity thresholds, is frozen while asleep, wakes the step a falling box makes
+    a manifold with it (new edge into a sleeping island), and both go back to sleep together.  Off by default."""
+    scene = E.scenes.sleep_and_wake()
+    o = O.OracleWorld(vel_iters=10, pos_iters=3)
+    o.add_bodies(scene["bodies"])
+    o.step(200)
+    assert not o.sleeping().any(), "sleeping is opt-in (benchmark configurations carry sleeping_disabled)"
+    o = O.OracleWorld(vel_iters=10, pos_iters=3)
+    o.add_bodies(scene["bodies"])
+    o.set_sleeping(True)
+    events, prev, frozen = [], np.zeros(2, bool), None
+    for k in range(420):
+        o.step(1)
+        s = o.sleeping()[:2]
+        if (s != prev).any():
+            events.append((k, s.tolist()))
+            prev = s
+        st = o.state()
+        if s[0]:
+            if frozen is None:
+                frozen = st["pos"][0].copy()
+            assert np.array_equal(st["pos"][0], frozen) and not st["linvel"][0].any(), "a sleeping body is not simulated"
+        else:
+            frozen = None
+    # dt = 1/60: the box is below the thresholds from the first update; timestamp taken at update 1 (time of update 0),
+    # sleep_dt first exceeds 2 s at update 122
+    assert events[0] == (121, [True, False])
+    assert events[1][1] == [False, False] and 190 < events[1][0] < 205, "the landing box wakes the sleeper"
+    assert events[2][1] == [True, True] and events[2][0] - events[1][0] > 120, "both rest for 2 s before sleeping again"
+    assert len(events) == 3
+    lab = o.islands()
+    assert lab[0] == lab[1] == 0
+    # wake_up_entity
+    o.wake_bodies([1])
+    o.step(1)
+    assert not o.sleeping()[:2].any(), "waking one member wakes the island at the next update"
