@@ -159,7 +159,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, std::min(per_sm, want)) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
     // the dataflow solve wants every resident warp it can get (latency hiding, no barrier cost per CTA)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, 256, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, B2D_SOLVE_THREADS, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, 256, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
     if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
 
@@ -466,7 +466,7 @@ static int enqueue_solver(b2d_world *w) {
     CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
     cudaEventRecord(w->ev_solve0[slot], s);
     if (w->barrier_solver) CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
-    else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, 256, d, vi));
+    else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
     cudaEventRecord(w->ev_solve1[slot], s);
     cudaEventRecord(w->ev_int0[slot], s);
     LAUNCH(k_integrate, d.nbodies, 256, d, pi == 0 ? 1 : 0);

@@ -253,9 +253,15 @@ B2D_D void bp_candidate(const Dev &d, uint32_t A, uint32_t fA, const box3 &bbA, 
     ++count;
 }
 
+#ifndef B2D_BP_CELL_ORDER
+#define B2D_BP_CELL_ORDER 1
+#endif
 template<bool FILL>
 __global__ void k_bp_pairs(Dev d) {
-    GRID_STRIDE(A, d.nbodies) {
+    GRID_STRIDE(t, d.nbodies) {
+        // threads walk the bodies in cell order: a warp's queries hit the same cells and candidate records (output
+        // slots are still indexed by body id, so the pair order does not change)
+        const uint32_t A = B2D_BP_CELL_ORDER ? d.cellbody_s[t] : t;
         uint32_t fA = d.flags[A];
         uint32_t count = 0;
         uint2 *out = nullptr;
@@ -1008,8 +1014,8 @@ B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
 // Development build (-DB2D_DF_PROFILE, tools/dbg4.py): per-warp cycle accounting of the dataflow solver, flushed once per
 // warp into Counters::dbg -- [0]/[1] cycles in poll iterations without/with progress, [2]/[3] their counts, [4] chunk
 // passes, [5] total cycles, [6] warps.
-__shared__ unsigned long long s_prof[8][8];
-__shared__ long long s_prof_t[8];
+__shared__ unsigned long long s_prof[16][8];
+__shared__ long long s_prof_t[16];
 #endif
 B2D_D bool acquire_more(const Dev &d, const Ticket &t, bool pending, bool progressed, uint32_t &spins) {
     if (!t.on) return false;
@@ -1249,7 +1255,10 @@ B2D_D uint32_t chunk_index(const uint32_t *chunk, const uint32_t *off, uint32_t 
     while (j >= chunk[col + 1]) ++col;
     return off[col] + (j - chunk[col]) * 32u;
 }
-__global__ void __launch_bounds__(256, 2) k_solve_df(Dev d, int iters) {
+#ifndef B2D_SOLVE_THREADS
+#define B2D_SOLVE_THREADS 256
+#endif
+__global__ void __launch_bounds__(B2D_SOLVE_THREADS, 2) k_solve_df(Dev d, int iters) {
     // colour tables live in shared memory: every chunk walk reads them, and a global read costs an L2 round trip
     __shared__ uint32_t s_coff[MAX_COLORS + 2], s_cchunk[MAX_COLORS + 2], s_hoff[MAX_COLORS + 2], s_hchunk[MAX_COLORS + 2];
     const Counters &c = *d.cnt;
