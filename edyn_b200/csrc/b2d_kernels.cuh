@@ -1011,7 +1011,7 @@ B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
     return (!A.proc || vb_try(d, A, t.ta)) & (!B.proc || vb_try(d, B, t.tb));
 }
 #ifdef B2D_DF_PROFILE
-// Development build (-DB2D_DF_PROFILE, tools/dbg4.py): per-warp cycle accounting of the dataflow solver, flushed once per
+// Development build (-DB2D_DF_PROFILE, tools/solver_profile.py): per-warp cycle accounting of the dataflow solver, flushed once per
 // warp into Counters::dbg -- [0]/[1] cycles in poll iterations without/with progress, [2]/[3] their counts, [4] chunk
 // passes, [5] total cycles, [6] warps.
 __shared__ unsigned long long s_prof[16][8];
