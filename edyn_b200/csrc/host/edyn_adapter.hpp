@@ -56,6 +56,7 @@ struct init_config {                                 // include/edyn/edyn.hpp:39
     std::uint32_t max_bodies{1u << 16}, max_manifolds{1u << 19}, max_hinges{0};
     unsigned num_solver_velocity_iterations{8}, num_solver_position_iterations{3};
     vector3 gravity{0, scalar(-9.8), 0};
+    bool sleeping{false};                            // false = rigidbody_def::sleeping_disabled on every body (benchmark configurations)
 };
 
 struct AABB { vector3 min, max; };
@@ -124,6 +125,7 @@ inline void attach(registry &r, const init_config &config = {}) {
     c.device = config.device; c.max_bodies = config.max_bodies; c.max_manifolds = config.max_manifolds; c.max_hinges = config.max_hinges;
     c.fixed_dt = config.fixed_dt; c.velocity_iterations = config.num_solver_velocity_iterations;
     c.position_iterations = config.num_solver_position_iterations;
+    c.flags = config.sleeping ? B2D_FLAG_SLEEPING : 0u;
     r.world = b2d_create(&c);
     if (!r.world) throw std::runtime_error(std::string("edyn::attach: ") + b2d_last_error(nullptr));
 }
@@ -167,6 +169,17 @@ inline void make_hinge(registry &r, entity a, entity b, vector3 pivot_a, vector3
     detail::check(r, b2d_add_hinges(r.world, 1, &a, &b, pa, pb, xa, xb), "b2d_add_hinges");
 }
 inline void exclude_collision(registry &r, entity a, entity b) { detail::check(r, b2d_add_exclusions(r.world, 1, &a, &b), "b2d_add_exclusions"); }
+
+// registry.destroy(entity) of a rigid body: its manifolds and joints go with it (island_manager.cpp:47-66); ids are not reused.
+inline void destroy_rigidbody(registry &r, entity e) { detail::check(r, b2d_remove_bodies(r.world, &e, 1), "b2d_remove_bodies"); }
+// edyn::wake_up_entity (util/island_util.cpp)
+inline void wake_up_entity(registry &r, entity e) { detail::check(r, b2d_wake_bodies(r.world, &e, 1), "b2d_wake_bodies"); }
+// presence of sleeping_tag
+inline bool is_sleeping(registry &r, entity e) {
+    std::vector<std::uint32_t> asleep(r.position.size() / 3 + 1);
+    detail::check(r, b2d_download_sleeping(r.world, asleep.data()), "b2d_download_sleeping");
+    return asleep[e] != 0;
+}
 
 inline void set_paused(registry &r, bool paused) { r.paused = paused; }
 
