@@ -160,7 +160,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
     // the dataflow solve wants every resident warp it can get (latency hiding, no barrier cost per CTA)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, B2D_SOLVE_THREADS, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, 256, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, B2D_POS_THREADS, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
     if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
@@ -476,7 +476,7 @@ static int enqueue_solver(b2d_world *w) {
     if (pi > 0) {
         CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
         if (w->barrier_solver) CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
-        else CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, 256, d, pi));
+        else CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
     w->timed = true;

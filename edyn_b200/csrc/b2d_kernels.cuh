@@ -1525,6 +1525,9 @@ __global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
 #ifndef B2D_POS_MIN_BLOCKS
 #define B2D_POS_MIN_BLOCKS 1
 #endif
+#ifndef B2D_POS_THREADS
+#define B2D_POS_THREADS 256
+#endif
 // ---- dataflow flavour of the position iterations (default).  Same idea as k_solve_df: what a constraint needs from a
 // body AND the body's ticket travel in the same 16-byte vectors, so a poll that sees the expected ticket in all three
 // vectors of a record already holds a consistent position / orientation and no fence or separate counter is needed.
@@ -1644,7 +1647,7 @@ B2D_D void hinge_position_df(const Dev &d, uint4 hd, uint2 tk2, uint32_t isl, in
         return max_error;
     });
 }
-__global__ void __launch_bounds__(256, B2D_POS_MIN_BLOCKS) k_position_df(Dev d, int iters) {
+__global__ void __launch_bounds__(B2D_POS_THREADS, B2D_POS_MIN_BLOCKS) k_position_df(Dev d, int iters) {
     __shared__ uint32_t s_coff[MAX_COLORS + 2], s_cchunk[MAX_COLORS + 2], s_hoff[MAX_COLORS + 2], s_hchunk[MAX_COLORS + 2];
     GridBarrier grid(&d.cnt->bar);
     const Counters &c = *d.cnt;
