@@ -351,14 +351,9 @@ int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *
     return B2D_OK;
 }
 
-int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
-    if (!w) return B2D_ERR_ARGUMENT;
-    cudaSetDevice(w->cfg.device);
+// collision_exclusion as a pair hash set, rebuilt on every change (host list -> device open-addressing table)
+static int upload_exclusions(b2d_world *w) {
     Dev &d = w->d;
-    for (uint32_t i = 0; i < n; ++i) {
-        uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
-        w->exclusions.push_back((lo << 32) | hi);
-    }
     uint32_t size = pow2_at_least(2ull * w->exclusions.size() + 2);
     std::vector<unsigned long long> table(size, ~0ULL);
     auto h64 = [](unsigned long long k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return (uint32_t)k; };
@@ -371,8 +366,30 @@ int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32
     if (!dalloc(w, dev, size)) return B2D_ERR_CUDA;
     CK(cudaMemcpyAsync(dev, table.data(), size * sizeof(unsigned long long), cudaMemcpyHostToDevice, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    d.xhash_key = dev; d.xhash_size = size;
+    d.xhash_key = dev; d.xhash_size = w->exclusions.empty() ? 0u : size;
     return B2D_OK;
+}
+
+int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
+    if (!w || (n && (!a || !b))) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
+        const uint64_t k = (lo << 32) | hi;
+        if (std::find(w->exclusions.begin(), w->exclusions.end(), k) == w->exclusions.end()) w->exclusions.push_back(k);
+    }
+    return upload_exclusions(w);
+}
+
+int b2d_remove_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
+    if (!w || (n && (!a || !b))) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
+        const uint64_t k = (lo << 32) | hi;
+        w->exclusions.erase(std::remove(w->exclusions.begin(), w->exclusions.end(), k), w->exclusions.end());
+    }
+    return upload_exclusions(w);
 }
 
 // ------------------------------------------------------------------ one step

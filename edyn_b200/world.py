@@ -54,6 +54,7 @@ class World:
         self.num_bodies = 0
         self.num_hinges = 0
         self._defs, self._hinges = [], []
+        self.exclusions = set()          # collision_exclusion, as unordered pairs
         self.removed = np.zeros(max_bodies, bool)
         self.hinge_alive = np.zeros(0, bool)
         self.max_manifolds = max_manifolds
@@ -146,6 +147,12 @@ class World:
     def add_exclusions(self, a, b):
         a, b = _c(a, u32), _c(b, u32)
         self._check(self.l.b2d_add_exclusions(self.h, C.c_uint32(len(a)), _p(a), _p(b)))
+        self.exclusions |= {(min(x, y), max(x, y)) for x, y in zip(a.tolist(), b.tolist())}
+
+    def remove_exclusions(self, a, b):
+        a, b = _c(a, u32), _c(b, u32)
+        self._check(self.l.b2d_remove_exclusions(self.h, C.c_uint32(len(a)), _p(a), _p(b)))
+        self.exclusions -= {(min(x, y), max(x, y)) for x, y in zip(a.tolist(), b.tolist())}
 
     # -- stepping
     def step(self, n=1):
@@ -261,7 +268,20 @@ def make_hinge(world: World, body_a, body_b, pivot_a, pivot_b, axis_a, axis_b):
 
 
 def exclude_collision(world: World, a, b):
+    """edyn::exclude_collision (src/edyn/util/exclude_collision.cpp)."""
     world.add_exclusions([a], [b])
+
+
+def remove_collision_exclusion(world: World, a, b):
+    """edyn::remove_collision_exclusion."""
+    world.remove_exclusions([a], [b])
+
+
+def clear_collision_exclusion(world: World, e):
+    """edyn::clear_collision_exclusion: drops every exclusion body `e` takes part in."""
+    mine = [p for p in world.exclusions if e in p]
+    if mine:
+        world.remove_exclusions([p[0] for p in mine], [p[1] for p in mine])
 
 
 def step_simulation(world: World):

@@ -130,6 +130,8 @@ int b2d_wake_bodies(b2d_world *w, const uint32_t *body_ids, uint32_t n);
 int b2d_download_sleeping(b2d_world *w, uint32_t *asleep);
 /* exclude_collision (src/edyn/util/exclude_collision.cpp): pairs that never collide. */
 int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
+/* remove_collision_exclusion (src/edyn/util/exclude_collision.cpp); unknown pairs are ignored. */
+int b2d_remove_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
 
 /* n fixed steps: broadphase -> narrowphase -> islands -> solve/integrate (step_simulation semantics). */
 int b2d_step(b2d_world *w, uint32_t num_steps);

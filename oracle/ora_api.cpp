@@ -89,6 +89,11 @@ void ora_add_exclusions(void *h, uint32_t n, const uint32_t *a, const uint32_t *
     for (uint32_t i = 0; i < n; ++i) w.exclusions.insert(World::key(a[i], b[i]));
 }
 
+void ora_remove_exclusions(void *h, uint32_t n, const uint32_t *a, const uint32_t *b) {      // remove_collision_exclusion
+    World &w = *static_cast<World *>(h);
+    for (uint32_t i = 0; i < n; ++i) w.exclusions.erase(World::key(a[i], b[i]));
+}
+
 void ora_step(void *h, int n) { World &w = *static_cast<World *>(h); for (int i = 0; i < n; ++i) w.step(); }
 
 // mask bits: 1 broadphase, 2 narrowphase, 4 islands, 8 solver

@@ -239,6 +239,10 @@ class OracleWorld:
         a, b = _arr(a, _u), _arr(b, _u)
         self.l.ora_add_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))
 
+    def remove_exclusions(self, a, b):
+        a, b = _arr(a, _u), _arr(b, _u)
+        self.l.ora_remove_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))
+
     def step(self, n=1):
         self.l.ora_step(self.h, int(n))
 

@@ -186,3 +186,52 @@ def test_island_sleeping_matches_oracle(gpu, E, O, name):
     w.wake_bodies([0]); o.wake_bodies([0])
     w.run_phases(E.world.PH_ISLANDS); o.run_phases(O.PH_ISLANDS)
     assert np.array_equal(w.sleeping(), o.sleeping()) and not w.sleeping()[0]
+
+
+def test_collision_exclusion_add_remove_clear_device(gpu, E, O):
+    """test/edyn/collision/test_exclusion.cpp on the device path: b2d_add_exclusions / b2d_remove_exclusions and the
+    edyn-style wrappers change which pairs the broadphase makes, identically to the oracle."""
+    from edyn_b200.rigidbody import RigidBodyDef, bodies_soa, box_shape
+    soa = bodies_soa([RigidBodyDef(position=(0.1 * i, 0, 0), mass=1.0, shape=box_shape((0.2, 0.2, 0.2))) for i in range(3)], (0.0, 0.0, 0.0))
+
+    def run(ops):
+        w = E.World(3, max_manifolds=64); w.add_bodies(soa)
+        o = O.OracleWorld(); o.add_bodies(soa)
+        for op, a, b in ops:
+            if op == "+":
+                E.exclude_collision(w, a, b); o.add_exclusions([a], [b])
+            elif op == "-":
+                E.remove_collision_exclusion(w, a, b); o.remove_exclusions([a], [b])
+            else:
+                gone = [p for p in w.exclusions if a in p]
+                E.clear_collision_exclusion(w, a)
+                for p in gone:
+                    o.remove_exclusions([p[0]], [p[1]])
+        w.run_phases(E.world.PH_BROAD); o.run_phases(O.PH_BROAD)
+        got = _pairset(w.pairs())
+        assert got == _pairset(o.pairs())
+        return {tuple(sorted(p)) for p in got}
+    assert run([]) == {(0, 1), (0, 2), (1, 2)}
+    assert run([("+", 0, 1), ("+", 0, 2)]) == {(1, 2)}
+    assert run([("+", 0, 1), ("+", 0, 2), ("-", 1, 0)]) == {(0, 1), (1, 2)}
+    assert run([("+", 0, 1), ("+", 0, 2), ("+", 1, 2), ("clear", 0, 0)]) == {(0, 1), (0, 2)}
+
+
+def test_issue_76_destroy_then_recreate_device(gpu, E):
+    """test/edyn/issues/issue76.cpp through the C ABI: static floor made, destroyed, made again, stepped."""
+    from edyn_b200.rigidbody import RigidBodyDef, box_shape, plane_shape
+    w = E.attach(max_bodies=8, max_manifolds=64)
+    floor_def = RigidBodyDef(kind=E.STATIC, shape=plane_shape((0, 1, 0), 0.0))
+    f0 = E.make_rigidbody(w, floor_def)
+    w.remove_bodies([f0])
+    box = E.make_rigidbody(w, RigidBodyDef(position=(0, 0.5, 0), mass=1.0, shape=box_shape((0.5, 0.5, 0.5))))
+    w.step(30)
+    assert w.download_state()["pos"][box, 1] < 0.0 and len(w.pairs()) == 0, "the destroyed floor holds nothing up"
+    f1 = E.make_rigidbody(w, floor_def)
+    st = w.download_state()
+    pos = st["pos"].copy(); pos[box] = (0, 0.5, 0)
+    w.upload_state(pos, st["orn"], np.zeros_like(st["linvel"]), np.zeros_like(st["angvel"]))
+    w.step(30)
+    assert abs(w.download_state()["pos"][box, 1] - 0.5) < 1e-3
+    assert _pairset(w.pairs()) == {(box, f1)}
+    assert w.stats()["error_flags"] == 0

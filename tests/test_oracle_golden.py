@@ -167,3 +167,44 @@ def test_island_sleeping_and_wake_up(E, O):
     o.wake_bodies([1])
     o.step(1)
     assert not o.sleeping()[:2].any(), "waking one member wakes the island at the next update"
+
+
+def _three_overlapping_boxes(E):
+    from edyn_b200.rigidbody import RigidBodyDef, bodies_soa, box_shape
+    defs = [RigidBodyDef(position=(0.1 * i, 0, 0), mass=1.0, shape=box_shape((0.2, 0.2, 0.2))) for i in range(3)]
+    return bodies_soa(defs, (0.0, 0.0, 0.0))
+
+
+def test_collision_exclusion_add_remove_clear(O, E):
+    """test/edyn/collision/test_exclusion.cpp restated on behaviour: exclude e0-e1 and e0-e2, remove e1-e0, clear e0;
+    after each change the broadphase makes exactly the pairs that are not excluded."""
+    def pairs_after(excl_ops):
+        o = O.OracleWorld()
+        o.add_bodies(_three_overlapping_boxes(E))
+        for op, a, b in excl_ops:
+            (o.add_exclusions if op == "+" else o.remove_exclusions)([a], [b])
+        o.run_phases(O.PH_BROAD)
+        return {tuple(sorted(p)) for p in o.pairs().tolist()}
+    assert pairs_after([]) == {(0, 1), (0, 2), (1, 2)}
+    assert pairs_after([("+", 0, 1), ("+", 0, 2)]) == {(1, 2)}
+    assert pairs_after([("+", 0, 1), ("+", 0, 2), ("-", 1, 0)]) == {(0, 1), (1, 2)}, "removal is symmetric in the pair"
+    assert pairs_after([("+", 0, 1), ("+", 0, 2), ("-", 1, 0), ("-", 0, 2)]) == {(0, 1), (0, 2), (1, 2)}
+
+
+def test_issue_76_destroy_then_recreate(O, E):
+    """test/edyn/issues/issue76.cpp: make a static floor, destroy it, make it again, update -- must simply work, and the
+    destroyed floor must no longer hold anything up."""
+    from edyn_b200.rigidbody import RigidBodyDef, bodies_soa, box_shape, plane_shape
+    floor = bodies_soa([RigidBodyDef(kind=E.STATIC, shape=plane_shape((0, 1, 0), 0.0))], (0.0, -9.8, 0.0))
+    box = bodies_soa([RigidBodyDef(position=(0, 0.5, 0), mass=1.0, shape=box_shape((0.5, 0.5, 0.5)))], (0.0, -9.8, 0.0))
+    o = O.OracleWorld()
+    f0 = o.add_bodies(floor)
+    o.remove_bodies([f0])
+    o.add_bodies(box)
+    o.step(30)
+    assert o.state()["pos"][1, 1] < 0.0 and len(o.pairs()) == 0, "nothing left to rest on"
+    f1 = o.add_bodies(floor)
+    st = o.state()
+    o.set_state(np.array([[0, 0, 0], [0, 0.5, 0], [0, 0, 0]], np.float32), st["orn"], np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32))
+    o.step(30)
+    assert abs(o.state()["pos"][1, 1] - 0.5) < 1e-3 and {tuple(p) for p in o.pairs().tolist()} == {(1, f1)}
