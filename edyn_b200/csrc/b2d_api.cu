@@ -366,6 +366,10 @@ static int upload_exclusions(b2d_world *w) {
     if (!dalloc(w, dev, size)) return B2D_ERR_CUDA;
     CK(cudaMemcpyAsync(dev, table.data(), size * sizeof(unsigned long long), cudaMemcpyHostToDevice, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    if (d.xhash_key) {                                   // the table this one replaces
+        auto it = std::find(w->allocs.begin(), w->allocs.end(), (void *)d.xhash_key);
+        if (it != w->allocs.end()) { cudaFree(*it); w->allocs.erase(it); }
+    }
     d.xhash_key = dev; d.xhash_size = w->exclusions.empty() ? 0u : size;
     return B2D_OK;
 }
@@ -373,10 +377,11 @@ static int upload_exclusions(b2d_world *w) {
 int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
     if (!w || (n && (!a || !b))) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
+    std::unordered_set<uint64_t> seen(w->exclusions.begin(), w->exclusions.end());
     for (uint32_t i = 0; i < n; ++i) {
         uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
         const uint64_t k = (lo << 32) | hi;
-        if (std::find(w->exclusions.begin(), w->exclusions.end(), k) == w->exclusions.end()) w->exclusions.push_back(k);
+        if (seen.insert(k).second) w->exclusions.push_back(k);
     }
     return upload_exclusions(w);
 }
@@ -384,11 +389,12 @@ int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32
 int b2d_remove_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *b) {
     if (!w || (n && (!a || !b))) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
+    std::unordered_set<uint64_t> gone;
     for (uint32_t i = 0; i < n; ++i) {
         uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
-        const uint64_t k = (lo << 32) | hi;
-        w->exclusions.erase(std::remove(w->exclusions.begin(), w->exclusions.end(), k), w->exclusions.end());
+        gone.insert((lo << 32) | hi);
     }
+    w->exclusions.erase(std::remove_if(w->exclusions.begin(), w->exclusions.end(), [&](uint64_t k) { return gone.count(k) != 0; }), w->exclusions.end());
     return upload_exclusions(w);
 }
 
