@@ -172,7 +172,7 @@ class ShardedWorld:
     Migration (mirrors merge_islands' "move into the other island", island_manager.cpp:297-350): when the
     boxes of two ranks come within the broadphase margin, the higher rank hands every island of its own that reaches
     into the lower rank's box over to it -- body definitions with their current state, the joints between them and
-    their contact manifolds (points, lifetimes and warm-start impulses) -- and destroys its copies.  Bodies are named
+    their contact manifolds (points, lifetimes and warm-start impulses), collision exclusions -- and destroys its copies.  Bodies are named
     by scene-global ids on the wire; static bodies are replicated, so a manifold against the ground keeps its partner.
     The transfer is one all_gather_object (sizes first, then payloads: NCCL on GPUs, gloo on CPU) and only happens on
     the steps where `overlapping_ranks` is non-empty."""
@@ -235,8 +235,12 @@ class ShardedWorld:
         defs = w.body_defs(ids)
         for k in ("pos", "orn", "linvel", "angvel"):
             defs[k] = st[k][ids].copy()
-        msg = dict(gid=gol[ids], defs=defs, hinges=None, contacts=None)
+        msg = dict(gid=gol[ids], defs=defs, hinges=None, contacts=None, exclusions=None)
         sel = np.zeros(w.num_bodies, bool); sel[ids] = True
+        ex = [(a, b) for a, b in getattr(w, "exclusions", ()) if sel[a] and sel[b]]       # collision_exclusion among the movers
+        if ex:
+            ex = np.asarray(ex, np.int64)
+            msg["exclusions"] = (gol[ex[:, 0]], gol[ex[:, 1]])
         h = w.hinge_defs()
         if h is not None:
             m = w.hinge_alive & sel[h["a"]] & sel[h["b"]]
@@ -263,6 +267,8 @@ class ShardedWorld:
         if msg["hinges"] is not None:
             h = msg["hinges"]
             w.add_hinges(to_local(h["a"]), to_local(h["b"]), h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
+        if msg.get("exclusions") is not None:
+            w.add_exclusions(to_local(msg["exclusions"][0]), to_local(msg["exclusions"][1]))
         return n, (None if msg["contacts"] is None else dict(msg["contacts"], pairs=to_local(msg["contacts"]["pairs"])))
 
     def migrate(self, pairs, bounds, st):

@@ -18,8 +18,9 @@ class OracleBackedWorld:
         if scene["hinges"]:
             h = scene["hinges"]
             self.add_hinges(h["a"], h["b"], h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
+        self.exclusions = set()
         if scene["exclusions"] is not None:
-            self.o.add_exclusions(*scene["exclusions"])
+            self.add_exclusions(*scene["exclusions"])
 
     @property
     def num_bodies(self):
@@ -44,6 +45,11 @@ class OracleBackedWorld:
         self._hinges.append(dict(a=np.asarray(a, np.uint32), b=np.asarray(b, np.uint32), pivot_a=np.asarray(pa, f).reshape(n, 3),
                                  pivot_b=np.asarray(pb, f).reshape(n, 3), axis_a=np.asarray(xa, f).reshape(n, 3), axis_b=np.asarray(xb, f).reshape(n, 3)))
         self.hinge_alive = np.concatenate([self.hinge_alive, np.ones(n, bool)])
+
+    def add_exclusions(self, a, b):
+        a, b = np.asarray(a, np.uint32), np.asarray(b, np.uint32)
+        self.o.add_exclusions(a, b)
+        self.exclusions |= {(min(x, y), max(x, y)) for x, y in zip(a.tolist(), b.tolist())}
 
     def hinge_defs(self):
         if len(self._hinges) > 1:

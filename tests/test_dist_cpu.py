@@ -165,3 +165,64 @@ def test_island_migration_gloo_world_size_2(E):
     # body ids (hence pair and Gauss-Seidel order) differ after the move, so the runs agree to solver tolerance, not bitwise
     assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
     assert np.abs(got[:, 0].mean() - want[:, 0].mean()) < 1e-3
+
+
+def _chain_migration_worker(rank, world_size, port, q):
+    import torch.distributed as dist_mod
+    import edyn_b200 as E
+    from edyn_b200 import dist
+    from tests._oracle_world import OracleBackedWorld
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist_mod.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scene = E.scenes.hinge_chains(2, 2, 4)
+        sw = dist.ShardedWorld(scene, rank, world_size, dist_mod, world_factory=OracleBackedWorld)
+        sw.world.step(10)
+        st = sw.world.download_state()
+        bounds = sw.exchange_bounds(sw.local_bounds(st["aabb"]))
+        assert dist.overlapping_ranks(bounds) == [], "the two chain groups are 3.5 m apart"
+        # force the hand-over: pretend rank 0's box has grown over everything
+        bounds[0] = np.array([-1e3, -1e3, -1e3, 1e3, 1e3, 1e3], f32)
+        sw.migrate([(0, 1)], bounds, st)
+        sw.world.step(20)
+        st = sw.world.download_state()
+        gids = np.asarray(sw.global_of_local)[sw.dynamic_local]
+        h = sw.world.hinge_defs()
+        alive = int(sw.world.hinge_alive.sum()) if h is not None else 0
+        q.put((rank, sw.migrated_in, sw.migrated_out, gids.tolist(), st["pos"][sw.dynamic_local].tolist(), alive,
+               len(sw.world.exclusions), sorted(map(tuple, sw.world.o.pairs().tolist()))))
+    finally:
+        dist_mod.destroy_process_group()
+
+
+def test_chain_islands_migrate_with_joints_and_exclusions(E):
+    """Hinge chains change rank: the joints and the collision exclusions between adjacent links travel with the bodies
+    (otherwise neighbouring links would start colliding on the new rank), and the result equals the single-world run."""
+    import torch.multiprocessing as mp
+    from tests._oracle_world import OracleBackedWorld
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chain_migration_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, in0, out0, gid0, pos0, h0, x0, pairs0), (_, in1, out1, gid1, pos1, h1, x1, pairs1) = res
+    assert (in0, out0, in1, out1) == (8, 0, 0, 8)
+    assert sorted(gid0) == list(range(16)) and gid1 == []
+    assert h0 == 12 and h1 == 0, "3 joints per chain, all alive on rank 0, none left on rank 1"
+    assert x0 == 12, "one exclusion per joint travelled along"
+    scene = E.scenes.hinge_chains(2, 2, 4)
+    ref = OracleBackedWorld(scene)
+    ref.step(30)
+    want = ref.download_state()["pos"][:16]
+    got = np.zeros((16, 3), f32)
+    got[np.asarray(gid0)] = np.asarray(pos0, f32)
+    assert np.abs(got - want).max() < 1e-5, np.abs(got - want).max()
+    # same number of manifolds as the single world: adjacent links are excluded on the new rank too
+    ref_pairs = {tuple(p) for p in ref.o.pairs().tolist()}
+    assert len(pairs0) == len(ref_pairs), (len(pairs0), len(ref_pairs))
