@@ -288,4 +288,19 @@ float ora_solve_row(const float *J, float *row5, const float *dv12) {
     return d;
 }
 
+// constraint_row_friction: J24 = row[0].J[0..3], row[1].J[0..3]; fr6 = eff_mass[2] rhs[2] impulse[2] (impulse updated);
+// masses20 = inv_mA, inv_IA(9), inv_mB, inv_IB(9); dv12 = dvA dwA dvB dwB (updated).  warm != 0: warm_start only.
+void ora_solve_friction(const float *J24, float *fr6, float mu, float normal_impulse, const float *masses20, float *dv12, int warm) {
+    FrictionPair f{};
+    for (int i = 0; i < 2; ++i) for (int k = 0; k < 4; ++k) f.J[i][k] = v3(J24 + 12 * i + 3 * k);
+    for (int i = 0; i < 2; ++i) { f.eff_mass[i] = fr6[i]; f.rhs[i] = fr6[2 + i]; f.impulse[i] = fr6[4 + i]; }
+    f.mu = mu;
+    vec3 dvA = v3(dv12), dwA = v3(dv12 + 3), dvB = v3(dv12 + 6), dwB = v3(dv12 + 9);
+    const mat3 IA = m9(masses20 + 1), IB = m9(masses20 + 11);
+    if (warm) warm_start_friction(f, masses20[0], IA, masses20[10], IB, dvA, dwA, dvB, dwB);
+    else solve_friction(f, normal_impulse, masses20[0], IA, masses20[10], IB, dvA, dwA, dvB, dwB);
+    fr6[4] = f.impulse[0]; fr6[5] = f.impulse[1];
+    put3(dv12, dvA); put3(dv12 + 3, dwA); put3(dv12 + 6, dvB); put3(dv12 + 9, dwB);
+}
+
 } // extern "C"

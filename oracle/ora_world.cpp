@@ -506,12 +506,48 @@ struct SBody {                 // constraint_body + row masses, solver.cpp:101-1
     vec3 v, w; scalar inv_m; mat3 inv_I; bool proc;
 };
 struct SRow { Row r; uint32_t a, b; };
-struct SFric { vec3 J[2][4]; scalar eff_mass[2], rhs[2], impulse[2]; scalar mu; uint32_t normal_row; };
+struct SFric : FrictionPair { uint32_t normal_row; };
 struct IslandWork {
     std::vector<uint32_t> hinges;                 // indices into World::hinges
     std::vector<std::pair<uint32_t, uint32_t>> pts;   // (manifold, point)
     std::vector<uint32_t> bodies;
 };
+}
+
+// solve_friction, constraint_row_friction.cpp:11-54
+void solve_friction(FrictionPair &f, scalar normal_impulse, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
+                    vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB) {
+    scalar delta[2], imp[2];
+    for (int i = 0; i < 2; ++i) {
+        scalar drs = relative_speed(f.J[i], dvA, dwA, dvB, dwB);
+        delta[i] = (f.rhs[i] - drs) * f.eff_mass[i];
+        imp[i] = f.impulse[i] + delta[i];
+    }
+    scalar len_sqr = imp[0] * imp[0] + imp[1] * imp[1];
+    scalar max_len = f.mu * normal_impulse;
+    if (len_sqr > square(max_len)) {
+        scalar len = std::sqrt(len_sqr);
+        if (len > EPS) { imp[0] = imp[0] / len * max_len; imp[1] = imp[1] / len * max_len; }
+        else { imp[0] = imp[1] = 0; }
+        for (int i = 0; i < 2; ++i) delta[i] = imp[i] - f.impulse[i];
+    }
+    for (int i = 0; i < 2; ++i) {
+        f.impulse[i] = imp[i];
+        dvA += inv_mA * f.J[i][0] * delta[i];
+        dwA += inv_IA * f.J[i][1] * delta[i];
+        dvB += inv_mB * f.J[i][2] * delta[i];
+        dwB += inv_IB * f.J[i][3] * delta[i];
+    }
+}
+// warm_start(constraint_row_friction&), constraint_row_friction.cpp:56-66
+void warm_start_friction(const FrictionPair &f, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
+                         vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB) {
+    for (int i = 0; i < 2; ++i) {
+        dvA += inv_mA * f.J[i][0] * f.impulse[i];
+        dwA += inv_IA * f.J[i][1] * f.impulse[i];
+        dvB += inv_mB * f.J[i][2] * f.impulse[i];
+        dwB += inv_IB * f.J[i][3] * f.impulse[i];
+    }
 }
 
 static SBody solver_body(const Body &b) {
@@ -668,40 +704,23 @@ void World::solve() {
             DW(sr.b) += IA(sr.b) * sr.r.J[3] * imp;
             dummy_dv = dummy_dw = vec3{0, 0, 0};
         };
-        auto apply_fric = [&](const SFric &f, int i, scalar imp) {   // constraint_row_friction.cpp:47-53,59-65
-            const SRow &nr = rows[f.normal_row];
-            DV(nr.a) += MA(nr.a) * f.J[i][0] * imp;
-            DW(nr.a) += IA(nr.a) * f.J[i][1] * imp;
-            DV(nr.b) += MA(nr.b) * f.J[i][2] * imp;
-            DW(nr.b) += IA(nr.b) * f.J[i][3] * imp;
-            dummy_dv = dummy_dw = vec3{0, 0, 0};
-        };
         // ---- warm start (island_solver.cpp:76-92)
         for (SRow &sr : rows) apply(sr, sr.r.impulse);
-        for (SFric &f : fric) for (int i = 0; i < 2; ++i) apply_fric(f, i, f.impulse[i]);
+        for (SFric &f : fric) {
+            const SRow &nr = rows[f.normal_row];
+            warm_start_friction(f, MA(nr.a), IA(nr.a), MA(nr.b), IA(nr.b), DV(nr.a), DW(nr.a), DV(nr.b), DW(nr.b));
+            dummy_dv = dummy_dw = vec3{0, 0, 0};
+        }
         // ---- velocity iterations (island_solver.cpp:94-111)
         for (int it = 0; it < vi; ++it) {
             for (SRow &sr : rows) {
                 scalar d = solve_row(sr.r, DV(sr.a), DW(sr.a), DV(sr.b), DW(sr.b));
                 apply(sr, d);
             }
-            for (SFric &f : fric) {                          // solve_friction, constraint_row_friction.cpp:11-54
+            for (SFric &f : fric) {
                 const SRow &nr = rows[f.normal_row];
-                scalar delta[2], imp[2];
-                for (int i = 0; i < 2; ++i) {
-                    scalar drs = relative_speed(f.J[i], DV(nr.a), DW(nr.a), DV(nr.b), DW(nr.b));
-                    delta[i] = (f.rhs[i] - drs) * f.eff_mass[i];
-                    imp[i] = f.impulse[i] + delta[i];
-                }
-                scalar len_sqr = imp[0] * imp[0] + imp[1] * imp[1];
-                scalar max_len = f.mu * nr.r.impulse;
-                if (len_sqr > square(max_len)) {
-                    scalar len = std::sqrt(len_sqr);
-                    if (len > EPS) { imp[0] = imp[0] / len * max_len; imp[1] = imp[1] / len * max_len; }
-                    else { imp[0] = imp[1] = 0; }
-                    for (int i = 0; i < 2; ++i) delta[i] = imp[i] - f.impulse[i];
-                }
-                for (int i = 0; i < 2; ++i) { f.impulse[i] = imp[i]; apply_fric(f, i, delta[i]); }
+                solve_friction(f, nr.r.impulse, MA(nr.a), IA(nr.a), MA(nr.b), IA(nr.b), DV(nr.a), DW(nr.a), DV(nr.b), DW(nr.b));
+                dummy_dv = dummy_dw = vec3{0, 0, 0};
             }
         }
         // ---- integrate_velocities (island_solver.cpp:358-376)

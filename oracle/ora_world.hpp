@@ -102,5 +102,12 @@ void prepare_row(Row &row, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, con
                  scalar error, scalar erp, scalar restitution, vec3 vA, vec3 wA, vec3 vB, vec3 wB);
 scalar solve_row(Row &row, vec3 dvA, vec3 dwA, vec3 dvB, vec3 dwB);
 mat3 moment_of_inertia(const shape &sh, scalar mass);
+// constraint_row_friction (constraints/constraint_row_friction.hpp:12-24) and its two functions, pinned against the
+// reference's solve_friction / warm_start (constraint_row_friction.cpp:11-66) by tests/test_oracle_fixtures.py
+struct FrictionPair { vec3 J[2][4]; scalar eff_mass[2], rhs[2], impulse[2]; scalar mu; };
+void solve_friction(FrictionPair &f, scalar normal_impulse, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
+                    vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB);
+void warm_start_friction(const FrictionPair &f, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
+                         vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB);
 
 } // namespace ora

@@ -160,6 +160,14 @@ class PureFns:
         return np.float32(d), r
 
 
+    def solve_friction(self, J24, fr6, mu, normal_impulse, masses20, dv12, warm=False):
+        """solve_friction / warm_start of a constraint_row_friction; returns (impulse[2], dv12) after the call."""
+        fr, dv = _arr(fr6, _f).copy(), _arr(dv12, _f).copy()
+        a = [_arr(J24, _f), _arr(masses20, _f)]
+        self._fn("solve_friction")(_ptr(a[0]), _ptr(fr), C.c_float(mu), C.c_float(normal_impulse), _ptr(a[1]), _ptr(dv), C.c_int(int(warm)))
+        return fr[4:6].copy(), dv
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

@@ -128,6 +128,28 @@ REF_API float ref_solve_row(const float *J, float *row5, const float *dv12) {
     return d;
 }
 
+// solve_friction / warm_start(constraint_row_friction&), constraint_row_friction.cpp:11-66.  Same argument layout as
+// ora_solve_friction: the friction pair points at a one-element row cache holding the normal row (impulse, masses, deltas).
+REF_API void ref_solve_friction(const float *J24, float *fr6, float mu, float normal_impulse, const float *masses20, float *dv12, int warm) {
+    std::vector<constraint_row> cache(1);
+    constraint_row &nr = cache[0];
+    nr = constraint_row{};
+    nr.impulse = normal_impulse;
+    nr.inv_mA = masses20[0]; nr.inv_IA = m9(masses20 + 1); nr.inv_mB = masses20[10]; nr.inv_IB = m9(masses20 + 11);
+    delta_linvel dvA{v3(dv12)}, dvB{v3(dv12 + 6)};
+    delta_angvel dwA{v3(dv12 + 3)}, dwB{v3(dv12 + 9)};
+    nr.dvA = &dvA; nr.dwA = &dwA; nr.dvB = &dvB; nr.dwB = &dwB;
+    constraint_row_friction fr{};
+    for (int i = 0; i < 2; ++i) {
+        for (int k = 0; k < 4; ++k) fr.row[i].J[k] = v3(J24 + 12 * i + 3 * k);
+        fr.row[i].eff_mass = fr6[i]; fr.row[i].rhs = fr6[2 + i]; fr.row[i].impulse = fr6[4 + i];
+    }
+    fr.friction_coefficient = mu; fr.normal_row_index = 0;
+    if (warm) warm_start(fr, cache); else solve_friction(fr, cache);
+    fr6[4] = fr.row[0].impulse; fr6[5] = fr.row[1].impulse;
+    put3(dv12, dvA); put3(dv12 + 3, dwA); put3(dv12 + 6, dvB); put3(dv12 + 9, dwB);
+}
+
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for
 // pivot/axes given in body space.  bodies: pos(3) orn(4) per body.
 REF_API int ref_hinge_rows(const float *pivotA, const float *pivotB, const float *axisA, const float *axisB,

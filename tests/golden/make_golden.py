@@ -151,7 +151,41 @@ def main():
     np.savez_compressed(os.path.join(HERE, "rows.npz"), J=J, inv_mA=mA, inv_IA=IA, inv_mB=mB, inv_IB=IB, error=err, restitution=rest,
                         vel=vel, prepared=prep, row5=row5, dv=dv, delta=delta, impulse=imp, normal=nrm, plane_space=ps,
                         hinge_params=hpar, hinge_J=hin)
+    make_friction(r)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+
+
+def friction_inputs(rng, m):
+    """Random constraint_row_friction cases: tangent Jacobians, prepared rows, warm impulses, normal loads that put about
+    half of the cases outside the friction circle (clamped) and a few at zero load (the |impulse| <= epsilon branch)."""
+    J = rng.normal(size=(m, 24)).astype(f32)
+    fr = np.concatenate([(0.2 + rng.random((m, 2))), rng.normal(size=(m, 2)), rng.normal(size=(m, 2)) * 0.2], axis=1).astype(f32)
+    mu = (0.1 + rng.random(m)).astype(f32)
+    nimp = np.abs(rng.normal(size=m)).astype(f32) * np.where(rng.random(m) < 0.5, 0.05, 3.0).astype(f32)
+    nimp[::17] = 0
+    fr[::34, 2:6] = 0                                                   # zero rhs and impulse with zero load
+    masses = np.zeros((m, 20), f32)
+    masses[:, 0], masses[:, 10] = rng.random(m), rng.random(m)
+    for i in range(m):
+        masses[i, 1:10] = np.diag(1 + rng.random(3)).reshape(9)
+        masses[i, 11:20] = np.diag(1 + rng.random(3)).reshape(9)
+    masses[::5, 10:20] = 0                                              # static second body
+    dv = (rng.normal(size=(m, 12)) * 0.3).astype(f32)
+    dv[::5, 6:12] = 0
+    return J, fr, mu, nimp, masses, dv
+
+
+def make_friction(r):
+    """solve_friction + warm_start (constraints/constraint_row_friction.cpp:11-66)."""
+    rng = np.random.default_rng(4321)
+    m = 600
+    J, fr, mu, nimp, masses, dv = friction_inputs(rng, m)
+    out_imp, out_dv, warm_dv = np.zeros((m, 2), f32), np.zeros((m, 12), f32), np.zeros((m, 12), f32)
+    for i in range(m):
+        out_imp[i], out_dv[i] = r.solve_friction(J[i], fr[i], mu[i], nimp[i], masses[i], dv[i])
+        _, warm_dv[i] = r.solve_friction(J[i], fr[i], mu[i], nimp[i], masses[i], dv[i], warm=True)
+    np.savez_compressed(os.path.join(HERE, "friction.npz"), J=J, fr=fr, mu=mu, normal_impulse=nimp, masses=masses, dv=dv,
+                        impulse=out_imp, dv_out=out_dv, dv_warm=warm_dv)
 
 
 if __name__ == "__main__":

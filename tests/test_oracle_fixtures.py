@@ -68,6 +68,22 @@ def test_rows_match_reference_vectors(O):
         assert n == 5 and np.array_equal(J, g["hinge_J"][i])
 
 
+def test_friction_rows_match_reference_vectors(O):
+    """solve_friction and warm_start of constraint_row_friction (constraint_row_friction.cpp:11-66): 600 committed cases
+    produced by the reference's own object code, two thirds of them clamped to the friction circle, some at zero load."""
+    g = load("friction.npz")
+    o = O.ora_fns()
+    clamped = 0
+    for i in range(len(g["J"])):
+        imp, dv = o.solve_friction(g["J"][i], g["fr"][i], g["mu"][i], g["normal_impulse"][i], g["masses"][i], g["dv"][i])
+        assert np.array_equal(imp, g["impulse"][i]) and np.array_equal(dv, g["dv_out"][i]), i
+        _, wdv = o.solve_friction(g["J"][i], g["fr"][i], g["mu"][i], g["normal_impulse"][i], g["masses"][i], g["dv"][i], warm=True)
+        assert np.array_equal(wdv, g["dv_warm"][i]), i
+        lim = g["mu"][i] * g["normal_impulse"][i]
+        clamped += bool(lim > 0 and abs(np.hypot(*imp) - lim) <= 1e-5 * max(1.0, lim))
+    assert clamped > 300
+
+
 def _rq(rng):
     q = rng.normal(size=4)
     return (q / np.linalg.norm(q)).astype(f32)
@@ -104,9 +120,15 @@ def test_random_against_reference_library(O, ref):
             pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
         a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    from tests.golden.make_golden import friction_inputs
+    J, fr, mu, nimp, masses, dv = friction_inputs(rng, 800)
+    for i in range(len(J)):
+        for warm in (False, True):
+            a, b = o.solve_friction(J[i], fr[i], mu[i], nimp[i], masses[i], dv[i], warm), ref.solve_friction(J[i], fr[i], mu[i], nimp[i], masses[i], dv[i], warm)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (i, warm)
 
 
 def test_golden_generator_is_committed():
     assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
-    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz"):
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz"):
         assert os.path.exists(os.path.join(GOLD, f))
