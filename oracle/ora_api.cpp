@@ -303,4 +303,43 @@ void ora_solve_friction(const float *J24, float *fr6, float mu, float normal_imp
     put3(dv12, dvA); put3(dv12 + 3, dwA); put3(dv12 + 6, dvB); put3(dv12 + 9, dwB);
 }
 
+// contact_constraint::prepare; argument layout of ref_contact_prepare (oracle/ref_glue.cpp)
+void ora_contact_prepare(const float *cp14, float dt, const float *a23, const float *b23,
+                         float *nJ12, float *n5, float *fJ24, float *fr6, float *mu) {
+    Point cp{};
+    cp.pivotA = v3(cp14); cp.pivotB = v3(cp14 + 3); cp.normal = v3(cp14 + 6); cp.distance = cp14[9];
+    cp.friction = cp14[10]; cp.restitution = cp14[11]; cp.imp_n = cp14[12]; cp.imp_t[0] = cp14[13]; cp.imp_t[1] = cp14[14];
+    Row nr{}; FrictionPair f{}; scalar error = 0;
+    prepare_contact(cp, dt, v3(a23), q4(a23 + 3), v3(b23), q4(b23 + 3), v3(a23 + 7), v3(a23 + 10), a23[13], m9(a23 + 14),
+                    v3(b23 + 7), v3(b23 + 10), b23[13], m9(b23 + 14), nr, error, f);
+    for (int k = 0; k < 4; ++k) put3(nJ12 + 3 * k, nr.J[k]);
+    n5[0] = nr.lo; n5[1] = nr.hi; n5[2] = nr.impulse; n5[3] = error; n5[4] = cp.restitution;
+    for (int i = 0; i < 2; ++i) {
+        for (int k = 0; k < 4; ++k) put3(fJ24 + 12 * i + 3 * k, f.J[i][k]);
+        fr6[i] = f.eff_mass[i]; fr6[2 + i] = f.rhs[i]; fr6[4 + i] = f.impulse[i];
+    }
+    *mu = f.mu;
+}
+
+// contact_constraint::solve_position + position_solver::solve; argument layout of ref_contact_solve_position.
+// A body with inv_m == 0 is non-procedural here (the restatement leaves it untouched, see position_solve).
+int ora_contact_solve_position(const float *cp13, float *a26, float *b26, float *out5) {
+    Point cp{};
+    cp.pivotA = v3(cp13); cp.pivotB = v3(cp13 + 3); cp.normal = v3(cp13 + 6); cp.local_normal = v3(cp13 + 9);
+    cp.att = uint32_t(cp13[12]);
+    auto load = [](const float *p) {
+        Body b{};
+        b.pos = v3(p); b.orn = q4(p + 3); b.inv_m = p[7]; b.inv_IW = m9(p + 8); b.inv_I = m9(p + 17);
+        b.kind = p[7] != 0 ? BK_DYNAMIC : BK_STATIC;
+        return b;
+    };
+    Body A = load(a26), B = load(b26);
+    scalar max_error = 0;
+    const bool solved = contact_solve_position(cp, A, B, max_error);
+    auto store = [](float *p, const Body &b) { put3(p, b.pos); p[3] = b.orn.x; p[4] = b.orn.y; p[5] = b.orn.z; p[6] = b.orn.w; put9(p + 8, b.inv_IW); };
+    store(a26, A); store(b26, B);
+    put3(out5, cp.normal); out5[3] = cp.distance; out5[4] = max_error;
+    return solved ? 1 : 0;
+}
+
 } // extern "C"

@@ -550,6 +550,42 @@ void warm_start_friction(const FrictionPair &f, scalar inv_mA, const mat3 &inv_I
     }
 }
 
+// contact_constraint::prepare, contact_constraint.cpp:15-56 (origin == position: no centre-of-mass offset is staged)
+void prepare_contact(const Point &cp, scalar dt, vec3 posA, quat ornA, vec3 posB, quat ornB,
+                     vec3 vA, vec3 wA, scalar inv_mA, const mat3 &inv_IA, vec3 vB, vec3 wB, scalar inv_mB, const mat3 &inv_IB,
+                     Row &nr, scalar &error, FrictionPair &f) {
+    vec3 pAw = to_world(cp.pivotA, posA, ornA);
+    vec3 pBw = to_world(cp.pivotB, posB, ornB);
+    vec3 rA = pAw - posA, rB = pBw - posB;
+    nr.J[0] = cp.normal; nr.J[1] = cross(rA, cp.normal); nr.J[2] = -cp.normal; nr.J[3] = -cross(rB, cp.normal);
+    nr.impulse = cp.imp_n; nr.lo = 0; nr.hi = LARGE;
+    error = 0;
+    if (cp.distance > 0) error = cp.distance / dt;
+    f.mu = cp.friction;
+    vec3 t[2]; plane_space(cp.normal, t[0], t[1]);
+    for (int i = 0; i < 2; ++i) {
+        f.J[i][0] = t[i]; f.J[i][1] = cross(rA, t[i]); f.J[i][2] = -t[i]; f.J[i][3] = -cross(rB, t[i]);
+        f.impulse[i] = cp.imp_t[i];
+        f.eff_mass[i] = effective_mass(f.J[i], inv_mA, inv_IA, inv_mB, inv_IB);
+        f.rhs[i] = -relative_speed(f.J[i], vA, wA, vB, wB);
+    }
+}
+
+// contact_constraint::solve_position, contact_constraint.cpp:58-90
+bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error) {
+    vec3 pAw = to_world(cp.pivotA, A.pos, A.orn);
+    vec3 pBw = to_world(cp.pivotB, B.pos, B.orn);
+    if (cp.att == ATT_A) cp.normal = rotate(A.orn, cp.local_normal);
+    else if (cp.att == ATT_B) cp.normal = rotate(B.orn, cp.local_normal);
+    cp.distance = dot(pAw - pBw, cp.normal);
+    vec3 rA = pAw - A.pos, rB = pBw - B.pos;
+    if (cp.distance > -EPS) return false;
+    scalar error = -cp.distance;
+    vec3 J[4] = {cp.normal, cross(rA, cp.normal), -cp.normal, -cross(rB, cp.normal)};
+    position_solve(A, B, J, error, max_error);
+    return true;
+}
+
 static SBody solver_body(const Body &b) {
     SBody s;
     s.proc = b.awake();
@@ -559,7 +595,7 @@ static SBody solver_body(const Body &b) {
 }
 
 // position_solver::solve, dynamics/position_solver.hpp:16-51
-static void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error) {
+void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error) {
     const bool pA = A.awake(), pB = B.awake();
     const scalar inv_mA = pA ? A.inv_m : 0, inv_mB = pB ? B.inv_m : 0;
     mat3 zero = mat3_zero();
@@ -669,23 +705,11 @@ void World::solve() {
             Point &cp = m.pt[p];
             const Body &A = bodies[m.a], &B = bodies[m.b];
             SBody sA = solver_body(A), sB = solver_body(B);
-            vec3 pAw = to_world(cp.pivotA, A.pos, A.orn);
-            vec3 pBw = to_world(cp.pivotB, B.pos, B.orn);
-            vec3 rA = pAw - A.pos, rB = pBw - B.pos;
             SRow sr{}; sr.a = m.a; sr.b = m.b;
-            sr.r.J[0] = cp.normal; sr.r.J[1] = cross(rA, cp.normal); sr.r.J[2] = -cp.normal; sr.r.J[3] = -cross(rB, cp.normal);
-            sr.r.impulse = cp.imp_n; sr.r.lo = 0; sr.r.hi = LARGE;
-            scalar error = 0;
-            if (cp.distance > 0) error = cp.distance / dt;
+            SFric f{}; f.normal_row = uint32_t(rows.size());
+            scalar error;
+            prepare_contact(cp, dt, A.pos, A.orn, B.pos, B.orn, sA.v, sA.w, sA.inv_m, sA.inv_I, sB.v, sB.w, sB.inv_m, sB.inv_I, sr.r, error, f);
             prepare_row(sr.r, sA.inv_m, sA.inv_I, sB.inv_m, sB.inv_I, error, scalar(0.2), cp.restitution, sA.v, sA.w, sB.v, sB.w);
-            SFric f{}; f.mu = cp.friction; f.normal_row = uint32_t(rows.size());
-            vec3 t[2]; plane_space(cp.normal, t[0], t[1]);
-            for (int i = 0; i < 2; ++i) {
-                f.J[i][0] = t[i]; f.J[i][1] = cross(rA, t[i]); f.J[i][2] = -t[i]; f.J[i][3] = -cross(rB, t[i]);
-                f.impulse[i] = cp.imp_t[i];
-                f.eff_mass[i] = effective_mass(f.J[i], sA.inv_m, sA.inv_I, sB.inv_m, sB.inv_I);
-                f.rhs[i] = -relative_speed(f.J[i], sA.v, sA.w, sB.v, sB.w);
-            }
             rows.push_back(sr); fric.push_back(f);
         }
         (void)first_contact_row;
@@ -779,16 +803,7 @@ void World::solve() {
                     Manifold &m = manifolds[mi];
                     Point &cp = m.pt[p];
                     Body &A = bodies[m.a], &B = bodies[m.b];
-                    vec3 pAw = to_world(cp.pivotA, A.pos, A.orn);
-                    vec3 pBw = to_world(cp.pivotB, B.pos, B.orn);
-                    if (cp.att == ATT_A) cp.normal = rotate(A.orn, cp.local_normal);
-                    else if (cp.att == ATT_B) cp.normal = rotate(B.orn, cp.local_normal);
-                    cp.distance = dot(pAw - pBw, cp.normal);
-                    vec3 rA = pAw - A.pos, rB = pBw - B.pos;
-                    if (cp.distance > -EPS) continue;
-                    scalar error = -cp.distance;
-                    vec3 J[4] = {cp.normal, cross(rA, cp.normal), -cp.normal, -cross(rB, cp.normal)};
-                    position_solve(A, B, J, error, type_err);
+                    contact_solve_position(cp, A, B, type_err);
                 }
                 max_error = std::max(max_error, type_err);
             }

@@ -105,6 +105,16 @@ mat3 moment_of_inertia(const shape &sh, scalar mass);
 // constraint_row_friction (constraints/constraint_row_friction.hpp:12-24) and its two functions, pinned against the
 // reference's solve_friction / warm_start (constraint_row_friction.cpp:11-66) by tests/test_oracle_fixtures.py
 struct FrictionPair { vec3 J[2][4]; scalar eff_mass[2], rhs[2], impulse[2]; scalar mu; };
+// contact_constraint::prepare (constraints/contact_constraint.cpp:15-56): builds the normal row (not yet passed through
+// prepare_row: `error` and the point's restitution are what constraint_row_options would carry) and the friction pair.
+// Pinned against the reference's own object code by tests/test_oracle_fixtures.py.
+void prepare_contact(const Point &cp, scalar dt, vec3 posA, quat ornA, vec3 posB, quat ornB,
+                     vec3 vA, vec3 wA, scalar inv_mA, const mat3 &inv_IA, vec3 vB, vec3 wB, scalar inv_mB, const mat3 &inv_IB,
+                     Row &normal_row, scalar &error, FrictionPair &f);
+// position_solver::solve (dynamics/position_solver.hpp:16-51) and contact_constraint::solve_position
+// (contact_constraint.cpp:58-90) on two bodies; returns false when the point is not penetrating (nothing solved)
+void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error);
+bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error);
 void solve_friction(FrictionPair &f, scalar normal_impulse, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
                     vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB);
 void warm_start_friction(const FrictionPair &f, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,

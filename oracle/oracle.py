@@ -168,6 +168,23 @@ class PureFns:
         return fr[4:6].copy(), dv
 
 
+    def contact_prepare(self, cp15, dt, bodyA23, bodyB23):
+        """contact_constraint::prepare -> dict(nJ, n5 = lower upper impulse error restitution, fJ, fr6, mu)."""
+        nJ, n5, fJ, fr6, mu = np.zeros(12, _f), np.zeros(5, _f), np.zeros(24, _f), np.zeros(6, _f), C.c_float(0)
+        a = [_arr(cp15, _f), _arr(bodyA23, _f), _arr(bodyB23, _f)]
+        self._fn("contact_prepare")(_ptr(a[0]), C.c_float(dt), _ptr(a[1]), _ptr(a[2]), _ptr(nJ), _ptr(n5), _ptr(fJ), _ptr(fr6), C.byref(mu))
+        return dict(nJ=nJ, n5=n5, fJ=fJ, fr6=fr6, mu=np.float32(mu.value))
+
+    def contact_solve_position(self, cp13, bodyA26, bodyB26):
+        """contact_constraint::solve_position + position_solver::solve -> (solved, bodyA26', bodyB26', out5 = normal distance max_error)."""
+        a, b, out = _arr(bodyA26, _f).copy(), _arr(bodyB26, _f).copy(), np.zeros(5, _f)
+        cp = _arr(cp13, _f)
+        fn = self._fn("contact_solve_position")
+        fn.restype = C.c_int
+        solved = fn(_ptr(cp), _ptr(a), _ptr(b), _ptr(out))
+        return int(solved), a, b, out
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

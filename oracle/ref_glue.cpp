@@ -10,6 +10,12 @@
 #include <edyn/constraints/constraint_body.hpp>
 #include <edyn/dynamics/moment_of_inertia.hpp>
 #include <edyn/dynamics/row_cache.hpp>
+#include <edyn/dynamics/position_solver.hpp>
+#include <edyn/constraints/constraint_row_friction.hpp>
+#include <edyn/constraints/contact_constraint.hpp>
+#include <edyn/comp/position.hpp>
+#include <edyn/comp/orientation.hpp>
+#include <edyn/comp/inertia.hpp>
 #include <edyn/math/geom.hpp>
 #include <edyn/math/quaternion.hpp>
 #include <edyn/math/matrix3x3.hpp>
@@ -148,6 +154,59 @@ REF_API void ref_solve_friction(const float *J24, float *fr6, float mu, float no
     if (warm) warm_start(fr, cache); else solve_friction(fr, cache);
     fr6[4] = fr.row[0].impulse; fr6[5] = fr.row[1].impulse;
     put3(dv12, dvA); put3(dv12 + 3, dwA); put3(dv12 + 6, dvB); put3(dv12 + 9, dwB);
+}
+
+// contact_constraint::prepare (contact_constraint.cpp:15-56).  cp14 = pivotA pivotB normal distance friction restitution
+// applied_normal_impulse applied_friction_impulse[2]; body23 = pos(3) orn(4) linvel(3) angvel(3) inv_m inv_I(9), origin == pos.
+// out: nJ12, n5 = lower upper impulse options.error options.restitution, fJ24, fr6 = eff_mass[2] rhs[2] impulse[2], mu.
+static constraint_body glue_body(const float *b) {
+    constraint_body cb{};
+    cb.origin = v3(b); cb.pos = v3(b); cb.orn = q4(b + 3); cb.linvel = v3(b + 7); cb.angvel = v3(b + 10); cb.inv_m = b[13]; cb.inv_I = m9(b + 14);
+    return cb;
+}
+REF_API void ref_contact_prepare(const float *cp14, float dt, const float *bodyA23, const float *bodyB23,
+                                 float *nJ12, float *n5, float *fJ24, float *fr6, float *mu) {
+    contact_constraint con{};
+    con.pivotA = v3(cp14); con.pivotB = v3(cp14 + 3); con.normal = v3(cp14 + 6); con.distance = cp14[9];
+    con.friction = cp14[10]; con.restitution = cp14[11]; con.applied_normal_impulse = cp14[12];
+    con.applied_friction_impulse = {cp14[13], cp14[14]};
+    constraint_row_prep_cache cache;
+    cache.add_constraint();
+    con.prepare(cache, dt, glue_body(bodyA23), glue_body(bodyB23));
+    const auto &e = cache.rows[0];
+    for (int k = 0; k < 4; ++k) put3(nJ12 + 3 * k, e.row.J[k]);
+    n5[0] = e.row.lower_limit; n5[1] = e.row.upper_limit; n5[2] = e.row.impulse; n5[3] = e.options.error; n5[4] = e.options.restitution;
+    for (int i = 0; i < 2; ++i) {
+        for (int k = 0; k < 4; ++k) put3(fJ24 + 12 * i + 3 * k, e.friction.row[i].J[k]);
+        fr6[i] = e.friction.row[i].eff_mass; fr6[2 + i] = e.friction.row[i].rhs; fr6[4 + i] = e.friction.row[i].impulse;
+    }
+    *mu = e.friction.friction_coefficient;
+}
+
+// contact_constraint::solve_position (contact_constraint.cpp:58-90) through position_solver::solve
+// (dynamics/position_solver.hpp:16-51).  cp13 = pivotA pivotB normal local_normal attachment(as float 0/1/2);
+// body26 = pos(3) orn(4) inv_m inv_IW(9) inv_I_local(9), updated in place; out5 = normal(3) distance max_error.
+REF_API int ref_contact_solve_position(const float *cp13, float *bodyA26, float *bodyB26, float *out5) {
+    contact_constraint con{};
+    con.pivotA = v3(cp13); con.pivotB = v3(cp13 + 3); con.normal = v3(cp13 + 6); con.local_normal = v3(cp13 + 9);
+    con.normal_attachment = cp13[12] == 1.0f ? contact_normal_attachment::normal_on_A
+                          : cp13[12] == 2.0f ? contact_normal_attachment::normal_on_B : contact_normal_attachment::none;
+    position posA{v3(bodyA26)}, posB{v3(bodyB26)};
+    orientation ornA{q4(bodyA26 + 3)}, ornB{q4(bodyB26 + 3)};
+    inertia_world_inv iwA{m9(bodyA26 + 8)}, iwB{m9(bodyB26 + 8)};
+    inertia_inv ilA{m9(bodyA26 + 17)}, ilB{m9(bodyB26 + 17)};
+    position_solver solver{};
+    solver.originA = nullptr; solver.originB = nullptr; solver.comA = vector3_zero; solver.comB = vector3_zero;
+    solver.posA = &posA; solver.posB = &posB; solver.ornA = &ornA; solver.ornB = &ornB;
+    solver.inv_mA = bodyA26[7]; solver.inv_mB = bodyB26[7];
+    solver.inv_IA = &iwA; solver.inv_IB = &iwB; solver.inv_IA_local = &ilA; solver.inv_IB_local = &ilB;
+    const scalar before = solver.max_error;
+    con.solve_position(solver);
+    put3(bodyA26, posA); put4(bodyA26 + 3, ornA); put9(bodyA26 + 8, iwA);
+    put3(bodyB26, posB); put4(bodyB26 + 3, ornB); put9(bodyB26 + 8, iwB);
+    put3(out5, con.normal); out5[3] = con.distance; out5[4] = solver.max_error;
+    (void)before;
+    return con.distance > -EDYN_EPSILON ? 0 : 1;
 }
 
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for

@@ -152,6 +152,7 @@ def main():
                         vel=vel, prepared=prep, row5=row5, dv=dv, delta=delta, impulse=imp, normal=nrm, plane_space=ps,
                         hinge_params=hpar, hinge_J=hin)
     make_friction(r)
+    make_contacts(r)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -186,6 +187,57 @@ def make_friction(r):
         _, warm_dv[i] = r.solve_friction(J[i], fr[i], mu[i], nimp[i], masses[i], dv[i], warm=True)
     np.savez_compressed(os.path.join(HERE, "friction.npz"), J=J, fr=fr, mu=mu, normal_impulse=nimp, masses=masses, dv=dv,
                         impulse=out_imp, dv_out=out_dv, dv_warm=warm_dv)
+
+
+def contact_inputs(rng, m):
+    """Random contact points between two bodies a few centimetres apart: prepare inputs (cp15, two body23) and
+    solve_position inputs (cp13, two body26).  Every fifth second body is static; a third of the points is separated
+    (distance > 0: the error = distance / dt branch, and the early return of solve_position)."""
+    def bodies(k):
+        pos = (rng.normal(size=(m, 3)) * 0.5).astype(f32)
+        orn = np.stack([rq(rng) for _ in range(m)])
+        inv_m = (0.2 + rng.random(m)).astype(f32)
+        inv_I = np.stack([np.diag(0.5 + rng.random(3)).reshape(9) for _ in range(m)]).astype(f32)
+        return pos, orn, inv_m, inv_I
+    pa, qa, ma, Ia = bodies(0)
+    pb, qb, mb, Ib = bodies(1)
+    mb[::5] = 0; Ib[::5] = 0
+    lv = lambda: (rng.normal(size=(m, 3)) * 0.5).astype(f32)
+    va, wa, vb, wb = lv(), lv(), lv(), lv()
+    vb[::5] = 0; wb[::5] = 0
+    nrm = np.stack([x / np.linalg.norm(x) for x in rng.normal(size=(m, 3))]).astype(f32)
+    pivA, pivB = (rng.normal(size=(m, 3)) * 0.4).astype(f32), (rng.normal(size=(m, 3)) * 0.4).astype(f32)
+    dist = (rng.normal(size=m) * 0.02).astype(f32)
+    cp15 = np.concatenate([pivA, pivB, nrm, dist[:, None], (0.1 + rng.random((m, 1))), rng.random((m, 1)) * 0.5,
+                           np.abs(rng.normal(size=(m, 1))), rng.normal(size=(m, 2)) * 0.2], axis=1).astype(f32)
+    bA23 = np.concatenate([pa, qa, va, wa, ma[:, None], Ia], axis=1).astype(f32)
+    bB23 = np.concatenate([pb, qb, vb, wb, mb[:, None], Ib], axis=1).astype(f32)
+    # position solve: world inertia consistent with the orientation, like update_inertias leaves it
+    o = O.ora_fns()
+    IWa = np.stack([o.world_inertia(qa[i], Ia[i]).reshape(9) for i in range(m)])
+    IWb = np.stack([o.world_inertia(qb[i], Ib[i]).reshape(9) for i in range(m)])
+    att = rng.integers(0, 3, size=m).astype(f32)
+    local_n = np.stack([x / np.linalg.norm(x) for x in rng.normal(size=(m, 3))]).astype(f32)
+    cp13 = np.concatenate([pivA, pivB, nrm, local_n, att[:, None]], axis=1).astype(f32)
+    # put pivotB where pivotA is (in world space) shifted along the normal, so that distances are a few centimetres
+    bA26 = np.concatenate([pa, qa, ma[:, None], IWa, Ia], axis=1).astype(f32)
+    bB26 = np.concatenate([pb, qb, mb[:, None], IWb, Ib], axis=1).astype(f32)
+    return cp15, bA23, bB23, cp13, bA26, bB26
+
+
+def make_contacts(r):
+    """contact_constraint::prepare and ::solve_position (constraints/contact_constraint.cpp:15-90) with
+    position_solver::solve (dynamics/position_solver.hpp:16-51)."""
+    rng = np.random.default_rng(97531)
+    m = 500
+    cp15, bA23, bB23, cp13, bA26, bB26 = contact_inputs(rng, m)
+    prep = [r.contact_prepare(cp15[i], 1.0 / 60, bA23[i], bB23[i]) for i in range(m)]
+    pos = [r.contact_solve_position(cp13[i], bA26[i], bB26[i]) for i in range(m)]
+    np.savez_compressed(os.path.join(HERE, "contacts.npz"), cp15=cp15, bodyA23=bA23, bodyB23=bB23, cp13=cp13, bodyA26=bA26, bodyB26=bB26,
+                        nJ=np.stack([p["nJ"] for p in prep]), n5=np.stack([p["n5"] for p in prep]), fJ=np.stack([p["fJ"] for p in prep]),
+                        fr6=np.stack([p["fr6"] for p in prep]), mu=np.array([p["mu"] for p in prep], f32),
+                        solved=np.array([p[0] for p in pos], np.int32), outA=np.stack([p[1] for p in pos]), outB=np.stack([p[2] for p in pos]),
+                        out5=np.stack([p[3] for p in pos]))
 
 
 if __name__ == "__main__":

@@ -84,6 +84,23 @@ def test_friction_rows_match_reference_vectors(O):
     assert clamped > 300
 
 
+def test_contact_rows_and_position_solve_match_reference_vectors(O):
+    """contact_constraint::prepare and ::solve_position with position_solver::solve (contact_constraint.cpp:15-90,
+    position_solver.hpp:16-51): 500 committed cases produced by the reference's own object code."""
+    g = load("contacts.npz")
+    o = O.ora_fns()
+    assert 150 < int(g["solved"].sum()) < 400, "both the penetrating and the separated branch are exercised"
+    for i in range(len(g["cp15"])):
+        p = o.contact_prepare(g["cp15"][i], 1.0 / 60, g["bodyA23"][i], g["bodyB23"][i])
+        for k in ("nJ", "n5", "fJ", "fr6"):
+            assert np.array_equal(p[k], g[k][i]), (i, k)
+        assert p["mu"] == g["mu"][i]
+        solved, a, b, out = o.contact_solve_position(g["cp13"][i], g["bodyA26"][i], g["bodyB26"][i])
+        assert solved == g["solved"][i] and np.array_equal(a, g["outA"][i]) and np.array_equal(out, g["out5"][i]), i
+        if g["bodyB26"][i][7] != 0:        # a static second body: the reference re-normalises its orientation, the oracle leaves it alone
+            assert np.array_equal(b, g["outB"][i]), i
+
+
 def _rq(rng):
     q = rng.normal(size=4)
     return (q / np.linalg.norm(q)).astype(f32)
@@ -120,6 +137,15 @@ def test_random_against_reference_library(O, ref):
             pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
         a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    from tests.golden.make_golden import contact_inputs
+    cp15, bA23, bB23, cp13, bA26, bB26 = contact_inputs(rng, 400)
+    for i in range(len(cp15)):
+        a, b = o.contact_prepare(cp15[i], 1.0 / 60, bA23[i], bB23[i]), ref.contact_prepare(cp15[i], 1.0 / 60, bA23[i], bB23[i])
+        assert all(np.array_equal(a[k], b[k]) for k in ("nJ", "n5", "fJ", "fr6")) and a["mu"] == b["mu"], i
+        a, b = o.contact_solve_position(cp13[i], bA26[i], bB26[i]), ref.contact_solve_position(cp13[i], bA26[i], bB26[i])
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3]), i
+        if bB26[i][7] != 0:
+            assert np.array_equal(a[2], b[2]), i
     from tests.golden.make_golden import friction_inputs
     J, fr, mu, nimp, masses, dv = friction_inputs(rng, 800)
     for i in range(len(J)):
@@ -130,5 +156,5 @@ def test_random_against_reference_library(O, ref):
 
 def test_golden_generator_is_committed():
     assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
-    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz"):
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz"):
         assert os.path.exists(os.path.join(GOLD, f))
