@@ -342,4 +342,23 @@ int ora_contact_solve_position(const float *cp13, float *a26, float *b26, float 
     return solved ? 1 : 0;
 }
 
+// find_nearest_contact / find_nearest_contact_rolling / should_remove_point; argument layouts of the ref_* twins
+uint32_t ora_find_nearest_contact(const float *cpA, const float *cpB, uint32_t n, const float *resA, const float *resB) {
+    Point cp{}; cp.pivotA = v3(cpA); cp.pivotB = v3(cpB);
+    cresult res{}; res.num = n;
+    for (uint32_t i = 0; i < n; ++i) { res.pt[i].pivotA = v3(resA + 3 * i); res.pt[i].pivotB = v3(resB + 3 * i); }
+    return uint32_t(find_nearest_contact(cp, res));
+}
+uint32_t ora_find_nearest_contact_rolling(uint32_t n, const float *resA, const float *cp_pivot, const float *origin, const float *orn,
+                                          const float *angvel, float dt) {
+    cresult res{}; res.num = n;
+    for (uint32_t i = 0; i < n; ++i) res.pt[i].pivotA = v3(resA + 3 * i);
+    return uint32_t(find_nearest_contact_rolling(res, v3(cp_pivot), v3(origin), q4(orn), v3(angvel), dt));
+}
+int ora_should_remove_point(const float *pivotA, const float *pivotB, const float *normal, const float *posA, const float *ornA,
+                            const float *posB, const float *ornB) {
+    Point cp{}; cp.pivotA = v3(pivotA); cp.pivotB = v3(pivotB); cp.normal = v3(normal);
+    return should_remove_point(cp, v3(posA), q4(ornA), v3(posB), q4(ornB)) ? 1 : 0;
+}
+
 } // extern "C"

@@ -262,7 +262,7 @@ void World::broadphase() {
 // ------------------------------------------------------------------ narrowphase
 
 // src/edyn/util/collision_util.cpp:233-255
-static size_t find_nearest_contact(const Point &cp, const cresult &res) {
+size_t find_nearest_contact(const Point &cp, const cresult &res) {
     scalar shortest = square(CACHING_THRESHOLD);
     size_t nearest = res.num;
     for (size_t i = 0; i < res.num; ++i) {
@@ -274,7 +274,7 @@ static size_t find_nearest_contact(const Point &cp, const cresult &res) {
     return nearest;
 }
 // src/edyn/util/collision_util.cpp:257-280 (uses result.pivotA for either body, as the reference does)
-static size_t find_nearest_contact_rolling(const cresult &res, vec3 cp_pivot, vec3 origin, quat orn, vec3 angvel, scalar dt) {
+size_t find_nearest_contact_rolling(const cresult &res, vec3 cp_pivot, vec3 origin, quat orn, vec3 angvel, scalar dt) {
     size_t nearest = res.num;
     quat prev_orn = integrate(orn, angvel, -dt);
     vec3 prev_pivot = to_world(cp_pivot, origin, prev_orn);
@@ -287,7 +287,7 @@ static size_t find_nearest_contact_rolling(const cresult &res, vec3 cp_pivot, ve
     return nearest;
 }
 // src/edyn/util/collision_util.cpp:397-413
-static bool should_remove_point(const Point &cp, vec3 posA, quat ornA, vec3 posB, quat ornB) {
+bool should_remove_point(const Point &cp, vec3 posA, quat ornA, vec3 posB, quat ornB) {
     const scalar thr = BREAKING_THRESHOLD;
     const scalar thr_sqr = thr * thr;
     vec3 pA = to_world(cp.pivotA, posA, ornA);

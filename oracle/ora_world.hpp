@@ -115,6 +115,11 @@ void prepare_contact(const Point &cp, scalar dt, vec3 posA, quat ornA, vec3 posB
 // (contact_constraint.cpp:58-90) on two bodies; returns false when the point is not penetrating (nothing solved)
 void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error);
 bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error);
+// the three decisions process_collision takes per persisted point (util/collision_util.cpp:233-280, :397-413), pinned
+// against the reference functions cut out of that unit at build time
+size_t find_nearest_contact(const Point &cp, const cresult &res);
+size_t find_nearest_contact_rolling(const cresult &res, vec3 cp_pivot, vec3 origin, quat orn, vec3 angvel, scalar dt);
+bool should_remove_point(const Point &cp, vec3 posA, quat ornA, vec3 posB, quat ornB);
 void solve_friction(FrictionPair &f, scalar normal_impulse, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,
                     vec3 &dvA, vec3 &dwA, vec3 &dvB, vec3 &dwB);
 void warm_start_friction(const FrictionPair &f, scalar inv_mA, const mat3 &inv_IA, scalar inv_mB, const mat3 &inv_IB,

@@ -185,6 +185,23 @@ class PureFns:
         return int(solved), a, b, out
 
 
+    def find_nearest_contact(self, cpA, cpB, resA, resB):
+        resA, resB = _arr(resA, _f, (-1, 3)), _arr(resB, _f, (-1, 3))
+        fn = self._fn("find_nearest_contact"); fn.restype = C.c_uint32
+        return int(fn(_ptr(_arr(cpA, _f)), _ptr(_arr(cpB, _f)), C.c_uint32(len(resA)), _ptr(resA), _ptr(resB)))
+
+    def find_nearest_contact_rolling(self, resA, cp_pivot, origin, orn, angvel, dt):
+        resA = _arr(resA, _f, (-1, 3))
+        fn = self._fn("find_nearest_contact_rolling"); fn.restype = C.c_uint32
+        a = [_arr(cp_pivot, _f), _arr(origin, _f), _arr(orn, _f), _arr(angvel, _f)]
+        return int(fn(C.c_uint32(len(resA)), _ptr(resA), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), C.c_float(dt)))
+
+    def should_remove_point(self, pivotA, pivotB, normal, posA, ornA, posB, ornB):
+        fn = self._fn("should_remove_point"); fn.restype = C.c_int
+        a = [_arr(x, _f) for x in (pivotA, pivotB, normal, posA, ornA, posB, ornB)]
+        return bool(fn(*[_ptr(x) for x in a]))
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

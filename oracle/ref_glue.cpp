@@ -16,6 +16,8 @@
 #include <edyn/comp/position.hpp>
 #include <edyn/comp/orientation.hpp>
 #include <edyn/comp/inertia.hpp>
+#include <edyn/collision/contact_point.hpp>
+#include <edyn/util/collision_util.hpp>
 #include <edyn/math/geom.hpp>
 #include <edyn/math/quaternion.hpp>
 #include <edyn/math/matrix3x3.hpp>
@@ -207,6 +209,26 @@ REF_API int ref_contact_solve_position(const float *cp13, float *bodyA26, float 
     put3(out5, con.normal); out5[3] = con.distance; out5[4] = solver.max_error;
     (void)before;
     return con.distance > -EDYN_EPSILON ? 0 : 1;
+}
+
+// find_nearest_contact / find_nearest_contact_rolling / should_remove_point (util/collision_util.cpp:233-280, :397-413;
+// cut out of that unit at build time, see oracle/Makefile).
+REF_API uint32_t ref_find_nearest_contact(const float *cpA, const float *cpB, uint32_t n, const float *resA, const float *resB) {
+    contact_point cp{}; cp.pivotA = v3(cpA); cp.pivotB = v3(cpB);
+    collision_result res{}; res.num_points = n;
+    for (uint32_t i = 0; i < n; ++i) { res.point[i].pivotA = v3(resA + 3 * i); res.point[i].pivotB = v3(resB + 3 * i); }
+    return uint32_t(find_nearest_contact(cp, res));
+}
+REF_API uint32_t ref_find_nearest_contact_rolling(uint32_t n, const float *resA, const float *cp_pivot, const float *origin, const float *orn,
+                                                  const float *angvel, float dt) {
+    collision_result res{}; res.num_points = n;
+    for (uint32_t i = 0; i < n; ++i) res.point[i].pivotA = v3(resA + 3 * i);
+    return uint32_t(find_nearest_contact_rolling(res, v3(cp_pivot), v3(origin), q4(orn), v3(angvel), dt));
+}
+REF_API int ref_should_remove_point(const float *pivotA, const float *pivotB, const float *normal, const float *posA, const float *ornA,
+                                    const float *posB, const float *ornB) {
+    contact_point cp{}; cp.pivotA = v3(pivotA); cp.pivotB = v3(pivotB); cp.normal = v3(normal);
+    return should_remove_point(cp, v3(posA), q4(ornA), v3(posB), q4(ornB)) ? 1 : 0;
 }
 
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for

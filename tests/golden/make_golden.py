@@ -152,6 +152,7 @@ def main():
                         vel=vel, prepared=prep, row5=row5, dv=dv, delta=delta, impulse=imp, normal=nrm, plane_space=ps,
                         hinge_params=hpar, hinge_J=hin)
     make_friction(r)
+    make_manifold_decisions(r)
     make_contacts(r)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
@@ -238,6 +239,47 @@ def make_contacts(r):
                         fr6=np.stack([p["fr6"] for p in prep]), mu=np.array([p["mu"] for p in prep], f32),
                         solved=np.array([p[0] for p in pos], np.int32), outA=np.stack([p[1] for p in pos]), outB=np.stack([p[2] for p in pos]),
                         out5=np.stack([p[3] for p in pos]))
+
+
+def manifold_decision_inputs(rng, m):
+    """Inputs for the three per-point decisions of process_collision, scaled around their thresholds (caching 0.04,
+    breaking 0.02) so that both outcomes and ties between result points occur."""
+    n = rng.integers(1, 5, size=m)
+    cpA, cpB = (rng.normal(size=(m, 3)) * 0.3).astype(f32), (rng.normal(size=(m, 3)) * 0.3).astype(f32)
+    resA = (cpA[:, None, :] + rng.normal(size=(m, 4, 3)) * rng.choice([0.01, 0.03, 0.08], size=(m, 4, 1))).astype(f32)
+    resB = (cpB[:, None, :] + rng.normal(size=(m, 4, 3)) * rng.choice([0.01, 0.03, 0.08], size=(m, 4, 1))).astype(f32)
+    resA[::7, 1] = resA[::7, 0]                                         # exact ties: the first one must win
+    origin = (rng.normal(size=(m, 3))).astype(f32)
+    orn = np.stack([rq(rng) for _ in range(m)])
+    angvel = (rng.normal(size=(m, 3)) * rng.choice([0.01, 1.0, 6.0], size=(m, 1))).astype(f32)
+    posB = (origin + rng.normal(size=(m, 3)) * 0.5).astype(f32)
+    ornB = np.stack([rq(rng) for _ in range(m)])
+    normal = np.stack([x / np.linalg.norm(x) for x in rng.normal(size=(m, 3))]).astype(f32)
+    return n, cpA, cpB, resA, resB, origin, orn, angvel, posB, ornB, normal
+
+
+def make_manifold_decisions(r):
+    """find_nearest_contact, find_nearest_contact_rolling, should_remove_point (util/collision_util.cpp:233-280, :397-413)."""
+    rng = np.random.default_rng(24680)
+    m = 800
+    n, cpA, cpB, resA, resB, origin, orn, angvel, posB, ornB, normal = manifold_decision_inputs(rng, m)
+    o = O.ora_fns()
+    near = np.array([r.find_nearest_contact(cpA[i], cpB[i], resA[i, :n[i]], resB[i, :n[i]]) for i in range(m)], np.uint32)
+    roll = np.array([r.find_nearest_contact_rolling(resA[i, :n[i]], cpA[i], origin[i], orn[i], angvel[i], 1.0 / 60) for i in range(m)], np.uint32)
+    # should_remove_point: pivotB placed so that the world-space separation is a few centimetres in a random direction
+    pAw = np.stack([o.integrate(orn[i], [0, 0, 0], 0.0) for i in range(m)])        # (normalised orientation, unused)
+    sep = (rng.normal(size=(m, 3)) * 0.015).astype(f32)
+    pivB = np.zeros((m, 3), f32)
+    for i in range(m):
+        R = lambda q, v: np.asarray(v, np.float64) + 2 * np.cross(q[:3], np.cross(q[:3], v) + q[3] * np.asarray(v, np.float64))
+        world_A = origin[i].astype(np.float64) + R(orn[i].astype(np.float64), cpA[i])
+        target = world_A - sep[i]
+        qc = ornB[i].astype(np.float64) * np.array([-1, -1, -1, 1])
+        pivB[i] = R(qc, target - posB[i]).astype(f32)
+    rem = np.array([r.should_remove_point(cpA[i], pivB[i], normal[i], origin[i], orn[i], posB[i], ornB[i]) for i in range(m)], np.uint8)
+    np.savez_compressed(os.path.join(HERE, "manifold.npz"), n=n.astype(np.uint32), cpA=cpA, cpB=cpB, resA=resA, resB=resB, origin=origin, orn=orn,
+                        angvel=angvel, posB=posB, ornB=ornB, normal=normal, pivB=pivB, nearest=near, nearest_rolling=roll, remove=rem)
+    del pAw
 
 
 if __name__ == "__main__":

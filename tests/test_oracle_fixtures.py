@@ -101,6 +101,20 @@ def test_contact_rows_and_position_solve_match_reference_vectors(O):
             assert np.array_equal(b, g["outB"][i]), i
 
 
+def test_manifold_decisions_match_reference_vectors(O):
+    """find_nearest_contact, find_nearest_contact_rolling, should_remove_point (util/collision_util.cpp:233-280, :397-413):
+    the per-point decisions of process_collision, 800 committed cases around the caching / breaking thresholds."""
+    g = load("manifold.npz")
+    o = O.ora_fns()
+    for i in range(len(g["n"])):
+        n = int(g["n"][i])
+        assert o.find_nearest_contact(g["cpA"][i], g["cpB"][i], g["resA"][i, :n], g["resB"][i, :n]) == g["nearest"][i], i
+        assert o.find_nearest_contact_rolling(g["resA"][i, :n], g["cpA"][i], g["origin"][i], g["orn"][i], g["angvel"][i], 1.0 / 60) == g["nearest_rolling"][i], i
+        assert o.should_remove_point(g["cpA"][i], g["pivB"][i], g["normal"][i], g["origin"][i], g["orn"][i], g["posB"][i], g["ornB"][i]) == bool(g["remove"][i]), i
+    found, kept = (g["nearest"] < g["n"]).mean(), 1 - g["remove"].mean()
+    assert 0.5 < found < 0.98 and 0.3 < kept < 0.8, "both outcomes of every decision are exercised"
+
+
 def _rq(rng):
     q = rng.normal(size=4)
     return (q / np.linalg.norm(q)).astype(f32)
@@ -137,6 +151,16 @@ def test_random_against_reference_library(O, ref):
             pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
         a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    from tests.golden.make_golden import manifold_decision_inputs
+    n, cpA, cpB, resA, resB, origin, orn, angvel, posB, ornB, normal = manifold_decision_inputs(rng, 600)
+    for i in range(len(n)):
+        k = int(n[i])
+        assert o.find_nearest_contact(cpA[i], cpB[i], resA[i, :k], resB[i, :k]) == ref.find_nearest_contact(cpA[i], cpB[i], resA[i, :k], resB[i, :k])
+        assert (o.find_nearest_contact_rolling(resA[i, :k], cpA[i], origin[i], orn[i], angvel[i], 1.0 / 60)
+                == ref.find_nearest_contact_rolling(resA[i, :k], cpA[i], origin[i], orn[i], angvel[i], 1.0 / 60))
+        piv = (cpB[i] * np.float32(0.1)).astype(f32)
+        assert (o.should_remove_point(cpA[i] * np.float32(0.05), piv, normal[i], origin[i], orn[i], origin[i], ornB[i])
+                == ref.should_remove_point(cpA[i] * np.float32(0.05), piv, normal[i], origin[i], orn[i], origin[i], ornB[i]))
     from tests.golden.make_golden import contact_inputs
     cp15, bA23, bB23, cp13, bA26, bB26 = contact_inputs(rng, 400)
     for i in range(len(cp15)):
@@ -156,5 +180,5 @@ def test_random_against_reference_library(O, ref):
 
 def test_golden_generator_is_committed():
     assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
-    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz"):
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz", "manifold.npz"):
         assert os.path.exists(os.path.join(GOLD, f))
