@@ -361,4 +361,35 @@ int ora_should_remove_point(const float *pivotA, const float *pivotB, const floa
     return should_remove_point(cp, v3(posA), q4(ornA), v3(posB), q4(ornB)) ? 1 : 0;
 }
 
+// hinge_constraint::solve_position through position_solver::solve; hinge12 = pivotA pivotB axisA axisB (set_axes);
+// body26 as in ora_contact_solve_position; returns the max error.
+float ora_hinge_solve_position(const float *hinge12, float *a26, float *b26) {
+    Hinge hc{};
+    hc.pivot[0] = v3(hinge12); hc.pivot[1] = v3(hinge12 + 3);
+    vec3 p, q;
+    vec3 ax = v3(hinge12 + 6); plane_space(ax, p, q); hc.frame[0] = mat3_columns(ax, p, q);
+    ax = v3(hinge12 + 9); plane_space(ax, p, q); hc.frame[1] = mat3_columns(ax, p, q);
+    auto load = [](const float *pb) {
+        Body b{};
+        b.pos = v3(pb); b.orn = q4(pb + 3); b.inv_m = pb[7]; b.inv_IW = m9(pb + 8); b.inv_I = m9(pb + 17);
+        b.kind = pb[7] != 0 ? BK_DYNAMIC : BK_STATIC;
+        return b;
+    };
+    Body A = load(a26), B = load(b26);
+    scalar max_error = 0;
+    hinge_solve_position(hc, A, B, max_error);
+    auto store = [](float *pb, const Body &b) { put3(pb, b.pos); pb[3] = b.orn.x; pb[4] = b.orn.y; pb[5] = b.orn.z; pb[6] = b.orn.w; put9(pb + 8, b.inv_IW); };
+    store(a26, A); store(b26, B);
+    return max_error;
+}
+
+// material mixing (dynamics/material_mixing.hpp:12-34) and the closed-interval AABB test (math/geom.cpp:762-770)
+void ora_material_mix(float frictionA, float frictionB, float restitutionA, float restitutionB, float *out2) {
+    out2[0] = material_mix_friction(frictionA, frictionB); out2[1] = material_mix_restitution(restitutionA, restitutionB);
+}
+int ora_intersect_aabb(const float *a6, const float *b6) {
+    aabb a{v3(a6), v3(a6 + 3)}, b{v3(b6), v3(b6 + 3)};
+    return intersect(a, b) ? 1 : 0;
+}
+
 } // extern "C"

@@ -312,8 +312,8 @@ static Point create_point(const cpoint &rp, const Body &A, const Body &B) {
     cp.att = rp.att; cp.distance = rp.distance;
     if (rp.att != ATT_NONE) cp.local_normal = rotate(conjugate(rp.att == ATT_A ? A.orn : B.orn), rp.normal);
     else cp.local_normal = vec3{0, 0, 0};
-    cp.friction = std::sqrt(A.friction * B.friction);
-    cp.restitution = std::min(A.restitution, B.restitution);
+    cp.friction = material_mix_friction(A.friction, B.friction);
+    cp.restitution = material_mix_restitution(A.restitution, B.restitution);
     cp.lifetime = 0; cp.imp_n = 0; cp.imp_t[0] = cp.imp_t[1] = 0;
     return cp;
 }
@@ -586,6 +586,27 @@ bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error) {
     return true;
 }
 
+// hinge_constraint::solve_position, hinge_constraint.cpp:180-213
+void hinge_solve_position(const Hinge &hc, Body &A, Body &B, scalar &max_error) {
+    vec3 axisA = rotate(A.orn, hc.frame[0].column(0));
+    vec3 axisB = rotate(B.orn, hc.frame[1].column(0));
+    vec3 p, q; plane_space(axisA, p, q);
+    vec3 u = cross(axisA, axisB);
+    const vec3 z{0, 0, 0};
+    { scalar e = dot(u, p); if (std::abs(e) > EPS) { vec3 J[4] = {z, p, z, -p}; position_solve(A, B, J, e, max_error); } }
+    { scalar e = dot(u, q); if (std::abs(e) > EPS) { vec3 J[4] = {z, q, z, -q}; position_solve(A, B, J, e, max_error); } }
+    vec3 pivotA = to_world(hc.pivot[0], A.pos, A.orn);
+    vec3 pivotB = to_world(hc.pivot[1], B.pos, B.orn);
+    vec3 dir = pivotA - pivotB;
+    scalar e = length(dir);
+    if (e > EPS) {
+        dir /= e;
+        vec3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+        vec3 J[4] = {dir, cross(rA, dir), -dir, -cross(rB, dir)};
+        position_solve(A, B, J, -e, max_error);
+    }
+}
+
 static SBody solver_body(const Body &b) {
     SBody s;
     s.proc = b.awake();
@@ -776,24 +797,7 @@ void World::solve() {
                 scalar type_err = 0;
                 for (uint32_t h : W.hinges) {                // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
                     Hinge &hc = hinges[h];
-                    Body &A = bodies[hc.a], &B = bodies[hc.b];
-                    vec3 axisA = rotate(A.orn, hc.frame[0].column(0));
-                    vec3 axisB = rotate(B.orn, hc.frame[1].column(0));
-                    vec3 p, q; plane_space(axisA, p, q);
-                    vec3 u = cross(axisA, axisB);
-                    const vec3 z{0, 0, 0};
-                    { scalar e = dot(u, p); if (std::abs(e) > EPS) { vec3 J[4] = {z, p, z, -p}; position_solve(A, B, J, e, type_err); } }
-                    { scalar e = dot(u, q); if (std::abs(e) > EPS) { vec3 J[4] = {z, q, z, -q}; position_solve(A, B, J, e, type_err); } }
-                    vec3 pivotA = to_world(hc.pivot[0], A.pos, A.orn);
-                    vec3 pivotB = to_world(hc.pivot[1], B.pos, B.orn);
-                    vec3 dir = pivotA - pivotB;
-                    scalar e = length(dir);
-                    if (e > EPS) {
-                        dir /= e;
-                        vec3 rA = pivotA - A.pos, rB = pivotB - B.pos;
-                        vec3 J[4] = {dir, cross(rA, dir), -dir, -cross(rB, dir)};
-                        position_solve(A, B, J, -e, type_err);
-                    }
+                    hinge_solve_position(hc, bodies[hc.a], bodies[hc.b], type_err);
                 }
                 max_error = std::max(max_error, type_err);
             }

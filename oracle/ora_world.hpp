@@ -11,6 +11,8 @@
 #include "ora_collide.hpp"
 #include <unordered_map>
 #include <unordered_set>
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace ora {
@@ -93,6 +95,10 @@ struct World {
     bool should_collide(uint32_t a, uint32_t b) const;
 };
 
+// dynamics/material_mixing.hpp:12-18
+inline scalar material_mix_restitution(scalar a, scalar b) { return std::min(a, b); }
+inline scalar material_mix_friction(scalar a, scalar b) { return std::sqrt(a * b); }
+
 // Row-level helpers exposed for pinning against the reference's constraint_row.cpp
 struct Row {
     vec3 J[4];
@@ -115,6 +121,7 @@ void prepare_contact(const Point &cp, scalar dt, vec3 posA, quat ornA, vec3 posB
 // (contact_constraint.cpp:58-90) on two bodies; returns false when the point is not penetrating (nothing solved)
 void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error);
 bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error);
+void hinge_solve_position(const Hinge &hc, Body &A, Body &B, scalar &max_error);   // hinge_constraint.cpp:180-213
 // the three decisions process_collision takes per persisted point (util/collision_util.cpp:233-280, :397-413), pinned
 // against the reference functions cut out of that unit at build time
 size_t find_nearest_contact(const Point &cp, const cresult &res);

@@ -202,6 +202,22 @@ class PureFns:
         return bool(fn(*[_ptr(x) for x in a]))
 
 
+    def hinge_solve_position(self, hinge12, bodyA26, bodyB26):
+        a, b = _arr(bodyA26, _f).copy(), _arr(bodyB26, _f).copy()
+        fn = self._fn("hinge_solve_position"); fn.restype = C.c_float
+        err = fn(_ptr(_arr(hinge12, _f)), _ptr(a), _ptr(b))
+        return np.float32(err), a, b
+
+    def material_mix(self, fa, fb, ra, rb):
+        out = np.zeros(2, _f)
+        self._fn("material_mix")(C.c_float(fa), C.c_float(fb), C.c_float(ra), C.c_float(rb), _ptr(out))
+        return out
+
+    def intersect_aabb(self, a6, b6):
+        fn = self._fn("intersect_aabb"); fn.restype = C.c_int
+        return bool(fn(_ptr(_arr(a6, _f)), _ptr(_arr(b6, _f))))
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

@@ -18,6 +18,8 @@
 #include <edyn/comp/inertia.hpp>
 #include <edyn/collision/contact_point.hpp>
 #include <edyn/util/collision_util.hpp>
+#include <edyn/dynamics/material_mixing.hpp>
+#include <edyn/comp/aabb.hpp>
 #include <edyn/math/geom.hpp>
 #include <edyn/math/quaternion.hpp>
 #include <edyn/math/matrix3x3.hpp>
@@ -229,6 +231,36 @@ REF_API int ref_should_remove_point(const float *pivotA, const float *pivotB, co
                                     const float *posB, const float *ornB) {
     contact_point cp{}; cp.pivotA = v3(pivotA); cp.pivotB = v3(pivotB); cp.normal = v3(normal);
     return should_remove_point(cp, v3(posA), q4(ornA), v3(posB), q4(ornB)) ? 1 : 0;
+}
+
+// hinge_constraint::solve_position (hinge_constraint.cpp:180-213) through position_solver::solve; layouts of
+// ora_hinge_solve_position.
+REF_API float ref_hinge_solve_position(const float *hinge12, float *bodyA26, float *bodyB26) {
+    hinge_constraint con{};
+    con.pivot[0] = v3(hinge12); con.pivot[1] = v3(hinge12 + 3);
+    con.set_axes(v3(hinge12 + 6), v3(hinge12 + 9));
+    position posA{v3(bodyA26)}, posB{v3(bodyB26)};
+    orientation ornA{q4(bodyA26 + 3)}, ornB{q4(bodyB26 + 3)};
+    inertia_world_inv iwA{m9(bodyA26 + 8)}, iwB{m9(bodyB26 + 8)};
+    inertia_inv ilA{m9(bodyA26 + 17)}, ilB{m9(bodyB26 + 17)};
+    position_solver solver{};
+    solver.originA = nullptr; solver.originB = nullptr; solver.comA = vector3_zero; solver.comB = vector3_zero;
+    solver.posA = &posA; solver.posB = &posB; solver.ornA = &ornA; solver.ornB = &ornB;
+    solver.inv_mA = bodyA26[7]; solver.inv_mB = bodyB26[7];
+    solver.inv_IA = &iwA; solver.inv_IB = &iwB; solver.inv_IA_local = &ilA; solver.inv_IB_local = &ilB;
+    con.solve_position(solver);
+    put3(bodyA26, posA); put4(bodyA26 + 3, ornA); put9(bodyA26 + 8, iwA);
+    put3(bodyB26, posB); put4(bodyB26 + 3, ornB); put9(bodyB26 + 8, iwB);
+    return solver.max_error;
+}
+
+// material mixing (dynamics/material_mixing.hpp:12-18) and the closed-interval AABB test (math/geom.cpp:762-770)
+REF_API void ref_material_mix(float frictionA, float frictionB, float restitutionA, float restitutionB, float *out2) {
+    out2[0] = material_mix_friction(frictionA, frictionB); out2[1] = material_mix_restitution(restitutionA, restitutionB);
+}
+REF_API int ref_intersect_aabb(const float *a6, const float *b6) {
+    AABB a{v3(a6), v3(a6 + 3)}, b{v3(b6), v3(b6 + 3)};
+    return intersect(a, b) ? 1 : 0;
 }
 
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for

@@ -154,6 +154,7 @@ def main():
     make_friction(r)
     make_manifold_decisions(r)
     make_contacts(r)
+    make_misc(r)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -280,6 +281,53 @@ def make_manifold_decisions(r):
     np.savez_compressed(os.path.join(HERE, "manifold.npz"), n=n.astype(np.uint32), cpA=cpA, cpB=cpB, resA=resA, resB=resB, origin=origin, orn=orn,
                         angvel=angvel, posB=posB, ornB=ornB, normal=normal, pivB=pivB, nearest=near, nearest_rolling=roll, remove=rem)
     del pAw
+
+
+def misc_inputs(rng, m):
+    """Hinge position solve inputs (hinge12 + two body26: bodies a little off their hinge), material pairs, AABB pairs
+    that touch exactly on a face (closed-interval test) or miss by an ulp."""
+    o = O.ora_fns()
+    def body(pos, static=False):
+        # a static body keeps the identity orientation: position_solver::solve re-normalises the orientation of BOTH
+        # bodies in place (position_solver.hpp:26-32), also of a static one, which the restatement deliberately does not
+        # (DESIGN.md section 6); with an exactly unit quaternion the two agree bit for bit
+        q = np.array([0, 0, 0, 1], f32) if static else rq(rng)
+        inv_m = f32(0) if static else f32(0.2 + rng.random())
+        I = np.zeros(9, f32) if static else np.diag(0.5 + rng.random(3)).reshape(9).astype(f32)
+        IW = o.world_inertia(q, I).reshape(9)
+        return np.concatenate([pos, q, [inv_m], IW, I]).astype(f32)
+    hinge, bA, bB = np.zeros((m, 12), f32), np.zeros((m, 26), f32), np.zeros((m, 26), f32)
+    for i in range(m):
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        hinge[i] = np.concatenate([rng.normal(size=3) * 0.3, rng.normal(size=3) * 0.3, ax, ax + rng.normal(size=3) * 0.05])
+        hinge[i, 9:12] /= np.linalg.norm(hinge[i, 9:12])
+        pa = rng.normal(size=3)
+        bA[i] = body(pa.astype(f32))
+        bB[i] = body((pa + rng.normal(size=3) * 0.4).astype(f32), static=(i % 5 == 0))
+    mats = rng.random((m, 4)).astype(f32)
+    a = np.concatenate([rng.normal(size=(m, 3)), np.zeros((m, 3))], axis=1).astype(f32)
+    a[:, 3:] = a[:, :3] + (0.1 + rng.random((m, 3))).astype(f32)
+    b = a.copy()
+    shift = (rng.normal(size=(m, 3)) * 0.6).astype(f32)
+    b[:, :3] += shift; b[:, 3:] += shift
+    k = np.arange(m) % 3 == 0                                            # touching exactly: b.min.x == a.max.x
+    b[k, 3] = a[k, 3] + (b[k, 3] - b[k, 0]); b[k, 0] = a[k, 3]
+    k2 = np.arange(m) % 6 == 0                                           # ... or one ulp beyond
+    b[k2, 0] = np.nextafter(b[k2, 0], f32(np.inf))
+    return hinge, bA, bB, mats, a, b
+
+
+def make_misc(r):
+    """hinge_constraint::solve_position (hinge_constraint.cpp:180-213), material mixing (material_mixing.hpp:12-18),
+    intersect(AABB, AABB) (geom.cpp:762-770)."""
+    rng = np.random.default_rng(1357)
+    m = 400
+    hinge, bA, bB, mats, a, b = misc_inputs(rng, m)
+    hs = [r.hinge_solve_position(hinge[i], bA[i], bB[i]) for i in range(m)]
+    mix = np.stack([r.material_mix(*mats[i]) for i in range(m)])
+    hit = np.array([r.intersect_aabb(a[i], b[i]) for i in range(m)], np.uint8)
+    np.savez_compressed(os.path.join(HERE, "misc.npz"), hinge=hinge, bodyA26=bA, bodyB26=bB, hinge_err=np.array([h[0] for h in hs], f32),
+                        outA=np.stack([h[1] for h in hs]), outB=np.stack([h[2] for h in hs]), materials=mats, mixed=mix, aabb_a=a, aabb_b=b, hit=hit)
 
 
 if __name__ == "__main__":

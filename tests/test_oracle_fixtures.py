@@ -115,6 +115,22 @@ def test_manifold_decisions_match_reference_vectors(O):
     assert 0.5 < found < 0.98 and 0.3 < kept < 0.8, "both outcomes of every decision are exercised"
 
 
+def test_hinge_position_material_mix_aabb_test_match_reference_vectors(O):
+    """hinge_constraint::solve_position (hinge_constraint.cpp:180-213, three position_solver::solve calls per hinge),
+    material mixing (material_mixing.hpp:12-18) and intersect(AABB, AABB) (geom.cpp:762-770, closed intervals: boxes
+    that touch on a face intersect, one ulp apart they do not)."""
+    g = load("misc.npz")
+    o = O.ora_fns()
+    for i in range(len(g["hinge"])):
+        e, a, b = o.hinge_solve_position(g["hinge"][i], g["bodyA26"][i], g["bodyB26"][i])
+        assert e == g["hinge_err"][i] and np.array_equal(a, g["outA"][i]) and np.array_equal(b, g["outB"][i]), i
+        assert np.array_equal(o.material_mix(*g["materials"][i]), g["mixed"][i])
+        assert o.intersect_aabb(g["aabb_a"][i], g["aabb_b"][i]) == bool(g["hit"][i]), i
+    touching = np.arange(len(g["hit"])) % 3 == 0
+    ulp_off = np.arange(len(g["hit"])) % 6 == 0
+    assert g["hit"][touching & ~ulp_off].any() and not g["hit"][ulp_off].all()
+
+
 def _rq(rng):
     q = rng.normal(size=4)
     return (q / np.linalg.norm(q)).astype(f32)
@@ -151,6 +167,13 @@ def test_random_against_reference_library(O, ref):
             pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
         a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    from tests.golden.make_golden import misc_inputs
+    hinge, bA, bB, mats, a6, b6 = misc_inputs(rng, 300)
+    for i in range(len(hinge)):
+        x, y = o.hinge_solve_position(hinge[i], bA[i], bB[i]), ref.hinge_solve_position(hinge[i], bA[i], bB[i])
+        assert x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2]), i
+        assert np.array_equal(o.material_mix(*mats[i]), ref.material_mix(*mats[i]))
+        assert o.intersect_aabb(a6[i], b6[i]) == ref.intersect_aabb(a6[i], b6[i])
     from tests.golden.make_golden import manifold_decision_inputs
     n, cpA, cpB, resA, resB, origin, orn, angvel, posB, ornB, normal = manifold_decision_inputs(rng, 600)
     for i in range(len(n)):
@@ -180,5 +203,5 @@ def test_random_against_reference_library(O, ref):
 
 def test_golden_generator_is_committed():
     assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
-    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz", "manifold.npz"):
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz", "manifold.npz", "misc.npz"):
         assert os.path.exists(os.path.join(GOLD, f))
