@@ -218,6 +218,19 @@ class PureFns:
         return bool(fn(_ptr(_arr(a6, _f)), _ptr(_arr(b6, _f))))
 
 
+def ref_connected_components(non_connecting, edges):
+    """entity_graph::connected_components of the reference (None when oracle/_ref is absent): label per node."""
+    r = ref()
+    if r is None:
+        return None
+    nc = _arr(non_connecting, np.uint8)
+    e = _arr(edges, _u, (-1, 2))
+    out = np.zeros(len(nc), _u)
+    r.ref_connected_components.restype = C.c_uint32
+    r.ref_connected_components(C.c_uint32(len(nc)), _ptr(nc), C.c_uint32(len(e)), _ptr(e), _ptr(out))
+    return out
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

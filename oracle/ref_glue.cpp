@@ -20,6 +20,8 @@
 #include <edyn/util/collision_util.hpp>
 #include <edyn/dynamics/material_mixing.hpp>
 #include <edyn/comp/aabb.hpp>
+#include <edyn/core/entity_graph.hpp>
+#include <vector>
 #include <edyn/math/geom.hpp>
 #include <edyn/math/quaternion.hpp>
 #include <edyn/math/matrix3x3.hpp>
@@ -261,6 +263,27 @@ REF_API void ref_material_mix(float frictionA, float frictionB, float restitutio
 REF_API int ref_intersect_aabb(const float *a6, const float *b6) {
     AABB a{v3(a6), v3(a6 + 3)}, b{v3(b6), v3(b6 + 3)};
     return intersect(a, b) ? 1 : 0;
+}
+
+// entity_graph::connected_components (core/entity_graph.cpp): the island partition the reference's island manager
+// maintains incrementally.  Nodes 0..n-1 (non_connecting[i] != 0 = static / kinematic body), edges as node index pairs.
+// out_label[i] = smallest connecting node of i's component, 0xFFFFFFFF for non-connecting nodes.
+REF_API uint32_t ref_connected_components(uint32_t n, const uint8_t *non_connecting, uint32_t ne, const uint32_t *edges, uint32_t *out_label) {
+    entity_graph graph;
+    std::vector<entity_graph::index_type> node(n);
+    for (uint32_t i = 0; i < n; ++i) node[i] = graph.insert_node(entt::entity{i}, non_connecting[i] != 0);
+    for (uint32_t e = 0; e < ne; ++e) graph.insert_edge(entt::entity{n + e}, node[edges[2 * e]], node[edges[2 * e + 1]]);
+    for (uint32_t i = 0; i < n; ++i) out_label[i] = 0xFFFFFFFFu;
+    auto comps = graph.connected_components();
+    uint32_t count = 0;
+    for (auto &c : comps) {
+        uint32_t lab = 0xFFFFFFFFu;
+        for (auto ent : c.nodes) { uint32_t i = static_cast<uint32_t>(ent); if (!non_connecting[i] && i < lab) lab = i; }
+        if (lab == 0xFFFFFFFFu) continue;
+        ++count;
+        for (auto ent : c.nodes) { uint32_t i = static_cast<uint32_t>(ent); if (!non_connecting[i]) out_label[i] = lab; }
+    }
+    return count;
 }
 
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for

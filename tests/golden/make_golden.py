@@ -155,6 +155,7 @@ def main():
     make_manifold_decisions(r)
     make_contacts(r)
     make_misc(r)
+    make_graphs()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -328,6 +329,31 @@ def make_misc(r):
     hit = np.array([r.intersect_aabb(a[i], b[i]) for i in range(m)], np.uint8)
     np.savez_compressed(os.path.join(HERE, "misc.npz"), hinge=hinge, bodyA26=bA, bodyB26=bB, hinge_err=np.array([h[0] for h in hs], f32),
                         outA=np.stack([h[1] for h in hs]), outB=np.stack([h[2] for h in hs]), materials=mats, mixed=mix, aabb_a=a, aabb_b=b, hit=hit)
+
+
+def graph_inputs(rng, count):
+    """Random body graphs: 20-120 nodes, a fifth of them non-connecting (static), sparse to dense edge sets, with
+    duplicate edges and edges between two static nodes left out (a manifold always has a dynamic body)."""
+    out = []
+    for _ in range(count):
+        n = int(rng.integers(20, 121))
+        static = rng.random(n) < 0.2
+        ne = int(rng.integers(n // 3, 2 * n))
+        e = rng.integers(0, n, size=(ne, 2))
+        e = e[(e[:, 0] != e[:, 1]) & ~(static[e[:, 0]] & static[e[:, 1]])]
+        e = np.unique(np.sort(e, axis=1), axis=0)
+        out.append((static.astype(np.uint8), e.astype(np.uint32)))
+    return out
+
+
+def make_graphs():
+    """entity_graph::connected_components (core/entity_graph.cpp) on 60 random graphs, flattened into one file."""
+    rng = np.random.default_rng(8642)
+    graphs = graph_inputs(rng, 60)
+    labels = [O.ref_connected_components(s, e) for s, e in graphs]
+    np.savez_compressed(os.path.join(HERE, "graphs.npz"), sizes=np.array([len(s) for s, _ in graphs], np.uint32),
+                        edge_counts=np.array([len(e) for _, e in graphs], np.uint32), static=np.concatenate([s for s, _ in graphs]),
+                        edges=np.concatenate([e for _, e in graphs]), labels=np.concatenate(labels))
 
 
 if __name__ == "__main__":

@@ -131,6 +131,30 @@ def test_hinge_position_material_mix_aabb_test_match_reference_vectors(O):
     assert g["hit"][touching & ~ulp_off].any() and not g["hit"][ulp_off].all()
 
 
+def _oracle_island_labels(O, E, static, edges):
+    from edyn_b200.rigidbody import RigidBodyDef, bodies_soa, sphere_shape
+    n = len(static)
+    defs = [RigidBodyDef(kind=E.STATIC if static[i] else E.DYNAMIC, position=(3.0 * i, 0, 0), mass=1.0, shape=sphere_shape(0.1)) for i in range(n)]
+    o = O.OracleWorld()
+    o.add_bodies(bodies_soa(defs, (0.0, 0.0, 0.0)))
+    m = len(edges)
+    o.set_contacts(edges, np.zeros(m, np.uint32), np.zeros((m, 4, 18), f32), np.zeros((m, 4), np.uint32))
+    o.run_phases(O.PH_ISLANDS)
+    return o.islands()
+
+
+def test_island_partition_matches_reference_entity_graph(O, E):
+    """The oracle's island labels == entity_graph::connected_components of the reference (core/entity_graph.cpp) on 60
+    committed random graphs (908 components): static nodes belong to no island and do not connect their neighbours."""
+    g = load("graphs.npz")
+    off = eo = 0
+    for n, ne in zip(g["sizes"].tolist(), g["edge_counts"].tolist()):
+        st, ed, lab = g["static"][off:off + n], g["edges"][eo:eo + ne], g["labels"][off:off + n]
+        assert np.array_equal(_oracle_island_labels(O, E, st, ed), lab)
+        assert (lab[st != 0] == 0xFFFFFFFF).all()
+        off += n; eo += ne
+
+
 def _rq(rng):
     q = rng.normal(size=4)
     return (q / np.linalg.norm(q)).astype(f32)
@@ -167,6 +191,10 @@ def test_random_against_reference_library(O, ref):
             pa[:, 1] = 0                                                             # coplanar: area/collinearity rules
         a, b = o.maybe_add_points(pa, pb), ref.maybe_add_points(pa, pb)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    from tests.golden.make_golden import graph_inputs
+    import edyn_b200 as E
+    for st, ed in graph_inputs(rng, 25):
+        assert np.array_equal(_oracle_island_labels(O, E, st, ed), O.ref_connected_components(st, ed))
     from tests.golden.make_golden import misc_inputs
     hinge, bA, bB, mats, a6, b6 = misc_inputs(rng, 300)
     for i in range(len(hinge)):
@@ -203,5 +231,5 @@ def test_random_against_reference_library(O, ref):
 
 def test_golden_generator_is_committed():
     assert os.path.exists(os.path.join(GOLD, "make_golden.py"))
-    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz", "manifold.npz", "misc.npz"):
+    for f in ("collide.npz", "aabb.npz", "body_math.npz", "rows.npz", "friction.npz", "contacts.npz", "manifold.npz", "misc.npz", "graphs.npz"):
         assert os.path.exists(os.path.join(GOLD, f))
