@@ -231,6 +231,21 @@ def ref_connected_components(non_connecting, edges):
     return out
 
 
+def ref_broadphase_pairs(aabb0, aabb1, procedural, cap=1 << 16):
+    """Pair search of broadphase::update around the reference's real dynamic AABB trees (oracle/ref_glue.cpp); ordered
+    (querying body, other) pairs, or None when oracle/_ref is absent."""
+    r = ref()
+    if r is None:
+        return None
+    a0, a1 = _arr(aabb0, _f, (-1, 6)), _arr(aabb1, _f, (-1, 6))
+    pr = _arr(procedural, np.uint8)
+    out = np.zeros((cap, 2), _u)
+    r.ref_broadphase_pairs.restype = C.c_uint32
+    k = r.ref_broadphase_pairs(C.c_uint32(len(pr)), _ptr(a0), _ptr(a1), _ptr(pr), C.c_uint32(cap), _ptr(out))
+    assert k <= cap
+    return out[:k].copy()
+
+
 def ora_fns():
     return PureFns(lib(), "ora_")
 

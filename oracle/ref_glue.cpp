@@ -21,6 +21,8 @@
 #include <edyn/dynamics/material_mixing.hpp>
 #include <edyn/comp/aabb.hpp>
 #include <edyn/core/entity_graph.hpp>
+#include <edyn/collision/dynamic_tree.hpp>
+#include <edyn/config/constants.hpp>
 #include <vector>
 #include <edyn/math/geom.hpp>
 #include <edyn/math/quaternion.hpp>
@@ -284,6 +286,41 @@ REF_API uint32_t ref_connected_components(uint32_t n, const uint8_t *non_connect
         for (auto ent : c.nodes) { uint32_t i = static_cast<uint32_t>(ent); if (!non_connecting[i]) out_label[i] = lab; }
     }
     return count;
+}
+
+// The pair search of broadphase::update (broadphase.cpp:177-195) around the reference's REAL dynamic AABB trees
+// (collision/dynamic_tree.cpp: fat leaves, SAH insertion, rotations).  broadphase.cpp itself needs a registry, so the
+// ten lines of collide_tree (:136-155) are restated here: query the procedural tree, then the non-procedural one, with
+// the body's AABB inset by -0.02; for every leaf hit that is not the body itself, not paired yet and whose EXACT AABB
+// intersects the query, make the pair (body, other).  Bodies are created at aabb0 and moved to aabb1 (dynamic_tree::move,
+// what move_aabbs does) before the queries; procedural bodies are visited in descending index order.
+REF_API uint32_t ref_broadphase_pairs(uint32_t n, const float *aabb0, const float *aabb1, const uint8_t *procedural, uint32_t cap, uint32_t *out_pairs) {
+    dynamic_tree tree, np_tree;
+    std::vector<tree_node_id_t> id(n);
+    auto box = [](const float *p) { return AABB{v3(p), v3(p + 3)}; };
+    for (uint32_t i = 0; i < n; ++i) id[i] = (procedural[i] ? tree : np_tree).create(box(aabb0 + 6 * i), entt::entity{i});
+    for (uint32_t i = 0; i < n; ++i) (procedural[i] ? tree : np_tree).move(id[i], box(aabb1 + 6 * i));      // move_aabbs, broadphase.cpp:99-117
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;
+    auto paired = [&](uint32_t a, uint32_t b) {
+        for (auto &p : pairs) if ((p.first == a && p.second == b) || (p.first == b && p.second == a)) return true;
+        return false;
+    };
+    const vector3 offset = vector3_one * -contact_breaking_threshold;           // m_aabb_offset, broadphase.hpp:15
+    for (uint32_t i = n; i-- > 0;) {
+        if (!procedural[i]) continue;
+        const AABB query = box(aabb1 + 6 * i).inset(offset);
+        auto visit = [&](const dynamic_tree &t) {
+            t.query(query, [&](tree_node_id_t nid) {
+                const uint32_t j = static_cast<uint32_t>(t.get_node(nid).entity);
+                if (j == i || paired(i, j)) return;
+                if (intersect(query, box(aabb1 + 6 * j))) pairs.emplace_back(i, j);
+            });
+        };
+        visit(tree); visit(np_tree);
+    }
+    uint32_t k = 0;
+    for (auto &p : pairs) { if (k < cap) { out_pairs[2 * k] = p.first; out_pairs[2 * k + 1] = p.second; } ++k; }
+    return k;
 }
 
 // hinge_constraint::prepare (hinge_constraint.cpp:26-69): returns the 5 Jacobians (60 floats) built for

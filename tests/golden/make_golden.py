@@ -156,6 +156,7 @@ def main():
     make_contacts(r)
     make_misc(r)
     make_graphs()
+    make_broadphase()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -354,6 +355,43 @@ def make_graphs():
     np.savez_compressed(os.path.join(HERE, "graphs.npz"), sizes=np.array([len(s) for s, _ in graphs], np.uint32),
                         edge_counts=np.array([len(e) for _, e in graphs], np.uint32), static=np.concatenate([s for s, _ in graphs]),
                         edges=np.concatenate([e for _, e in graphs]), labels=np.concatenate(labels))
+
+
+def broadphase_scene(rng, n_dyn, n_static):
+    """A crowded box of unit-ish boxes, spheres and capsules (many AABBs within the 0.02 margin of each other), a floor
+    plane and a few big static slabs: bodies SoA for OracleWorld.add_bodies."""
+    from edyn_b200.rigidbody import DYNAMIC, STATIC, RigidBodyDef, bodies_soa, box_shape, capsule_shape, plane_shape, sphere_shape
+    side = max(2.0, (n_dyn ** (1 / 3)) * 0.9)
+    defs = []
+    for _ in range(n_dyn):
+        kind = rng.integers(0, 3)
+        shape = (box_shape(tuple((0.2 + 0.3 * rng.random(3)).tolist())) if kind == 0 else
+                 sphere_shape(float(0.2 + 0.3 * rng.random())) if kind == 1 else capsule_shape(float(0.15 + 0.1 * rng.random()), float(0.2 + 0.2 * rng.random())))
+        q = rq(rng) if kind != 1 else np.array([0, 0, 0, 1], f32)
+        defs.append(RigidBodyDef(kind=DYNAMIC, position=tuple((rng.random(3) * side).tolist()), orientation=tuple(q.tolist()), mass=1.0, shape=shape))
+    defs.append(RigidBodyDef(kind=STATIC, shape=plane_shape((0, 1, 0), 0.0)))
+    for _ in range(n_static):
+        defs.append(RigidBodyDef(kind=STATIC, position=tuple((rng.random(3) * side).tolist()), shape=box_shape((float(side), 0.3, 0.3))))
+    return bodies_soa(defs, (0.0, 0.0, 0.0))
+
+
+def make_broadphase():
+    """Ordered broadphase pair lists produced with the reference's real dynamic trees (ref_broadphase_pairs) for 12
+    crowded scenes; the AABBs the trees were built from are stored alongside (they come from the pinned shape_aabb)."""
+    rng = np.random.default_rng(112233)
+    sizes, procs, boxes0, boxes1, pairs, counts, scenes = [], [], [], [], [], [], []
+    for k in range(12):
+        soa = broadphase_scene(rng, int(rng.integers(40, 260)), int(rng.integers(0, 4)))
+        o = O.OracleWorld(); o.add_bodies(soa)
+        bb1 = o.state()["aabb"]
+        bb0 = (bb1 + np.tile((rng.normal(size=(len(bb1), 3)) * 0.3).astype(f32), 2)).astype(f32)       # where the leaves were created
+        proc = (soa["kind"] == 0).astype(np.uint8)
+        p = O.ref_broadphase_pairs(bb0, bb1, proc)
+        sizes.append(len(proc)); procs.append(proc); boxes0.append(bb0); boxes1.append(bb1); pairs.append(p); counts.append(len(p))
+        scenes.append({k2: v for k2, v in soa.items() if v is not None})
+    np.savez_compressed(os.path.join(HERE, "broadphase.npz"), sizes=np.array(sizes, np.uint32), counts=np.array(counts, np.uint32),
+                        procedural=np.concatenate(procs), aabb0=np.concatenate(boxes0), aabb1=np.concatenate(boxes1), pairs=np.concatenate(pairs),
+                        **{"soa_" + k2: np.concatenate([s[k2] for s in scenes]) for k2 in scenes[0]})
 
 
 if __name__ == "__main__":

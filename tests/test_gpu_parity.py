@@ -106,6 +106,23 @@ def test_integrate_matches_reference_vectors(gpu, E):
     assert (q == bm["q_out"][sel]).mean() > 0.9
 
 
+def test_broadphase_matches_reference_tree_vectors(gpu, E):
+    """Device broadphase (uniform grid) == the pair lists the reference's own dynamic AABB trees produce
+    (tests/golden/broadphase.npz, generated with oracle/_ref): ordered pairs, 12 crowded scenes."""
+    g = np.load(os.path.join(GOLD, "broadphase.npz"))
+    keys = [k[4:] for k in g.files if k.startswith("soa_")]
+    off = po = 0
+    for n, c in zip(g["sizes"].tolist(), g["counts"].tolist()):
+        soa = {k: g["soa_" + k][off:off + n] for k in keys}
+        w = E.World(n, max_manifolds=max(4096, 4 * c))
+        w.add_bodies(soa)
+        assert np.array_equal(w.download_state(aabb=True)["aabb"], g["aabb1"][off:off + n])
+        w.run_phases(E.world.PH_BROAD)
+        assert _pairset(w.pairs()) == {tuple(p) for p in g["pairs"][po:po + c].tolist()}
+        assert w.stats()["error_flags"] == 0
+        off += n; po += c
+
+
 # ----------------------------------------------------------------------------- lock-step against the oracle
 
 SCENES = {
