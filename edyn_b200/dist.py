@@ -170,18 +170,19 @@ class ShardedWorld:
     world (default: the device world of scenes.build_world; the CPU tests inject an oracle-backed stand-in).
 
     Migration (mirrors merge_islands' "move into the other island", island_manager.cpp:297-350): when the
-    boxes of two ranks come within the broadphase margin, the higher rank hands every island of its own that reaches
-    into the lower rank's box over to it -- body definitions with their current state, the joints between them and
+    boxes of two ranks come within the broadphase margin, the ranks gather each other's island AABBs and the higher
+    rank hands every island of its own that touches an island of the lower rank over to it -- body definitions with their current state, the joints between them and
     their contact manifolds (points, lifetimes and warm-start impulses), collision exclusions -- and destroys its copies.  Bodies are named
     by scene-global ids on the wire; static bodies are replicated, so a manifold against the ground keeps its partner.
     The transfer is one all_gather_object (sizes first, then payloads: NCCL on GPUs, gloo on CPU) and only happens on
     the steps where `overlapping_ranks` is non-empty."""
 
-    def __init__(self, scene, rank, world_size, dist=None, device=0, world_factory=None, **kw):
+    def __init__(self, scene, rank, world_size, dist=None, device=0, world_factory=None, owner=None, **kw):
         if world_factory is None:
             from .scenes import build_world as world_factory
         self.rank, self.world_size, self.dist = rank, world_size, dist
-        self.owner = partition(scene, world_size)
+        # owner: rank per body (-1 = replicated static), whole islands per rank; default = balanced x-slabs
+        self.owner = partition(scene, world_size) if owner is None else np.asarray(owner, np.int64)
         self.local = shard(scene, rank, world_size, self.owner)
         # any rank may end up owning every island: capacity for the whole scene
         kw.setdefault("max_bodies", len(self.owner))
@@ -211,21 +212,41 @@ class ShardedWorld:
         return torch.stack(out).cpu().numpy()
 
     # ------------------------------------------------------------------ migration
-    def _select_outgoing(self, pairs, bounds, st):
-        """Per destination rank: local ids of the islands this rank hands over (it is the higher rank of the pair)."""
+    def island_boxes(self, st):
+        """(labels, boxes): the AABB of every island this rank owns (update_island_aabbs, sys/update_aabbs.cpp:106-138)."""
+        dyn = self.dynamic_local
+        if len(dyn) == 0:
+            return np.zeros(0, np.int64), np.zeros((0, 6), np.float32)
+        lab = self.world.islands().astype(np.int64)[dyn]
+        ids, inv = np.unique(lab, return_inverse=True)
+        a = st["aabb"][dyn]
+        box = np.empty((len(ids), 6), np.float32)
+        for k in range(3):
+            mn = np.full(len(ids), np.inf, np.float32); np.minimum.at(mn, inv, a[:, k]); box[:, k] = mn
+            mx = np.full(len(ids), -np.inf, np.float32); np.maximum.at(mx, inv, a[:, 3 + k]); box[:, 3 + k] = mx
+        return ids, box
+
+    def _select_outgoing(self, pairs, all_boxes, my_labels):
+        """Per destination rank: local ids of the islands this rank hands over (it is the higher rank of the pair):
+        those whose island AABB, inflated by the broadphase margin, touches an island AABB of the destination."""
         dests = sorted(i for i, j in pairs if j == self.rank)
         if not dests or len(self.dynamic_local) == 0:
             return {}
+        ids, mine = my_labels, all_boxes[self.rank]
         lab = self.world.islands().astype(np.int64)
         dyn = self.dynamic_local
-        out, taken = {}, np.zeros(len(lab), bool)
+        out, taken = {}, np.zeros(len(ids), bool)
         for dst in dests:
-            hit = boxes_touch(st["aabb"][dyn], bounds[dst])
-            isl = np.unique(lab[dyn[hit]])
-            sel = dyn[np.isin(lab[dyn], isl) & ~taken[dyn]]
-            if len(sel):
-                out[dst] = sel
-                taken[sel] = True
+            theirs = all_boxes[dst]
+            if len(theirs) == 0:
+                continue
+            hit = np.zeros(len(ids), bool)
+            for b in theirs:
+                hit |= boxes_touch(mine, b)
+            hit &= ~taken
+            if hit.any():
+                out[dst] = dyn[np.isin(lab[dyn], ids[hit])]
+                taken |= hit
         return out
 
     def _pack(self, ids, st, contacts):
@@ -273,7 +294,11 @@ class ShardedWorld:
 
     def migrate(self, pairs, bounds, st):
         """Collective: every rank of the group must call it on the same step (they all see the same `pairs`)."""
-        out = self._select_outgoing(pairs, bounds, st)
+        # rank boxes are coarse (two ranks' regions may interleave): decide on island boxes, which every rank gathers
+        my_labels, my_boxes = self.island_boxes(st)
+        all_boxes = [None] * self.world_size
+        self.dist.all_gather_object(all_boxes, my_boxes)
+        out = self._select_outgoing(pairs, all_boxes, my_labels)
         outbox = {}
         if out:
             contacts = self.world.contacts()

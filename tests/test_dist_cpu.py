@@ -182,8 +182,13 @@ def _chain_migration_worker(rank, world_size, port, q):
         st = sw.world.download_state()
         bounds = sw.exchange_bounds(sw.local_bounds(st["aabb"]))
         assert dist.overlapping_ranks(bounds) == [], "the two chain groups are 3.5 m apart"
-        # force the hand-over: pretend rank 0's box has grown over everything
-        bounds[0] = np.array([-1e3, -1e3, -1e3, 1e3, 1e3, 1e3], f32)
+        # force the hand-over: pretend rank 0's islands have grown over everything
+        if rank == 0:
+            real = sw.island_boxes
+            def grown(state):
+                ids, box = real(state)
+                return ids, box + np.array([-10, -10, -10, 10, 10, 10], f32)
+            sw.island_boxes = grown
         sw.migrate([(0, 1)], bounds, st)
         sw.world.step(20)
         st = sw.world.download_state()
@@ -226,3 +231,44 @@ def test_chain_islands_migrate_with_joints_and_exclusions(E):
     # same number of manifolds as the single world: adjacent links are excluded on the new rank too
     ref_pairs = {tuple(p) for p in ref.o.pairs().tolist()}
     assert len(pairs0) == len(ref_pairs), (len(pairs0), len(ref_pairs))
+
+
+def _interleaved_worker(rank, world_size, port, q):
+    import torch.distributed as dist_mod
+    import edyn_b200 as E
+    from edyn_b200 import dist
+    from tests._oracle_world import OracleBackedWorld
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist_mod.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scene = E.scenes.hinge_chains(2, 8, 2)                  # 16 two-link chains, 0.5 m apart in z
+        n = scene["dynamic"]
+        owner = np.full(len(scene["bodies"]["kind"]), -1, np.int64)
+        owner[:n] = (np.arange(n) // 2) % 2                      # neighbouring chains alternate between the ranks
+        sw = dist.ShardedWorld(scene, rank, world_size, dist_mod, world_factory=OracleBackedWorld, owner=owner)
+        flagged = 0
+        for _ in range(15):
+            flagged += bool(sw.step(1))
+        q.put((rank, flagged, sw.migrated_in, sw.migrated_out, len(sw.dynamic_local)))
+    finally:
+        dist_mod.destroy_process_group()
+
+
+def test_interleaved_ranks_do_not_migrate_without_island_contact():
+    """Two ranks whose regions interleave (rank boxes overlap every step) keep their islands as long as no island of
+    one comes within the broadphase margin of an island of the other: the decision is taken on island AABBs."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_interleaved_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, flagged, mig_in, mig_out, owned in res:
+        assert flagged == 15, "the coarse rank-box test fires every step"
+        assert mig_in == mig_out == 0 and owned == 16, "but no island actually touches one of the other rank"
