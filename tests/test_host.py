@@ -51,6 +51,26 @@ def test_no_cpu_fallback_without_gpu():
         E.World(16)
 
 
+def test_cpp_adapter_builds_and_fails_loudly_without_gpu(tmp_path):
+    """The C++17 adapter (edyn::attach / make_rigidbody / update surface, edyn_b200/csrc/host) compiles and links against
+    the C ABI with plain g++; without a CUDA device the restated hello_world aborts in edyn::attach instead of falling back."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "hello_b2d"
+    libdir = os.path.join(ROOT, "edyn_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "edyn_b200", "csrc", "host"),
+           os.path.join(ROOT, "edyn_b200", "csrc", "host", "hello_world.cpp"), "-o", str(exe), "-L" + libdir, "-lb2d", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the example would simply run")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
 def test_product_never_imports_the_oracle():
     code = "import sys; import edyn_b200, edyn_b200.dist, edyn_b200.scenes; " \
            "bad=[m for m in sys.modules if m.split('.')[0]=='oracle']; print(bad); sys.exit(1 if bad else 0)"
