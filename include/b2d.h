@@ -168,6 +168,9 @@ int b2d_download_hinge_impulses(b2d_world *w, float *imp5);
 int b2d_get_stats(b2d_world *w, b2d_stats *out);
 /* Restart the per-kernel timing averages reported by b2d_get_stats. */
 int b2d_reset_timers(b2d_world *w);
+/* Development aid: raw copy of the device-side counter block (layout private to the library; used by
+ * tools/solver_profile.py with a -DB2D_DF_PROFILE build).  Not part of the reference-facing surface. */
+int b2d_debug_counters(b2d_world *w, void *out, uint32_t bytes);
 /* Multi-GPU exchange: enqueue, on the world's stream, the reduction of all dynamic AABBs into
  * device_out6 = {min xyz, max xyz} -- a DEVICE pointer (e.g. a buffer owned by the host framework) the adapter then all-gathers over
  * NCCL to detect island groups of different ranks coming within the broadphase margin of each other. */
