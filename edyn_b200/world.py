@@ -54,7 +54,7 @@ class World:
         self.num_bodies = 0
         self.num_hinges = 0
         self._defs, self._hinges = [], []
-        self.exclusions = set()          # collision_exclusion, as unordered pairs
+        self._excl_set, self._excl_log = set(), []          # collision_exclusion, as unordered pairs (see `exclusions`)
         self.removed = np.zeros(max_bodies, bool)
         self.hinge_alive = np.zeros(0, bool)
         self.max_manifolds = max_manifolds
@@ -147,12 +147,25 @@ class World:
     def add_exclusions(self, a, b):
         a, b = _c(a, u32), _c(b, u32)
         self._check(self.l.b2d_add_exclusions(self.h, C.c_uint32(len(a)), _p(a), _p(b)))
-        self.exclusions |= {(min(x, y), max(x, y)) for x, y in zip(a.tolist(), b.tolist())}
+        self._excl_log.append((True, np.minimum(a, b), np.maximum(a, b)))
 
     def remove_exclusions(self, a, b):
         a, b = _c(a, u32), _c(b, u32)
         self._check(self.l.b2d_remove_exclusions(self.h, C.c_uint32(len(a)), _p(a), _p(b)))
-        self.exclusions -= {(min(x, y), max(x, y)) for x, y in zip(a.tolist(), b.tolist())}
+        self._excl_log.append((False, np.minimum(a, b), np.maximum(a, b)))
+
+    @property
+    def exclusions(self):
+        """collision_exclusion as a set of unordered (lo, hi) pairs; materialised only when somebody asks (a million-link
+        scene registers ~800 k exclusions that nobody on the host ever reads)."""
+        for add, lo, hi in self._excl_log:
+            pairs = set(zip(lo.tolist(), hi.tolist()))
+            if add:
+                self._excl_set |= pairs
+            else:
+                self._excl_set -= pairs
+        self._excl_log = []
+        return self._excl_set
 
     # -- stepping
     def step(self, n=1):
