@@ -71,6 +71,40 @@ def test_cpp_adapter_builds_and_fails_loudly_without_gpu(tmp_path):
     assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
 
 
+def test_header_is_plain_c_and_create_fails_loudly(tmp_path):
+    """include/b2d.h compiles as C (gcc -std=c99 -pedantic), so any FFI can bind it; a C caller without a CUDA device gets
+    NULL from b2d_create and a reason from b2d_last_error -- never a CPU path."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "b2d.h"
+int main(void) {
+    b2d_config c; memset(&c, 0, sizeof c);
+    c.max_bodies = 16; c.max_manifolds = 64; c.fixed_dt = 1.0f / 60; c.velocity_iterations = 8; c.position_iterations = 3;
+    b2d_world *w = b2d_create(&c);
+    if (!w) { printf("create failed: %s\n", b2d_last_error(NULL)); return 3; }
+    b2d_destroy(w);
+    return 0;
+}
+""")
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.join(ROOT, "edyn_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L" + libdir, "-lb2d", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stdout
+
+
 def test_product_never_imports_the_oracle():
     code = "import sys; import edyn_b200, edyn_b200.dist, edyn_b200.scenes; " \
            "bad=[m for m in sys.modules if m.split('.')[0]=='oracle']; print(bad); sys.exit(1 if bad else 0)"
