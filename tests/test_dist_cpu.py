@@ -272,3 +272,50 @@ def test_interleaved_ranks_do_not_migrate_without_island_contact():
     for rank, flagged, mig_in, mig_out, owned in res:
         assert flagged == 15, "the coarse rank-box test fires every step"
         assert mig_in == mig_out == 0 and owned == 16, "but no island actually touches one of the other rank"
+
+
+def _three_rank_worker(rank, world_size, port, q):
+    import torch.distributed as dist_mod
+    import edyn_b200 as E
+    from edyn_b200 import dist
+    from tests._oracle_world import OracleBackedWorld
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist_mod.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scene = E.scenes.hinge_chains(3, 2, 2)                  # 6 two-link chains in three x-slabs
+        sw = dist.ShardedWorld(scene, rank, world_size, dist_mod, world_factory=OracleBackedWorld)
+        owned0 = len(sw.dynamic_local)
+        sw.world.step(5)
+        st = sw.world.download_state()
+        bounds = sw.exchange_bounds(sw.local_bounds(st["aabb"]))
+        real = sw.island_boxes
+        if rank < 2:                                             # ranks 0 and 1 pretend to have grown over everything
+            sw.island_boxes = lambda state: (real(state)[0], real(state)[1] + np.array([-20, -20, -20, 20, 20, 20], f32))
+        sw.migrate([(0, 1), (0, 2), (1, 2)], bounds, st)
+        sw.world.step(5)
+        gids = np.asarray(sw.global_of_local)[sw.dynamic_local]
+        q.put((rank, owned0, sw.migrated_in, sw.migrated_out, sorted(gids.tolist())))
+    finally:
+        dist_mod.destroy_process_group()
+
+
+def test_three_ranks_lowest_destination_wins():
+    """A rank that touches two lower ranks hands each island over once, to the lowest of them; a rank that is both a
+    destination and a source in the same exchange ends up consistent."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_three_rank_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, o0, in0, out0, g0), (_, o1, in1, out1, g1), (_, o2, in2, out2, g2) = res
+    assert o0 == o1 == o2 == 4
+    assert (in0, out0) == (8, 0) and g0 == list(range(12)), "everything ends up on rank 0"
+    assert (in1, out1) == (0, 4) and g1 == [], "rank 1 gave its islands to rank 0 and received none from rank 2"
+    assert (in2, out2) == (0, 4) and g2 == []
