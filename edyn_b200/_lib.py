@@ -38,6 +38,11 @@ class Bodies(C.Structure):
         "shape_params", "friction", "restitution", "group", "mask")]
 
 
+class BodyPatch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos", "orn", "linvel", "angvel", "inv_mass", "inv_inertia", "gravity",
+                                          "friction", "restitution", "kind")]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("bodies", "manifolds", "contact_points", "hinges", "contact_colors",
                                          "hinge_colors", "islands", "manifold_high_water")] + \
@@ -48,7 +53,9 @@ class Stats(C.Structure):
 EXPORTS = ["b2d_create", "b2d_destroy", "b2d_last_error", "b2d_add_bodies", "b2d_remove_bodies", "b2d_wake_bodies", "b2d_download_sleeping", "b2d_add_hinges", "b2d_add_exclusions", "b2d_remove_exclusions",
            "b2d_step", "b2d_run_phases", "b2d_upload_state", "b2d_download_state", "b2d_num_manifolds",
            "b2d_download_pairs", "b2d_download_contacts", "b2d_upload_contacts", "b2d_download_islands",
-           "b2d_download_solver_order", "b2d_download_hinge_impulses", "b2d_get_stats", "b2d_reset_timers", "b2d_debug_counters", "b2d_device_bounds", "b2d_sync", "b2d_stream"]
+           "b2d_download_solver_order", "b2d_download_hinge_impulses", "b2d_get_stats", "b2d_reset_timers", "b2d_debug_counters", "b2d_device_bounds", "b2d_sync", "b2d_stream",
+           "b2d_upload_bodies", "b2d_set_entities", "b2d_download_entities", "b2d_island_halo", "b2d_handover_plan",
+           "b2d_handover_bytes", "b2d_handover_pack", "b2d_handover_unpack", "b2d_set_timing"]
 
 _lib = None
 
@@ -67,5 +74,7 @@ def lib():
         l.b2d_last_error.argtypes = [C.c_void_p]
         l.b2d_stream.restype = C.c_void_p
         l.b2d_stream.argtypes = [C.c_void_p]
+        l.b2d_handover_bytes.restype = C.c_uint64
+        l.b2d_handover_bytes.argtypes = [C.c_void_p]
         _lib = l
     return _lib

@@ -4,7 +4,7 @@
 // (/root/reference/src/edyn/simulation/stepper_sequential.cpp:82-91).
 // There is deliberately no CPU path: if CUDA is unavailable every entry point fails with B2D_ERR_CUDA.
 #include "../../include/b2d.h"
-#include "b2d_kernels.cuh"
+#include "b2d_dist.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
@@ -42,7 +42,26 @@ struct b2d_world {
     std::vector<uint64_t> exclusions;
     bool contacts_dirty = false;
     uint64_t updates = 0;             // island updates so far (sleep timestamps)
+    // broadphase classes: bounding diameter and kind per body (host mirror), re-derived lazily before the next step
+    std::vector<float> diam; std::vector<unsigned char> isdyn;
+    bool class_dirty = false, ehash_dirty = true, labels_stale = true;
+    std::vector<uint32_t> plan_counts;   // nranks x 4 of the current plan (bodies, manifolds, hinges, exclusions)
+    // one step as CUDA graphs: [broadphase .. row preparation] [velocity solve, bracketed by the timing events]
+    // [integration .. refresh].  Captured lazily, dropped whenever a host-side parameter of the sequence changes.
+    bool use_graph = true, graph_valid = false;
+    cudaGraphExec_t gx_pre = nullptr, gx_solve = nullptr, gx_post = nullptr, gx_all = nullptr;
+    uint64_t graph_launches = 0;      // kernels one replay of the step graphs launches
+    bool timing = true;               // per-kernel event ring (b2d_get_stats); off = the whole step is one graph
+    // multi-GPU hand-over
+    std::vector<uint32_t> host_bdst;  // destination rank per body of the current plan
+    uint32_t *dev_counts = nullptr;   // nranks x 4 counters of the plan
+    uint32_t plan_ranks = 0;
 };
+
+static void drop_graphs(b2d_world *w) {
+    for (cudaGraphExec_t *g : {&w->gx_pre, &w->gx_solve, &w->gx_post, &w->gx_all}) if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
+    w->graph_valid = false;
+}
 
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { w->error = std::string(#call) + ": " + cudaGetErrorString(_e); return B2D_ERR_CUDA; } } while (0)
 
@@ -129,6 +148,9 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.hfA2, NH) && dalloc(w, d.hfB0, NH) && dalloc(w, d.himp, 5 * (size_t)NH) && dalloc(w, d.hcolor, NH, 0xFF);
     ok = ok && dalloc(w, d.HR, 7 * (size_t)NH) && dalloc(w, d.hhdr, NH) && dalloc(w, d.cnt, 1);
     ok = ok && dalloc(w, d.tkt, NM) && dalloc(w, d.htkt, NH) && dalloc(w, d.pisl, NM) && dalloc(w, d.hisl, NH) && dalloc(w, d.prec, 3 * NB);
+    d.ehash_size = pow2_at_least(2ull * NB);
+    ok = ok && dalloc(w, d.entity, NB) && dalloc(w, d.ehash, d.ehash_size, 0xFF) && dalloc(w, d.ibox, 6 * (size_t)NB) && dalloc(w, d.isl_dst, NB, 0xFF) && dalloc(w, d.bdst, NB, 0xFF);
+    ok = ok && dalloc(w, w->dev_counts, 4 * 64);
     d.sleeping = (cfg->flags & B2D_FLAG_SLEEPING) ? 1u : 0u;
     if (d.sleeping) {
         ok = ok && dalloc(w, d.prev_label, NB, 0xFF) && dalloc(w, d.isl_size, NB) && dalloc(w, d.size_new, NB) && dalloc(w, d.isl_flags, NB)
@@ -143,6 +165,8 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, COLOR_KEY_BITS, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)NH, 0, 8, w->stream); need = std::max(need, t);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, d.hidx, d.hidx_s, (int)NH, w->stream); need = std::max(need, t);
     w->cub_tmp_bytes = need + 256;
     void *tmp = nullptr;
     if (ok && cudaMalloc(&tmp, w->cub_tmp_bytes) != cudaSuccess) ok = false;
@@ -162,6 +186,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, B2D_SOLVE_THREADS, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, B2D_POS_THREADS, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
     if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
+    if (const char *e = getenv("B2D_GRAPH")) w->use_graph = atoi(e) != 0;
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
         g_create_error = "b2d_create: device allocation failed: " + w->error;
@@ -175,6 +200,7 @@ void b2d_destroy(b2d_world *w) {
     if (!w) return;
     cudaSetDevice(w->cfg.device);
     if (w->stream) cudaStreamSynchronize(w->stream);
+    drop_graphs(w);
     for (void *p : w->allocs) cudaFree(p);
     if (w->ev_step0) cudaEventDestroy(w->ev_step0);
     if (w->ev_step1) cudaEventDestroy(w->ev_step1);
@@ -184,7 +210,23 @@ void b2d_destroy(b2d_world *w) {
 }
 
 void *b2d_stream(b2d_world *w) { return w ? (void *)w->stream : nullptr; }
-int b2d_sync(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; cudaSetDevice(w->cfg.device); CK(cudaStreamSynchronize(w->stream)); return B2D_OK; }
+// Device-side overflow flags become return codes here (the step itself is asynchronous).
+static int check_device_flags(b2d_world *w) {
+    uint32_t err = 0;
+    CK(cudaMemcpyAsync(&err, &w->d.cnt->err, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    if (!err) return B2D_OK;
+    w->error = "device error flags:";
+    if (err & ERR_MANIFOLD_CAPACITY) w->error += " max_manifolds exceeded;";
+    if (err & ERR_LARGE_CAPACITY) w->error += " large-body list overflow;";
+    if (err & ERR_COLOR_OVERFLOW) w->error += " more than 64 constraints of one kind on one dynamic body;";
+    if (err & ERR_SOLVER_TIMEOUT) w->error += " solver dataflow wait timed out;";
+    if (err & ERR_UNKNOWN_ENTITY) w->error += " hand-over blob names an unknown entity;";
+    if (err & (ERR_MANIFOLD_CAPACITY | ERR_LARGE_CAPACITY)) return B2D_ERR_CAPACITY;
+    if (err & ERR_COLOR_OVERFLOW) return B2D_ERR_UNSUPPORTED;
+    return B2D_ERR_CUDA;
+}
+int b2d_sync(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; cudaSetDevice(w->cfg.device); CK(cudaStreamSynchronize(w->stream)); return check_device_flags(w); }
 
 // Bounding diameter of a shape: an upper bound of any AABB extent it can have.
 static float shape_diameter(uint32_t kind, const float *p) {
@@ -194,6 +236,34 @@ static float shape_diameter(uint32_t kind, const float *p) {
     case B2D_SHAPE_BOX: return 2 * std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
     default: return INFINITY;
     }
+}
+
+// Broadphase classes, world-wide: the grid pitch is the largest bounding diameter among the bodies that go into the
+// grid; planes and bodies much larger than the typical dynamic body (4 x the mean dynamic diameter of the WHOLE world,
+// however the bodies were batched) are kept in a brute-force list instead.  Runs before the first step after the body
+// population changed; results do not depend on the classification (the exact AABB tests decide), only speed does.
+static int reclassify(b2d_world *w) {
+    Dev &d = w->d;
+    double sum = 0; uint64_t cnt = 0;
+    for (uint32_t i = 0; i < d.nbodies; ++i) if (w->isdyn[i] && w->diam[i] > 0 && std::isfinite(w->diam[i])) { sum += w->diam[i]; ++cnt; }
+    const float big = cnt ? float(4.0 * sum / cnt) : 1e30f;
+    w->large.clear(); w->max_extent = 0.0f;
+    for (uint32_t i = 0; i < d.nbodies; ++i) {
+        const float dm = w->diam[i];
+        if (dm <= 0) continue;                                       // shapeless or removed
+        if (!std::isfinite(dm) || dm > big) w->large.push_back(i);
+        else w->max_extent = std::max(w->max_extent, dm);
+    }
+    cudaStream_t s = w->stream;
+    if (!w->large.empty()) CK(cudaMemcpyAsync(d.large_list, w->large.data(), w->large.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    d.nlarge = (uint32_t)w->large.size();
+    d.cell = w->max_extent + 2 * BREAKING_THRESHOLD + 1e-3f;
+    d.inv_cell = 1.0f / d.cell;
+    if (d.nbodies) { LAUNCH(k_large_clear, d.nbodies, 256, d); if (d.nlarge) LAUNCH(k_large_set, d.nlarge, 256, d); }
+    CK(cudaStreamSynchronize(s));
+    w->class_dirty = false;
+    drop_graphs(w);
+    return B2D_OK;
 }
 
 int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
@@ -210,12 +280,6 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
         if (sk == B2D_SHAPE_PLANE && b->kind[i] != B2D_STATIC) { w->error = "b2d_add_bodies: plane shapes must be static"; return B2D_ERR_UNSUPPORTED; }
         if (b->kind[i] > B2D_STATIC) { w->error = "b2d_add_bodies: bad body kind"; return B2D_ERR_ARGUMENT; }
     }
-    // Grid pitch: largest bounding diameter among the bodies that go into the grid.  Bodies much larger
-    // than the typical dynamic body (and all planes) are kept in a brute-force list instead.
-    double sum = 0; uint32_t cnt = 0;
-    for (uint32_t i = 0; i < n; ++i) if (b->kind[i] == B2D_DYNAMIC && b->shape_kind[i] != B2D_SHAPE_NONE) { sum += shape_diameter(b->shape_kind[i], b->shape_params + 4 * i); ++cnt; }
-    const float big = cnt ? float(4.0 * sum / cnt) : 1e30f;
-
     std::vector<float4> pos(n), orn(n), lv(n), av(n), invI(3 * (size_t)n), grav(n), shp(n);
     std::vector<uint32_t> flags(n); std::vector<float2> mat(n); std::vector<unsigned long long> grp(n), msk(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -232,14 +296,10 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
         if (dyn && (sk == B2D_SHAPE_SPHERE || sk == B2D_SHAPE_CAPSULE)) f |= F_ROLLING;
         unsigned long long g = b->group ? b->group[i] : ~0ULL, m = b->mask ? b->mask[i] : ~0ULL;
         if (b->group && b->mask && !(g == ~0ULL && m == ~0ULL)) f |= F_FILTER;
-        if (sk != B2D_SHAPE_NONE) {
-            float diam = shape_diameter(sk, b->shape_params + 4 * i);
-            if (sk == B2D_SHAPE_PLANE || diam > big) { f |= F_LARGE; w->large.push_back(first + i); }
-            else w->max_extent = std::max(w->max_extent, diam);
-        }
+        w->diam.push_back(sk != B2D_SHAPE_NONE ? shape_diameter(sk, b->shape_params + 4 * i) : 0.0f);
+        w->isdyn.push_back(dyn ? 1 : 0);
         flags[i] = f; mat[i] = make_float2(b->friction[i], b->restitution[i]); grp[i] = g; msk[i] = m;
     }
-    if (w->large.size() > d.NB) { w->error = "large list overflow"; return B2D_ERR_CAPACITY; }
     cudaStream_t s = w->stream;
     CK(cudaMemcpyAsync(d.pos + first, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d.orn + first, orn.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
@@ -252,13 +312,12 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
     CK(cudaMemcpyAsync(d.mat + first, mat.data(), n * sizeof(float2), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d.group + first, grp.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d.fmask + first, msk.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d.large_list, w->large.data(), w->large.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     d.nbodies = first + n;
-    d.nlarge = (uint32_t)w->large.size();
-    d.cell = w->max_extent + 2 * BREAKING_THRESHOLD + 1e-3f;
-    d.inv_cell = 1.0f / d.cell;
+    LAUNCH(k_entities_default, n, 256, d, first, n);
     LAUNCH(k_refresh_bodies, n, 256, d, first, n);
     CK(cudaStreamSynchronize(s));
+    w->class_dirty = true;
+    drop_graphs(w);
     if (first_id) *first_id = first;
     return B2D_OK;
 }
@@ -279,7 +338,9 @@ int b2d_remove_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
     if (d.sleeping) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies);
     CK(cudaFreeAsync(dev_ids, s));
     CK(cudaStreamSynchronize(s));
-    w->contacts_dirty = true;
+    for (uint32_t k = 0; k < n; ++k) { w->diam[ids[k]] = 0.0f; w->isdyn[ids[k]] = 0; }
+    w->contacts_dirty = true; w->class_dirty = true; w->ehash_dirty = true;
+    drop_graphs(w);
     return B2D_OK;
 }
 
@@ -348,6 +409,7 @@ int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *
     CK(cudaMemsetAsync(d.himp + 5 * (size_t)first, 0, 5 * (size_t)n * sizeof(float), s));
     CK(cudaStreamSynchronize(s));
     d.nhinges = first + n;
+    drop_graphs(w);
     return B2D_OK;
 }
 
@@ -371,6 +433,7 @@ static int upload_exclusions(b2d_world *w) {
         if (it != w->allocs.end()) { cudaFree(*it); w->allocs.erase(it); }
     }
     d.xhash_key = dev; d.xhash_size = w->exclusions.empty() ? 0u : size;
+    drop_graphs(w);
     return B2D_OK;
 }
 
@@ -379,6 +442,7 @@ int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *a, const uint32
     cudaSetDevice(w->cfg.device);
     std::unordered_set<uint64_t> seen(w->exclusions.begin(), w->exclusions.end());
     for (uint32_t i = 0; i < n; ++i) {
+        if (a[i] >= w->d.nbodies || b[i] >= w->d.nbodies) { w->error = "b2d_add_exclusions: body id out of range"; return B2D_ERR_ARGUMENT; }
         uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
         const uint64_t k = (lo << 32) | hi;
         if (seen.insert(k).second) w->exclusions.push_back(k);
@@ -435,7 +499,8 @@ static int enqueue_narrowphase(b2d_world *w) {
     LAUNCH(k_np_merge, d.NM, 128, d);
     return B2D_OK;
 }
-static int enqueue_islands(b2d_world *w) {
+// connected components over the current edges (manifolds + joints): island label per body
+static int enqueue_cc(b2d_world *w) {
     Dev &d = w->d;
     CK(cudaMemsetAsync(&d.cnt->nislands, 0, sizeof(uint32_t), w->stream));
     LAUNCH(k_cc_init, d.nbodies, 256, d);
@@ -443,6 +508,12 @@ static int enqueue_islands(b2d_world *w) {
     LAUNCH(k_cc_flatten, d.nbodies, 256, d, 0);
     LAUNCH(k_cc_union, (uint64_t)d.NM + d.nhinges, 256, d, 1);
     LAUNCH(k_cc_flatten, d.nbodies, 256, d, 1);
+    w->labels_stale = false;
+    return B2D_OK;
+}
+static int enqueue_islands(b2d_world *w) {
+    Dev &d = w->d;
+    { int rc = enqueue_cc(w); if (rc) return rc; }
     const uint64_t j = w->updates++;                                 // island_manager::update calls so far
     if (d.sleeping && d.nbodies) {
         // m_last_time inside put_islands_to_sleep is the time of the PREVIOUS update (island_manager.cpp:538, :611-613);
@@ -462,12 +533,11 @@ static int enqueue_islands(b2d_world *w) {
     }
     return B2D_OK;
 }
-static int enqueue_solver(b2d_world *w) {
+// solver.update in three segments so that the velocity solve can be bracketed by timing events between two graphs:
+// A gravity .. row preparation, B the velocity iterations, C integration .. refresh.
+static int enqueue_solver_a(b2d_world *w, int recolor) {
     Dev &d = w->d; cudaStream_t s = w->stream;
-    const int vi = (int)w->cfg.velocity_iterations, pi = (int)w->cfg.position_iterations;
     LAUNCH(k_gravity, d.nbodies, 256, d);
-    const int recolor = ((w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->contacts_dirty) ? 1 : 0;
-    w->contacts_dirty = false;
     CK(cudaMemsetAsync(&d.cnt->remaining[0], 0, 2 * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(&d.cnt->nlist, 0, 2 * sizeof(uint32_t), s));          // nlist + bar
     CK(cudaMemsetAsync(d.bmask, 0, (size_t)d.nbodies * sizeof(unsigned long long), s));
@@ -485,16 +555,24 @@ static int enqueue_solver(b2d_world *w) {
     LAUNCH(k_color_fixup, 1, 32, d);
     LAUNCH(k_prepare_contacts, d.NM, 256, d);
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
-    const int slot = (int)(w->timed_steps % b2d_world::RING);
     CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
-    cudaEventRecord(w->ev_solve0[slot], s);
+    return B2D_OK;
+}
+static int enqueue_solver_b(b2d_world *w) {
+    Dev &d = w->d;
+    const int vi = (int)w->cfg.velocity_iterations;
     if (w->barrier_solver) CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
     else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
-    cudaEventRecord(w->ev_solve1[slot], s);
-    cudaEventRecord(w->ev_int0[slot], s);
-    LAUNCH(k_integrate, d.nbodies, 256, d, pi == 0 ? 1 : 0);
-    cudaEventRecord(w->ev_int1[slot], s);
-    ++w->timed_steps;
+    return B2D_OK;
+}
+static int enqueue_integrate(b2d_world *w) {
+    Dev &d = w->d;
+    LAUNCH(k_integrate, d.nbodies, 256, d, w->cfg.position_iterations == 0 ? 1 : 0);
+    return B2D_OK;
+}
+static int enqueue_solver_c(b2d_world *w) {
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    const int pi = (int)w->cfg.position_iterations;
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
         CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
@@ -502,14 +580,32 @@ static int enqueue_solver(b2d_world *w) {
         else CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
-    w->timed = true;
+    return B2D_OK;
+}
+static int enqueue_solver(b2d_world *w) {
+    const int recolor = ((w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->contacts_dirty) ? 1 : 0;
+    w->contacts_dirty = false;
+    int rc = enqueue_solver_a(w, recolor); if (rc) return rc;
+    const int slot = (int)(w->timed_steps % b2d_world::RING);
+    if (w->timing) cudaEventRecord(w->ev_solve0[slot], w->stream);
+    rc = enqueue_solver_b(w); if (rc) return rc;
+    if (w->timing) { cudaEventRecord(w->ev_solve1[slot], w->stream); cudaEventRecord(w->ev_int0[slot], w->stream); }
+    rc = enqueue_integrate(w); if (rc) return rc;
+    if (w->timing) cudaEventRecord(w->ev_int1[slot], w->stream);
+    rc = enqueue_solver_c(w); if (rc) return rc;
+    if (w->timing) { ++w->timed_steps; w->timed = true; }
+    return B2D_OK;
+}
+
+static int prepare_step(b2d_world *w) {
+    if (w->class_dirty) return reclassify(w);
     return B2D_OK;
 }
 
 int b2d_run_phases(b2d_world *w, uint32_t mask) {
     if (!w) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
-    int rc = B2D_OK;
+    int rc = prepare_step(w); if (rc) return rc;
     if (mask & B2D_PHASE_BROAD) if ((rc = enqueue_broadphase(w))) return rc;
     if (mask & B2D_PHASE_NARROW) if ((rc = enqueue_narrowphase(w))) return rc;
     if (mask & B2D_PHASE_ISLANDS) if ((rc = enqueue_islands(w))) return rc;
@@ -518,13 +614,71 @@ int b2d_run_phases(b2d_world *w, uint32_t mask) {
     return B2D_OK;
 }
 
+extern "C++" {
+// Capture [begin, end) of the step sequence into an executable graph.  Returns false (and leaves the stream usable)
+// if the capture is refused; the caller then falls back to plain launches for good.
+template<typename F>
+static bool capture(b2d_world *w, cudaGraphExec_t &out, F body) {
+    const uint64_t launches0 = w->launches, updates0 = w->updates;
+    if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    const int rc = body();
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(w->stream, &g);
+    w->launches = launches0; w->updates = updates0;                // nothing ran yet
+    if (rc != B2D_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return false; }
+    const bool ok = cudaGraphInstantiate(&out, g, 0) == cudaSuccess;
+    cudaGraphDestroy(g);
+    if (!ok) { cudaGetLastError(); out = nullptr; }
+    return ok;
+}
+static bool build_graphs(b2d_world *w) {
+    drop_graphs(w);
+    uint64_t n_pre = 0, n_solve = 0, n_post = 0;
+    auto counted = [&](uint64_t &n, auto fn) { return [&, fn]() { const uint64_t l0 = w->launches; int rc = fn(); n = w->launches - l0; return rc; }; };
+    bool ok = capture(w, w->gx_pre, counted(n_pre, [&]() { int rc; if ((rc = enqueue_broadphase(w))) return rc; if ((rc = enqueue_narrowphase(w))) return rc;
+                                                            if ((rc = enqueue_islands(w))) return rc; return enqueue_solver_a(w, 0); }));
+    ok = ok && capture(w, w->gx_solve, counted(n_solve, [&]() { return enqueue_solver_b(w); }));
+    ok = ok && capture(w, w->gx_post, counted(n_post, [&]() { return enqueue_solver_c(w); }));
+    ok = ok && capture(w, w->gx_all, [&]() { int rc; if ((rc = enqueue_broadphase(w))) return rc; if ((rc = enqueue_narrowphase(w))) return rc;
+                                             if ((rc = enqueue_islands(w))) return rc; if ((rc = enqueue_solver_a(w, 0))) return rc;
+                                             if ((rc = enqueue_solver_b(w))) return rc; if ((rc = enqueue_integrate(w))) return rc; return enqueue_solver_c(w); });
+    if (!ok) { drop_graphs(w); w->use_graph = false; return false; }
+    w->graph_launches = n_pre + n_solve + n_post + 1;
+    w->graph_valid = true;
+    return true;
+}
+} // extern "C++"
+
 int b2d_step(b2d_world *w, uint32_t num_steps) {
     if (!w) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
+    int rc = prepare_step(w); if (rc) return rc;
     cudaEventRecord(w->ev_step0, w->stream);
     for (uint32_t i = 0; i < num_steps; ++i) {
-        int rc = b2d_run_phases(w, B2D_PHASE_ALL);
-        if (rc) return rc;
+        // graphs replay a fixed sequence: island sleeping passes a fresh timestamp every step and a recolouring step
+        // runs a different colouring kernel argument, both go the plain way
+        const bool plain = !w->use_graph || w->d.sleeping || w->contacts_dirty || (w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->d.nbodies == 0;
+        if (!plain && !w->graph_valid) build_graphs(w);
+        if (plain || !w->graph_valid) {
+            rc = b2d_run_phases(w, B2D_PHASE_ALL);
+            if (rc) return rc;
+        } else if (w->timing) {
+            const int slot = (int)(w->timed_steps % b2d_world::RING);
+            CK(cudaGraphLaunch(w->gx_pre, w->stream));
+            cudaEventRecord(w->ev_solve0[slot], w->stream);
+            CK(cudaGraphLaunch(w->gx_solve, w->stream));
+            cudaEventRecord(w->ev_solve1[slot], w->stream);
+            cudaEventRecord(w->ev_int0[slot], w->stream);
+            { const uint64_t l0 = w->launches; rc = enqueue_integrate(w); w->launches = l0; if (rc) return rc; }
+            cudaEventRecord(w->ev_int1[slot], w->stream);
+            CK(cudaGraphLaunch(w->gx_post, w->stream));
+            ++w->timed_steps; w->timed = true; ++w->updates;
+            w->launches += w->graph_launches;
+        } else {
+            CK(cudaGraphLaunch(w->gx_all, w->stream));
+            ++w->updates;
+            w->launches += w->graph_launches;
+        }
         ++w->steps;
     }
     cudaEventRecord(w->ev_step1, w->stream);
@@ -762,6 +916,234 @@ int b2d_device_bounds(b2d_world *w, float *device_out6) {
     LAUNCH(k_bounds_final, 1, 32, d, device_out6);
     CK(cudaGetLastError());
     return B2D_OK;
+}
+
+
+int b2d_set_timing(b2d_world *w, int enabled) { if (!w) return B2D_ERR_ARGUMENT; w->timing = enabled != 0; return B2D_OK; }
+
+// ------------------------------------------------------------------ dirty-subset staging
+
+int b2d_upload_bodies(b2d_world *w, uint32_t n, const uint32_t *ids, const b2d_body_patch *p) {
+    if (!w || !p || (n && !ids)) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    if (!n) return B2D_OK;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (ids[k] >= d.nbodies) { w->error = "b2d_upload_bodies: body id out of range"; return B2D_ERR_ARGUMENT; }
+        if (p->kind && p->kind[k] > B2D_STATIC) { w->error = "b2d_upload_bodies: bad body kind"; return B2D_ERR_ARGUMENT; }
+    }
+    if ((size_t)n * 30 > w->stage_floats) { w->error = "b2d_upload_bodies: patch larger than the staging buffer"; return B2D_ERR_CAPACITY; }
+    cudaStream_t s = w->stream;
+    float *cur = w->stage;
+    auto put = [&](const void *host, size_t words) -> const float * {
+        if (!host) return nullptr;
+        float *dst = cur; cur += words;
+        cudaMemcpyAsync(dst, host, words * sizeof(float), cudaMemcpyHostToDevice, s);
+        return dst;
+    };
+    const uint32_t *dev_ids = (const uint32_t *)put(ids, n);
+    Patch q;
+    q.pos = put(p->pos, 3 * (size_t)n); q.orn = put(p->orn, 4 * (size_t)n); q.linvel = put(p->linvel, 3 * (size_t)n); q.angvel = put(p->angvel, 3 * (size_t)n);
+    q.inv_mass = put(p->inv_mass, n); q.inv_inertia = put(p->inv_inertia, 9 * (size_t)n); q.gravity = put(p->gravity, 3 * (size_t)n);
+    q.friction = put(p->friction, n); q.restitution = put(p->restitution, n); q.kind = (const uint32_t *)put(p->kind, n);
+    LAUNCH(k_patch_bodies, n, 256, d, dev_ids, n, q);
+    CK(cudaStreamSynchronize(s));                    // the host arrays may be reused by the caller
+    if (p->kind) {
+        for (uint32_t k = 0; k < n; ++k) w->isdyn[ids[k]] = p->kind[k] == B2D_DYNAMIC ? 1 : 0;
+        w->class_dirty = true;
+    }
+    return B2D_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU: names, halo, plan, hand-over
+
+int b2d_set_entities(b2d_world *w, uint32_t first, uint32_t n, const uint32_t *entity) {
+    if (!w || (n && !entity)) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    if ((uint64_t)first + n > d.nbodies) { w->error = "b2d_set_entities: body id out of range"; return B2D_ERR_ARGUMENT; }
+    if (!n) return B2D_OK;
+    uint32_t *tmp = (uint32_t *)w->stage;
+    CK(cudaMemcpyAsync(tmp, entity, n * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    LAUNCH(k_entities_set, n, 256, d, first, n, (const uint32_t *)tmp);
+    CK(cudaStreamSynchronize(w->stream));
+    w->ehash_dirty = true;
+    return B2D_OK;
+}
+int b2d_download_entities(b2d_world *w, uint32_t *entity) {
+    if (!w || !entity) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    CK(cudaMemcpyAsync(entity, w->d.entity, w->d.nbodies * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return B2D_OK;
+}
+
+int b2d_island_halo(b2d_world *w, const float *device_boxes, uint32_t nboxes, uint32_t self, uint64_t peer_mask,
+                    void *device_records, uint32_t capacity, uint32_t *device_count) {
+    if (!w || !device_boxes || !device_records || !device_count || nboxes > 64 || self >= nboxes) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d;
+    if (w->labels_stale) { int rc = enqueue_cc(w); if (rc) return rc; }
+    CK(cudaMemsetAsync(device_count, 0, sizeof(uint32_t), w->stream));
+    if (d.nbodies) {
+        LAUNCH(k_ibox_init, d.nbodies, 256, d);
+        LAUNCH(k_ibox_reduce, d.nbodies, 256, d);
+        LAUNCH(k_halo_collect, d.nbodies, 256, d, device_boxes, nboxes, self, (unsigned long long)peer_mask, (HaloRec *)device_records, capacity, device_count);
+    }
+    CK(cudaGetLastError());
+    return B2D_OK;
+}
+
+int b2d_handover_plan(b2d_world *w, const void *device_records, uint32_t my_begin, uint32_t my_end, uint32_t nranks, uint32_t *counts) {
+    if (!w || !counts || nranks == 0 || nranks > 64 || my_end < my_begin || (my_end > my_begin && !device_records)) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    CK(cudaMemsetAsync(w->dev_counts, 0, 4 * 64 * sizeof(uint32_t), s));
+    if (my_end > my_begin && my_begin > 0)
+        LAUNCH(k_plan_islands, (uint64_t)(my_end - my_begin) * my_begin, 256, d, (const HaloRec *)device_records, my_begin, my_end);
+    if (d.nbodies) {
+        LAUNCH(k_plan_bodies, d.nbodies, 256, d, w->dev_counts);
+        LAUNCH(k_plan_constraints, (uint64_t)d.NM + d.nhinges, 256, d, w->dev_counts);
+    }
+    w->plan_counts.assign(4 * (size_t)nranks, 0);
+    w->host_bdst.resize(d.nbodies);
+    CK(cudaMemcpyAsync(w->plan_counts.data(), w->dev_counts, 4 * nranks * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (d.nbodies) CK(cudaMemcpyAsync(w->host_bdst.data(), d.bdst, d.nbodies * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    // collision_exclusion between two movers travels with them
+    for (uint64_t k : w->exclusions) {
+        const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
+        if (a < d.nbodies && b < d.nbodies && w->host_bdst[a] != NO_RANK && w->host_bdst[a] == w->host_bdst[b] && w->host_bdst[a] < nranks) ++w->plan_counts[4 * w->host_bdst[a] + 3];
+    }
+    w->plan_ranks = nranks;
+    std::memcpy(counts, w->plan_counts.data(), 4 * nranks * sizeof(uint32_t));
+    return B2D_OK;
+}
+
+uint64_t b2d_handover_bytes(const uint32_t *c) {
+    if (!c) return 0;
+    uint64_t b = sizeof(BlobHeader) + 16ull * (BLOB_BODY_F4 * (uint64_t)c[0] + BLOB_MANIFOLD_F4 * (uint64_t)c[1] + BLOB_HINGE_F4 * (uint64_t)c[2]) + 8ull * c[3];
+    return (b + 15) & ~15ull;
+}
+
+int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t capacity) {
+    if (!w || !device_blob || dst >= w->plan_ranks) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    const uint32_t *c = &w->plan_counts[4 * dst];
+    if (capacity < b2d_handover_bytes(c)) { w->error = "b2d_handover_pack: blob too small"; return B2D_ERR_CAPACITY; }
+    std::vector<uint32_t> ids; ids.reserve(c[0]);
+    for (uint32_t i = 0; i < d.nbodies; ++i) if (w->host_bdst[i] == dst) ids.push_back(i);
+    std::vector<uint2> ex; std::vector<uint64_t> keep;
+    for (uint64_t k : w->exclusions) {
+        const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
+        if (a < d.nbodies && b < d.nbodies && w->host_bdst[a] == dst && w->host_bdst[b] == dst) ex.push_back(make_uint2(a, b)); else keep.push_back(k);
+    }
+    if (ids.size() != c[0] || ex.size() != c[3]) { w->error = "b2d_handover_pack: plan is stale"; return B2D_ERR_ARGUMENT; }
+    char *blob = (char *)device_blob;
+    BlobHeader *hdr = (BlobHeader *)blob;
+    float4 *ob = (float4 *)(blob + sizeof(BlobHeader)), *om = ob + (size_t)BLOB_BODY_F4 * c[0], *oh = om + (size_t)BLOB_MANIFOLD_F4 * c[1];
+    uint2 *ox = (uint2 *)(oh + (size_t)BLOB_HINGE_F4 * c[2]);
+    k_pack_header<<<1, 32, 0, s>>>(hdr, c[0], c[1], c[2], c[3]); ++w->launches;
+    uint32_t *dev_ids = nullptr; uint2 *dev_ex = nullptr;
+    if (c[0]) {
+        CK(cudaMallocAsync(&dev_ids, c[0] * sizeof(uint32_t), s));
+        CK(cudaMemcpyAsync(dev_ids, ids.data(), c[0] * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        LAUNCH(k_pack_bodies, c[0], 256, d, (const uint32_t *)dev_ids, c[0], ob);
+    }
+    size_t t;
+    if (c[1]) {
+        LAUNCH(k_pack_flag_manifolds, d.NM, 256, d, dst);
+        t = w->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.free_flag, d.free_rank, (int)d.NM, s)); ++w->launches;
+        LAUNCH(k_pack_manifolds, d.NM, 256, d, om);
+    }
+    if (c[2]) {
+        LAUNCH(k_pack_flag_hinges, d.NH, 256, d, dst);
+        t = w->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.hidx, d.hidx_s, (int)d.NH, s)); ++w->launches;
+        LAUNCH(k_pack_hinges, d.nhinges, 256, d, oh);
+    }
+    if (c[3]) {
+        CK(cudaMallocAsync(&dev_ex, c[3] * sizeof(uint2), s));
+        CK(cudaMemcpyAsync(dev_ex, ex.data(), c[3] * sizeof(uint2), cudaMemcpyHostToDevice, s));
+        LAUNCH(k_pack_exclusions, c[3], 256, d, (const uint2 *)dev_ex, c[3], ox);
+    }
+    // registry.destroy of the local copies: the bodies turn into removed slots, their manifolds and joints die with them
+    if (c[0]) {
+        LAUNCH(k_remove_bodies, c[0], 256, d, (const uint32_t *)dev_ids, c[0]);
+        if (d.nhinges) LAUNCH(k_remove_hinges, d.nhinges, 256, d);
+        CK(cudaFreeAsync(dev_ids, s));
+    }
+    if (dev_ex) CK(cudaFreeAsync(dev_ex, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t i : ids) { w->diam[i] = 0.0f; w->isdyn[i] = 0; w->host_bdst[i] = NO_RANK; }
+    if (!ex.empty()) { w->exclusions.swap(keep); int rc = upload_exclusions(w); if (rc) return rc; }
+    w->contacts_dirty = true; w->class_dirty = true; w->ehash_dirty = true; w->labels_stale = true;
+    drop_graphs(w);
+    return B2D_OK;
+}
+
+int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, uint32_t *counts_out) {
+    if (!w || !device_blob || bytes < sizeof(BlobHeader)) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    BlobHeader h;
+    CK(cudaMemcpyAsync(&h, device_blob, sizeof(h), cudaMemcpyDeviceToHost, s));
+    Counters cn; { int rc = fetch_counters(w, cn); if (rc) return rc; }
+    if (h.magic != BLOB_MAGIC) { w->error = "b2d_handover_unpack: not a hand-over blob"; return B2D_ERR_ARGUMENT; }
+    const uint32_t c[4] = {h.nb, h.nm, h.nh, h.nx};
+    if (bytes < b2d_handover_bytes(c)) { w->error = "b2d_handover_unpack: blob truncated"; return B2D_ERR_ARGUMENT; }
+    if ((uint64_t)d.nbodies + h.nb > d.NB) { w->error = "b2d_handover_unpack: max_bodies exceeded"; return B2D_ERR_CAPACITY; }
+    if ((uint64_t)cn.hwm + h.nm > d.NM) { w->error = "b2d_handover_unpack: max_manifolds exceeded"; return B2D_ERR_CAPACITY; }
+    if ((uint64_t)d.nhinges + h.nh > w->cfg.max_hinges) { w->error = "b2d_handover_unpack: max_hinges exceeded"; return B2D_ERR_CAPACITY; }
+    const char *blob = (const char *)device_blob;
+    const float4 *ib = (const float4 *)(blob + sizeof(BlobHeader)), *im = ib + (size_t)BLOB_BODY_F4 * h.nb, *ih = im + (size_t)BLOB_MANIFOLD_F4 * h.nm;
+    const uint2 *ix = (const uint2 *)(ih + (size_t)BLOB_HINGE_F4 * h.nh);
+    const uint32_t first = d.nbodies;
+    d.nbodies = first + h.nb;                       // the entity table below must see the newcomers' slots as live
+    if (w->ehash_dirty) {
+        CK(cudaMemsetAsync(d.ehash, 0xFF, (size_t)d.ehash_size * sizeof(unsigned long long), s));
+        if (first) { Dev old = d; old.nbodies = first; LAUNCH(k_ehash_build, first, 256, old); }
+        w->ehash_dirty = false;
+    }
+    if (h.nb) {
+        LAUNCH(k_unpack_bodies, h.nb, 256, d, first, h.nb, ib);
+        LAUNCH(k_refresh_bodies, h.nb, 256, d, first, h.nb);
+        std::vector<float4> shp(h.nb); std::vector<uint32_t> fl(h.nb);
+        CK(cudaMemcpyAsync(shp.data(), d.shp + first, h.nb * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(fl.data(), d.flags + first, h.nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t k = 0; k < h.nb; ++k) {
+            const uint32_t sk = (fl[k] >> F_SHAPE_SHIFT) & 0xFFu;
+            const float p[4] = {shp[k].x, shp[k].y, shp[k].z, shp[k].w};
+            w->diam.push_back(sk != B2D_SHAPE_NONE ? shape_diameter(sk, p) : 0.0f);
+            w->isdyn.push_back((fl[k] & F_KIND_MASK) == 0u ? 1 : 0);
+        }
+    }
+    if (h.nm) { LAUNCH(k_unpack_manifolds, h.nm, 256, d, h.nm, im, cn.hwm); LAUNCH(k_bump_hwm, 1, 32, d, h.nm); }
+    if (h.nh) { LAUNCH(k_unpack_hinges, h.nh, 256, d, d.nhinges, h.nh, ih); d.nhinges += h.nh; }
+    if (h.nx) {
+        uint2 *loc = nullptr;
+        CK(cudaMallocAsync(&loc, h.nx * sizeof(uint2), s));
+        LAUNCH(k_unpack_exclusions, h.nx, 256, d, ix, h.nx, loc);
+        std::vector<uint2> host(h.nx);
+        CK(cudaMemcpyAsync(host.data(), loc, h.nx * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+        CK(cudaFreeAsync(loc, s));
+        CK(cudaStreamSynchronize(s));
+        std::unordered_set<uint64_t> seen(w->exclusions.begin(), w->exclusions.end());
+        for (const uint2 &e : host) {
+            if (e.x == 0xFFFFFFFFu || e.y == 0xFFFFFFFFu) continue;
+            const uint64_t lo = std::min(e.x, e.y), hi = std::max(e.x, e.y), k = (lo << 32) | hi;
+            if (seen.insert(k).second) w->exclusions.push_back(k);
+        }
+        int rc = upload_exclusions(w); if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(s));
+    w->contacts_dirty = true; w->class_dirty = true; w->labels_stale = true;
+    drop_graphs(w);
+    if (counts_out) std::memcpy(counts_out, c, sizeof(c));
+    return check_device_flags(w);
 }
 
 } // extern "C"

@@ -265,7 +265,13 @@ __global__ void k_bp_pairs(Dev d) {
         uint32_t fA = d.flags[A];
         uint32_t count = 0;
         uint2 *out = nullptr;
-        if (FILL) { if (d.newcount[A] == 0) continue; out = d.newpairs + d.newoff[A]; }
+        if (FILL) {
+            if (d.newcount[A] == 0) continue;
+            // newpairs holds max_manifolds entries: a body whose range would run past it (and therefore every body behind
+            // it in the scan) is dropped, the append below stops in front of the first hole
+            if ((unsigned long long)d.newoff[A] + d.newcount[A] > d.NM) { atomicMin(&d.cnt->nnew, d.newoff[A]); atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
+            out = d.newpairs + d.newoff[A];
+        }
         if (is_dynamic(fA) && shape_of(fA) != SH_NONE) {
             box3 bbA = body_box(d, A);
             box3 qA = inset(bbA, BP_OFFSET);

@@ -32,6 +32,7 @@ constexpr int COLOR_KEY_BITS = 6 + 2 + COLOR_KEY_SPATIAL_BITS + 1;      // + the
 constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
 constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
 constexpr uint32_t ERR_LARGE_CAPACITY = 4u;
+constexpr uint32_t ERR_UNKNOWN_ENTITY = 16u;    // a hand-over blob names a body this world does not hold
 constexpr uint32_t ERR_SOLVER_TIMEOUT = 8u;     // a dataflow wait exceeded its spin budget (would have been a hang)
 
 struct Counters {
@@ -134,6 +135,12 @@ struct Dev {
     uint32_t *pisl, *hisl;       // per sorted constraint: island label (position solver early exit)
     float4 *prec;                // position solver: 3 float4 per body, (pos,t) (orn.xyz,t) (orn.w,fresh,0,t)
     uint2 *tkt, *htkt;           // per sorted constraint, per body side: S | base << 8 | k << 16 (see k_prepare_*)
+
+    // ---- multi-GPU hand-over (b2d_dist.cuh): scene-global body names and the island / destination scratch
+    uint32_t *entity;                    // scene-global name per body (entt::entity in the EnTT binding); default = local id
+    unsigned long long *ehash; uint32_t ehash_size;      // entity -> local id, open addressing, key << 32 | value
+    int *ibox;                           // 6 ints per body id: order-preserving encoding of the island AABB, stored at the root
+    uint32_t *isl_dst, *bdst;            // destination rank per island root / per body (0xFFFFFFFF = stays)
 
     Counters *cnt;
 };

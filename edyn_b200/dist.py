@@ -67,8 +67,10 @@ def initial_islands(scene, reach=MARGIN):
                 parent[rx] = ry
 
     if scene.get("hinges"):
+        isdyn = b["kind"] == DYNAMIC
         for x, y in zip(scene["hinges"]["a"].tolist(), scene["hinges"]["b"].tolist()):
-            union(x, y)
+            if isdyn[x] and isdyn[y]:                      # static / kinematic nodes do not connect islands
+                union(x, y)
     shaped = dyn[b["shape_kind"][dyn] != SHAPE_NONE]
     if len(shaped):
         half = host_aabbs(b, shaped)
@@ -99,24 +101,40 @@ def initial_islands(scene, reach=MARGIN):
 
 def partition(scene, world_size, labels=None):
     """Assign whole islands to ranks: islands ordered by centroid along x, cut into `world_size` runs of roughly equal
-    body count.  Static bodies go to every rank.  Returns owner[n] (rank, or -1 = replicated)."""
+    body count (an island joins the next rank once the current one holds its share; a rank is never skipped while
+    islands remain).  Static bodies go to every rank.  Returns owner[n] (rank, or -1 = replicated)."""
     b = scene["bodies"]
-    lab = initial_islands(scene) if labels is None else labels
+    lab = initial_islands(scene) if labels is None else np.asarray(labels, np.int64)
     owner = np.full(len(lab), -1, np.int64)
-    ids = np.unique(lab[lab >= 0])
-    if len(ids) == 0:
+    dyn = np.where(lab >= 0)[0]
+    if len(dyn) == 0:
         return owner
-    cx = np.array([b["pos"][lab == i, 0].mean() for i in ids])
-    size = np.array([(lab == i).sum() for i in ids])
+    ids, inv = np.unique(lab[dyn], return_inverse=True)
+    size = np.bincount(inv, minlength=len(ids))
+    cx = np.bincount(inv, weights=b["pos"][dyn, 0].astype(np.float64), minlength=len(ids)) / size
     order = np.argsort(cx, kind="stable")
-    total, acc, rank = size.sum(), 0, 0
-    for k in order:
-        # move to the next rank once this one holds its share (never leave a later rank empty if islands remain)
-        if acc >= (rank + 1) * total / world_size and rank < world_size - 1:
-            rank += 1
-        owner[lab == ids[k]] = rank
-        acc += size[k]
+    before = np.cumsum(size[order]) - size[order]                      # bodies placed before each island
+    share = (before * world_size) // size.sum()                        # rank whose share the island starts in
+    k = np.arange(len(order))
+    rank_sorted = np.minimum(np.minimum.accumulate(share - k) + k, world_size - 1)     # at most one rank further per island
+    rank_of = np.empty(len(ids), np.int64)
+    rank_of[order] = rank_sorted
+    owner[dyn] = rank_of[inv]
     return owner
+
+
+def device_islands(scene, device=0):
+    """Island label per body (-1 for non-dynamic) as the simulation itself sees them at step 0: one broadphase +
+    narrowphase + island pass of the WHOLE scene on `device` (connected components of island_manager's graph).  The
+    host-side `initial_islands` is O(minutes) beyond ~10^5 bodies; this is what bench.py partitions with."""
+    from .scenes import build_world
+    from .world import PH_BROAD, PH_ISLANDS, PH_NARROW
+    w = build_world(scene, device=device)
+    w.run_phases(PH_BROAD | PH_NARROW | PH_ISLANDS)
+    lab = w.islands().astype(np.int64)
+    w.close()
+    lab[lab == 0xFFFFFFFF] = -1
+    return lab
 
 
 def shard(scene, rank, world_size, owner=None):
@@ -130,7 +148,9 @@ def shard(scene, rank, world_size, owner=None):
     hinges = None
     if scene.get("hinges"):
         h = scene["hinges"]
-        sel = (owner[h["a"]] == rank)
+        # a joint lives where its dynamic endpoint(s) live; a static / kinematic endpoint is replicated on every rank
+        oa, ob = owner[h["a"]], owner[h["b"]]
+        sel = ((oa == rank) | (ob == rank)) & ((oa == rank) | (oa < 0)) & ((ob == rank) | (ob < 0))
         hinges = {k: (remap[v[sel]].astype(np.uint32) if k in ("a", "b") else v[sel]) for k, v in h.items()}
     excl = None
     if scene.get("exclusions") is not None:
@@ -144,18 +164,14 @@ def shard(scene, rank, world_size, owner=None):
 
 
 def overlapping_ranks(bounds, margin=MARGIN):
-    """bounds: (world_size, 6) array of min/max of each rank's dynamic bodies (NaN rows = rank owns nothing).
-    Returns the list of rank pairs whose boxes, inflated by `margin`, intersect."""
-    out = []
-    n = len(bounds)
-    for i in range(n):
-        for j in range(i + 1, n):
-            a, b = bounds[i], bounds[j]
-            if np.isnan(a).any() or np.isnan(b).any():
-                continue
-            if np.all(a[0:3] - margin <= b[3:6]) and np.all(a[3:6] + margin >= b[0:3]):
-                out.append((i, j))
-    return out
+    """bounds: (world_size, 6) array of min/max of each rank's dynamic bodies (NaN or inverted rows = rank owns nothing).
+    Returns the list of rank pairs (i < j) whose boxes, inflated by `margin`, intersect."""
+    b = np.asarray(bounds, np.float64)
+    lo, hi = b[:, None, 0:3], b[:, None, 3:6]
+    with np.errstate(invalid="ignore"):
+        hit = np.all((lo - margin <= hi.transpose(1, 0, 2)) & (hi + margin >= lo.transpose(1, 0, 2)), axis=2)
+    i, j = np.nonzero(np.triu(hit, 1))
+    return list(zip(i.tolist(), j.tolist()))
 
 
 def boxes_touch(a, b, margin=MARGIN):
@@ -264,7 +280,9 @@ class ShardedWorld:
             msg["exclusions"] = (gol[ex[:, 0]], gol[ex[:, 1]])
         h = w.hinge_defs()
         if h is not None:
-            m = w.hinge_alive & sel[h["a"]] & sel[h["b"]]
+            # both endpoints travel, or one travels and the other is a replicated static body
+            static = np.zeros(w.num_bodies, bool); static[:len(self.local["bodies"]["kind"])] = self.local["bodies"]["kind"] != DYNAMIC
+            m = w.hinge_alive & (sel[h["a"]] | sel[h["b"]]) & (sel[h["a"]] | static[h["a"]]) & (sel[h["b"]] | static[h["b"]])
             if m.any():
                 msg["hinges"] = {k: (gol[v[m]] if k in ("a", "b") else v[m].copy()) for k, v in h.items()}
         if len(contacts["pairs"]):
@@ -339,3 +357,194 @@ class ShardedWorld:
         if pairs and migrate and self.dist is not None and self.world_size > 1:
             self.migrate(pairs, bounds, st)
         return pairs
+
+
+# ======================================================================================================================
+# Device-resident flavour (what bench.py --gpus N and the GPU tests run): nothing but 24-byte rank boxes crosses the
+# host per step, and a hand-over moves DEVICE blobs over the communicator.
+
+class TorchComm:
+    """torch.distributed transport (NCCL over NVLink on GPUs).  All tensors are device tensors; collectives are issued
+    on the caller's current stream, which DeviceShardedWorld sets to the world's own stream."""
+
+    def __init__(self, dist, rank, world_size):
+        self.dist, self.rank, self.world_size = dist, rank, world_size
+        self.bytes_sent = 0                         # payload bytes this rank contributed to collectives / sends
+
+    def all_gather(self, t):
+        import torch
+        out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous())
+        self.bytes_sent += t.numel() * t.element_size()
+        return out
+
+    def exchange(self, send, recv_bytes, device):
+        """send: {dst: uint8 tensor}; recv_bytes: {src: nbytes}.  Grouped ncclSend / ncclRecv."""
+        import torch
+        recv = {src: torch.empty(n, dtype=torch.uint8, device=device) for src, n in recv_bytes.items()}
+        ops = [self.dist.P2POp(self.dist.isend, t, dst) for dst, t in sorted(send.items())]
+        ops += [self.dist.P2POp(self.dist.irecv, t, src) for src, t in sorted(recv.items())]
+        if ops:
+            for r in self.dist.batch_isend_irecv(ops):
+                r.wait()
+        self.bytes_sent += sum(t.numel() for t in send.values())
+        return recv
+
+
+class ThreadComm:
+    """The same interface for `world_size` ranks living in threads of ONE process on ONE device: the GPU tests use it so
+    the hand-over path is exercised (and the native library loaded) on a single-GPU box too."""
+
+    class Shared:
+        def __init__(self, world_size):
+            import threading
+            self.world_size = world_size
+            self.barrier = threading.Barrier(world_size)
+            self.slots = [None] * world_size
+            self.mail = {}
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.world_size = shared, rank, shared.world_size
+        self.bytes_sent = 0
+
+    def all_gather(self, t):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        self.s.slots[self.rank] = t
+        self.s.barrier.wait()
+        out = torch.stack([x.clone() for x in self.s.slots])
+        torch.cuda.current_stream().synchronize()
+        self.s.barrier.wait()
+        self.bytes_sent += t.numel() * t.element_size()
+        return out
+
+    def exchange(self, send, recv_bytes, device):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        for dst, t in send.items():
+            self.s.mail[(self.rank, dst)] = t
+        self.s.barrier.wait()
+        recv = {src: self.s.mail[(src, self.rank)].clone() for src in recv_bytes}
+        torch.cuda.current_stream().synchronize()
+        self.s.barrier.wait()
+        for dst in send:
+            del self.s.mail[(self.rank, dst)]
+        self.bytes_sent += sum(t.numel() for t in send.values())
+        return recv
+
+
+class DeviceShardedWorld:
+    """One rank's share of a scene with the cross-rank exchange done on the device.
+
+    Per step (`step`): b2d_step; the box of the rank's dynamic bodies is reduced on the device straight into the
+    communicator's send buffer (b2d_device_bounds), all-gathered (24 B per rank), and the N x 6 floats are the only
+    thing the host reads -- it has to, because whether a hand-over happens decides what the NEXT step's broadphase sees.
+
+    When two rank boxes come within the broadphase margin (`_handover`): each rank computes its island AABBs on the
+    device and lists those near a peer (b2d_island_halo); the lists are all-gathered; an island that touches an island
+    of a lower rank is handed over whole to the lowest such rank (b2d_handover_plan, merge_islands' "move into the
+    other island", island_manager.cpp:297-350); the blobs (b2d_handover_pack: bodies with state, manifolds with
+    points / lifetimes / warm-start impulses, joints, exclusions, named by entity) travel as device buffers over grouped
+    send / recv, sizes having been all-gathered first; b2d_handover_unpack appends them.  The check repeats until no
+    island moves (an island arriving at rank r may itself touch an island of a still lower rank)."""
+
+    def __init__(self, scene, rank, world_size, comm, device=0, owner=None, labels=None, slack=0.25, **kw):
+        import torch
+        from .scenes import build_world
+        self.torch = torch
+        self.rank, self.world_size, self.comm, self.device = rank, world_size, comm, device
+        self.owner = partition(scene, world_size, labels) if owner is None else np.asarray(owner, np.int64)
+        self.local = shard(scene, rank, world_size, self.owner)
+        n_local = len(self.local["bodies"]["kind"])
+        n_all = len(self.owner)
+        # room for arrivals: `slack` of the whole scene on top of the own share (ids of departed bodies are not reused)
+        kw.setdefault("max_bodies", min(2 * n_all, n_local + int(slack * n_all) + 1024))
+        nh_all = len(scene["hinges"]["a"]) if scene.get("hinges") else 0
+        nh_local = len(self.local["hinges"]["a"]) if self.local.get("hinges") else 0
+        kw.setdefault("max_hinges", (nh_local + int(slack * nh_all) + 1024) if nh_all else 0)
+        self.world = build_world(self.local, device=device, **kw)
+        self.world.set_entities(0, self.local["global_ids"].astype(np.uint32))
+        self.ext = torch.cuda.ExternalStream(self.world.stream, device=device)
+        dev = torch.device("cuda", device)
+        self.dev = dev
+        self.bounds = torch.zeros(6, dtype=torch.float32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rec_cap = kw["max_bodies"]
+        self.records = torch.zeros((self.rec_cap, 8), dtype=torch.float32, device=dev)
+        self.migrated_in = self.migrated_out = 0
+        self.handover_rounds = 0
+        self.halo_checks = 0
+        self.dynamic = int(self.local["dynamic"])           # dynamic bodies this rank owns right now
+        self.last_pairs = []
+
+    def close(self):
+        self.world.close()
+
+    def _gather_bounds(self):
+        self.world.device_bounds(self.bounds.data_ptr())
+        g = self.comm.all_gather(self.bounds)
+        return g, g.cpu().numpy()                            # the one per-step host read: N x 6 floats
+
+    def exchange(self):
+        """After a step: rank boxes, and a hand-over if any two came within the broadphase margin of each other."""
+        torch = self.torch
+        with torch.cuda.stream(self.ext):
+            g, gh = self._gather_bounds()
+            pairs = overlapping_ranks(gh)
+            while pairs:
+                self.halo_checks += 1
+                moved = self._handover(pairs, g)
+                if moved == 0:
+                    break
+                self.handover_rounds += 1
+                g, gh = self._gather_bounds()
+                pairs = overlapping_ranks(gh)
+        self.last_pairs = pairs
+        return pairs
+
+    def _handover(self, pairs, g):
+        torch, w, N, r = self.torch, self.world, self.world_size, self.rank
+        mask = 0
+        for i, j in pairs:
+            if i == r:
+                mask |= 1 << j
+            if j == r:
+                mask |= 1 << i
+        w.island_halo(g.data_ptr(), N, r, mask, self.records.data_ptr(), self.rec_cap, self.count.data_ptr())
+        nrec = self.comm.all_gather(self.count).cpu().numpy().reshape(-1).astype(np.int64)
+        if nrec[r] > self.rec_cap:
+            raise RuntimeError("halo record buffer overflow")
+        if nrec.sum() == 0:
+            return 0
+        mx = int(nrec.max())
+        allrec = self.comm.all_gather(self.records[:mx])                           # (N, mx, 8): 32 B per boundary island
+        recs = torch.cat([allrec[p, :int(nrec[p])] for p in range(N)]).contiguous()
+        my_b = int(nrec[:r].sum())
+        plan = w.handover_plan(recs.data_ptr(), my_b, my_b + int(nrec[r]), N)      # (N, 4) host
+        allplan = self.comm.all_gather(torch.from_numpy(plan.astype(np.int32)).to(self.dev)).cpu().numpy()   # (N, N, 4)
+        moved = int(allplan[:, :, 0].sum())
+        if moved == 0:
+            return 0
+        send = {}
+        for dst in range(N):
+            if plan[dst].any():
+                nbytes = w.handover_bytes(plan[dst])
+                blob = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                w.handover_pack(dst, blob.data_ptr(), nbytes)
+                send[dst] = blob
+        recv_bytes = {src: w.handover_bytes(allplan[src, r]) for src in range(N) if allplan[src, r].any()}
+        got = self.comm.exchange(send, recv_bytes, self.dev)
+        for src in sorted(got):
+            c = w.handover_unpack(got[src].data_ptr(), got[src].numel())
+            self.migrated_in += int(c[0])
+        out = int(plan[:, 0].sum())
+        self.migrated_out += out
+        self.dynamic += int(allplan[:, r, 0].sum()) - out
+        return moved
+
+    def step(self, n=1, exchange=True):
+        for _ in range(n):
+            self.world.step(1)
+            if exchange:
+                self.exchange()
+        return self.last_pairs

@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import B2DError, Bodies, Config, Stats
+from ._lib import B2DError, Bodies, BodyPatch, Config, Stats
 from .rigidbody import RigidBodyDef, bodies_soa
 
 f32, u32 = np.float32, np.uint32
@@ -188,6 +188,23 @@ class World:
         self._check(self.l.b2d_upload_state(self.h, *[_p(x) for x in a]))
         self._keep = a
 
+    def upload_bodies(self, ids, **comp):
+        """registry.patch on a subset of bodies (b2d_upload_bodies): comp = pos / orn / linvel / angvel / inv_mass /
+        inv_inertia / gravity / friction / restitution / kind, each packed per listed body; the rest stays untouched."""
+        ids = _c(ids, u32)
+        n = len(ids)
+        shapes = dict(pos=(n, 3), orn=(n, 4), linvel=(n, 3), angvel=(n, 3), inv_mass=(n,), inv_inertia=(n, 9),
+                      gravity=(n, 3), friction=(n,), restitution=(n,))
+        unknown = set(comp) - set(shapes) - {"kind"}
+        if unknown:
+            raise B2DError(f"upload_bodies: unknown components {sorted(unknown)}")
+        keep = {k: _c(v, f32, shapes[k]) for k, v in comp.items() if k in shapes}
+        if "kind" in comp:
+            keep["kind"] = _c(comp["kind"], u32, (n,))
+        patch = BodyPatch(*[_p(keep.get(k)) for k in ("pos", "orn", "linvel", "angvel", "inv_mass", "inv_inertia", "gravity",
+                                                      "friction", "restitution", "kind")])
+        self._check(self.l.b2d_upload_bodies(self.h, C.c_uint32(n), _p(ids), C.byref(patch)))
+
     def download_state(self, aabb=True, inv_IW=False, out=None):
         n = self.num_bodies
         o = out or dict(pos=np.zeros((n, 3), f32), orn=np.zeros((n, 4), f32), linvel=np.zeros((n, 3), f32), angvel=np.zeros((n, 3), f32))
@@ -247,6 +264,44 @@ class World:
     def device_bounds(self, device_ptr):
         """Enqueue the dynamic-AABB bounds reduction into 6 floats at `device_ptr` (an int device address)."""
         self._check(self.l.b2d_device_bounds(self.h, C.c_void_p(device_ptr)))
+
+    # -- multi-GPU hand-over (device buffers are passed as integer addresses; the transport belongs to the caller)
+    def set_entities(self, first, entity):
+        e = _c(entity, u32)
+        self._check(self.l.b2d_set_entities(self.h, C.c_uint32(first), C.c_uint32(len(e)), _p(e)))
+
+    def entities(self):
+        e = np.zeros(max(1, self.num_bodies), u32)
+        self._check(self.l.b2d_download_entities(self.h, _p(e)))
+        return e[:self.num_bodies]
+
+    def island_halo(self, boxes_ptr, nboxes, self_rank, peer_mask, records_ptr, capacity, count_ptr):
+        self._check(self.l.b2d_island_halo(self.h, C.c_void_p(boxes_ptr), C.c_uint32(nboxes), C.c_uint32(self_rank),
+                                           C.c_uint64(peer_mask), C.c_void_p(records_ptr), C.c_uint32(capacity), C.c_void_p(count_ptr)))
+
+    def handover_plan(self, records_ptr, my_begin, my_end, nranks):
+        counts = np.zeros((nranks, 4), u32)
+        self._check(self.l.b2d_handover_plan(self.h, C.c_void_p(records_ptr), C.c_uint32(my_begin), C.c_uint32(my_end),
+                                             C.c_uint32(nranks), _p(counts)))
+        return counts
+
+    def handover_bytes(self, counts4):
+        c = _c(counts4, u32, (4,))
+        return int(self.l.b2d_handover_bytes(_p(c)))
+
+    def handover_pack(self, dst, blob_ptr, capacity):
+        self._check(self.l.b2d_handover_pack(self.h, C.c_uint32(dst), C.c_void_p(blob_ptr), C.c_uint64(capacity)))
+
+    def handover_unpack(self, blob_ptr, nbytes):
+        c = np.zeros(4, u32)
+        self._check(self.l.b2d_handover_unpack(self.h, C.c_void_p(blob_ptr), C.c_uint64(nbytes), _p(c)))
+        self.num_bodies += int(c[0])
+        self.num_hinges += int(c[2])
+        self.hinge_alive = np.concatenate([self.hinge_alive, np.ones(int(c[2]), bool)])
+        return c
+
+    def set_timing(self, enabled=True):
+        self._check(self.l.b2d_set_timing(self.h, C.c_int(1 if enabled else 0)))
 
     def reset_timers(self):
         self._check(self.l.b2d_reset_timers(self.h))

@@ -133,6 +133,20 @@ int b2d_add_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const u
 /* remove_collision_exclusion (src/edyn/util/exclude_collision.cpp); unknown pairs are ignored. */
 int b2d_remove_exclusions(b2d_world *w, uint32_t n, const uint32_t *body_a, const uint32_t *body_b);
 
+/* Dirty-subset staging: the reference's remote-replica contract -- users write through
+ * registry.patch / replace and only the touched entities travel (include/edyn/comp/shared_comp.hpp:36-86,
+ * include/edyn/replication/registry_operation_observer.hpp:49-82).  Arrays are packed per listed body (3n, 4n, ...);
+ * a NULL array leaves that component untouched.  kind may change (dynamic <-> kinematic <-> static: a kinematic body
+ * keeps its velocity but has no mass, src/edyn/dynamics/solver.cpp:101-147).  AABB and inertia_world_inv follow. */
+typedef struct b2d_body_patch {
+    const float *pos, *orn, *linvel, *angvel;   /* 3n 4n 3n 3n */
+    const float *inv_mass, *inv_inertia;        /* n  9n */
+    const float *gravity;                       /* 3n */
+    const float *friction, *restitution;        /* n  n  */
+    const uint32_t *kind;                       /* n  */
+} b2d_body_patch;
+int b2d_upload_bodies(b2d_world *w, uint32_t n, const uint32_t *body_ids, const b2d_body_patch *patch);
+
 /* n fixed steps: broadphase -> narrowphase -> islands -> solve/integrate (step_simulation semantics). */
 int b2d_step(b2d_world *w, uint32_t num_steps);
 /* Selected phases of ONE step, in stepper order (parity tests of individual phases). */
@@ -175,7 +189,37 @@ int b2d_debug_counters(b2d_world *w, void *out, uint32_t bytes);
  * device_out6 = {min xyz, max xyz} -- a DEVICE pointer (e.g. a buffer owned by the host framework) the adapter then all-gathers over
  * NCCL to detect island groups of different ranks coming within the broadphase margin of each other. */
 int b2d_device_bounds(b2d_world *w, float *device_out6);
-/* Blocks until all queued device work of this world has finished. */
+/* ---- Island hand-over between the worlds of different GPUs.  The host framework owns the
+ * transport (NCCL send/recv of DEVICE buffers); every payload is produced and consumed on the device.
+ *   b2d_set_entities   scene-global name per body (the entt::entity of the EnTT binding); default = local id.
+ *   b2d_island_halo    update_island_aabbs (src/edyn/sys/update_aabbs.cpp:106-138) on the device, then the islands whose
+ *                      AABB, inflated by the manifold separation threshold, reaches into the box of a peer in peer_mask
+ *                      are appended to device_records: 8 words each {min xyz, max xyz, island label, self}.
+ *                      device_boxes: nboxes x 6 floats (the all-gathered b2d_device_bounds of all ranks).
+ *   b2d_handover_plan  device_records = the halo records of ALL ranks concatenated in rank order, [my_begin, my_end)
+ *                      being this world's.  An island that touches an island of a lower rank moves there, whole
+ *                      (merge_islands: "move into the other island", src/edyn/simulation/island_manager.cpp:297-350).
+ *                      counts: nranks x 4 = bodies, manifolds, joints, exclusions leaving for each rank (host array).
+ *   b2d_handover_pack  everything rank dst needs to continue those islands -- body components with their current state,
+ *                      manifolds with points, lifetimes and warm-start impulses, joints, exclusions, all named by
+ *                      entity -- into device_blob (b2d_handover_bytes(counts + 4 * dst) bytes); the local copies are
+ *                      destroyed (b2d_remove_bodies semantics).
+ *   b2d_handover_unpack  appends a received blob; counts_out (4 words, may be NULL) = what it held. */
+int b2d_set_entities(b2d_world *w, uint32_t first_body, uint32_t n, const uint32_t *entity);
+int b2d_download_entities(b2d_world *w, uint32_t *entity);
+int b2d_island_halo(b2d_world *w, const float *device_boxes, uint32_t nboxes, uint32_t self, uint64_t peer_mask,
+                    void *device_records, uint32_t capacity, uint32_t *device_count);
+int b2d_handover_plan(b2d_world *w, const void *device_records, uint32_t my_begin, uint32_t my_end, uint32_t nranks,
+                      uint32_t *counts);
+uint64_t b2d_handover_bytes(const uint32_t *counts4);
+int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t capacity);
+int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, uint32_t *counts_out);
+
+/* Per-kernel CUDA-event timing of the velocity solve and the integrator (b2d_get_stats).  On (default): a step is
+ * replayed as three CUDA graphs with the events in between; off: as one graph. */
+int b2d_set_timing(b2d_world *w, int enabled);
+/* Blocks until all queued device work of this world has finished; device-side overflow flags (b2d_stats.error_flags)
+ * come back as B2D_ERR_CAPACITY / B2D_ERR_UNSUPPORTED / B2D_ERR_CUDA with the text in b2d_last_error. */
 int b2d_sync(b2d_world *w);
 /* The CUDA stream (cudaStream_t) the world launches on, for event timing by the caller. */
 void *b2d_stream(b2d_world *w);
