@@ -3,20 +3,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2d|reference] [--workload NAME]
 
-A "step" is one fixed simulation step (broadphase -> narrowphase -> islands -> solve -> integrate) over the
-whole scene.  N = 1 runs BASELINE.json's 262 144-body mixed pile (config 4, the one the >=10x / >=40 % targets
-are quoted on); N > 1 is weak scaling: every rank owns an independent island group of the same size (islands
-shard with no data-path collective) and `value` is total dynamic bodies x steps / max-over-ranks time.
+A "step" is one fixed simulation step (broadphase -> narrowphase -> islands -> solve -> integrate) of the whole scene.
+
+Workload (same at every N, so the driver's 1 -> 8 comparison is a STRONG-scaling one): BASELINE.json's config 5,
+`chains_1048576` = 262 144 four-link hinge chains (1 048 576 bodies) resting on a plane -- the config the >= 6x
+1 -> 8 target is quoted on.
+  N = 1   the whole scene on one GPU.  The same line carries `workloads`: the other BASELINE configs at 1 GPU
+          (`mixed_262144` -- the config the >= 10x CPU / >= 40 % roofline targets are quoted on --, `boxes_4096`,
+          `spheres_65536`), each with its own value / e2e / roofline / cpu_baseline.
+  N > 1   ONE scene, islands partitioned over the ranks (edyn_b200.dist.DeviceShardedWorld): every step each rank steps
+          its islands, reduces the box of its bodies on the device, all-gathers the N boxes over NCCL (24 B per rank) and
+          tests them; boxes within the broadphase margin trigger the island hand-over (device blobs over NCCL send/recv).
+          One hand-over is forced inside the timed region: after the first timed step every rank r > 0 shoves its first
+          column of chains into rank r-1's territory; `config.handover` reports what moved.
 
 Keys beyond the base contract:
-  roofline      dominant kernel (k_solve): algorithmic bytes (388 B per contact point per velocity iteration,
-                544 B per hinge per iteration, + 0.75 pass for the warm start) / mean CUDA-event
-                duration of that kernel over the timed steps, against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample (rank 0, N = 1 only).
+  roofline      velocity-solve kernel: algorithmic bytes (388 B per contact point per velocity iteration, 544 B per hinge
+                per iteration, + 0.75 pass for the warm start) / mean CUDA-event duration of that
+                kernel over the timed steps, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the oracle port timed on this box's host cores (rank 0, N = 1 only) on the same settled state.
   e2e           same metric through the C ABI with HOST buffers: every step uploads the body state from pinned
                 host memory (b2d_upload_state), steps, and downloads it again (b2d_download_state).
 --impl reference times the reference's CPU path (the oracle port: the reference stepper itself needs EnTT,
-which this image lacks -- DESIGN.md section 6) on a bounded sample of the same workload.
+which this image lacks -- DESIGN.md section 6) on the SAME workload with all host threads.
 """
 import argparse
 import json
@@ -31,10 +40,14 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SETTLE_STEPS = 150            # untimed: lets the dropped pile come to rest so contact counts are stationary
+SETTLE_STEPS = 150            # untimed: lets the dropped bodies come to rest so contact counts are stationary
 BYTES_PER_POINT_ITER = 388
 BYTES_PER_HINGE_ITER = 544
 BYTES_PER_BODY_INTEGRATE = 276
+DEFAULT_WORKLOAD = "chains_1048576"
+OTHER_WORKLOADS = ["mixed_262144", "boxes_4096", "spheres_65536"]
+# manifold capacity per body (AABB-overlap pairs incl. those without points), measured high-water marks x 1.3
+MANIFOLDS_PER_BODY = {"mixed_262144": 9.0, "boxes_4096": 6.0, "spheres_65536": 7.0, "chains_1048576": 2.0}
 
 
 def make_scene(name, scale=1.0):
@@ -50,6 +63,10 @@ def make_scene(name, scale=1.0):
         k = max(2, int(round(512 * scale ** 0.5)))
         return E.scenes.hinge_chains(k, k)
     raise SystemExit(f"unknown workload {name}")
+
+
+def capacity(name, n_bodies):
+    return max(4096, int(MANIFOLDS_PER_BODY.get(name, 10.0) * n_bodies))
 
 
 def peaks():
@@ -76,7 +93,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(0.1)
 
     def start(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -94,8 +111,7 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def oracle_from_device(scene, w, threads):
-    """Oracle world holding the device's current (settled) state, contacts included."""
+def make_oracle(scene, threads):
     from oracle import oracle as O
     o = O.OracleWorld(vel_iters=scene["settings"]["velocity_iterations"], pos_iters=scene["settings"]["position_iterations"], threads=threads)
     o.add_bodies(scene["bodies"])
@@ -104,6 +120,12 @@ def oracle_from_device(scene, w, threads):
         o.add_hinges(h["a"], h["b"], h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
     if scene["exclusions"] is not None:
         o.add_exclusions(*scene["exclusions"])
+    return o
+
+
+def oracle_from_device(scene, w, threads):
+    """Oracle world holding the device's current (settled) state, contacts included."""
+    o = make_oracle(scene, threads)
     st = w.download_state(aabb=False)
     o.set_state(st["pos"], st["orn"], st["linvel"], st["angvel"])
     c = w.contacts()
@@ -111,136 +133,115 @@ def oracle_from_device(scene, w, threads):
     return o
 
 
+# ---------------------------------------------------------------------------------------------------------- CPU arm
+
+def reference_one(args, name, steps, warmup, settle, budget_s):
+    """The CPU path (oracle port, all host threads) on the full workload `name`.  If the untimed settle would blow the
+    time budget the settled state is approached with fewer settle steps and the line says so."""
+    cores = os.cpu_count() or 1
+    scene = make_scene(name, args.scale)
+    o = make_oracle(scene, cores)
+    t0 = time.perf_counter()
+    o.step(1)
+    per_step = time.perf_counter() - t0
+    # keep the whole run inside the budget: settle as far as the budget allows (the dropped scenes are at rest long
+    # before 150 steps; chains start 5 cm above the plane)
+    n_settle = int(max(10, min(settle, (budget_s - per_step * (warmup + steps)) / max(per_step, 1e-6) - 1)))
+    o.step(n_settle)
+    for _ in range(warmup):
+        o.step(1)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    value = scene["dynamic"] * steps / dt
+    sample = f"{scene['name']}: all {scene['dynamic']} dynamic bodies, same generator and settings as the device arm, " \
+             f"{1 + n_settle} untimed settle steps, {steps} timed steps, {cores} threads (broadphase queries, narrowphase, per-island solve)"
+    return scene, value, dt, sample, cores
+
+
 def run_reference(args):
-    """Reference arm: the CPU path (oracle port, all host threads) on a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    cores = os.cpu_count() or 1
-    scale = args.ref_scale
-    scene = make_scene(args.workload, scale)
-    o = O.OracleWorld(vel_iters=scene["settings"]["velocity_iterations"], pos_iters=scene["settings"]["position_iterations"], threads=cores)
-    o.add_bodies(scene["bodies"])
-    if scene["hinges"]:
-        h = scene["hinges"]
-        o.add_hinges(h["a"], h["b"], h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
-    if scene["exclusions"] is not None:
-        o.add_exclusions(*scene["exclusions"])
-    o.step(args.ref_settle)                      # untimed settle, like the device arm
-    for _ in range(args.warmup):
-        o.step(1)
-    t0 = time.perf_counter()
-    o.step(args.steps)
-    dt = time.perf_counter() - t0
-    value = scene["dynamic"] * args.steps / dt
-    sample = f"{scene['name']} ({scene['dynamic']} dynamic bodies, same generator and settings as the device arm, " \
-             f"{args.ref_settle} settle steps), {args.steps} timed steps"
+    scene, value, dt, sample, cores = reference_one(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget)
     line = {"impl": "reference", "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}", "scene": scene["name"],
+                       "dynamic_bodies": scene["dynamic"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_device(args):
+# ---------------------------------------------------------------------------------------------------------- device arm
+
+def solver_roofline(st, scene, step_ms):
+    peak, peak_src = peaks()
+    iters = scene["settings"]["velocity_iterations"]
+    algo_bytes = (iters + 0.75) * (BYTES_PER_POINT_ITER * st["contact_points"] + BYTES_PER_HINGE_ITER * st["hinges"])
+    achieved = algo_bytes / (st["solve_ms"] * 1e-3) / 1e9 if st["solve_ms"] > 0 else 0.0
+    n_dyn = scene["dynamic"]
+    integ_gbs = BYTES_PER_BODY_INTEGRATE * n_dyn / (st["integrate_ms"] * 1e-3) / 1e9 if st["integrate_ms"] > 0 else 0.0
+    return {"bound": "hbm", "kernel": "velocity solve (k_solve_df / k_solve_tiles)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+            "kernel_ms": st["solve_ms"], "kernel_share_of_step": st["solve_ms"] / step_ms if step_ms > 0 else None,
+            "integrate": {"kernel": "k_integrate", "achieved": integ_gbs, "frac": integ_gbs / peak, "kernel_ms": st["integrate_ms"]}}
+
+
+def traffic_for(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel per launch from the committed ncu capture."""
+    for fn in ("traffic_r02.json", "traffic_r01.json"):
+        p = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(p):
+            tj = json.load(open(p))
+            ent = tj.get(name) if isinstance(tj.get(name), dict) else (tj if tj.get("workload") == name else None)
+            if ent and "k_solve" in ent:
+                return ent["k_solve"]["dram_bytes_read"] + ent["k_solve"]["dram_bytes_write"]
+    return None
+
+
+def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_clocks):
+    """One workload, whole scene on one GPU: device-resident value, e2e through host buffers, roofline, CPU baseline."""
     import torch
     import edyn_b200 as E
-
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world_size > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    scene = make_scene(args.workload, args.scale)
+    scene = make_scene(name, args.scale)
     n_dyn = scene["dynamic"]
-    if world_size > 1:
-        # weak scaling: rank r owns an island group of the same size, placed side by side along x
-        b = scene["bodies"]
-        p = b["pos"][b["kind"] == 0]
-        stride_x = float(p[:, 0].max() - p[:, 0].min()) + 20.0
-        b["pos"] = b["pos"].copy()
-        b["pos"][:, 0] += np.float32(rank * stride_x)
-    w = E.scenes.build_world(scene, device=local_rank)
+    w = E.scenes.build_world(scene, device=local_rank, max_manifolds=capacity(name, len(scene["bodies"]["kind"])))
     w.step(SETTLE_STEPS)
     w.sync()
     stream = torch.cuda.ExternalStream(w.stream, device=local_rank)
-    # cross-GPU AABB exchange (SURVEY 8e): per step, bounds of the owned islands reduced on the device, all-gathered
-    # over NCCL, overlap-tested on the device; the hit counter is read once after the timed region
-    bounds = torch.zeros(6, dtype=torch.float32, device="cuda")
-    gathered = torch.zeros(world_size, 6, dtype=torch.float32, device="cuda")
-    hits = torch.zeros((), dtype=torch.int64, device="cuda")
-    margin = 0.026
-
-    def exchange():
-        if dist is None:
-            return
-        w.device_bounds(bounds.data_ptr())
-        torch.cuda.current_stream().wait_stream(stream)
-        dist.all_gather_into_tensor(gathered, bounds)
-        lo, hi = gathered[:, None, :3], gathered[:, None, 3:]
-        ov = ((lo - margin <= hi.transpose(0, 1)) & (hi + margin >= lo.transpose(0, 1))).all(dim=2)
-        hits.add_(ov.sum() - world_size)               # minus the diagonal
-        stream.wait_stream(torch.cuda.current_stream())
-    st0 = w.stats()
-    if st0["error_flags"]:
-        raise SystemExit(f"device error flags {st0['error_flags']} after settling")
-
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    # ---------------- device-resident throughput ("value")
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         w.step(1)
-        exchange()
-    barrier()
     w.sync()
     w.reset_timers()
     launches0 = w.stats()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         w.step(1)
-        exchange()
     e1.record(stream)
     w.sync()
-    barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     st = w.stats()
     launches = st["kernel_launches"] - launches0 - 1        # minus the stats kernel itself
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_bodies = n_dyn * world_size
-    value = total_bodies * args.steps / (ms_max * 1e-3)
+    value = n_dyn * steps / (ms * 1e-3)
 
-    # ---------------- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers
     n_all = w.num_bodies
     pinned = {k: torch.empty((n_all, d), dtype=torch.float32).pin_memory() for k, d in (("pos", 3), ("orn", 4), ("linvel", 3), ("angvel", 3))}
     host = {k: v.numpy() for k, v in pinned.items()}
     w.download_state(aabb=False, out=host)
-    e2e_steps = max(3, min(args.steps, 50))
+    e2e_steps = max(3, min(steps, 50))
     for _ in range(3):
         w.upload_state(host["pos"], host["orn"], host["linvel"], host["angvel"])
         w.step(1)
         w.download_state(aabb=False, out=host)
-    barrier()
+    w.sync()
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(e2e_steps):
@@ -249,81 +250,220 @@ def run_device(args):
         w.download_state(aabb=False, out=host)         # blocks until the step's results are on the host
     e1.record(stream)
     w.sync()
-    barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_bodies * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_value = n_dyn * e2e_steps / (e2e_ms * 1e-3)
     bytes_state = n_all * 13 * 4
 
-    # ---------------- roofline of the dominant kernel
-    peak, peak_src = peaks()
-    iters = scene["settings"]["velocity_iterations"]
-    algo_bytes = (iters + 0.75) * (BYTES_PER_POINT_ITER * st["contact_points"] + BYTES_PER_HINGE_ITER * st["hinges"])
-    achieved = algo_bytes / (st["solve_ms"] * 1e-3) / 1e9 if st["solve_ms"] > 0 else 0.0
-    integ_gbs = BYTES_PER_BODY_INTEGRATE * n_dyn / (st["integrate_ms"] * 1e-3) / 1e9 if st["integrate_ms"] > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and args.scale == 1.0:
-        tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload:
-            traffic = tj["k_solve"]["dram_bytes_read"] + tj["k_solve"]["dram_bytes_write"]     # ncu --set full capture, per launch
-    roofline = {"bound": "hbm", "kernel": "k_solve_df", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_ms": st["solve_ms"], "kernel_share_of_step": st["solve_ms"] / (ms / args.steps),
-                "integrate": {"kernel": "k_integrate", "achieved": integ_gbs, "frac": integ_gbs / peak, "kernel_ms": st["integrate_ms"]}}
+    roofline = solver_roofline(st, scene, ms / steps)
+    roofline["traffic"] = traffic_for(name) if args.scale == 1.0 else None
 
-    # ---------------- CPU baseline on a bounded sample (rank 0, N = 1)
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu:
+    if cpu_seconds > 0:
         cores = os.cpu_count() or 1
         o = oracle_from_device(scene, w, cores)
         o.step(1)                                   # untimed: first touch
         nsteps, t0 = 0, time.perf_counter()
-        while nsteps < 2 or (time.perf_counter() - t0 < args.cpu_seconds and nsteps < 50):
+        while nsteps < 3 or (time.perf_counter() - t0 < cpu_seconds and nsteps < 200):
             o.step(1)
             nsteps += 1
         dt = time.perf_counter() - t0
         cpu = {"value": n_dyn * nsteps / dt, "unit": "body-steps/s", "cores": cores, "kind": "port",
                "sample": f"{nsteps} steps of the same settled {scene['name']} state downloaded from the device "
-                         f"(oracle/ CPU restatement of stepper_sequential, narrowphase + per-island solve on {cores} threads)"}
+                         f"(oracle/ CPU restatement of stepper_sequential; broadphase queries, narrowphase and per-island solve on {cores} threads)"}
+    if st["error_flags"]:
+        raise SystemExit(f"{name}: device error flags {st['error_flags']}")
+    res = {"value": value, "unit": "body-steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "config": {"workload": name if args.scale == 1.0 else f"{name} x{args.scale}", "scene": scene["name"], "dynamic_bodies": n_dyn,
+                      "velocity_iterations": scene["settings"]["velocity_iterations"], "position_iterations": scene["settings"]["position_iterations"],
+                      "settle_steps": SETTLE_STEPS, "manifolds": st["manifolds"], "contact_points": st["contact_points"], "hinges": st["hinges"],
+                      "contact_colors": st["contact_colors"], "islands": st["islands"],
+                      "l2": "inputs change every step and the per-step working set (rows + manifolds + bodies) exceeds the 126 MB L2 for the "
+                            "two large configs; no explicit flush"},
+           "gpu_launches": int(launches),
+           "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state, "steps": e2e_steps},
+           "roofline": roofline}
+    if cpu:
+        res["cpu_baseline"] = cpu
+    if clocks:
+        res["clocks"] = clocks
+    w.close()
+    return res
 
+
+def run_single(args, local_rank):
+    top = measure_single(args, args.workload, local_rank, args.steps, args.warmup, 0 if args.no_cpu else args.cpu_seconds, True)
+    line = {"metric": "body-steps/sec", "value": top["value"], "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(top["config"], parallelism="1 GPU: whole scene in one device world"),
+            "clocks": top.get("clocks"), "gpu_launches": top["gpu_launches"], "e2e": top["e2e"], "roofline": top["roofline"]}
+    if "cpu_baseline" in top:
+        line["cpu_baseline"] = top["cpu_baseline"]
+    if args.workload == DEFAULT_WORKLOAD and args.scale == 1.0 and not args.only:
+        subs = {}
+        for name in OTHER_WORKLOADS:
+            subs[name] = measure_single(args, name, local_rank, args.steps, args.warmup, 0 if args.no_cpu else args.cpu_seconds / 2, False)
+        line["workloads"] = subs
+    print(json.dumps(line), flush=True)
+
+
+def run_sharded(args, world_size, rank, local_rank):
+    """N > 1: ONE scene, islands partitioned over the ranks, strong scaling."""
+    import torch
+    import torch.distributed as dist
+    import edyn_b200 as E
+    from edyn_b200 import dist as D
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    scene = make_scene(args.workload, args.scale)
+    n_total = scene["dynamic"]
+    labels = D.device_islands(scene, device=local_rank)            # island_manager's connected components, computed on the device
+    comm = D.TorchComm(dist, rank, world_size)
+    n_all = len(scene["bodies"]["kind"])
+    sw = D.DeviceShardedWorld(scene, rank, world_size, comm, device=local_rank, labels=labels, slack=2.0 / world_size,
+                              max_manifolds=capacity(args.workload, int(n_all * (1.0 / world_size + 2.0 / world_size))))
+    w = sw.world
+    owner = sw.owner
+    sw.step(SETTLE_STEPS)
+    w.sync()
+    stream = sw.ext
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # the forced hand-over: rank r > 0 shoves its first column of islands (lowest x) towards rank r-1
+    push_ids = np.zeros(0, np.uint32)
+    if rank > 0 and sw.local["dynamic"] > 0:
+        b = sw.local["bodies"]
+        dyn = np.where(b["kind"] == 0)[0]
+        x = b["pos"][dyn, 0]
+        push_ids = dyn[x < x.min() + 2.5].astype(np.uint32)          # one column of chains spans 2.1 in x, columns are 3.5 apart
+    push_v = np.zeros((len(push_ids), 3), np.float32)
+    push_v[:, 0] = -6.0
+
+    for _ in range(args.warmup):
+        sw.step(1)
+    barrier()
+    w.sync()
+    w.reset_timers()
+    launches0 = w.stats()["kernel_launches"]
+    bytes0 = comm.bytes_sent
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms = []
+    t_prev = time.perf_counter()
+    e0.record(stream)
+    for k in range(args.steps):
+        if k == 1 and len(push_ids):
+            w.upload_bodies(push_ids, linvel=push_v)
+        sw.step(1)
+        t_now = time.perf_counter(); step_ms.append((t_now - t_prev) * 1e3); t_prev = t_now
+    e1.record(stream)
+    w.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st = w.stats()
+    launches = st["kernel_launches"] - launches0 - 1
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_total * args.steps / (ms_max * 1e-3)
+    moved = torch.tensor([sw.migrated_in, sw.migrated_out, sw.handover_rounds, sw.halo_checks, sw.dynamic, comm.bytes_sent - bytes0], dtype=torch.int64, device="cuda")
+    allmoved = [torch.zeros_like(moved) for _ in range(world_size)]
+    dist.all_gather(allmoved, moved)
+    allmoved = torch.stack(allmoved).cpu().numpy()
+
+    # ---- end to end: host buffers in and out every step on every rank
+    n_loc = w.num_bodies
+    pinned = {k: torch.empty((n_loc, d), dtype=torch.float32).pin_memory() for k, d in (("pos", 3), ("orn", 4), ("linvel", 3), ("angvel", 3))}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    w.download_state(aabb=False, out=host)
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        w.upload_state(host["pos"], host["orn"], host["linvel"], host["angvel"])
+        sw.step(1)
+        w.download_state(aabb=False, out=host)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        w.upload_state(host["pos"], host["orn"], host["linvel"], host["angvel"])
+        sw.step(1)
+        w.download_state(aabb=False, out=host)
+    e1.record(stream)
+    w.sync()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(e0.elapsed_time(e1), wall_ms), float(n_loc)], dtype=torch.float64, device="cuda")
+    tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    e2e_value = n_total * e2e_steps / (float(tm[0].item()) * 1e-3)
+    bytes_state = int(ts[1].item()) * 13 * 4
+
+    if st["error_flags"]:
+        raise SystemExit(f"rank {rank}: device error flags {st['error_flags']}")
     if rank == 0:
-        line = {"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world_size, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}",
-                           "scene": scene["name"], "dynamic_bodies_per_gpu": n_dyn,
-                           "velocity_iterations": iters, "position_iterations": scene["settings"]["position_iterations"],
-                           "settle_steps": SETTLE_STEPS, "manifolds": st["manifolds"], "contact_points": st["contact_points"],
-                           "hinges": st["hinges"], "contact_colors": st["contact_colors"], "islands": st["islands"],
-                           "parallelism": f"islands sharded over {world_size} GPU(s); per-step NCCL all-gather of island-group bounds "
-                                          f"(24 B/rank), {int(hits.item())} cross-rank overlaps seen",
-                           "l2": "working set (rows + bodies) exceeds the 126 MB L2; no explicit flush"},
+        local_scene = dict(scene, dynamic=sw.dynamic)
+        roofline = solver_roofline(st, local_scene, ms / args.steps)
+        roofline["note"] = "rank 0's velocity-solve kernel over rank 0's constraints"
+        srt = sorted(step_ms)
+        line = {"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}", "scene": scene["name"],
+                           "dynamic_bodies": n_total, "dynamic_bodies_rank0": int(sw.dynamic),
+                           "velocity_iterations": scene["settings"]["velocity_iterations"], "position_iterations": scene["settings"]["position_iterations"],
+                           "settle_steps": SETTLE_STEPS, "manifolds_rank0": st["manifolds"], "contact_points_rank0": st["contact_points"], "hinges_rank0": st["hinges"],
+                           "islands_rank0": st["islands"],
+                           "parallelism": f"ONE scene, islands (connected components computed on the device) partitioned over {world_size} GPUs by x-slabs of equal "
+                                          "body count; per step: b2d_step + device reduction of the rank box + NCCL all-gather of 24 B/rank (the limiting "
+                                          "collective: latency-bound, its result is read by the host before the next broadphase); island hand-over as device "
+                                          "blobs over NCCL send/recv when boxes touch",
+                           "handover": {"bodies_in_per_rank": allmoved[:, 0].tolist(), "bodies_out_per_rank": allmoved[:, 1].tolist(),
+                                        "rounds_per_rank": allmoved[:, 2].tolist(), "halo_checks_per_rank": allmoved[:, 3].tolist(),
+                                        "dynamic_bodies_per_rank_after": allmoved[:, 4].tolist(),
+                                        "collective_payload_bytes_per_rank_timed_region": allmoved[:, 5].tolist(),
+                                        "forced": "after timed step 1 every rank r > 0 gives its first column of chains -6 m/s in x (b2d_upload_bodies)",
+                                        "rank0_host_ms_per_step": {"median": srt[len(srt) // 2], "max": srt[-1]},
+                                        "rank0_handover_round_ms": sw.handover_ms},
+                           "l2": "per-step working set per rank exceeds L2 at N <= 4 (rows + manifolds + bodies); inputs change every step; no explicit flush"},
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,
-                        "steps": e2e_steps},
+                "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state, "steps": e2e_steps},
                 "roofline": roofline}
-        if cpu:
-            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    sw.close()
+    dist.destroy_process_group()
+
+
+def run_device(args):
+    import torch  # noqa: F401
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        run_sharded(args, world_size, rank, local_rank)
+    else:
+        torch.cuda.set_device(local_rank)
+        run_single(args, local_rank)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2d", choices=["b2d", "reference"])
-    ap.add_argument("--workload", default="mixed_262144")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--only", action="store_true", help="N = 1: skip the `workloads` sub-results of the other BASELINE configs")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only; invalid as a bench value)")
-    ap.add_argument("--ref-scale", type=float, default=1.0 / 16, help="reference arm: fraction of the workload simulated on the CPU")
     ap.add_argument("--ref-settle", type=int, default=SETTLE_STEPS)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: seconds the untimed settle + timed steps may take")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

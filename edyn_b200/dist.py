@@ -12,6 +12,8 @@ that reach into the lower rank's box move there (`ShardedWorld.migrate`), so an 
 Everything here is host/plumbing code: numpy for the partitioning, torch.distributed (NCCL on GPUs, gloo in the CPU
 tests) for the exchange.  The simulation itself runs in libb2d.so.
 """
+import time
+
 import numpy as np
 
 from .rigidbody import DYNAMIC, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_NONE, SHAPE_PLANE, SHAPE_SPHERE
@@ -378,6 +380,17 @@ class TorchComm:
         self.bytes_sent += t.numel() * t.element_size()
         return out
 
+    def warmup(self, device):
+        """NCCL sets its point-to-point channels up lazily (hundreds of milliseconds on first use): touch every pair once
+        so a hand-over inside a timed region pays for the transfer only."""
+        import torch
+        sent = self.bytes_sent
+        send = {p: torch.zeros(16, dtype=torch.uint8, device=device) for p in range(self.world_size) if p != self.rank}
+        self.exchange(send, {p: 16 for p in send}, device)
+        self.all_gather(torch.zeros(8, dtype=torch.float32, device=device))
+        torch.cuda.synchronize()
+        self.bytes_sent = sent
+
     def exchange(self, send, recv_bytes, device):
         """send: {dst: uint8 tensor}; recv_bytes: {src: nbytes}.  Grouped ncclSend / ncclRecv."""
         import torch
@@ -406,6 +419,9 @@ class ThreadComm:
     def __init__(self, shared, rank):
         self.s, self.rank, self.world_size = shared, rank, shared.world_size
         self.bytes_sent = 0
+
+    def warmup(self, device):
+        pass
 
     def all_gather(self, t):
         import torch
@@ -476,6 +492,9 @@ class DeviceShardedWorld:
         self.halo_checks = 0
         self.dynamic = int(self.local["dynamic"])           # dynamic bodies this rank owns right now
         self.last_pairs = []
+        self.handover_ms = []                               # host wall time of every hand-over round (plan .. unpack)
+        with torch.cuda.stream(self.ext):
+            comm.warmup(dev)
 
     def close(self):
         self.world.close()
@@ -493,10 +512,12 @@ class DeviceShardedWorld:
             pairs = overlapping_ranks(gh)
             while pairs:
                 self.halo_checks += 1
+                t0 = time.perf_counter()
                 moved = self._handover(pairs, g)
                 if moved == 0:
                     break
                 self.handover_rounds += 1
+                self.handover_ms.append((time.perf_counter() - t0) * 1e3)
                 g, gh = self._gather_bounds()
                 pairs = overlapping_ranks(gh)
         self.last_pairs = pairs

@@ -220,14 +220,18 @@ void World::broadphase() {
     }
 
     const vec3 off = vec3{1, 1, 1} * -BREAKING_THRESHOLD;      // m_aabb_offset, broadphase.hpp:15
-    std::vector<uint32_t> cand;
     // Awake procedural bodies issue the queries (broadphase.cpp:183).  EnTT views are believed to iterate
     // newest-first: descending index.  This fixes which body becomes body[0].
-    for (uint32_t ii = n; ii-- > 0;) {
+    // The queries themselves are independent and run on all threads (collide_tree_async, broadphase.cpp:157-175, stores the
+    // hits per entity); the manifolds are then created serially in view order (finish_async_update, :197-214), because
+    // a pair found by an earlier query must not be created again by its partner's.
+    std::vector<std::vector<uint32_t>> hits(n);
+    parallel_for(threads, n, [&](size_t idx) {
+        const uint32_t ii = uint32_t(idx);
         const Body &A = bodies[ii];
-        if (!A.awake() || A.sh.kind == SH_NONE) continue;         // view<AABB, procedural_tag>(exclude_sleeping_disabled)
+        if (!A.awake() || A.sh.kind == SH_NONE) return;          // view<AABB, procedural_tag>(exclude_sleeping_disabled)
         const aabb q = inset(A.bb, off);
-        cand.clear();
+        std::vector<uint32_t> &cand = hits[ii];
         auto test = [&](uint32_t j) {
             if (j == ii) return;
             if (!should_collide(ii, j)) return;
@@ -251,7 +255,10 @@ void World::broadphase() {
             if (px != py) return px;
             return x < y;
         });
-        for (uint32_t j : cand) {                       // make_contact_manifold, util/constraint_util.cpp:67-102
+    });
+    for (uint32_t ii = n; ii-- > 0;) {
+        for (uint32_t j : hits[ii]) {                   // make_contact_manifold, util/constraint_util.cpp:67-102
+            if (manifold_map.count(key(ii, j))) continue;        // made a moment ago by the partner's (earlier) query
             Manifold m{}; m.a = ii; m.b = j; m.num = 0;
             manifold_map[key(ii, j)] = uint32_t(manifolds.size());
             manifolds.push_back(m);

@@ -176,7 +176,8 @@ def test_collision_filter_truth_table_device(gpu, E, O):
     cases = [  # (groupA, maskA, groupB, maskB, collide?)   None = no collision_filter component
         (1, 1, 1, 1, True), (1, 2, 2, 1, True), (1, 2, 1, 2, False), (1, 1, 2, 2, False), (3, 4, 4, 3, True),
         (None, None, 1, 1, True), (None, None, 0, 1, False), (None, None, 1, 0, False), (2, 2, None, None, True),
-        (0xFFFFFFFFFFFFFFFF, 1, 1, 0x8000000000000000, False), (0x8000000000000000, 1, 1, 0x8000000000000000, True),
+        (0xFFFFFFFFFFFFFFFF, 1, 1, 0x8000000000000000, True), (0x8000000000000000, 1, 2, 0x8000000000000000, False),
+        (0x8000000000000000, 1, 1, 0x8000000000000000, True),
     ]
     for ga, ma, gb, mb, want in cases:
         defs = [RigidBodyDef(position=(0.0, 0, 0), mass=1.0, shape=box_shape((0.2, 0.2, 0.2))),
@@ -218,9 +219,9 @@ def _rank_body(rank, N, comm, scene_name, steps, q, device):
             col = np.where((sw.owner[ent] == 1) & (b["pos"][ent, 0] < b["pos"][sw.owner == 1, 0].min() + 2.9))[0]
             v = np.zeros((len(col), 3), f32); v[:, 0] = -6.0
             sw.world.upload_bodies(col.astype(np.uint32), linvel=v)
-        pairs = sw.step(1)
-        if pairs and first_hit is None:
-            first_hit = k
+        sw.step(1)
+        if sw.halo_checks and first_hit is None:
+            first_hit = k                        # first step whose rank boxes came within the broadphase margin
     w = sw.world
     st = w.download_state()
     ent = w.entities()
