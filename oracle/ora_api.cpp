@@ -192,6 +192,15 @@ void ora_get_hinge_impulses(void *h, float *imp5) {
     }
 }
 
+// Warm-start impulses of the joints (store_applied_impulses, hinge_constraint.cpp:215-259), e.g. taken from the device.
+void ora_set_hinge_impulses(void *h, const float *imp5) {
+    World &w = *static_cast<World *>(h);
+    for (size_t i = 0; i < w.hinges.size(); ++i) {
+        for (int k = 0; k < 3; ++k) w.hinges[i].imp_lin[k] = imp5[i * 5 + k];
+        for (int k = 0; k < 2; ++k) w.hinges[i].imp_hinge[k] = imp5[i * 5 + 3 + k];
+    }
+}
+
 // Inject the Gauss-Seidel order the device used: hinge indices, then manifold body pairs.
 void ora_set_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32_t nm, const uint32_t *pairs) {
     World &w = *static_cast<World *>(h);

@@ -273,6 +273,7 @@ class OracleWorld:
         self.l = lib()
         self.h = C.c_void_p(self.l.ora_create(C.c_float(dt), vel_iters, pos_iters, threads))
         self.dt = dt
+        self.num_hinges = 0
 
     def __del__(self):
         try:
@@ -303,6 +304,7 @@ class OracleWorld:
         n = len(a)
         arrs = [_arr(a, _u), _arr(b, _u), _arr(pivotA, _f, (n, 3)), _arr(pivotB, _f, (n, 3)), _arr(axisA, _f, (n, 3)),
                 _arr(axisB, _f, (n, 3))]
+        self.num_hinges += n
         return self.l.ora_add_hinges(self.h, C.c_uint32(n), *[_ptr(x) for x in arrs])
 
     def remove_bodies(self, ids):
@@ -386,6 +388,16 @@ class OracleWorld:
     def should_collide(self, a, b):
         self.l.ora_should_collide.restype = C.c_int
         return bool(self.l.ora_should_collide(self.h, C.c_uint32(a), C.c_uint32(b)))
+
+    def hinge_impulses(self):
+        imp = np.zeros((max(1, self.num_hinges), 5), _f)
+        self.l.ora_get_hinge_impulses(self.h, _ptr(imp))
+        return imp[:self.num_hinges]
+
+    def set_hinge_impulses(self, imp5):
+        imp = _arr(imp5, _f, (self.num_hinges, 5))
+        if self.num_hinges:
+            self.l.ora_set_hinge_impulses(self.h, _ptr(imp))
 
     def set_order(self, hinge_idx, pairs):
         h = _arr(hinge_idx, _u)
