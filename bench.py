@@ -430,7 +430,8 @@ def run_sharded(args, world_size, rank, local_rank):
                                         "collective_payload_bytes_per_rank_timed_region": allmoved[:, 5].tolist(),
                                         "forced": "after timed step 1 every rank r > 0 gives its first column of chains -6 m/s in x (b2d_upload_bodies)",
                                         "rank0_host_ms_per_step": {"median": srt[len(srt) // 2], "max": srt[-1]},
-                                        "rank0_handover_round_ms": sw.handover_ms},
+                                        "rank0_handover_round_ms": sw.handover_ms, "rank0_handover_phases_ms": sw.handover_phases,
+                                        "rank0_host_ms_each_step": [round(x, 3) for x in step_ms]},
                            "l2": "per-step working set per rank exceeds L2 at N <= 4 (rows + manifolds + bodies); inputs change every step; no explicit flush"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state, "steps": e2e_steps},

@@ -25,8 +25,8 @@ struct b2d_world {
     std::vector<void *> allocs;
     std::string error;
     int num_sms = 0;
-    int coop_blocks_color = 0, coop_blocks_solve = 0, coop_blocks_pos = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
-    bool barrier_solver = false;
+    int coop_blocks_color = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
+    int tile_blocks = 0, tile_pos_blocks = 0;       // grids of the island-tile kernels (CTAs loop over the tiles)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
     uint64_t launches = 0, steps = 0;
@@ -40,11 +40,14 @@ struct b2d_world {
     float max_extent = 0.0f;
     std::vector<uint32_t> large;
     std::vector<uint64_t> exclusions;
+    uint32_t xhash_capacity = 0, xhash_used = 0;      // device exclusion table: slots, keys inserted (stale ones included)
     bool contacts_dirty = false;
     uint64_t updates = 0;             // island updates so far (sleep timestamps)
     // broadphase classes: bounding diameter and kind per body (host mirror), re-derived lazily before the next step
     std::vector<float> diam; std::vector<unsigned char> isdyn;
     bool class_dirty = false, ehash_dirty = true, labels_stale = true;
+    // running figures of the classification so that a hand-over (a few arrivals / departures) does not re-walk every body
+    double class_sum = 0; uint64_t class_cnt = 0; float class_big = 1e30f; uint32_t class_new_first = 0; bool class_removed = false;
     std::vector<uint32_t> plan_counts;   // nranks x 4 of the current plan (bodies, manifolds, hinges, exclusions)
     // one step as CUDA graphs: [broadphase .. row preparation] [velocity solve, bracketed by the timing events]
     // [integration .. refresh].  Captured lazily, dropped whenever a host-side parameter of the sequence changes.
@@ -58,7 +61,10 @@ struct b2d_world {
     uint32_t plan_ranks = 0;
 };
 
-static void drop_graphs(b2d_world *w) {
+// The captured step no longer matches the world (counts, table pointers, grid pitch changed): re-capture before the next
+// replay.  The executable graphs are kept so that the re-capture can patch them in place (capture()).
+static void drop_graphs(b2d_world *w) { w->graph_valid = false; }
+static void destroy_graphs(b2d_world *w) {
     for (cudaGraphExec_t *g : {&w->gx_pre, &w->gx_solve, &w->gx_post, &w->gx_all}) if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
     w->graph_valid = false;
 }
@@ -141,6 +147,12 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.parent, NB) && dalloc(w, d.bmask, NB) && dalloc(w, d.jmask, NB) && dalloc(w, d.prop, NB) && dalloc(w, d.jprop, NB);
     ok = ok && dalloc(w, d.ckey, NM) && dalloc(w, d.ckey_s, NM) && dalloc(w, d.cidx, NM) && dalloc(w, d.cidx_s, NM);
     ok = ok && dalloc(w, d.hkey, NH) && dalloc(w, d.hkey_s, NH) && dalloc(w, d.hidx, NH) && dalloc(w, d.hidx_s, NH);
+    // island tiles: the census arrays are one allocation (zeroed together every step), so are the per-tile tables
+    d.max_tiles = (uint32_t)(((uint64_t)NB + NM + NH) / TILE_ISLAND_MAX + 64);
+    ok = ok && dalloc(w, d.isl_nb, 3 * (size_t)NB) && dalloc(w, d.swgt, NB) && dalloc(w, d.swsum, NB) && dalloc(w, d.btile, NB, 0xFF) && dalloc(w, d.bslot, NB, 0xFF);
+    d.isl_nm = d.isl_nb + NB; d.isl_nh = d.isl_nb + 2 * (size_t)NB;
+    ok = ok && dalloc(w, d.tile_nb, 5 * (size_t)d.max_tiles) && dalloc(w, d.tile_body, (size_t)d.max_tiles * TILE_CAP);
+    d.tile_c0 = d.tile_nb + d.max_tiles; d.tile_c1 = d.tile_c0 + d.max_tiles; d.tile_h0 = d.tile_c1 + d.max_tiles; d.tile_h1 = d.tile_h0 + d.max_tiles;
     ok = ok && dalloc(w, d.isl_err, NB) && dalloc(w, d.isl_done, NB);
     ok = ok && dalloc(w, d.hdr, NM) && dalloc(w, d.R0, 4 * (size_t)NM) && dalloc(w, d.R1, 4 * (size_t)NM) && dalloc(w, d.R2, 4 * (size_t)NM);
     ok = ok && dalloc(w, d.R3, 4 * (size_t)NM) && dalloc(w, d.IMP, 4 * (size_t)NM);
@@ -165,7 +177,8 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, COLOR_KEY_BITS, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
-    cub::DeviceRadixSort::SortPairs(nullptr, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)NH, 0, 8, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)NH, 0, COLOR_KEY_BITS, w->stream); need = std::max(need, t);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, d.swgt, d.swsum, (int)NB, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.hidx, d.hidx_s, (int)NH, w->stream); need = std::max(need, t);
     w->cub_tmp_bytes = need + 256;
     void *tmp = nullptr;
@@ -176,16 +189,19 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     if (ok && cudaMalloc(&st, w->stage_floats * sizeof(float)) != cudaSuccess) ok = false;
     w->stage = st; if (st) w->allocs.push_back(st);
 
-    // Persistent kernels: co-resident grid, a few CTAs per SM (barrier cost grows with the CTA count).
+    // Persistent kernels: co-resident grids.  The colouring kernel has a grid barrier per round (its cost grows with the
+    // CTA count): a few CTAs per SM.  The dataflow solve wants every resident warp it can get (latency hiding, no
+    // barrier cost per CTA).  The island-tile kernels need no co-residency: their CTAs loop over the tiles.
     int per_sm = 0, want = 2;
     if (const char *e = getenv("B2D_COOP_BLOCKS_PER_SM")) want = std::max(1, atoi(e));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, 256, 0); w->coop_blocks_color = std::max(1, std::min(per_sm, want)) * w->num_sms;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0); w->coop_blocks_solve = std::max(1, std::min(per_sm, want)) * w->num_sms;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position, 256, 0); w->coop_blocks_pos = std::max(1, std::min(per_sm, want)) * w->num_sms;
-    // the dataflow solve wants every resident warp it can get (latency hiding, no barrier cost per CTA)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df, B2D_SOLVE_THREADS, 0); w->coop_blocks_df = std::max(1, per_sm) * w->num_sms;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, B2D_POS_THREADS, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
-    if (const char *e = getenv("B2D_SOLVER")) w->barrier_solver = std::string(e) == "barrier";
+    cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SOLVE_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, TILE_CAP, TILE_SOLVE_SMEM); w->tile_blocks = std::max(1, per_sm) * w->num_sms;
+    cudaFuncSetAttribute(k_position_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_POS_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_tiles, TILE_CAP, TILE_POS_SMEM); w->tile_pos_blocks = std::max(1, per_sm) * w->num_sms;
+    if (const char *e = getenv("B2D_TILES")) if (atoi(e) == 0) d.max_tiles = 0;          // development: everything through the dataflow path
     if (const char *e = getenv("B2D_GRAPH")) w->use_graph = atoi(e) != 0;
 
     if (!ok || cudaStreamSynchronize(w->stream) != cudaSuccess) {
@@ -200,7 +216,7 @@ void b2d_destroy(b2d_world *w) {
     if (!w) return;
     cudaSetDevice(w->cfg.device);
     if (w->stream) cudaStreamSynchronize(w->stream);
-    drop_graphs(w);
+    destroy_graphs(w);
     for (void *p : w->allocs) cudaFree(p);
     if (w->ev_step0) cudaEventDestroy(w->ev_step0);
     if (w->ev_step1) cudaEventDestroy(w->ev_step1);
@@ -242,11 +258,20 @@ static float shape_diameter(uint32_t kind, const float *p) {
 // grid; planes and bodies much larger than the typical dynamic body (4 x the mean dynamic diameter of the WHOLE world,
 // however the bodies were batched) are kept in a brute-force list instead.  Runs before the first step after the body
 // population changed; results do not depend on the classification (the exact AABB tests decide), only speed does.
+static void class_add(b2d_world *w, float diam, bool dyn) {
+    w->diam.push_back(diam); w->isdyn.push_back(dyn ? 1 : 0);
+    if (dyn && diam > 0 && std::isfinite(diam)) { w->class_sum += diam; ++w->class_cnt; }
+}
+static void class_forget(b2d_world *w, uint32_t i) {
+    if (w->isdyn[i] && w->diam[i] > 0 && std::isfinite(w->diam[i])) { w->class_sum -= w->diam[i]; --w->class_cnt; }
+    w->diam[i] = 0.0f; w->isdyn[i] = 0;
+}
 static int reclassify(b2d_world *w) {
     Dev &d = w->d;
     double sum = 0; uint64_t cnt = 0;
     for (uint32_t i = 0; i < d.nbodies; ++i) if (w->isdyn[i] && w->diam[i] > 0 && std::isfinite(w->diam[i])) { sum += w->diam[i]; ++cnt; }
     const float big = cnt ? float(4.0 * sum / cnt) : 1e30f;
+    w->class_sum = sum; w->class_cnt = cnt; w->class_big = big; w->class_new_first = d.nbodies; w->class_removed = false;
     w->large.clear(); w->max_extent = 0.0f;
     for (uint32_t i = 0; i < d.nbodies; ++i) {
         const float dm = w->diam[i];
@@ -296,8 +321,7 @@ int b2d_add_bodies(b2d_world *w, const b2d_bodies *b, uint32_t *first_id) {
         if (dyn && (sk == B2D_SHAPE_SPHERE || sk == B2D_SHAPE_CAPSULE)) f |= F_ROLLING;
         unsigned long long g = b->group ? b->group[i] : ~0ULL, m = b->mask ? b->mask[i] : ~0ULL;
         if (b->group && b->mask && !(g == ~0ULL && m == ~0ULL)) f |= F_FILTER;
-        w->diam.push_back(sk != B2D_SHAPE_NONE ? shape_diameter(sk, b->shape_params + 4 * i) : 0.0f);
-        w->isdyn.push_back(dyn ? 1 : 0);
+        class_add(w, sk != B2D_SHAPE_NONE ? shape_diameter(sk, b->shape_params + 4 * i) : 0.0f, dyn);
         flags[i] = f; mat[i] = make_float2(b->friction[i], b->restitution[i]); grp[i] = g; msk[i] = m;
     }
     cudaStream_t s = w->stream;
@@ -338,7 +362,7 @@ int b2d_remove_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
     if (d.sleeping) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies);
     CK(cudaFreeAsync(dev_ids, s));
     CK(cudaStreamSynchronize(s));
-    for (uint32_t k = 0; k < n; ++k) { w->diam[ids[k]] = 0.0f; w->isdyn[ids[k]] = 0; }
+    for (uint32_t k = 0; k < n; ++k) class_forget(w, ids[k]);
     w->contacts_dirty = true; w->class_dirty = true; w->ehash_dirty = true;
     drop_graphs(w);
     return B2D_OK;
@@ -416,7 +440,7 @@ int b2d_add_hinges(b2d_world *w, uint32_t n, const uint32_t *a, const uint32_t *
 // collision_exclusion as a pair hash set, rebuilt on every change (host list -> device open-addressing table)
 static int upload_exclusions(b2d_world *w) {
     Dev &d = w->d;
-    uint32_t size = pow2_at_least(2ull * w->exclusions.size() + 2);
+    uint32_t size = pow2_at_least(4ull * w->exclusions.size() + 1024);    // load <= 1/4: room for insert_exclusions
     std::vector<unsigned long long> table(size, ~0ULL);
     auto h64 = [](unsigned long long k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return (uint32_t)k; };
     for (uint64_t k : w->exclusions) {
@@ -433,7 +457,23 @@ static int upload_exclusions(b2d_world *w) {
         if (it != w->allocs.end()) { cudaFree(*it); w->allocs.erase(it); }
     }
     d.xhash_key = dev; d.xhash_size = w->exclusions.empty() ? 0u : size;
+    w->xhash_capacity = size; w->xhash_used = (uint32_t)w->exclusions.size();
     drop_graphs(w);
+    return B2D_OK;
+}
+// Append pairs that are known to be new (the ids of arriving bodies are fresh) without rebuilding the table: entries of
+// departed bodies stay behind as harmless garbage (ids are never reused) until the load factor asks for a rebuild.
+static int insert_exclusions(b2d_world *w, const std::vector<uint64_t> &keys) {
+    if (keys.empty()) return B2D_OK;
+    Dev &d = w->d;
+    w->exclusions.insert(w->exclusions.end(), keys.begin(), keys.end());
+    if (!d.xhash_key || d.xhash_size == 0 || 2ull * (w->xhash_used + keys.size()) > w->xhash_capacity) return upload_exclusions(w);
+    if (keys.size() * 2 > w->stage_floats) return upload_exclusions(w);
+    unsigned long long *tmp = (unsigned long long *)w->stage;
+    CK(cudaMemcpyAsync(tmp, keys.data(), keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    LAUNCH(k_xhash_insert, keys.size(), 256, d, (const unsigned long long *)tmp, (uint32_t)keys.size());
+    CK(cudaStreamSynchronize(w->stream));             // `keys` may go out of scope, the staging buffer be reused
+    w->xhash_used += (uint32_t)keys.size();
     return B2D_OK;
 }
 
@@ -537,6 +577,9 @@ static int enqueue_islands(b2d_world *w) {
 // A gravity .. row preparation, B the velocity iterations, C integration .. refresh.
 static int enqueue_solver_a(b2d_world *w, int recolor) {
     Dev &d = w->d; cudaStream_t s = w->stream;
+    CK(cudaMemsetAsync(d.isl_nb, 0, 3 * (size_t)d.NB * sizeof(uint32_t), s));             // island census: bodies, manifolds, joints
+    CK(cudaMemsetAsync(d.tile_nb, 0, 5 * (size_t)d.max_tiles * sizeof(uint32_t), s));      // tile body counts and (empty) ranges
+    CK(cudaMemsetAsync(&d.cnt->tile_wmax, 0, 3 * sizeof(uint32_t), s));                    // + ncolors_all, nhcolors_all
     LAUNCH(k_gravity, d.nbodies, 256, d);
     CK(cudaMemsetAsync(&d.cnt->remaining[0], 0, 2 * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(&d.cnt->nlist, 0, 2 * sizeof(uint32_t), s));          // nlist + bar
@@ -546,11 +589,18 @@ static int enqueue_solver_a(b2d_world *w, int recolor) {
     CK(cudaMemsetAsync(d.jprop, 0xFF, (size_t)d.nbodies * sizeof(unsigned long long), s));
     LAUNCH(k_color_list, d.NM, 256, d, recolor);
     CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d));
+    size_t t;
+    if (d.nbodies) {        // island tiles: pack the small islands
+        LAUNCH(k_tile_weights, d.nbodies, 256, d);
+        t = w->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.swgt, d.swsum, (int)d.nbodies, s)); ++w->launches;
+        LAUNCH(k_tile_assign, d.nbodies, 256, d);
+    }
     LAUNCH(k_color_keys, d.NM, 256, d);
-    size_t t = w->cub_tmp_bytes;
+    t = w->cub_tmp_bytes;
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, COLOR_KEY_BITS, s)); w->launches += 3;
     t = w->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)d.NH, 0, 8, s)); w->launches += 3;
+    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.hkey, d.hkey_s, d.hidx, d.hidx_s, (int)d.NH, 0, COLOR_KEY_BITS, s)); w->launches += 3;
     LAUNCH(k_color_offsets, d.NM, 256, d);
     LAUNCH(k_color_fixup, 1, 32, d);
     LAUNCH(k_prepare_contacts, d.NM, 256, d);
@@ -561,8 +611,9 @@ static int enqueue_solver_a(b2d_world *w, int recolor) {
 static int enqueue_solver_b(b2d_world *w) {
     Dev &d = w->d;
     const int vi = (int)w->cfg.velocity_iterations;
-    if (w->barrier_solver) CK(coop_launch(w, k_solve, w->coop_blocks_solve, 256, d, vi));
-    else CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
+    // the two schedules work on disjoint islands
+    if (d.max_tiles) { k_solve_tiles<<<w->tile_blocks, TILE_CAP, TILE_SOLVE_SMEM, w->stream>>>(d, vi); ++w->launches; }
+    CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
     return B2D_OK;
 }
 static int enqueue_integrate(b2d_world *w) {
@@ -576,8 +627,8 @@ static int enqueue_solver_c(b2d_world *w) {
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
         CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
-        if (w->barrier_solver) CK(coop_launch(w, k_position, w->coop_blocks_pos, 256, d, pi));
-        else CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
+        if (d.max_tiles) { k_position_tiles<<<w->tile_pos_blocks, TILE_CAP, TILE_POS_SMEM, s>>>(d, pi); ++w->launches; }
+        CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
     return B2D_OK;
@@ -597,8 +648,26 @@ static int enqueue_solver(b2d_world *w) {
     return B2D_OK;
 }
 
+// A hand-over added bodies at the end and / or removed some: the classes of everybody else stand unless the typical
+// size moved; departures only ever make the grid pitch an over-estimate.
+static int classify_arrivals(b2d_world *w) {
+    Dev &d = w->d;
+    const float big = w->class_cnt ? float(4.0 * w->class_sum / w->class_cnt) : 1e30f;
+    if (std::fabs(big - w->class_big) > 0.1f * w->class_big) return reclassify(w);
+    bool grew = false;
+    for (uint32_t i = w->class_new_first; i < d.nbodies; ++i) {
+        const float dm = w->diam[i];
+        if (dm <= 0) continue;
+        if (!std::isfinite(dm) || dm > w->class_big) return reclassify(w);
+        if (dm > w->max_extent) { w->max_extent = dm; grew = true; }
+    }
+    if (grew) { d.cell = w->max_extent + 2 * BREAKING_THRESHOLD + 1e-3f; d.inv_cell = 1.0f / d.cell; drop_graphs(w); }
+    w->class_new_first = d.nbodies; w->class_removed = false;
+    return B2D_OK;
+}
 static int prepare_step(b2d_world *w) {
     if (w->class_dirty) return reclassify(w);
+    if (w->class_new_first < w->d.nbodies || w->class_removed) return classify_arrivals(w);
     return B2D_OK;
 }
 
@@ -626,13 +695,21 @@ static bool capture(b2d_world *w, cudaGraphExec_t &out, F body) {
     const cudaError_t e = cudaStreamEndCapture(w->stream, &g);
     w->launches = launches0; w->updates = updates0;                // nothing ran yet
     if (rc != B2D_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return false; }
+    // same kernels in the same order with new arguments / grid sizes (bodies came or went): patch the executable graph in
+    // place, which is much cheaper than instantiating a new one
+    if (out) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(out, g, &info) == cudaSuccess) { cudaGraphDestroy(g); return true; }
+        cudaGetLastError();
+        cudaGraphExecDestroy(out); out = nullptr;
+    }
     const bool ok = cudaGraphInstantiate(&out, g, 0) == cudaSuccess;
     cudaGraphDestroy(g);
     if (!ok) { cudaGetLastError(); out = nullptr; }
     return ok;
 }
 static bool build_graphs(b2d_world *w) {
-    drop_graphs(w);
+    w->graph_valid = false;
     uint64_t n_pre = 0, n_solve = 0, n_post = 0;
     auto counted = [&](uint64_t &n, auto fn) { return [&, fn]() { const uint64_t l0 = w->launches; int rc = fn(); n = w->launches - l0; return rc; }; };
     bool ok = capture(w, w->gx_pre, counted(n_pre, [&]() { int rc; if ((rc = enqueue_broadphase(w))) return rc; if ((rc = enqueue_narrowphase(w))) return rc;
@@ -642,7 +719,7 @@ static bool build_graphs(b2d_world *w) {
     ok = ok && capture(w, w->gx_all, [&]() { int rc; if ((rc = enqueue_broadphase(w))) return rc; if ((rc = enqueue_narrowphase(w))) return rc;
                                              if ((rc = enqueue_islands(w))) return rc; if ((rc = enqueue_solver_a(w, 0))) return rc;
                                              if ((rc = enqueue_solver_b(w))) return rc; if ((rc = enqueue_integrate(w))) return rc; return enqueue_solver_c(w); });
-    if (!ok) { drop_graphs(w); w->use_graph = false; return false; }
+    if (!ok) { destroy_graphs(w); w->use_graph = false; return false; }
     w->graph_launches = n_pre + n_solve + n_post + 1;
     w->graph_valid = true;
     return true;
@@ -847,14 +924,25 @@ int b2d_download_solver_order(b2d_world *w, uint32_t *hinge_ids, uint32_t *nh, u
     if (!w || !nh || !nm) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
     Counters c; int rc = fetch_counters(w, c); if (rc) return rc;
-    const uint32_t na = c.nactive, nhh = c.hoff[MAX_COLORS];
+    const uint32_t na = c.nactive, nhh = c.nhactive;
     if (na > *nm || nhh > *nh) { w->error = "b2d_download_solver_order: capacity too small"; return B2D_ERR_CAPACITY; }
     std::vector<uint4> hdr(na), hh(nhh);
+    std::vector<uint32_t> ck(na), hk(nhh);
     if (na) CK(cudaMemcpyAsync(hdr.data(), w->d.hdr, na * sizeof(uint4), cudaMemcpyDeviceToHost, w->stream));
+    if (na) CK(cudaMemcpyAsync(ck.data(), w->d.ckey_s, na * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     if (nhh) CK(cudaMemcpyAsync(hh.data(), w->d.hhdr, nhh * sizeof(uint4), cudaMemcpyDeviceToHost, w->stream));
+    if (nhh) CK(cudaMemcpyAsync(hk.data(), w->d.hkey_s, nhh * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    for (uint32_t i = 0; i < na; ++i) { pairs[2 * i] = hdr[i].x & 0x7FFFFFFFu; pairs[2 * i + 1] = hdr[i].y & 0x7FFFFFFFu; }
-    for (uint32_t i = 0; i < nhh; ++i) hinge_ids[i] = hh[i].z;
+    // The device arrays are tile-major for the tiled islands; the serial sweep that reproduces the per-body order is
+    // colour-major (within a colour the constraints touch disjoint dynamic bodies, so their mutual order is immaterial).
+    std::vector<uint32_t> oc(na), oh(nhh);
+    for (uint32_t i = 0; i < na; ++i) oc[i] = i;
+    for (uint32_t i = 0; i < nhh; ++i) oh[i] = i;
+    auto colour = [](uint32_t key) { return (key & KEY_DF) ? (key >> KEY_DF_COLOR_SHIFT) & 63u : key & 63u; };
+    std::stable_sort(oc.begin(), oc.end(), [&](uint32_t x, uint32_t y) { return colour(ck[x]) < colour(ck[y]); });
+    std::stable_sort(oh.begin(), oh.end(), [&](uint32_t x, uint32_t y) { return colour(hk[x]) < colour(hk[y]); });
+    for (uint32_t i = 0; i < na; ++i) { pairs[2 * i] = hdr[oc[i]].x & 0x7FFFFFFFu; pairs[2 * i + 1] = hdr[oc[i]].y & 0x7FFFFFFFu; }
+    for (uint32_t i = 0; i < nhh; ++i) hinge_ids[i] = hh[oh[i]].z;
     *nm = na; *nh = nhh;
     return B2D_OK;
 }
@@ -877,7 +965,7 @@ int b2d_get_stats(b2d_world *w, b2d_stats *out) {
     HostManifolds hm; uint32_t hwm; rc = fetch_manifolds(w, hm, hwm); if (rc) return rc;
     std::memset(out, 0, sizeof(*out));
     out->bodies = d.nbodies; out->manifolds = (uint32_t)hm.slots.size(); out->contact_points = c.npoints; out->hinges = d.nhinges;
-    out->contact_colors = c.ncolors; out->hinge_colors = c.nhcolors; out->islands = c.nislands; out->manifold_high_water = c.hwm;
+    out->contact_colors = c.ncolors_all; out->hinge_colors = c.nhcolors_all; out->islands = c.nislands; out->manifold_high_water = c.hwm;
     out->kernel_launches = w->launches; out->steps = w->steps; out->error_flags = c.err;
     if (w->timed && w->timed_steps) {
         // average over the steps since b2d_reset_timers (at most the ring size)
@@ -903,6 +991,17 @@ int b2d_debug_counters(b2d_world *w, void *out, uint32_t bytes) {
     cudaSetDevice(w->cfg.device);
     CK(cudaStreamSynchronize(w->stream));
     CK(cudaMemcpy(out, w->d.cnt, std::min<size_t>(bytes, sizeof(Counters)), cudaMemcpyDeviceToHost));
+    return B2D_OK;
+}
+// development aid: island tiles of the last step: out = {tiles, tiled manifolds, tiled hinges, manifolds with rows, hinges with rows, max bodies per tile}
+int b2d_debug_tiles(b2d_world *w, uint32_t *out6) {
+    if (!w || !out6) return B2D_ERR_ARGUMENT;
+    cudaSetDevice(w->cfg.device);
+    Counters c; int rc = fetch_counters(w, c); if (rc) return rc;
+    std::vector<uint32_t> nb(std::min(c.ntiles, w->d.max_tiles));
+    if (!nb.empty()) CK(cudaMemcpy(nb.data(), w->d.tile_nb, nb.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    out6[0] = c.ntiles; out6[1] = c.ntiled; out6[2] = c.nhtiled; out6[3] = c.nactive; out6[4] = c.nhactive;
+    out6[5] = nb.empty() ? 0u : *std::max_element(nb.begin(), nb.end());
     return B2D_OK;
 }
 int b2d_reset_timers(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; w->timed_steps = 0; return B2D_OK; }
@@ -1034,10 +1133,16 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
     if (capacity < b2d_handover_bytes(c)) { w->error = "b2d_handover_pack: blob too small"; return B2D_ERR_CAPACITY; }
     std::vector<uint32_t> ids; ids.reserve(c[0]);
     for (uint32_t i = 0; i < d.nbodies; ++i) if (w->host_bdst[i] == dst) ids.push_back(i);
-    std::vector<uint2> ex; std::vector<uint64_t> keep;
-    for (uint64_t k : w->exclusions) {
-        const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
-        if (a < d.nbodies && b < d.nbodies && w->host_bdst[a] == dst && w->host_bdst[b] == dst) ex.push_back(make_uint2(a, b)); else keep.push_back(k);
+    // exclusions among the movers travel with them; the local entries stay behind as garbage (ids are never reused) and
+    // are dropped from the host list in one sweep
+    std::vector<uint2> ex;
+    if (c[3]) {
+        size_t keep = 0;
+        for (uint64_t k : w->exclusions) {
+            const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
+            if (a < d.nbodies && b < d.nbodies && w->host_bdst[a] == dst && w->host_bdst[b] == dst) ex.push_back(make_uint2(a, b)); else w->exclusions[keep++] = k;
+        }
+        w->exclusions.resize(keep);
     }
     if (ids.size() != c[0] || ex.size() != c[3]) { w->error = "b2d_handover_pack: plan is stale"; return B2D_ERR_ARGUMENT; }
     char *blob = (char *)device_blob;
@@ -1077,9 +1182,8 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
     }
     if (dev_ex) CK(cudaFreeAsync(dev_ex, s));
     CK(cudaStreamSynchronize(s));
-    for (uint32_t i : ids) { w->diam[i] = 0.0f; w->isdyn[i] = 0; w->host_bdst[i] = NO_RANK; }
-    if (!ex.empty()) { w->exclusions.swap(keep); int rc = upload_exclusions(w); if (rc) return rc; }
-    w->contacts_dirty = true; w->class_dirty = true; w->ehash_dirty = true; w->labels_stale = true;
+    for (uint32_t i : ids) { class_forget(w, i); w->host_bdst[i] = NO_RANK; }
+    w->class_removed = true; w->ehash_dirty = true; w->labels_stale = true;
     drop_graphs(w);
     return B2D_OK;
 }
@@ -1117,8 +1221,7 @@ int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, u
         for (uint32_t k = 0; k < h.nb; ++k) {
             const uint32_t sk = (fl[k] >> F_SHAPE_SHIFT) & 0xFFu;
             const float p[4] = {shp[k].x, shp[k].y, shp[k].z, shp[k].w};
-            w->diam.push_back(sk != B2D_SHAPE_NONE ? shape_diameter(sk, p) : 0.0f);
-            w->isdyn.push_back((fl[k] & F_KIND_MASK) == 0u ? 1 : 0);
+            class_add(w, sk != B2D_SHAPE_NONE ? shape_diameter(sk, p) : 0.0f, (fl[k] & F_KIND_MASK) == 0u);
         }
     }
     if (h.nm) { LAUNCH(k_unpack_manifolds, h.nm, 256, d, h.nm, im, cn.hwm); LAUNCH(k_bump_hwm, 1, 32, d, h.nm); }
@@ -1131,16 +1234,16 @@ int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, u
         CK(cudaMemcpyAsync(host.data(), loc, h.nx * sizeof(uint2), cudaMemcpyDeviceToHost, s));
         CK(cudaFreeAsync(loc, s));
         CK(cudaStreamSynchronize(s));
-        std::unordered_set<uint64_t> seen(w->exclusions.begin(), w->exclusions.end());
+        std::vector<uint64_t> keys; keys.reserve(h.nx);     // both ends are newcomers with fresh local ids: the pairs cannot exist yet
         for (const uint2 &e : host) {
             if (e.x == 0xFFFFFFFFu || e.y == 0xFFFFFFFFu) continue;
-            const uint64_t lo = std::min(e.x, e.y), hi = std::max(e.x, e.y), k = (lo << 32) | hi;
-            if (seen.insert(k).second) w->exclusions.push_back(k);
+            const uint64_t lo = std::min(e.x, e.y), hi = std::max(e.x, e.y);
+            keys.push_back((lo << 32) | hi);
         }
-        int rc = upload_exclusions(w); if (rc) return rc;
+        int rc = insert_exclusions(w, keys); if (rc) return rc;
     }
     CK(cudaStreamSynchronize(s));
-    w->contacts_dirty = true; w->class_dirty = true; w->labels_stale = true;
+    w->labels_stale = true;
     drop_graphs(w);
     if (counts_out) std::memcpy(counts_out, c, sizeof(c));
     return check_device_flags(w);

@@ -309,6 +309,10 @@ __global__ void k_unpack_hinges(Dev d, uint32_t first, uint32_t n, const float4 
 __global__ void k_unpack_exclusions(Dev d, const uint2 *ent, uint32_t n, uint2 *local) {
     GRID_STRIDE(k, n) { local[k] = make_uint2(ehash_find(d.ehash, d.ehash_size, ent[k].x), ehash_find(d.ehash, d.ehash_size, ent[k].y)); }
 }
+// collision_exclusion pairs appended to the device table (keys are known not to be in it)
+__global__ void k_xhash_insert(Dev d, const unsigned long long *keys, uint32_t n) {
+    GRID_STRIDE(k, n) hash_insert(d.xhash_key, nullptr, d.xhash_size, keys[k], 0u);
+}
 __global__ void k_bump_hwm(Dev d, uint32_t n) {
     if (blockIdx.x == 0 && threadIdx.x == 0) d.cnt->hwm = min(d.NM, d.cnt->hwm + n);
 }

@@ -563,6 +563,11 @@ B2D_D void cc_union(uint32_t *parent, uint32_t a, uint32_t b) {
     }
 }
 __global__ void k_cc_init(Dev d) { GRID_STRIDE(i, d.nbodies) d.parent[i] = i; }
+// one atomic per distinct address per warp (a pile is ONE island: 262 144 lanes would otherwise queue on one word)
+B2D_D void island_count(uint32_t *ctr, uint32_t root) {
+    const uint32_t grp = __match_any_sync(__activemask(), root);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(grp) - 1)) atomicAdd(&ctr[root], (uint32_t)__popc(grp));
+}
 // Two rounds: a quarter of the edges is hooked first and the forest flattened; in a dense contact graph that already
 // joins most of every island, so the remaining edges mostly find parent[a] == parent[b] with two plain reads and never
 // reach the find / compare-and-swap path (which otherwise funnels the whole grid through the root of a giant island).
@@ -666,6 +671,7 @@ __global__ void k_gravity(Dev d) {
         if (!is_dynamic(d.flags[i])) continue;
         v3 v = mk3(d.linvel[i]); v += mk3(d.grav[i]) * d.dt;
         d.linvel[i] = f4(v, 0);
+        island_count(d.isl_nb, d.parent[i]);          // census for the island tiles (zeroed by the host, k_tile_weights)
     }
 }
 
@@ -695,11 +701,13 @@ __global__ void k_color_list(Dev d, int recolor) {
             if (da) atomicOr(&d.bmask[p.x], 1ULL << col);
             if (db) atomicOr(&d.bmask[p.y], 1ULL << col);
         }
+        island_count(d.isl_nm, d.parent[da ? p.x : p.y]);
     }
     GRID_STRIDE(h, d.nhinges) {
         uint2 p = d.hpair[h];
         const bool da = is_dynamic(d.flags[p.x]), db = is_dynamic(d.flags[p.y]);
         if (recolor || (!da && !db)) d.hcolor[h] = COLOR_NONE;
+        if (da || db) island_count(d.isl_nh, d.parent[da ? p.x : p.y]);
         uint32_t col = d.hcolor[h];
         if (col == COLOR_NONE) continue;
         if (da) atomicOr(&d.jmask[p.x], 1ULL << col);
@@ -756,55 +764,127 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
     }
 }
 
-// Sort keys: colour for constraints that have rows this step, 0xFF otherwise.
+// ---- island tiles.  An island with at most TILE_ISLAND_MAX dynamic bodies, manifolds with points and joints is solved
+// inside one CTA (k_solve_tiles, k_position_tiles).  Islands are packed into tiles in root-id order: with weight
+// w = max(bodies, manifolds, joints) <= TILE_ISLAND_MAX per island and P the exclusive prefix sum of the weights, island
+// -> tile P / g with g = TILE_CAP + 1 - (heaviest tiled island) puts at most TILE_CAP of each into every tile.  Which islands
+// are tiled changes speed, never results: the per-body constraint order is fixed by the colours alone.
+__global__ void k_tile_weights(Dev d) {
+    uint32_t wmax = 0;
+    GRID_STRIDE(i, d.nbodies) {
+        uint32_t w = 0;
+        if (is_dynamic(d.flags[i]) && d.parent[i] == i) {
+            const uint32_t nb = d.isl_nb[i], nm = d.isl_nm[i], nh = d.isl_nh[i];
+            if (nb <= TILE_ISLAND_MAX && nm <= TILE_ISLAND_MAX && nh <= TILE_ISLAND_MAX && (nm | nh)) w = max(nb, max(nm, nh));
+        }
+        d.swgt[i] = w;
+        wmax = max(wmax, w);
+    }
+    wmax = __reduce_max_sync(0xffffffffu, wmax);
+    if ((threadIdx.x & 31u) == 0 && wmax) atomicMax(&d.cnt->tile_wmax, wmax);
+}
+// islands start a new tile every `granule` units of weight: a tile then holds less than granule + heaviest island <= TILE_CAP
+B2D_D uint32_t tile_granule(const Dev &d) { return (uint32_t)TILE_CAP + 1u - max(d.cnt->tile_wmax, 1u); }
+__global__ void k_tile_assign(Dev d) {
+    const uint32_t n = d.nbodies, g = tile_granule(d);
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.cnt->ntiles = min(d.max_tiles, (d.swsum[n - 1] + d.swgt[n - 1] + g - 1) / g);
+    GRID_STRIDE(i, n) {
+        uint32_t tile = TILE_NONE, slot = SLOT_NONE;
+        if (is_dynamic(d.flags[i])) {
+            const uint32_t r = d.parent[i];
+            if (d.swgt[r]) {
+                tile = d.swsum[r] / g;
+                if (tile < d.max_tiles) {
+                    slot = atomicAdd(&d.tile_nb[tile], 1u);         // order within the tile is immaterial
+                    d.tile_body[(size_t)tile * TILE_CAP + slot] = i;
+                } else tile = TILE_NONE;
+            }
+        }
+        d.btile[i] = tile; d.bslot[i] = slot;
+    }
+}
+B2D_D uint32_t key_body(const Dev &d, uint2 pr) {      // the body a constraint is filed under: its (smaller) dynamic one
+    const uint32_t fa = d.flags[pr.x];
+    return (is_dynamic(fa) && !(fa & F_LARGE)) ? pr.x : pr.y;
+}
+// Sort keys.  Tiled constraints first, tile-major then colour; then the dataflow path's constraints by colour, point
+// count (a chunk of 32 manifolds runs the same number of row solves in every lane) and the spatial rank of the
+// manifold's dynamic body (lanes of a chunk touch neighbouring bodies, whose predecessors finish at about the same
+// time and whose records share L2 sectors); constraints without rows this step last.
 __global__ void k_color_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
+    uint32_t cmax = 0, hmax = 0;
     GRID_STRIDE(m, d.NM) {
-        // sort key: colour, then point count (a chunk of 32 manifolds runs the same number of row solves in every
-        // lane), then the spatial rank of the manifold's dynamic body (lanes of a chunk touch neighbouring bodies, whose
-        // predecessors finish at about the same time and whose records share L2 sectors)
-        uint32_t key = 1u << (COLOR_KEY_BITS - 1);
+        uint32_t key = KEY_INACTIVE;
         if (m < hwm) {
             uint32_t st = d.mstate[m];
             if ((st & MS_ALIVE) && (st & MS_NPTS_MASK) && ((st >> MS_COLOR_SHIFT) & 0xFFu) != COLOR_NONE) {      // uncoloured = sleeping
                 const uint2 pr = d.mpair[m];
-                const uint32_t fa = d.flags[pr.x];
-                const uint32_t b = (is_dynamic(fa) && !(fa & F_LARGE)) ? pr.x : pr.y;
-                const uint32_t sp = (uint32_t)(((unsigned long long)d.brank[b] << COLOR_KEY_SPATIAL_BITS) / d.nbodies);
-                key = (((st >> MS_COLOR_SHIFT) & 0x3Fu) << (COLOR_KEY_SPATIAL_BITS + 2)) | (((st & MS_NPTS_MASK) - 1u) << COLOR_KEY_SPATIAL_BITS) | sp;
+                const uint32_t b = key_body(d, pr), col = (st >> MS_COLOR_SHIFT) & 0x3Fu;
+                const uint32_t tile = d.btile[b];
+                cmax = max(cmax, col + 1u);
+                if (tile != TILE_NONE) key = (tile << 6) | col;
+                else {
+                    const uint32_t sp = (uint32_t)(((unsigned long long)d.brank[b] << KEY_DF_SPATIAL_BITS) / d.nbodies);
+                    key = KEY_DF | (col << KEY_DF_COLOR_SHIFT) | (((st & MS_NPTS_MASK) - 1u) << KEY_DF_SPATIAL_BITS) | sp;
+                }
             }
         }
         d.ckey[m] = key; d.cidx[m] = m;
     }
     GRID_STRIDE(h, d.NH) {
-        unsigned char key = 0xFF;
-        if (h < d.nhinges) { uint2 p = d.hpair[h]; if (is_dynamic(d.flags[p.x]) || is_dynamic(d.flags[p.y])) key = (unsigned char)d.hcolor[h]; }
+        uint32_t key = KEY_INACTIVE;
+        if (h < d.nhinges) {
+            const uint2 p = d.hpair[h];
+            if (is_dynamic(d.flags[p.x]) || is_dynamic(d.flags[p.y])) {
+                const uint32_t tile = d.btile[is_dynamic(d.flags[p.x]) ? p.x : p.y], col = d.hcolor[h] & 0x3Fu;
+                hmax = max(hmax, col + 1u);
+                key = tile != TILE_NONE ? ((tile << 6) | col) : (KEY_DF | (col << KEY_DF_COLOR_SHIFT));
+            }
+        }
         d.hkey[h] = key; d.hidx[h] = h;
     }
+    cmax = __reduce_max_sync(0xffffffffu, cmax); hmax = __reduce_max_sync(0xffffffffu, hmax);
+    if ((threadIdx.x & 31u) == 0) { if (cmax) atomicMax(&d.cnt->ncolors_all, cmax); if (hmax) atomicMax(&d.cnt->nhcolors_all, hmax); }
     if (blockIdx.x == 0 && threadIdx.x < MAX_COLORS + 2) { d.cnt->coff[threadIdx.x] = 0xFFFFFFFFu; d.cnt->hoff[threadIdx.x] = 0xFFFFFFFFu; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { Counters &c = *d.cnt; c.nactive = d.NM; c.nhactive = d.NH; c.ntiled = 0xFFFFFFFFu; c.nhtiled = 0xFFFFFFFFu; }
+}
+// Range boundaries in the sorted arrays: [tile_c0, tile_c1) per tile (preset to empty by the host), the start of each
+// dataflow colour, the first constraint without rows.
+B2D_D void key_boundary(uint32_t i, uint32_t prev, uint32_t key, bool first, uint32_t *t0, uint32_t *t1, uint32_t *off, uint32_t *ntiled, uint32_t *nact) {
+    const uint32_t cls = key >> (KEY_TILE_BITS + 6), pcls = prev >> (KEY_TILE_BITS + 6);      // 0 tiled, 1 dataflow, 2 inactive
+    if (cls == 0) {
+        if (first || (prev >> 6) != (key >> 6)) { t0[key >> 6] = i; if (!first) t1[prev >> 6] = i; }
+        return;
+    }
+    if (!first && pcls == 0) t1[prev >> 6] = i;                                                   // the last tile ends here
+    if (first || pcls != cls) { if (cls == 1) *ntiled = i; else { *nact = i; if (first || pcls == 0) *ntiled = i; } }
+    if (cls == 1) { const uint32_t col = (key >> KEY_DF_COLOR_SHIFT) & 63u; if (first || pcls != 1 || ((prev >> KEY_DF_COLOR_SHIFT) & 63u) != col) off[col] = i; }
 }
 __global__ void k_color_offsets(Dev d) {
-    GRID_STRIDE(i, d.NM) {
-        uint32_t k = d.ckey_s[i] >> (COLOR_KEY_SPATIAL_BITS + 2);
-        if (i == 0 || (d.ckey_s[i - 1] >> (COLOR_KEY_SPATIAL_BITS + 2)) != k) d.cnt->coff[k >= MAX_COLORS ? MAX_COLORS : k] = i;
-    }
-    GRID_STRIDE(i, d.NH) {
-        unsigned char k = d.hkey_s[i];
-        if (i == 0 || d.hkey_s[i - 1] != k) d.cnt->hoff[k == 0xFF ? MAX_COLORS : k] = i;
-    }
+    Counters &c = *d.cnt;
+    GRID_STRIDE(i, d.NM) key_boundary(i, i ? d.ckey_s[i - 1] : 0u, d.ckey_s[i], i == 0, d.tile_c0, d.tile_c1, c.coff, &c.ntiled, &c.nactive);
+    GRID_STRIDE(i, d.NH) key_boundary(i, i ? d.hkey_s[i - 1] : 0u, d.hkey_s[i], i == 0, d.tile_h0, d.tile_h1, c.hoff, &c.nhtiled, &c.nhactive);
 }
 __global__ void k_color_fixup(Dev d) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     Counters &c = *d.cnt;
-    if (c.coff[MAX_COLORS] == 0xFFFFFFFFu) c.coff[MAX_COLORS] = d.NM;
-    if (c.hoff[MAX_COLORS] == 0xFFFFFFFFu) c.hoff[MAX_COLORS] = d.NH;
+    // every entry has rows: no boundary was seen (presets: nactive = capacity, ntiled = 0xFFFFFFFF)
+    if (c.ntiled == 0xFFFFFFFFu) c.ntiled = c.nactive;
+    if (c.nhtiled == 0xFFFFFFFFu) c.nhtiled = c.nhactive;
+    // the last tile runs to the end of the tiled range when nothing follows it (no boundary closes it)
+    if (c.ntiles) {
+        if (c.ntiled && d.ckey_s[c.ntiled - 1] >> (KEY_TILE_BITS + 6) == 0) d.tile_c1[d.ckey_s[c.ntiled - 1] >> 6] = c.ntiled;
+        if (c.nhtiled && d.hkey_s[c.nhtiled - 1] >> (KEY_TILE_BITS + 6) == 0) d.tile_h1[d.hkey_s[c.nhtiled - 1] >> 6] = c.nhtiled;
+    }
+    c.coff[MAX_COLORS] = c.nactive; c.hoff[MAX_COLORS] = c.nhactive;
     c.coff[MAX_COLORS + 1] = c.coff[MAX_COLORS]; c.hoff[MAX_COLORS + 1] = c.hoff[MAX_COLORS];
     uint32_t nc = 0, nh = 0;
     for (int k = MAX_COLORS - 1; k >= 0; --k) {
         if (c.coff[k] == 0xFFFFFFFFu) c.coff[k] = c.coff[k + 1]; else if (!nc) nc = k + 1;
         if (c.hoff[k] == 0xFFFFFFFFu) c.hoff[k] = c.hoff[k + 1]; else if (!nh) nh = k + 1;
     }
-    c.ncolors = nc; c.nhcolors = nh; c.nactive = c.coff[MAX_COLORS];
+    c.ncolors = nc; c.nhcolors = nh;
     c.cchunk[0] = 0; c.hchunk[0] = 0;
     for (int k = 0; k <= MAX_COLORS; ++k) {
         c.cchunk[k + 1] = c.cchunk[k] + (k < (int)nc ? (c.coff[k + 1] - c.coff[k] + 31) / 32 : 0);
@@ -847,7 +927,8 @@ __global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
         SBody A = solver_body(d, pr.x, fa), B = solver_body(d, pr.y, fb);
         v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
         q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
-        d.hdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), npts, m);
+        d.hdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), npts,
+                              (A.proc ? d.bslot[pr.x] : SLOT_NONE) | ((B.proc ? d.bslot[pr.y] : SLOT_NONE) << 16));
         {   // dataflow tickets: per iteration a body sees its hinges (by colour), then its contact normals, then the
             // friction pairs; colours are unique per body, so the rank of this manifold is a popcount
             const uint32_t col = (d.mstate[m] >> MS_COLOR_SHIFT) & 0xFFu;
@@ -889,7 +970,7 @@ __global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
 
 // hinge_constraint::prepare, hinge_constraint.cpp:26-69 (no limits / springs / torque rows)
 __global__ void k_prepare_hinges(Dev d) {
-    const uint32_t n = d.cnt->hoff[MAX_COLORS];
+    const uint32_t n = d.cnt->nhactive;
     GRID_STRIDE(i, n) {
         uint32_t h = d.hidx_s[i];
         uint2 pr = d.hpair[h];
@@ -920,7 +1001,8 @@ __global__ void k_prepare_hinges(Dev d) {
         R[4] = make_float4(em[4], rhs[0], rhs[1], rhs[2]);
         R[5] = make_float4(rhs[3], rhs[4], imp[0], imp[1]);
         R[6] = make_float4(imp[2], imp[3], imp[4], 0);
-        d.hhdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), h, 0);
+        d.hhdr[i] = make_uint4(pr.x | (A.proc ? 0u : 0x80000000u), pr.y | (B.proc ? 0u : 0x80000000u), h,
+                               (A.proc ? d.bslot[pr.x] : SLOT_NONE) | ((B.proc ? d.bslot[pr.y] : SLOT_NONE) << 16));
         {
             const unsigned long long below = (1ULL << d.hcolor[h]) - 1ULL;
             uint32_t t[2];
@@ -938,114 +1020,13 @@ __global__ void k_prepare_hinges(Dev d) {
 
 // ====================================================================== solver: velocity iterations
 
-// ---- dataflow synchronisation: instead of a grid barrier per colour, every dynamic body carries a ticket counter.
-// A constraint pass may touch its two bodies when both counters equal the tickets computed for it in k_prepare_*
-// (position of this pass in the body's fixed sequence: iteration-major, then hinges / normals / frictions, then
-// colour); afterwards it bumps them.  The per-body order -- and therefore every bit of the result -- is the same as
-// in the barrier version, but a pass waits only for its own two predecessors (an L2 round trip) rather than for the
-// slowest CTA of the whole grid.
-B2D_D uint32_t ld_relaxed(const uint32_t *p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-B2D_D void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-B2D_D void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-struct Ticket { uint32_t a, b, ta, tb, mask; bool pa, pb, on; };
-// pass = (iteration + 1); kind: 0 hinge, 1 contact normal, 2 friction
-B2D_D Ticket ticket_of(uint32_t tagA, uint32_t tagB, uint2 tk, int pass, int kind, uint32_t mask) {
-    Ticket t;
-    t.on = pass >= 0; t.mask = mask;
-    t.pa = !(tagA & 0x80000000u); t.pb = !(tagB & 0x80000000u);
-    t.a = tagA & 0x7FFFFFFFu; t.b = tagB & 0x7FFFFFFFu;
-    const uint32_t SA = tk.x & 0xFFu, bA = (tk.x >> 8) & 0xFFu, kA = (tk.x >> 16) & 0xFFu;
-    const uint32_t SB = tk.y & 0xFFu, bB = (tk.y >> 8) & 0xFFu, kB = (tk.y >> 16) & 0xFFu;
-    t.ta = (uint32_t)pass * SA + bA + (kind == 2 ? kA : 0u);
-    t.tb = (uint32_t)pass * SB + bB + (kind == 2 ? kB : 0u);
-    return t;
-}
-// ptxas recycles the unused lanes of a 128-bit load as scratch registers straight away, and the write-after-write hazard
-// then parks the warp until the load has landed -- in front of the ticket poll.  keep() pins such a lane as live up to
-// the point where the rest of the vector is consumed.
-B2D_D void keep(float x) { asm volatile("" :: "f"(x)); }
-B2D_D void keep(uint32_t x) { asm volatile("" :: "r"(x)); }
+// The reference sweeps the rows of an island serially (island_solver.cpp:94-111): per iteration all joint rows, all
+// contact normal rows, then all friction pairs.  Here the constraints of a type are coloured so that a colour touches
+// disjoint dynamic bodies; any schedule that runs a body's constraints in (iteration, type, colour) order produces the
+// bits of a serial sweep in that order.  Two schedules do: k_solve_tiles for small islands (everything on chip,
+// __syncthreads between colours) and k_solve_df for the rest (per-body tickets in global memory).
+
 struct VBody { v3 dv, dw; float inv_m; m3 inv_I; uint32_t id; bool proc; float pad1, pad2; };
-B2D_D void keep(const VBody &b) { keep(b.pad1); keep(b.pad2); }
-B2D_D void vb_load(const Dev &d, uint32_t tag, VBody &b) {
-    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
-    if (b.proc) {
-        b.dv = mk3(__ldcg(&d.dvw[2 * b.id])); b.dw = mk3(__ldcg(&d.dvw[2 * b.id + 1]));
-        float4 r0 = d.invIW[3 * b.id], r1 = d.invIW[3 * b.id + 1], r2 = d.invIW[3 * b.id + 2];
-        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2); b.pad1 = r1.w; b.pad2 = r2.w;
-    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); b.pad1 = b.pad2 = 0; }
-}
-B2D_D void vb_store(const Dev &d, const VBody &b) {
-    if (b.proc) { __stcg(&d.dvw[2 * b.id], f4(b.dv, 0)); __stcg(&d.dvw[2 * b.id + 1], f4(b.dw, 0)); }
-}
-// Dataflow acquire / publish.  The delta-velocity record of a body (two float4 = one 32 B sector) carries the
-// body's ticket in BOTH .w lanes, so data and synchronisation travel in the same L2 transactions: a reader that
-// sees the expected ticket in both halves has a consistent record (16 B aligned vector stores are single
-// transactions; a torn pair is rejected by the double check) and needs no fence, a writer needs none either.
-#ifndef B2D_LD_POLL
-#define B2D_LD_POLL "ld.relaxed.gpu.global.v4.f32"     // gpu scope is all the protocol needs (.volatile = relaxed.sys)
-#define B2D_ST_POLL "st.relaxed.gpu.global.v4.f32"
-#endif
-B2D_D float4 ld_volatile4(const float4 *p) {
-    float4 v; asm volatile(B2D_LD_POLL " {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
-}
-B2D_D void st_volatile4(float4 *p, float4 v) {
-    asm volatile(B2D_ST_POLL " [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-B2D_D void vb_static(const Dev &d, uint32_t tag, VBody &b) {
-    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
-    b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0);
-    if (b.proc) {
-        float4 r0 = d.invIW[3 * b.id], r1 = d.invIW[3 * b.id + 1], r2 = d.invIW[3 * b.id + 2];
-        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2); b.pad1 = r1.w; b.pad2 = r2.w;
-    } else { b.inv_m = 0; b.inv_I = m3_zero(); b.pad1 = b.pad2 = 0; }
-}
-B2D_D bool vb_try(const Dev &d, VBody &b, uint32_t expect) {
-    float4 a = ld_volatile4(&d.dvw[2 * b.id]), w = ld_volatile4(&d.dvw[2 * b.id + 1]);
-    b.dv = mk3(a); b.dw = mk3(w);
-    return __float_as_uint(a.w) == expect && __float_as_uint(w.w) == expect;
-}
-// Lanes of a chunk become ready one by one; each lane solves as soon as ITS two bodies carry the expected tickets
-// (the ready subset runs the solve converged, the rest keep polling), so one late predecessor delays one constraint
-// and not the 31 others that happen to share its warp.
-B2D_D void acquire_begin(const Dev &d, const Ticket &t, uint32_t tagA, uint32_t tagB, VBody &A, VBody &B) {
-    if (!t.on) { vb_load(d, tagA, A); vb_load(d, tagB, B); return; }
-    vb_static(d, tagA, A); vb_static(d, tagB, B);
-}
-B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
-    if (!t.on) return true;
-    return (!A.proc || vb_try(d, A, t.ta)) & (!B.proc || vb_try(d, B, t.tb));
-}
-#ifdef B2D_DF_PROFILE
-// Development build (-DB2D_DF_PROFILE, tools/solver_profile.py): per-warp cycle accounting of the dataflow solver, flushed once per
-// warp into Counters::dbg -- [0]/[1] cycles in poll iterations without/with progress, [2]/[3] their counts, [4] chunk
-// passes, [5] total cycles, [6] warps.
-__shared__ unsigned long long s_prof[16][8];
-__shared__ long long s_prof_t[16];
-#endif
-B2D_D bool acquire_more(const Dev &d, const Ticket &t, bool pending, bool progressed, uint32_t &spins) {
-    if (!t.on) return false;
-#ifdef B2D_DF_PROFILE
-    {
-        const bool prog = __any_sync(t.mask, progressed);
-        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(t.mask) - 1)) {
-            const uint32_t w = threadIdx.x >> 5; const long long now = clock64();
-            s_prof[w][prog ? 1 : 0] += (unsigned long long)(now - s_prof_t[w]); s_prof[w][prog ? 3 : 2] += 1; s_prof_t[w] = now;
-        }
-    }
-#endif
-    if (!__any_sync(t.mask, pending)) return false;
-    if (!__any_sync(t.mask, progressed)) {
-        if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); return false; }      // never hang the GPU
-        if (spins > 64) __nanosleep(20);
-    }
-    return true;
-}
-B2D_D void bodies_publish(const Dev &d, const Ticket &t, const VBody &A, const VBody &B) {
-    if (!t.on) { vb_store(d, A); vb_store(d, B); return; }
-    if (A.proc) { st_volatile4(&d.dvw[2 * A.id], f4(A.dv, __uint_as_float(t.ta + 1))); st_volatile4(&d.dvw[2 * A.id + 1], f4(A.dw, __uint_as_float(t.ta + 1))); }
-    if (B.proc) { st_volatile4(&d.dvw[2 * B.id], f4(B.dv, __uint_as_float(t.tb + 1))); st_volatile4(&d.dvw[2 * B.id + 1], f4(B.dw, __uint_as_float(t.tb + 1))); }
-}
 // apply_row_impulse, constraint_row.cpp:24-32
 B2D_D void apply_imp(VBody &A, VBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float imp) {
     A.dv += A.inv_m * J0 * imp;
@@ -1069,21 +1050,42 @@ B2D_D float solve_row(float rhs, float em, float lo, float hi, float &impulse, f
     else impulse = imp;
     return delta;
 }
-
-B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
-    uint4 hd = d.hhdr[i];
-    float4 *R = d.HR + 7 * (size_t)i;
-    float4 r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6];
-    const Ticket tk = ticket_of(hd.x, hd.y, pass >= 0 ? d.htkt[i] : make_uint2(0, 0), pass, 0, mask);
-    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
-    bool pending = true; uint32_t spins = 0;
-    v3 rA = mk3(r0), rB = mk3(r1), p = mk3(r2), q = mk3(r3);
-    float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x};
-    float rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
-    float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
-    do {
-    const bool ok = pending && acquire_try(d, tk, A, B);
-    if (ok) {
+// one contact normal row; rows: r0 = normal | rhs, r1 = rA | eff_mass, r2 = rB | friction, im = impulses (n, t0, t1)
+B2D_D void nrow_solve(const float4 &r0, const float4 &r1, const float4 &r2, float4 &im, VBody &A, VBody &B, bool warm) {
+    v3 nrm = mk3(r0), rA = mk3(r1), rB = mk3(r2);
+    v3 J1 = cross(rA, nrm), J2 = -nrm, J3 = -cross(rB, nrm);
+    float delta;
+    if (warm) delta = im.x;
+    else delta = solve_row(r0.w, r1.w, 0.0f, LARGE, im.x, rel_speed(nrm, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
+    apply_imp(A, B, nrm, J1, J2, J3, delta);
+}
+// solve_friction, constraint_row_friction.cpp:11-54: both tangent candidates from one delta-velocity snapshot,
+// clamped to the circle of radius mu * lambda_n (lambda_n of THIS iteration); r3 = eff_mass t0, t1, rhs t0, t1
+B2D_D void frow_solve(const float4 &r0, const float4 &r1, const float4 &r2, const float4 &r3, float4 &im, VBody &A, VBody &B, bool warm) {
+    v3 nrm = mk3(r0), rA = mk3(r1), rB = mk3(r2);
+    v3 t, u; plane_space(nrm, t, u);
+    v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
+    v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
+    float d0, d1;
+    if (warm) { d0 = im.y; d1 = im.z; }
+    else {
+        d0 = (r3.z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r3.x;
+        d1 = (r3.w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r3.y;
+        float i0 = im.y + d0, i1 = im.z + d1;
+        float len_sqr = i0 * i0 + i1 * i1;
+        float max_len = r2.w * im.x;
+        if (len_sqr > max_len * max_len) {
+            float len = sqrtf(len_sqr);
+            if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
+            d0 = i0 - im.y; d1 = i1 - im.z;
+        }
+        im.y = i0; im.z = i1;
+    }
+    apply_imp_f(A, B, t, T1, T2, T3, d0);
+    apply_imp_f(A, B, u, U1, U2, U3, d1);
+}
+// the five rows of a plain hinge (hinge_constraint.cpp:26-69): three point rows, two angular rows
+B2D_D void hinge_solve(v3 rA, v3 rB, v3 p, v3 q, const float em[5], const float rhs[5], float imp[5], VBody &A, VBody &B, bool warm) {
     #pragma unroll
     for (int k = 0; k < 5; ++k) {
         v3 J0, J1, J2, J3;
@@ -1098,6 +1100,215 @@ B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm, int pass = -1, uint32
         else delta = solve_row(rhs[k], em[k], -SCALAR_MAX, SCALAR_MAX, imp[k], rel_speed(J0, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
         apply_imp(A, B, J0, J1, J2, J3, delta);
     }
+}
+
+// ---------------------------------------------------------------------- island tiles: everything on chip
+// One CTA per tile, thread t owns joint t and contact manifold t of the tile for ALL iterations: the rows of the first
+// two contact points stay in registers, those of points 3 and 4 (box faces), the joint rows and the body records (delta
+// velocities + world inverse inertia) in shared memory.  Rows are read from DRAM once per step
+// instead of once per iteration, and colours are separated by __syncthreads instead of tickets.
+// shared memory of a tile: body records (dv, dw, inverse inertia rows | inverse mass), joint rows, rows of contact points 3 and 4
+constexpr size_t TILE_SOLVE_SMEM = (5 + 7 + 10) * TILE_CAP * sizeof(float4);
+B2D_D void tb_load(const float4 *sb, uint32_t tag, uint32_t slot, VBody &b) {
+    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
+    if (b.proc) {
+        const float4 *r = sb + 5 * slot;
+        const float4 a = r[0], w = r[1], r0 = r[2], r1 = r[3], r2 = r[4];
+        b.dv = mk3(a); b.dw = mk3(w); b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2);
+    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); }
+}
+B2D_D void tb_store(float4 *sb, uint32_t slot, const VBody &b) {
+    if (b.proc) { sb[5 * slot] = f4(b.dv, 0); sb[5 * slot + 1] = f4(b.dw, 0); }
+}
+__global__ void __launch_bounds__(TILE_CAP, 2) k_solve_tiles(Dev d, int iters) {
+    extern __shared__ float4 s_tile[];                     // TILE_SOLVE_SMEM bytes
+    float4 *s_body = s_tile;                               // 5 float4 per body
+    float4 *s_hr = s_tile + 5 * TILE_CAP;                  // joint rows, row-major over the tile's joints (conflict-free)
+    float4 *s_row = s_tile + 12 * TILE_CAP;                // contact points 3 and 4: (R0 R1 R2 R3 IMP) x 2, same layout
+    __shared__ uint32_t s_ncol[2];
+    const uint32_t ntiles = d.cnt->ntiles, t = threadIdx.x;
+    const size_t NM = d.NM;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t nb = min(d.tile_nb[tile], (uint32_t)TILE_CAP);
+        const uint32_t c0 = d.tile_c0[tile], c1 = min(d.tile_c1[tile], c0 + TILE_CAP), h0 = d.tile_h0[tile], h1 = min(d.tile_h1[tile], h0 + TILE_CAP);
+        if (t < 2) s_ncol[t] = 0;
+        if (t < nb) {
+            const uint32_t b = d.tile_body[(size_t)tile * TILE_CAP + t];
+            float4 *r = s_body + 5 * t;
+            r[0] = make_float4(0, 0, 0, 0); r[1] = make_float4(0, 0, 0, 0);
+            r[2] = d.invIW[3 * b]; r[3] = d.invIW[3 * b + 1]; r[4] = d.invIW[3 * b + 2];
+        }
+        __syncthreads();
+        const bool hasH = h0 + t < h1, hasC = c0 + t < c1;
+        const uint32_t hi = h0 + t, ci = c0 + t;
+        uint4 hh = make_uint4(0, 0, 0, 0), ch = make_uint4(0, 0, 0, 0);
+        uint32_t hcol = 0xFFu, ccol = 0xFFu;
+        float4 a0, a1, a2, a3, aim, b0, b1, b2, b3, bim;      // rows of contact points 1 and 2
+        a0 = a1 = a2 = a3 = aim = b0 = b1 = b2 = b3 = bim = make_float4(0, 0, 0, 0);
+        if (hasH) {
+            hh = d.hhdr[hi]; hcol = d.hkey_s[hi] & 63u;
+            const float4 *R = d.HR + 7 * (size_t)hi;
+            #pragma unroll
+            for (int k = 0; k < 7; ++k) s_hr[k * TILE_CAP + t] = R[k];
+            atomicMax(&s_ncol[0], hcol + 1u);
+        }
+        if (hasC) {
+            ch = d.hdr[ci]; ccol = d.ckey_s[ci] & 63u;
+            a0 = d.R0[ci]; a1 = d.R1[ci]; a2 = d.R2[ci]; a3 = d.R3[ci]; aim = d.IMP[ci];
+            if (ch.z > 1) { b0 = d.R0[NM + ci]; b1 = d.R1[NM + ci]; b2 = d.R2[NM + ci]; b3 = d.R3[NM + ci]; bim = d.IMP[NM + ci]; }
+            for (uint32_t s = 2; s < ch.z; ++s) {
+                const size_t ri = s * NM + ci;
+                float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                r[0] = d.R0[ri]; r[TILE_CAP] = d.R1[ri]; r[2 * TILE_CAP] = d.R2[ri]; r[3 * TILE_CAP] = d.R3[ri]; r[4 * TILE_CAP] = d.IMP[ri];
+            }
+            atomicMax(&s_ncol[1], ccol + 1u);
+        }
+        __syncthreads();
+        const uint32_t nhc = s_ncol[0], ncc = s_ncol[1];
+        for (int it = -1; it < iters; ++it) {
+            const bool warm = it < 0;
+            for (uint32_t c = 0; c < nhc; ++c) {
+                if (hcol == c) {
+                    const float4 r0 = s_hr[t], r1 = s_hr[TILE_CAP + t], r2 = s_hr[2 * TILE_CAP + t], r3 = s_hr[3 * TILE_CAP + t],
+                                 r4 = s_hr[4 * TILE_CAP + t], r5 = s_hr[5 * TILE_CAP + t], r6 = s_hr[6 * TILE_CAP + t];
+                    const float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x}, rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
+                    float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
+                    VBody A, B; tb_load(s_body, hh.x, hh.w & 0xFFFFu, A); tb_load(s_body, hh.y, hh.w >> 16, B);
+                    hinge_solve(mk3(r0), mk3(r1), mk3(r2), mk3(r3), em, rhs, imp, A, B, warm);
+                    tb_store(s_body, hh.w & 0xFFFFu, A); tb_store(s_body, hh.w >> 16, B);
+                    if (!warm) { s_hr[5 * TILE_CAP + t] = make_float4(r5.x, r5.y, imp[0], imp[1]); s_hr[6 * TILE_CAP + t] = make_float4(imp[2], imp[3], imp[4], 0); }
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                if (ccol == c) {
+                    VBody A, B; tb_load(s_body, ch.x, ch.w & 0xFFFFu, A); tb_load(s_body, ch.y, ch.w >> 16, B);
+                    nrow_solve(a0, a1, a2, aim, A, B, warm);
+                    if (ch.z > 1) nrow_solve(b0, b1, b2, bim, A, B, warm);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                        float4 im = r[4 * TILE_CAP];
+                        nrow_solve(r[0], r[TILE_CAP], r[2 * TILE_CAP], im, A, B, warm);
+                        r[4 * TILE_CAP] = im;
+                    }
+                    tb_store(s_body, ch.w & 0xFFFFu, A); tb_store(s_body, ch.w >> 16, B);
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                if (ccol == c) {
+                    VBody A, B; tb_load(s_body, ch.x, ch.w & 0xFFFFu, A); tb_load(s_body, ch.y, ch.w >> 16, B);
+                    frow_solve(a0, a1, a2, a3, aim, A, B, warm);
+                    if (ch.z > 1) frow_solve(b0, b1, b2, b3, bim, A, B, warm);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                        float4 im = r[4 * TILE_CAP];
+                        frow_solve(r[0], r[TILE_CAP], r[2 * TILE_CAP], r[3 * TILE_CAP], im, A, B, warm);
+                        r[4 * TILE_CAP] = im;
+                    }
+                    tb_store(s_body, ch.w & 0xFFFFu, A); tb_store(s_body, ch.w >> 16, B);
+                }
+                __syncthreads();
+            }
+        }
+        // results: impulses for the warm-start cache, delta velocities for k_integrate
+        if (hasH) { float4 *R = d.HR + 7 * (size_t)hi; R[5] = s_hr[5 * TILE_CAP + t]; R[6] = s_hr[6 * TILE_CAP + t]; }
+        if (hasC) {
+            d.IMP[ci] = aim; if (ch.z > 1) d.IMP[NM + ci] = bim;
+            for (uint32_t s = 2; s < ch.z; ++s) d.IMP[s * NM + ci] = s_row[((s - 2) * 5 + 4) * TILE_CAP + t];
+        }
+        if (t < nb) {
+            const uint32_t b = d.tile_body[(size_t)tile * TILE_CAP + t];
+            const float4 a = s_body[5 * t], w = s_body[5 * t + 1];
+            d.dvw[2 * b] = make_float4(a.x, a.y, a.z, 0.0f); d.dvw[2 * b + 1] = make_float4(w.x, w.y, w.z, 0.0f);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------- dataflow: per-body tickets in global memory
+// Instead of a grid barrier per colour, every dynamic body carries a ticket counter.  A constraint pass may touch its
+// two bodies when both counters equal the tickets computed for it in k_prepare_* (position of this pass in the body's
+// fixed sequence: iteration-major, then hinges / normals / frictions, then colour); afterwards it bumps them.  A pass
+// waits only for its own two predecessors (an L2 round trip) rather than for the slowest CTA of the whole grid.
+B2D_D void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+struct Ticket { uint32_t ta, tb, mask; };
+// pass = iteration + 1 (0 = warm start); kind: 0 hinge, 1 contact normal, 2 friction
+B2D_D Ticket ticket_of(uint2 tk, int pass, int kind, uint32_t mask) {
+    Ticket t;
+    t.mask = mask;
+    const uint32_t SA = tk.x & 0xFFu, bA = (tk.x >> 8) & 0xFFu, kA = (tk.x >> 16) & 0xFFu;
+    const uint32_t SB = tk.y & 0xFFu, bB = (tk.y >> 8) & 0xFFu, kB = (tk.y >> 16) & 0xFFu;
+    t.ta = (uint32_t)pass * SA + bA + (kind == 2 ? kA : 0u);
+    t.tb = (uint32_t)pass * SB + bB + (kind == 2 ? kB : 0u);
+    return t;
+}
+// ptxas recycles the unused lanes of a 128-bit load as scratch registers straight away, and the write-after-write hazard
+// then parks the warp until the load has landed -- in front of the ticket poll.  keep() pins such a lane as live up to
+// the point where the rest of the vector is consumed.
+B2D_D void keep(float x) { asm volatile("" :: "f"(x)); }
+B2D_D void keep(uint32_t x) { asm volatile("" :: "r"(x)); }
+B2D_D void keep(const VBody &b) { keep(b.pad1); keep(b.pad2); }
+// Dataflow acquire / publish.  The delta-velocity record of a body (two float4 = one 32 B sector) carries the
+// body's ticket in BOTH .w lanes, so data and synchronisation travel in the same L2 transactions: a reader that
+// sees the expected ticket in both halves has a consistent record (16 B aligned vector stores are single
+// transactions; a torn pair is rejected by the double check) and needs no fence, a writer needs none either.
+#ifndef B2D_LD_POLL
+#define B2D_LD_POLL "ld.relaxed.gpu.global.v4.f32"     // gpu scope is all the protocol needs (.volatile = relaxed.sys)
+#define B2D_ST_POLL "st.relaxed.gpu.global.v4.f32"
+#endif
+B2D_D float4 ld_volatile4(const float4 *p) {
+    float4 v; asm volatile(B2D_LD_POLL " {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+B2D_D void st_volatile4(float4 *p, float4 v) {
+    asm volatile(B2D_ST_POLL " [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// everything of a body that does not change during the solve
+B2D_D void vb_static(const Dev &d, uint32_t tag, VBody &b) {
+    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
+    b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0);
+    if (b.proc) {
+        float4 r0 = d.invIW[3 * b.id], r1 = d.invIW[3 * b.id + 1], r2 = d.invIW[3 * b.id + 2];
+        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2); b.pad1 = r1.w; b.pad2 = r2.w;
+    } else { b.inv_m = 0; b.inv_I = m3_zero(); b.pad1 = b.pad2 = 0; }
+}
+B2D_D bool vb_try(const Dev &d, VBody &b, uint32_t expect) {
+    float4 a = ld_volatile4(&d.dvw[2 * b.id]), w = ld_volatile4(&d.dvw[2 * b.id + 1]);
+    b.dv = mk3(a); b.dw = mk3(w);
+    return __float_as_uint(a.w) == expect && __float_as_uint(w.w) == expect;
+}
+// Lanes of a chunk become ready one by one; each lane solves as soon as ITS two bodies carry the expected tickets
+// (the ready subset runs the solve converged, the rest keep polling), so one late predecessor delays one constraint
+// and not the 31 others that happen to share its warp.
+B2D_D bool acquire_try(const Dev &d, const Ticket &t, VBody &A, VBody &B) {
+    return (!A.proc || vb_try(d, A, t.ta)) & (!B.proc || vb_try(d, B, t.tb));
+}
+B2D_D bool acquire_more(const Dev &d, const Ticket &t, bool pending, bool progressed, uint32_t &spins) {
+    if (!__any_sync(t.mask, pending)) return false;
+    if (!__any_sync(t.mask, progressed)) {
+        if (++spins > (1u << 20)) { atomicOr(&d.cnt->err, ERR_SOLVER_TIMEOUT); return false; }      // never hang the GPU
+        if (spins > 64) __nanosleep(20);
+    }
+    return true;
+}
+B2D_D void bodies_publish(const Dev &d, const Ticket &t, const VBody &A, const VBody &B) {
+    if (A.proc) { st_volatile4(&d.dvw[2 * A.id], f4(A.dv, __uint_as_float(t.ta + 1))); st_volatile4(&d.dvw[2 * A.id + 1], f4(A.dw, __uint_as_float(t.ta + 1))); }
+    if (B.proc) { st_volatile4(&d.dvw[2 * B.id], f4(B.dv, __uint_as_float(t.tb + 1))); st_volatile4(&d.dvw[2 * B.id + 1], f4(B.dw, __uint_as_float(t.tb + 1))); }
+}
+
+B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm, int pass, uint32_t mask) {
+    uint4 hd = d.hhdr[i];
+    float4 *R = d.HR + 7 * (size_t)i;
+    float4 r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6];
+    const Ticket tk = ticket_of(d.htkt[i], pass, 0, mask);
+    VBody A, B; vb_static(d, hd.x, A); vb_static(d, hd.y, B);
+    bool pending = true; uint32_t spins = 0;
+    const float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x}, rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
+    float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
+    do {
+    const bool ok = pending && acquire_try(d, tk, A, B);
+    if (ok) {
+    hinge_solve(mk3(r0), mk3(r1), mk3(r2), mk3(r3), em, rhs, imp, A, B, warm);
     bodies_publish(d, tk, A, B);
     if (!warm) { R[5] = make_float4(r5.x, r5.y, imp[0], imp[1]); R[6] = make_float4(imp[2], imp[3], imp[4], 0); }
     pending = false;
@@ -1113,24 +1324,17 @@ B2D_D void prefetch_L2(const void *p) { asm volatile("prefetch.global.L2 [%0];" 
 struct NRow { float4 r0, r1, r2, im; };
 B2D_D NRow load_nrow(const Dev &d, size_t ri) { NRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.im = d.IMP[ri]; return r; }
 B2D_D void solve_nrow(const Dev &d, NRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
-    v3 nrm = mk3(r.r0), rA = mk3(r.r1), rB = mk3(r.r2);
-    v3 J1 = cross(rA, nrm), J2 = -nrm, J3 = -cross(rB, nrm);
-    float delta;
-    if (warm) delta = r.im.x;
-    else {
-        delta = solve_row(r.r0.w, r.r1.w, 0.0f, LARGE, r.im.x, rel_speed(nrm, J1, J2, J3, A.dv, A.dw, B.dv, B.dw));
-        d.IMP[ri] = r.im;
-    }
-    apply_imp(A, B, nrm, J1, J2, J3, delta);
+    nrow_solve(r.r0, r.r1, r.r2, r.im, A, B, warm);
+    if (!warm) d.IMP[ri] = r.im;
 }
-B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
-    const Ticket tk = ticket_of(hd.x, hd.y, tk2, pass, 1, mask);
+B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass, uint32_t mask) {
+    const Ticket tk = ticket_of(tk2, pass, 1, mask);
     const uint32_t n = hd.z;
     const size_t NM = d.NM;
     NRow ra, rb;
     ra = load_nrow(d, i);
     rb = load_nrow(d, n > 1 ? NM + i : i);          // unconditional: a predicated load drags a zero-fill + WAW wait along
-    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
+    VBody A, B; vb_static(d, hd.x, A); vb_static(d, hd.y, B);
     bool pending = true; uint32_t spins = 0;
     do {
     const bool ok = pending && acquire_try(d, tk, A, B);
@@ -1150,42 +1354,20 @@ B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2
     } while (true);
 }
 
-// solve_friction, constraint_row_friction.cpp:11-54: both tangent candidates from one delta-velocity snapshot,
-// clamped to the circle of radius mu * lambda_n (lambda_n of THIS iteration).
 struct FRow { float4 r0, r1, r2, r3, im; };
 B2D_D FRow load_frow(const Dev &d, size_t ri) { FRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.r3 = d.R3[ri]; r.im = d.IMP[ri]; return r; }
 B2D_D void solve_frow(const Dev &d, FRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
-    v3 nrm = mk3(r.r0), rA = mk3(r.r1), rB = mk3(r.r2);
-    v3 t, u; plane_space(nrm, t, u);
-    v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
-    v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
-    float d0, d1;
-    if (warm) { d0 = r.im.y; d1 = r.im.z; }
-    else {
-        d0 = (r.r3.z - rel_speed(t, T1, T2, T3, A.dv, A.dw, B.dv, B.dw)) * r.r3.x;
-        d1 = (r.r3.w - rel_speed(u, U1, U2, U3, A.dv, A.dw, B.dv, B.dw)) * r.r3.y;
-        float i0 = r.im.y + d0, i1 = r.im.z + d1;
-        float len_sqr = i0 * i0 + i1 * i1;
-        float max_len = r.r2.w * r.im.x;
-        if (len_sqr > max_len * max_len) {
-            float len = sqrtf(len_sqr);
-            if (len > EPS) { i0 = i0 / len * max_len; i1 = i1 / len * max_len; } else { i0 = 0; i1 = 0; }
-            d0 = i0 - r.im.y; d1 = i1 - r.im.z;
-        }
-        r.im.y = i0; r.im.z = i1;
-        d.IMP[ri] = r.im;
-    }
-    apply_imp_f(A, B, t, T1, T2, T3, d0);
-    apply_imp_f(A, B, u, U1, U2, U3, d1);
+    frow_solve(r.r0, r.r1, r.r2, r.r3, r.im, A, B, warm);
+    if (!warm) d.IMP[ri] = r.im;
 }
-B2D_D void friction_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass = -1, uint32_t mask = 0xffffffffu) {
-    const Ticket tk = ticket_of(hd.x, hd.y, tk2, pass, 2, mask);
+B2D_D void friction_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2, bool warm, int pass, uint32_t mask) {
+    const Ticket tk = ticket_of(tk2, pass, 2, mask);
     const uint32_t n = hd.z;
     const size_t NM = d.NM;
     FRow ra, rb;
     ra = load_frow(d, i);
     rb = load_frow(d, n > 1 ? NM + i : i);
-    VBody A, B; acquire_begin(d, tk, hd.x, hd.y, A, B);
+    VBody A, B; vb_static(d, hd.x, A); vb_static(d, hd.y, B);
     bool pending = true; uint32_t spins = 0;
     do {
     const bool ok = pending && acquire_try(d, tk, A, B);
@@ -1205,57 +1387,10 @@ B2D_D void friction_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 t
     } while (true);
 }
 
-
-// Pass q of one iteration: hinge colours, then contact-normal colours, then friction colours.
-struct Pass { uint32_t b, e; int kind; };     // kind 0 hinge rows, 1 contact normal rows, 2 friction pairs
-B2D_D Pass get_pass(const Counters &c, uint32_t q, uint32_t nh, uint32_t nc) {
-    Pass p;
-    if (q < nh) { p.kind = 0; p.b = c.hoff[q]; p.e = c.hoff[q + 1]; }
-    else if (q < nh + nc) { p.kind = 1; p.b = c.coff[q - nh]; p.e = c.coff[q - nh + 1]; }
-    else { p.kind = 2; p.b = c.coff[q - nh - nc]; p.e = c.coff[q - nh - nc + 1]; }
-    return p;
-}
-// Rows never change during the solve and impulses are private to the thread that owns the constraint, so the
-// next pass's row data can be pulled towards L2 while this pass drains into the barrier; only the delta
-// velocities have to be read after it.
-B2D_D void prefetch_pass(const Dev &d, const Pass &p, uint32_t gtid) {
-    uint32_t i = p.b + gtid;
-    if (i >= p.e) return;
-    if (p.kind == 0) { const float4 *R = d.HR + 7 * (size_t)i; prefetch_L2(&d.hhdr[i]); prefetch_L2(R); prefetch_L2(R + 4); return; }
-    prefetch_L2(&d.hdr[i]);
-    #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        size_t ri = (size_t)s * d.NM + i;
-        prefetch_L2(&d.R0[ri]); prefetch_L2(&d.R1[ri]); prefetch_L2(&d.R2[ri]); prefetch_L2(&d.IMP[ri]);
-        if (p.kind == 2) prefetch_L2(&d.R3[ri]);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_solve(Dev d, int iters) {
-    GridBarrier grid(&d.cnt->bar);
-    const Counters &c = *d.cnt;
-    const uint32_t nc = c.ncolors, nh = c.nhcolors;
-    const uint32_t npass = nh + 2 * nc;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    if (npass == 0) return;
-    for (int it = -1; it < iters; ++it) {
-        const bool warm = it < 0;
-        for (uint32_t q = 0; q < npass; ++q) {
-            const Pass p = get_pass(c, q, nh, nc);
-            if (p.kind == 0) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) hinge_pass(d, i, warm); }
-            else if (p.kind == 1) { for (uint32_t i = p.b + gtid; i < p.e; i += stride) normal_pass(d, i, d.hdr[i], make_uint2(0, 0), warm); }
-            else { for (uint32_t i = p.b + gtid; i < p.e; i += stride) friction_pass(d, i, d.hdr[i], make_uint2(0, 0), warm); }
-            prefetch_pass(d, get_pass(c, q + 1 == npass ? 0 : q + 1, nh, nc), gtid);
-            grid.sync();
-        }
-    }
-}
-
-// Dataflow flavour of k_solve (default): same passes, same per-body order, no grid barriers.  Work is dealt to warps
-// in 32-constraint chunks that never span two colours (so lanes of a warp never wait on each other), chunk j to warp
-// j mod W, each warp walking its chunks in increasing (iteration, type, colour) order.  The globally smallest
-// unfinished chunk therefore always has its predecessors done and its warp working on it: no deadlock as long as the
-// grid is co-resident (cooperative launch).  wait_ticket() additionally bails out after a bounded number of spins.
+// Work is dealt to warps in 32-constraint chunks that never span two colours (so lanes of a warp never wait on each
+// other), chunk j to warp j mod W, each warp walking its chunks in increasing (iteration, type, colour) order.  The
+// globally smallest unfinished chunk therefore always has its predecessors done and its warp working on it: no deadlock
+// as long as the grid is co-resident (cooperative launch); the polls additionally bail out after a bounded number of spins.
 // chunk j of a pass type -> (colour, first sorted index); `col` is a monotone cursor
 B2D_D uint32_t chunk_index(const uint32_t *chunk, const uint32_t *off, uint32_t j, uint32_t &col) {
     while (j >= chunk[col + 1]) ++col;
@@ -1277,6 +1412,7 @@ __global__ void __launch_bounds__(B2D_SOLVE_THREADS, 2) k_solve_df(Dev d, int it
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const uint32_t hchunks = s_hchunk[nh], cchunks = s_cchunk[nc];
+    if (hchunks + cchunks == 0) return;
     // The header and ticket words of this warp's NEXT contact chunk are fetched one chunk ahead into registers (they
     // are the same for every pass and both row types), so a chunk starts polling its bodies without first waiting for
     // its own header; the rows of the next chunk are pulled towards L2 at the same time.
@@ -1285,11 +1421,6 @@ __global__ void __launch_bounds__(B2D_SOLVE_THREADS, 2) k_solve_df(Dev d, int it
         ni = chunk_index(s_cchunk, s_coff, wid, ncol) + lane; nact = ni < s_coff[ncol + 1];
         if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; }
     }
-#ifdef B2D_DF_PROFILE
-    if (lane < 8) s_prof[threadIdx.x >> 5][lane] = 0;
-    const long long t_begin = clock64();
-    __syncwarp();
-#endif
     for (int it = -1; it < iters; ++it) {
         const bool warm = it < 0;
         const int pass = it + 1;
@@ -1313,30 +1444,18 @@ __global__ void __launch_bounds__(B2D_SOLVE_THREADS, 2) k_solve_df(Dev d, int it
                     if (kind == 2 || jn == wid) prefetch_L2(&d.R3[ni]);
                 }
                 const uint32_t mask = __ballot_sync(0xffffffffu, act);
-#ifdef B2D_DF_PROFILE
-                __syncwarp(); if (lane == 0) { s_prof_t[threadIdx.x >> 5] = clock64(); s_prof[threadIdx.x >> 5][4] += 1; } __syncwarp();
-#endif
                 if (act) { if (kind == 1) normal_pass(d, i, hd, tk2, warm, pass, mask); else friction_pass(d, i, hd, tk2, warm, pass, mask); }
             }
         }
     }
-#ifdef B2D_DF_PROFILE
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t w = threadIdx.x >> 5;
-        for (int k = 0; k < 5; ++k) atomicAdd(&d.cnt->dbg[k], s_prof[w][k]);
-        atomicAdd(&d.cnt->dbg[5], (unsigned long long)(clock64() - t_begin));
-        atomicAdd(&d.cnt->dbg[6], 1ULL);
-    }
-#endif
 }
 
 // assign_applied_impulses (island_solver.cpp:232-248): rows -> warm-start cache of the constraints.
 __global__ void k_store_impulses(Dev d) {
-    const uint32_t n = d.cnt->nactive, nh = d.cnt->hoff[MAX_COLORS];
+    const uint32_t n = d.cnt->nactive, nh = d.cnt->nhactive;
     GRID_STRIDE(i, n) {
-        uint4 hd = d.hdr[i];
-        for (uint32_t s = 0; s < hd.z; ++s) d.pI[(size_t)s * d.NM + hd.w] = d.IMP[(size_t)s * d.NM + i];
+        const uint32_t npts = d.hdr[i].z, m = d.cidx_s[i];
+        for (uint32_t s = 0; s < npts; ++s) d.pI[(size_t)s * d.NM + m] = d.IMP[(size_t)s * d.NM + i];
     }
     GRID_STRIDE(i, nh) {
         uint4 hd = d.hhdr[i];
@@ -1386,22 +1505,6 @@ __global__ void __launch_bounds__(256) k_finalize(Dev d) {
 // ====================================================================== position iterations
 
 struct PBody { v3 pos; q4 orn; float inv_m; m3 inv_IW, inv_I; uint32_t id; bool proc; bool fresh; };   // fresh: corrected in this solve
-B2D_D void pb_load(const Dev &d, uint32_t id, PBody &b) {
-    b.id = id; b.proc = is_dynamic(d.flags[id]); b.fresh = false;
-    float4 p4 = __ldcg(&d.pos[id]);
-    b.pos = mk3(p4); b.orn = mkq(__ldcg(&d.orn[id]));
-    if (b.proc) {
-        b.inv_m = p4.w;
-        b.inv_IW.r0 = mk3(__ldcg(&d.invIW[3 * id])); b.inv_IW.r1 = mk3(__ldcg(&d.invIW[3 * id + 1])); b.inv_IW.r2 = mk3(__ldcg(&d.invIW[3 * id + 2]));
-        b.inv_I = load_m3(d.invI, id);
-    }
-    else { b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero(); }
-}
-B2D_D void pb_store(const Dev &d, const PBody &b) {
-    if (!b.proc) return;
-    d.pos[b.id] = f4(b.pos, b.inv_m); d.orn[b.id] = f4(b.orn);
-    store_invIW(d, b.id, b.inv_IW, b.inv_m);
-}
 // position_solver::solve, dynamics/position_solver.hpp:16-51.  Non-procedural bodies are left untouched
 // (the reference only re-normalises their unit orientation).
 B2D_D void position_solve(PBody &A, PBody &B, v3 J0, v3 J1, v3 J2, v3 J3, float error, float &max_error) {
@@ -1434,9 +1537,170 @@ B2D_D void island_error_max(const Dev &d, uint32_t isl, float err) {
 }
 B2D_D uint32_t island_of(const Dev &d, uint32_t a, uint32_t b) { uint32_t l = d.parent[a]; return l != 0xFFFFFFFFu ? l : d.parent[b]; }
 
-// contact_constraint::solve_position, contact_constraint.cpp:58-90
-// Dataflow tickets of the position sweeps: per iteration a body sees its hinges, then its contacts (no friction
-// pass), so the schedule is the velocity one with S' = S - k_contacts.
+
+// ---------------------------------------------------------------------- island tiles: position iterations on chip
+// <= N position iterations, each island stopping once its max error drops below 0.005 (island_solver.cpp:263-353,
+// :538-543).  Same tiles and colours as k_solve_tiles: thread t owns joint t and contact manifold t of the tile, the
+// body transforms (position, orientation, world inverse inertia) live in shared memory together with the per-island
+// error / done words (kept at the slot of the island's root body), colours are separated by __syncthreads.  The
+// contact points of the first two slots stay in registers; their refreshed normal and distance
+// (contact_constraint.cpp:72-76) are written back once at the end.
+// shared memory of a tile: per body pos | inverse mass, orn, world and body inverse inertia (8 float4); contact points 3 and 4
+constexpr size_t TILE_POS_SMEM = (8 + 8) * TILE_CAP * sizeof(float4);
+B2D_D void tp_load(const float4 *sb, const Dev &d, uint32_t tag, uint32_t slot, PBody &b) {
+    b.id = tag & 0x7FFFFFFFu; b.proc = !(tag >> 31); b.fresh = false;
+    if (b.proc) {
+        const float4 *r = sb + 8 * slot;
+        const float4 p = r[0];
+        b.pos = mk3(p); b.inv_m = p.w; b.orn = mkq(r[1]);
+        b.inv_IW.r0 = mk3(r[2]); b.inv_IW.r1 = mk3(r[3]); b.inv_IW.r2 = mk3(r[4]);
+        b.inv_I.r0 = mk3(r[5]); b.inv_I.r1 = mk3(r[6]); b.inv_I.r2 = mk3(r[7]);
+    } else {
+        b.pos = mk3(d.pos[b.id]); b.orn = mkq(d.orn[b.id]);
+        b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero();
+    }
+}
+B2D_D void tp_store(float4 *sb, uint32_t *fresh, uint32_t slot, const PBody &b) {
+    if (!b.proc || !b.fresh) return;
+    float4 *r = sb + 8 * slot;
+    r[0] = f4(b.pos, b.inv_m); r[1] = f4(b.orn);
+    r[2] = f4(b.inv_IW.r0, 0); r[3] = f4(b.inv_IW.r1, 0); r[4] = f4(b.inv_IW.r2, 0);
+    fresh[slot] = 1u;
+}
+B2D_D void tile_error_max(uint32_t *s_err, uint32_t islot, float err) { if (err != 0.0f) atomicMax(&s_err[islot], __float_as_uint(err)); }
+__global__ void __launch_bounds__(TILE_CAP, 2) k_position_tiles(Dev d, int iters) {
+    extern __shared__ float4 s_tile[];                     // TILE_POS_SMEM bytes
+    float4 *s_body = s_tile;                               // 8 float4 per body
+    float4 *s_pt = s_tile + 8 * TILE_CAP;                  // contact points 3 and 4: (pA pB pN pL) x 2, row-major over the tile's manifolds
+    __shared__ uint32_t s_err[TILE_CAP], s_done[TILE_CAP], s_fresh[TILE_CAP], s_root[TILE_CAP];
+    __shared__ uint32_t s_ncol[2];
+    const uint32_t ntiles = d.cnt->ntiles, t = threadIdx.x;
+    const size_t NM = d.NM;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t nb = min(d.tile_nb[tile], (uint32_t)TILE_CAP);
+        const uint32_t c0 = d.tile_c0[tile], c1 = min(d.tile_c1[tile], c0 + TILE_CAP), h0 = d.tile_h0[tile], h1 = min(d.tile_h1[tile], h0 + TILE_CAP);
+        if (t < 2) s_ncol[t] = 0;
+        uint32_t mybody = 0;
+        if (t < nb) {
+            const uint32_t b = d.tile_body[(size_t)tile * TILE_CAP + t];
+            mybody = b;
+            float4 *r = s_body + 8 * t;
+            r[0] = d.pos[b]; r[1] = d.orn[b];
+            const float4 w0 = d.invIW[3 * b];
+            r[0].w = w0.w;                                       // inverse mass as the solvers see it (0 unless dynamic)
+            r[2] = w0; r[3] = d.invIW[3 * b + 1]; r[4] = d.invIW[3 * b + 2];
+            r[5] = d.invI[3 * b]; r[6] = d.invI[3 * b + 1]; r[7] = d.invI[3 * b + 2];
+            s_err[t] = 0; s_done[t] = 0; s_fresh[t] = 0; s_root[t] = d.parent[b] == b ? 1u : 0u;
+        }
+        __syncthreads();
+        const bool hasH = h0 + t < h1, hasC = c0 + t < c1;
+        const uint32_t hi = h0 + t, ci = c0 + t;
+        uint4 hh = make_uint4(0, 0, 0, 0), ch = make_uint4(0, 0, 0, 0);
+        uint32_t hcol = 0xFFu, ccol = 0xFFu, hisl = 0, cisl = 0, m = 0;
+        v3 fA0 = mk3(0, 0, 0), fB0 = fA0, pvA = fA0, pvB = fA0;
+        float4 a40, b40, n40, l40, a41, b41, n41, l41;         // contact points 1 and 2
+        a40 = b40 = n40 = l40 = a41 = b41 = n41 = l41 = make_float4(0, 0, 0, 0);
+        bool touched = false;
+        if (hasH) {
+            hh = d.hhdr[hi]; hcol = d.hkey_s[hi] & 63u; hisl = d.bslot[d.hisl[hi]];
+            const uint32_t h = hh.z;
+            fA0 = mk3(d.hfA0[h]); fB0 = mk3(d.hfB0[h]); pvA = mk3(d.hpivA[h]); pvB = mk3(d.hpivB[h]);
+            atomicMax(&s_ncol[0], hcol + 1u);
+        }
+        if (hasC) {
+            ch = d.hdr[ci]; ccol = d.ckey_s[ci] & 63u; cisl = d.bslot[d.pisl[ci]]; m = d.cidx_s[ci];
+            a40 = d.pA[m]; b40 = d.pB[m]; n40 = d.pN[m]; l40 = d.pL[m];
+            if (ch.z > 1) { a41 = d.pA[NM + m]; b41 = d.pB[NM + m]; n41 = d.pN[NM + m]; l41 = d.pL[NM + m]; }
+            for (uint32_t s = 2; s < ch.z; ++s) {
+                const size_t mi = s * NM + m;
+                float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t;
+                r[0] = d.pA[mi]; r[TILE_CAP] = d.pB[mi]; r[2 * TILE_CAP] = d.pN[mi]; r[3 * TILE_CAP] = d.pL[mi];
+            }
+            atomicMax(&s_ncol[1], ccol + 1u);
+        }
+        __syncthreads();
+        const uint32_t nhc = s_ncol[0], ncc = s_ncol[1];
+        for (int it = 0; it < iters; ++it) {
+            for (uint32_t c = 0; c < nhc; ++c) {
+                // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
+                if (hcol == c && !s_done[hisl]) {
+                    PBody A, B; tp_load(s_body, d, hh.x, hh.w & 0xFFFFu, A); tp_load(s_body, d, hh.y, hh.w >> 16, B);
+                    float max_error = 0.0f;
+                    v3 axisA = rotate(A.orn, fA0), axisB = rotate(B.orn, fB0);
+                    v3 p, q; plane_space(axisA, p, q);
+                    v3 u = cross(axisA, axisB);
+                    const v3 z = mk3(0, 0, 0);
+                    { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
+                    { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
+                    v3 pivotA = to_world(pvA, A.pos, A.orn), pivotB = to_world(pvB, B.pos, B.orn);
+                    v3 dir = pivotA - pivotB;
+                    float e = length(dir);
+                    if (e > EPS) {
+                        dir /= e;
+                        v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+                        position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
+                    }
+                    tp_store(s_body, s_fresh, hh.w & 0xFFFFu, A); tp_store(s_body, s_fresh, hh.w >> 16, B);
+                    tile_error_max(s_err, hisl, max_error);
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                // contact_constraint::solve_position, contact_constraint.cpp:58-90
+                if (ccol == c && !s_done[cisl]) {
+                    PBody A, B; tp_load(s_body, d, ch.x, ch.w & 0xFFFFu, A); tp_load(s_body, d, ch.y, ch.w >> 16, B);
+                    float max_error = 0.0f;
+                    touched = true;
+                    // one contact point: refreshes its normal and distance in place, corrects the bodies if it penetrates
+                    auto point = [&](float4 &pa, const float4 &pb, float4 &pn, const float4 &pl) {
+                        v3 pAw = to_world(mk3(pa), A.pos, A.orn), pBw = to_world(mk3(pb), B.pos, B.orn);
+                        unsigned att = __float_as_uint(pl.w) & 3u;
+                        v3 normal = mk3(pn);
+                        if (att == ATT_A) normal = rotate(A.orn, mk3(pl)); else if (att == ATT_B) normal = rotate(B.orn, mk3(pl));
+                        float dist = dot(pAw - pBw, normal);
+                        v3 rA = pAw - A.pos, rB = pBw - B.pos;
+                        pn = f4(normal, pn.w); pa = f4(mk3(pa), dist);
+                        if (dist > -EPS) return;
+                        position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
+                    };
+                    point(a40, b40, n40, l40);
+                    if (ch.z > 1) point(a41, b41, n41, l41);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t;
+                        float4 pa = r[0], pn = r[2 * TILE_CAP];
+                        point(pa, r[TILE_CAP], pn, r[3 * TILE_CAP]);
+                        r[0] = pa; r[2 * TILE_CAP] = pn;
+                    }
+                    tp_store(s_body, s_fresh, ch.w & 0xFFFFu, A); tp_store(s_body, s_fresh, ch.w >> 16, B);
+                    tile_error_max(s_err, cisl, max_error);
+                }
+                __syncthreads();
+            }
+            if (it + 1 < iters) {
+                if (t < nb && s_root[t]) { if (__uint_as_float(s_err[t]) < 0.005f) s_done[t] = 1; s_err[t] = 0; }
+                __syncthreads();
+            }
+        }
+        if (hasC && touched) {
+            d.pN[m] = n40; d.pA[m] = a40;
+            if (ch.z > 1) { d.pN[NM + m] = n41; d.pA[NM + m] = a41; }
+            for (uint32_t s = 2; s < ch.z; ++s) { const float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t; d.pA[s * NM + m] = r[0]; d.pN[s * NM + m] = r[2 * TILE_CAP]; }
+        }
+        if (t < nb && s_fresh[t]) {
+            const float4 p = s_body[8 * t], o = s_body[8 * t + 1];
+            d.pos[mybody] = make_float4(p.x, p.y, p.z, d.pos[mybody].w); d.orn[mybody] = o;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------- dataflow: position iterations
+#ifndef B2D_POS_MIN_BLOCKS
+#define B2D_POS_MIN_BLOCKS 1
+#endif
+#ifndef B2D_POS_THREADS
+#define B2D_POS_THREADS 256
+#endif
 struct PTicket { uint32_t ta, tb, mask; bool on; };
 B2D_D PTicket pticket_of(uint2 tk, int it, uint32_t mask, bool on) {
     PTicket t; t.on = on; t.mask = mask;
@@ -1445,95 +1709,6 @@ B2D_D PTicket pticket_of(uint2 tk, int it, uint32_t mask, bool on) {
     return t;
 }
 
-// barrier flavour (k_position): colours are separated by grid barriers, bodies are read and written in place
-B2D_D void contact_position(const Dev &d, uint32_t i) {
-    uint4 hd = d.hdr[i];
-    uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, m = hd.w;
-    uint32_t isl = island_of(d, a, b);
-    // all constraints of a finished island skip together (and keep skipping), so their tickets stay consistent
-    const bool skip = d.isl_done[isl] != 0;
-    if (skip) return;
-    PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
-    float max_error = 0.0f;
-    for (uint32_t s = 0; s < hd.z; ++s) {
-        size_t mi = (size_t)s * d.NM + m;
-        float4 a4 = d.pA[mi], b4 = d.pB[mi], n4 = d.pN[mi], l4 = d.pL[mi];
-        v3 pAw = to_world(mk3(a4), A.pos, A.orn), pBw = to_world(mk3(b4), B.pos, B.orn);
-        unsigned att = __float_as_uint(l4.w) & 3u;
-        v3 normal = mk3(n4);
-        if (att == ATT_A) normal = rotate(A.orn, mk3(l4)); else if (att == ATT_B) normal = rotate(B.orn, mk3(l4));
-        float dist = dot(pAw - pBw, normal);
-        v3 rA = pAw - A.pos, rB = pBw - B.pos;
-        d.pN[mi] = f4(normal, n4.w); d.pA[mi] = f4(mk3(a4), dist);
-        if (dist > -EPS) continue;
-        position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
-    }
-    pb_store(d, A); pb_store(d, B);
-    island_error_max(d, isl, max_error);
-}
-// hinge_constraint::solve_position, hinge_constraint.cpp:180-213
-B2D_D void hinge_position(const Dev &d, uint32_t i) {
-    uint4 hd = d.hhdr[i];
-    uint32_t a = hd.x & 0x7FFFFFFFu, b = hd.y & 0x7FFFFFFFu, h = hd.z;
-    uint32_t isl = island_of(d, a, b);
-    const bool skip = d.isl_done[isl] != 0;
-    if (skip) return;
-    PBody A, B; pb_load(d, a, A); pb_load(d, b, B);
-    float max_error = 0.0f;
-    v3 axisA = rotate(A.orn, mk3(d.hfA0[h])), axisB = rotate(B.orn, mk3(d.hfB0[h]));
-    v3 p, q; plane_space(axisA, p, q);
-    v3 u = cross(axisA, axisB);
-    const v3 z = mk3(0, 0, 0);
-    { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
-    { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
-    v3 pivotA = to_world(mk3(d.hpivA[h]), A.pos, A.orn), pivotB = to_world(mk3(d.hpivB[h]), B.pos, B.orn);
-    v3 dir = pivotA - pivotB;
-    float e = length(dir);
-    if (e > EPS) {
-        dir /= e;
-        v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
-        position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
-    }
-    pb_store(d, A); pb_store(d, B);
-    island_error_max(d, isl, max_error);
-}
-
-// <= N position iterations, each island stopping once its max error drops below 0.005
-// (island_solver.cpp:263-353, :538-543).  Same colouring as the velocity solve; cooperative launch.
-__global__ void __launch_bounds__(256) k_position(Dev d, int iters) {
-    GridBarrier grid(&d.cnt->bar);
-    const Counters &c = *d.cnt;
-    const uint32_t nc = c.ncolors, nh = c.nhcolors;
-    GRID_STRIDE(i, d.nbodies) { d.isl_err[i] = 0; d.isl_done[i] = 0; }
-    grid.sync();
-    for (int it = 0; it < iters; ++it) {
-        for (uint32_t col = 0; col < nh; ++col) {
-            const uint32_t b = c.hoff[col], e = c.hoff[col + 1];
-            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) hinge_position(d, i);
-            grid.sync();
-        }
-        for (uint32_t col = 0; col < nc; ++col) {
-            const uint32_t b = c.coff[col], e = c.coff[col + 1];
-            for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) contact_position(d, i);
-            grid.sync();
-        }
-        if (it + 1 < iters) {
-            GRID_STRIDE(i, d.nbodies) {
-                if (d.parent[i] == i) { if (__uint_as_float(d.isl_err[i]) < 0.005f) d.isl_done[i] = 1; d.isl_err[i] = 0; }
-            }
-            grid.sync();
-        }
-    }
-}
-
-// Dataflow flavour (default): colours inside an iteration are ordered by per-body tickets instead of grid barriers;
-// only the per-island convergence test between iterations still needs the whole grid (2 barriers per iteration).
-#ifndef B2D_POS_MIN_BLOCKS
-#define B2D_POS_MIN_BLOCKS 1
-#endif
-#ifndef B2D_POS_THREADS
-#define B2D_POS_THREADS 256
-#endif
 // ---- dataflow flavour of the position iterations (default).  Same idea as k_solve_df: what a constraint needs from a
 // body AND the body's ticket travel in the same 16-byte vectors, so a poll that sees the expected ticket in all three
 // vectors of a record already holds a consistent position / orientation and no fence or separate counter is needed.
@@ -1606,8 +1781,8 @@ B2D_D void position_chunk_df(const Dev &d, uint32_t tagA, uint32_t tagB, uint2 t
     } while (true);
 }
 // contact_constraint::solve_position, contact_constraint.cpp:58-90
-B2D_D void contact_position_df(const Dev &d, uint4 hd, uint2 tk2, uint32_t isl, int it, uint32_t mask) {
-    const uint32_t m = hd.w, n = hd.z;
+B2D_D void contact_position_df(const Dev &d, uint4 hd, uint32_t m, uint2 tk2, uint32_t isl, int it, uint32_t mask) {
+    const uint32_t n = hd.z;
     const size_t NM = d.NM;
     // slot 0 of the manifold is in flight while the tickets are polled
     const float4 a0 = d.pA[m], b0 = d.pB[m], n0 = d.pN[m], l0 = d.pL[m];
@@ -1675,10 +1850,10 @@ __global__ void __launch_bounds__(B2D_POS_THREADS, B2D_POS_MIN_BLOCKS) k_positio
         }
     }
     // header, ticket and island words of this warp's next contact chunk are fetched one chunk ahead (as in k_solve_df)
-    uint32_t ncol = 0, ni = 0, nisl = 0; bool nact = false; uint4 nhd = make_uint4(0, 0, 0, 0); uint2 ntk = make_uint2(0, 0);
+    uint32_t ncol = 0, ni = 0, nisl = 0, nm = 0; bool nact = false; uint4 nhd = make_uint4(0, 0, 0, 0); uint2 ntk = make_uint2(0, 0);
     if (wid < cchunks) {
         ni = chunk_index(s_cchunk, s_coff, wid, ncol) + lane; nact = ni < s_coff[ncol + 1];
-        if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; }
+        if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; nm = d.cidx_s[ni]; }
     }
     grid.sync();
     for (int it = 0; it < iters; ++it) {
@@ -1690,13 +1865,13 @@ __global__ void __launch_bounds__(B2D_POS_THREADS, B2D_POS_MIN_BLOCKS) k_positio
               if (act) hinge_position_df(d, d.hhdr[i], d.htkt[i], d.hisl[i], it, mask);
           } }
         for (uint32_t j = wid; j < cchunks; j += nw) {
-            const bool act = nact; const uint4 hd = nhd; const uint2 tk2 = ntk; const uint32_t isl = nisl;
+            const bool act = nact; const uint4 hd = nhd; const uint2 tk2 = ntk; const uint32_t isl = nisl, m = nm;
             uint32_t jn = j + nw;
             if (jn >= cchunks) { jn = wid; ncol = 0; }
             ni = chunk_index(s_cchunk, s_coff, jn, ncol) + lane; nact = ni < s_coff[ncol + 1];
-            if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; }
+            if (nact) { nhd = d.hdr[ni]; ntk = d.tkt[ni]; nisl = d.pisl[ni]; nm = d.cidx_s[ni]; }
             const uint32_t mask = __ballot_sync(0xffffffffu, act);
-            if (act) contact_position_df(d, hd, tk2, isl, it, mask);
+            if (act) contact_position_df(d, hd, m, tk2, isl, it, mask);
         }
         if (it + 1 < iters) {
             grid.sync();

@@ -23,11 +23,21 @@ constexpr uint32_t MS_COLOR_SHIFT = 8;        // bits 8..15 colour, 0xFF = none
 constexpr uint32_t MS_COLOR_MASK = 0xFFu << MS_COLOR_SHIFT;
 constexpr uint32_t COLOR_NONE = 0xFFu;
 constexpr int MAX_COLORS = 64;
-#ifndef B2D_SPATIAL_BITS
-#define B2D_SPATIAL_BITS 16
-#endif
-constexpr int COLOR_KEY_SPATIAL_BITS = B2D_SPATIAL_BITS;                  // colour-sort key: colour(6) | points-1 (2) | spatial rank
-constexpr int COLOR_KEY_BITS = 6 + 2 + COLOR_KEY_SPATIAL_BITS + 1;      // + the 'inactive' bit on top
+// Island tiles: islands small enough to be solved inside one CTA -- body records in shared memory,
+// constraint rows in registers for all iterations, __syncthreads between colours, no global synchronisation at all --
+// are packed into tiles of up to TILE_CAP bodies / contact manifolds / joints; everything else (a pile is one island)
+// goes through the global dataflow kernels.
+constexpr int TILE_CAP = 256;                  // threads per tile CTA = capacity in bodies, manifolds and joints
+constexpr int TILE_ISLAND_MAX = 128;           // an island is tiled if it has at most this many bodies, manifolds and joints
+constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
+constexpr uint32_t SLOT_NONE = 0xFFFFu;
+// sort keys.  tiled: tile(20) | colour(6); dataflow: DF | colour(6) | points-1 (2) | spatial rank(16); no rows: INACTIVE
+constexpr int KEY_TILE_BITS = 20;
+constexpr uint32_t KEY_DF = 1u << (KEY_TILE_BITS + 6);
+constexpr uint32_t KEY_INACTIVE = 1u << (KEY_TILE_BITS + 7);
+constexpr int COLOR_KEY_BITS = KEY_TILE_BITS + 8;
+constexpr int KEY_DF_SPATIAL_BITS = 16;
+constexpr int KEY_DF_COLOR_SHIFT = KEY_DF_SPATIAL_BITS + 2;
 
 constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
 constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
@@ -49,11 +59,16 @@ struct Counters {
     uint32_t nlist;          // colouring work list length
     uint32_t bar;            // grid barrier counter (zeroed by the host before each persistent kernel)
     int bounds[6];           // order-preserving int encoding of the min/max of all dynamic AABBs (multi-GPU exchange)
-    uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
-    uint32_t coff[MAX_COLORS + 2];   // start of each contact colour in the sorted arrays
+    uint32_t nhactive;               // hinges with rows this step
+    uint32_t ntiles;                 // island tiles this step
+    uint32_t tile_wmax;              // heaviest tiled island (zeroed by the host, like the next two)
+    uint32_t ncolors_all, nhcolors_all;      // colours in use over both solver paths (statistics)
+    uint32_t ntiled, nhtiled;        // contact manifolds / hinges solved in tiles: [0, ntiled) of the sorted arrays
+    uint32_t coff[MAX_COLORS + 2];   // dataflow path: start of each contact colour in the sorted arrays
     uint32_t hoff[MAX_COLORS + 2];   // same for hinges
     uint32_t cchunk[MAX_COLORS + 2]; // prefix sum of ceil(colour size / 32): warp-sized chunks never span two colours
     uint32_t hchunk[MAX_COLORS + 2];
+    uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
     unsigned long long dbg[16];  // development counters (B2D_DF_PROFILE builds only)
 };
 
@@ -81,6 +96,13 @@ struct Dev {
     unsigned long long *cellkey, *cellkey_s;
     uint32_t *cellbody, *cellbody_s;
     uint32_t *brank;                     // position of every body in the sorted cell order (spatial rank)
+    // ---- island tiles
+    uint32_t max_tiles;
+    uint32_t *isl_nb, *isl_nm, *isl_nh;  // per island root: dynamic bodies, manifolds with points, joints
+    uint32_t *swgt, *swsum;              // per body id: packing weight of the island it is the root of, exclusive prefix sum
+    uint32_t *btile, *bslot;             // per body: tile of its island (TILE_NONE: dataflow path), record slot in the tile
+    uint32_t *tile_nb, *tile_body;       // per tile: bodies, slot -> body (TILE_CAP per tile)
+    uint32_t *tile_c0, *tile_c1, *tile_h0, *tile_h1;   // per tile: its range of the sorted contact / hinge arrays
     unsigned long long *chash_key; uint32_t *chash_val; uint32_t chash_size;
     uint32_t *large_list;
     uint32_t *newcount, *newoff;
@@ -105,11 +127,11 @@ struct Dev {
     unsigned long long *prop, *jprop;
     uint32_t *ckey, *ckey_s; uint32_t *cidx, *cidx_s;
     uint32_t *clist;             // colouring work list (manifold slots with points)
-    unsigned char *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
+    uint32_t *hkey, *hkey_s; uint32_t *hidx, *hidx_s;
     uint32_t *isl_err; uint32_t *isl_done;
 
     // ---- solver rows, colour-sorted order (index = slot * NM + sorted position)
-    uint4 *hdr;        // body a, body b, npts, manifold slot
+    uint4 *hdr;        // body a, body b, npts, shared-memory slots (a | b << 16); the manifold slot is cidx_s[i]
     float4 *R0;        // normal xyz, rhs_n
     float4 *R1;        // rA xyz, eff_mass_n
     float4 *R2;        // rB xyz, friction
@@ -124,7 +146,7 @@ struct Dev {
     float *himp;                 // 5 per hinge
     uint32_t *hcolor;
     float4 *HR;                  // 7 float4 per sorted hinge: rA|eff0, rB|eff1, p|eff2, q|eff3, (eff4,rhs0,rhs1,rhs2), (rhs3,rhs4,imp0,imp1), (imp2,imp3,imp4,0)
-    uint4 *hhdr;                 // a, b, hinge id, 0
+    uint4 *hhdr;                 // a, b, hinge id, shared-memory slots (a | b << 16)
 
     // ---- dataflow schedule of the velocity solve
     // island sleeping (island_manager.cpp:541-623); arrays are indexed by body id, island data sits at the root's id

@@ -493,6 +493,7 @@ class DeviceShardedWorld:
         self.dynamic = int(self.local["dynamic"])           # dynamic bodies this rank owns right now
         self.last_pairs = []
         self.handover_ms = []                               # host wall time of every hand-over round (plan .. unpack)
+        self.handover_phases = []                           # the same, split: halo / plan / pack / exchange / unpack
         with torch.cuda.stream(self.ext):
             comm.warmup(dev)
 
@@ -531,6 +532,8 @@ class DeviceShardedWorld:
                 mask |= 1 << j
             if j == r:
                 mask |= 1 << i
+        tm = {}
+        t_ = time.perf_counter()
         w.island_halo(g.data_ptr(), N, r, mask, self.records.data_ptr(), self.rec_cap, self.count.data_ptr())
         nrec = self.comm.all_gather(self.count).cpu().numpy().reshape(-1).astype(np.int64)
         if nrec[r] > self.rec_cap:
@@ -541,7 +544,9 @@ class DeviceShardedWorld:
         allrec = self.comm.all_gather(self.records[:mx])                           # (N, mx, 8): 32 B per boundary island
         recs = torch.cat([allrec[p, :int(nrec[p])] for p in range(N)]).contiguous()
         my_b = int(nrec[:r].sum())
+        tm["halo"] = (time.perf_counter() - t_) * 1e3; t_ = time.perf_counter()
         plan = w.handover_plan(recs.data_ptr(), my_b, my_b + int(nrec[r]), N)      # (N, 4) host
+        tm["plan"] = (time.perf_counter() - t_) * 1e3; t_ = time.perf_counter()
         allplan = self.comm.all_gather(torch.from_numpy(plan.astype(np.int32)).to(self.dev)).cpu().numpy()   # (N, N, 4)
         moved = int(allplan[:, :, 0].sum())
         if moved == 0:
@@ -553,11 +558,15 @@ class DeviceShardedWorld:
                 blob = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
                 w.handover_pack(dst, blob.data_ptr(), nbytes)
                 send[dst] = blob
+        tm["pack"] = (time.perf_counter() - t_) * 1e3; t_ = time.perf_counter()
         recv_bytes = {src: w.handover_bytes(allplan[src, r]) for src in range(N) if allplan[src, r].any()}
         got = self.comm.exchange(send, recv_bytes, self.dev)
+        tm["exchange"] = (time.perf_counter() - t_) * 1e3; t_ = time.perf_counter()
         for src in sorted(got):
             c = w.handover_unpack(got[src].data_ptr(), got[src].numel())
             self.migrated_in += int(c[0])
+        tm["unpack"] = (time.perf_counter() - t_) * 1e3
+        self.handover_phases.append({k: round(v, 3) for k, v in tm.items()})
         out = int(plan[:, 0].sum())
         self.migrated_out += out
         self.dynamic += int(allplan[:, r, 0].sum()) - out

@@ -306,6 +306,12 @@ class World:
     def reset_timers(self):
         self._check(self.l.b2d_reset_timers(self.h))
 
+    def debug_tiles(self):
+        """Development aid: island tiles of the last step."""
+        out = np.zeros(6, np.uint32)
+        self._check(self.l.b2d_debug_tiles(self.h, _p(out)))
+        return dict(zip(("tiles", "tiled_manifolds", "tiled_hinges", "active_manifolds", "active_hinges", "max_bodies_per_tile"), out.tolist()))
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self.l.b2d_get_stats(self.h, C.byref(s)))

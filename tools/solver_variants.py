@@ -16,9 +16,8 @@ w = E.scenes.build_world(scene, max_manifolds=bench.capacity('{wl}', len(scene['
 w.step(150); w.sync(); w.reset_timers()
 w.step(20); w.sync()
 st = w.stats()
-b = w.debug_blocks().astype(np.int64)
-print('{var!s:40s}', 'step %.3f ms  solve %.3f ms' % (st['last_step_ms'] / 20, st['solve_ms']), ' blocks', len(b), ' smem bodies', b[:,0].sum(), 'of', scene['dynamic'],
-      ' chunks/block min %d mean %.1f max %d' % (b[:,3].min(), b[:,3].mean(), b[:,3].max()), ' err', st['error_flags'])
+tl = w.debug_tiles()
+print('{var!s:44s}', 'step %.3f ms  solve %.3f ms' % (st['last_step_ms'] / 20, st['solve_ms']), tl, ' err', st['error_flags'])
 """
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr[-800:])
