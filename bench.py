@@ -309,6 +309,7 @@ def run_single(args, local_rank):
 
 def run_sharded(args, world_size, rank, local_rank):
     """N > 1: ONE scene, islands partitioned over the ranks, strong scaling."""
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")       # the hand-over kernels first run inside the timed region
     import torch
     import torch.distributed as dist
     import edyn_b200 as E
@@ -326,7 +327,7 @@ def run_sharded(args, world_size, rank, local_rank):
     labels = D.device_islands(scene, device=local_rank)            # island_manager's connected components, computed on the device
     comm = D.TorchComm(dist, rank, world_size)
     n_all = len(scene["bodies"]["kind"])
-    sw = D.DeviceShardedWorld(scene, rank, world_size, comm, device=local_rank, labels=labels, slack=2.0 / world_size,
+    sw = D.DeviceShardedWorld(scene, rank, world_size, comm, device=local_rank, labels=labels, slack=2.0 / world_size, pipeline=not args.exact_exchange,
                               max_manifolds=capacity(args.workload, int(n_all * (1.0 / world_size + 2.0 / world_size))))
     w = sw.world
     owner = sw.owner
@@ -345,11 +346,11 @@ def run_sharded(args, world_size, rank, local_rank):
     push_v = np.zeros((len(push_ids), 3), np.float32)
     push_v[:, 0] = -6.0
 
+    w.set_timing(False)                 # the whole step is ONE graph launch (the per-kernel event ring splits it in three)
     for _ in range(args.warmup):
         sw.step(1)
     barrier()
     w.sync()
-    w.reset_timers()
     launches0 = w.stats()["kernel_launches"]
     bytes0 = comm.bytes_sent
     sampler = ClockSampler(local_rank)
@@ -370,6 +371,13 @@ def run_sharded(args, world_size, rank, local_rank):
     clocks = sampler.stop()
     st = w.stats()
     launches = st["kernel_launches"] - launches0 - 1
+    last_step_device_ms = st["last_step_ms"]                    # the last b2d_step alone, between its own two events
+    # solver kernel time for the roofline note: a few more steps with the per-kernel events on (outside the timed region)
+    w.set_timing(True); w.reset_timers()
+    sw.step(5, exchange=False)
+    w.sync()
+    st = dict(st, **{k: w.stats()[k] for k in ("solve_ms", "integrate_ms")})
+    w.set_timing(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -421,15 +429,18 @@ def run_sharded(args, world_size, rank, local_rank):
                            "settle_steps": SETTLE_STEPS, "manifolds_rank0": st["manifolds"], "contact_points_rank0": st["contact_points"], "hinges_rank0": st["hinges"],
                            "islands_rank0": st["islands"],
                            "parallelism": f"ONE scene, islands (connected components computed on the device) partitioned over {world_size} GPUs by x-slabs of equal "
-                                          "body count; per step: b2d_step + device reduction of the rank box + NCCL all-gather of 24 B/rank (the limiting "
-                                          "collective: latency-bound, its result is read by the host before the next broadphase); island hand-over as device "
-                                          "blobs over NCCL send/recv when boxes touch",
+                                          "body count; per step: b2d_step (one CUDA graph) + device reduction of the rank box and the fastest body speed + NCCL "
+                                          "all-gather of 32 B/rank (the limiting collective: latency-bound) + copy to pinned memory; " +
+                                          ("the host reads the boxes before the next step starts; " if args.exact_exchange else
+                                           "the host reads the boxes of step k while step k+1 runs and widens the test margin by one step of closing travel "
+                                           "(4 v_max dt + 2 g dt^2), so a hand-over still lands before the broadphase that needs it; ") +
+                                          "island hand-over as device blobs over NCCL send/recv when boxes come within the margin",
                            "handover": {"bodies_in_per_rank": allmoved[:, 0].tolist(), "bodies_out_per_rank": allmoved[:, 1].tolist(),
                                         "rounds_per_rank": allmoved[:, 2].tolist(), "halo_checks_per_rank": allmoved[:, 3].tolist(),
                                         "dynamic_bodies_per_rank_after": allmoved[:, 4].tolist(),
                                         "collective_payload_bytes_per_rank_timed_region": allmoved[:, 5].tolist(),
                                         "forced": "after timed step 1 every rank r > 0 gives its first column of chains -6 m/s in x (b2d_upload_bodies)",
-                                        "rank0_host_ms_per_step": {"median": srt[len(srt) // 2], "max": srt[-1]},
+                                        "rank0_host_ms_per_step": {"median": srt[len(srt) // 2], "max": srt[-1]}, "rank0_last_step_device_ms": last_step_device_ms,
                                         "rank0_handover_round_ms": sw.handover_ms, "rank0_handover_phases_ms": sw.handover_phases,
                                         "rank0_host_ms_each_step": [round(x, 3) for x in step_ms]},
                            "l2": "per-step working set per rank exceeds L2 at N <= 4 (rows + manifolds + bodies); inputs change every step; no explicit flush"},
@@ -466,6 +477,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: seconds the untimed settle + timed steps may take")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exact-exchange", action="store_true", help="N > 1: read every step's rank boxes before the next step starts (no look-ahead margin)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -127,7 +127,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     Dev &d = w->d;
     const uint32_t NB = cfg->max_bodies, NM = cfg->max_manifolds, NH = std::max<uint32_t>(cfg->max_hinges, 1);
     d.NB = NB; d.NM = NM; d.NH = NH; d.dt = w->cfg.fixed_dt;
-    d.nbodies = 0; d.nhinges = 0; d.nlarge = 0; d.cell = 1.0f; d.inv_cell = 1.0f;
+    d.nbodies = 0; d.nhinges = 0; d.nlarge = 0; d.cell = 1.0f; d.inv_cell = 1.0f; d.halo_margin = HALO_MARGIN;
     bool ok = true;
     ok = ok && dalloc(w, d.pos, NB) && dalloc(w, d.orn, NB) && dalloc(w, d.linvel, NB) && dalloc(w, d.angvel, NB);
     ok = ok && dalloc(w, d.dvw, 2 * (size_t)NB) && dalloc(w, d.invI, 3 * (size_t)NB) && dalloc(w, d.invIW, 3 * (size_t)NB);
@@ -148,7 +148,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     ok = ok && dalloc(w, d.ckey, NM) && dalloc(w, d.ckey_s, NM) && dalloc(w, d.cidx, NM) && dalloc(w, d.cidx_s, NM);
     ok = ok && dalloc(w, d.hkey, NH) && dalloc(w, d.hkey_s, NH) && dalloc(w, d.hidx, NH) && dalloc(w, d.hidx_s, NH);
     // island tiles: the census arrays are one allocation (zeroed together every step), so are the per-tile tables
-    d.max_tiles = (uint32_t)(((uint64_t)NB + NM + NH) / TILE_ISLAND_MAX + 64);
+    d.max_tiles = (uint32_t)std::min<uint64_t>(((uint64_t)NB + NM + NH) / TILE_ISLAND_MAX + 64, 1u << KEY_TILE_BITS);   // beyond: dataflow path
     ok = ok && dalloc(w, d.isl_nb, 3 * (size_t)NB) && dalloc(w, d.swgt, NB) && dalloc(w, d.swsum, NB) && dalloc(w, d.btile, NB, 0xFF) && dalloc(w, d.bslot, NB, 0xFF);
     d.isl_nm = d.isl_nb + NB; d.isl_nh = d.isl_nb + 2 * (size_t)NB;
     ok = ok && dalloc(w, d.tile_nb, 5 * (size_t)d.max_tiles) && dalloc(w, d.tile_body, (size_t)d.max_tiles * TILE_CAP);
@@ -173,7 +173,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
 
     // CUB temp storage: the largest of the sorts/scans used per step
     size_t need = 0, t = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)NB, 0, 63, w->stream); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)NB, 0, 48, w->stream); need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)NM, 0, COLOR_KEY_BITS, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.free_flag, d.free_rank, (int)NM, w->stream); need = std::max(need, t);
     cub::DeviceScan::ExclusiveSum(nullptr, t, d.newcount, d.newoff, (int)NB, w->stream); need = std::max(need, t);
@@ -515,12 +515,11 @@ static int enqueue_broadphase(b2d_world *w) {
     if (d.nbodies) {
         LAUNCH(k_bp_cells, d.nbodies, 256, d);
         t = w->cub_tmp_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, 63, s)); w->launches += 4;
+        CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, 48, s)); w->launches += 4;
         LAUNCH(k_bp_cell_starts, d.nbodies, 256, d);
         LAUNCH(k_bp_pairs<false>, d.nbodies, 128, d);
         t = w->cub_tmp_bytes;
         CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.newcount, d.newoff, (int)d.nbodies, s)); ++w->launches;
-        LAUNCH(k_bp_total, 1, 32, d);
         LAUNCH(k_bp_pairs<true>, d.nbodies, 128, d);
         LAUNCH(k_bp_append, d.NM, 256, d);
         LAUNCH(k_bp_finish, 1, 32, d);
@@ -534,8 +533,8 @@ static int enqueue_narrowphase(b2d_world *w) {
     CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
     LAUNCH(k_np_offsets, d.NM, 256, d);
     LAUNCH(k_np_fixup, 1, 32, d);
-    launch_detect<1>(w); launch_detect<2>(w); launch_detect<3>(w); launch_detect<4>(w); launch_detect<5>(w);
-    launch_detect<6>(w); launch_detect<7>(w); launch_detect<8>(w); launch_detect<9>(w);
+    LAUNCH(k_np_detect_light, d.NM, 128, d);
+    launch_detect<5>(w); launch_detect<9>(w);
     LAUNCH(k_np_merge, d.NM, 128, d);
     return B2D_OK;
 }
@@ -579,14 +578,7 @@ static int enqueue_solver_a(b2d_world *w, int recolor) {
     Dev &d = w->d; cudaStream_t s = w->stream;
     CK(cudaMemsetAsync(d.isl_nb, 0, 3 * (size_t)d.NB * sizeof(uint32_t), s));             // island census: bodies, manifolds, joints
     CK(cudaMemsetAsync(d.tile_nb, 0, 5 * (size_t)d.max_tiles * sizeof(uint32_t), s));      // tile body counts and (empty) ranges
-    CK(cudaMemsetAsync(&d.cnt->tile_wmax, 0, 3 * sizeof(uint32_t), s));                    // + ncolors_all, nhcolors_all
-    LAUNCH(k_gravity, d.nbodies, 256, d);
-    CK(cudaMemsetAsync(&d.cnt->remaining[0], 0, 2 * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(&d.cnt->nlist, 0, 2 * sizeof(uint32_t), s));          // nlist + bar
-    CK(cudaMemsetAsync(d.bmask, 0, (size_t)d.nbodies * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(d.jmask, 0, (size_t)d.nbodies * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(d.prop, 0xFF, (size_t)d.nbodies * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(d.jprop, 0xFF, (size_t)d.nbodies * sizeof(unsigned long long), s));
+    LAUNCH(k_gravity, std::max<uint32_t>(d.nbodies, 1), 256, d);                             // + resets of the colouring / packing accumulators
     LAUNCH(k_color_list, d.NM, 256, d, recolor);
     CK(coop_launch(w, k_color, w->coop_blocks_color, 256, d));
     size_t t;
@@ -605,7 +597,6 @@ static int enqueue_solver_a(b2d_world *w, int recolor) {
     LAUNCH(k_color_fixup, 1, 32, d);
     LAUNCH(k_prepare_contacts, d.NM, 256, d);
     if (d.nhinges) LAUNCH(k_prepare_hinges, d.nhinges, 256, d);
-    CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
     return B2D_OK;
 }
 static int enqueue_solver_b(b2d_world *w) {
@@ -626,7 +617,6 @@ static int enqueue_solver_c(b2d_world *w) {
     const int pi = (int)w->cfg.position_iterations;
     LAUNCH(k_store_impulses, d.NM, 256, d);
     if (pi > 0) {
-        CK(cudaMemsetAsync(&d.cnt->bar, 0, sizeof(uint32_t), s));
         if (d.max_tiles) { k_position_tiles<<<w->tile_pos_blocks, TILE_CAP, TILE_POS_SMEM, s>>>(d, pi); ++w->launches; }
         CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
@@ -1006,13 +996,18 @@ int b2d_debug_tiles(b2d_world *w, uint32_t *out6) {
 }
 int b2d_reset_timers(b2d_world *w) { if (!w) return B2D_ERR_ARGUMENT; w->timed_steps = 0; return B2D_OK; }
 
-int b2d_device_bounds(b2d_world *w, float *device_out6) {
-    if (!w || !device_out6) return B2D_ERR_ARGUMENT;
+int b2d_set_halo_margin(b2d_world *w, float margin) {
+    if (!w || !(margin >= 0.0f)) return B2D_ERR_ARGUMENT;
+    w->d.halo_margin = std::max(margin, HALO_MARGIN);
+    return B2D_OK;
+}
+int b2d_device_bounds(b2d_world *w, float *device_out8) {
+    if (!w || !device_out8) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
     Dev &d = w->d;
     LAUNCH(k_bounds_init, 1, 32, d);
     LAUNCH(k_bounds_reduce, d.nbodies, 256, d);
-    LAUNCH(k_bounds_final, 1, 32, d, device_out6);
+    LAUNCH(k_bounds_final, 1, 32, d, device_out8);
     CK(cudaGetLastError());
     return B2D_OK;
 }

@@ -138,7 +138,7 @@ __global__ void k_halo_collect(Dev d, const float *boxes, uint32_t nboxes, uint3
         bool hit = false;
         for (uint32_t p = 0; p < nboxes && !hit; ++p) {
             if (p == self || !((peer_mask >> p) & 1ULL)) continue;
-            hit = boxes_touch(r.mn, r.mx, boxes + 6 * p, boxes + 6 * p + 3, HALO_MARGIN);
+            hit = boxes_touch(r.mn, r.mx, boxes + 6 * p, boxes + 6 * p + 3, d.halo_margin);
         }
         if (!hit) continue;
         const uint32_t k = atomicAdd(count, 1u);
@@ -155,7 +155,7 @@ __global__ void k_plan_islands(Dev d, const HaloRec *recs, uint32_t my_b, uint32
     for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t i = my_b + (uint32_t)(t / my_b), j = (uint32_t)(t % my_b);
         const HaloRec a = recs[i], b = recs[j];
-        if (boxes_touch(a.mn, a.mx, b.mn, b.mx, HALO_MARGIN)) atomicMin(&d.isl_dst[a.label], b.rank);
+        if (boxes_touch(a.mn, a.mx, b.mn, b.mx, d.halo_margin)) atomicMin(&d.isl_dst[a.label], b.rank);
     }
 }
 // counts: per destination rank {bodies, manifolds, hinges, 0}

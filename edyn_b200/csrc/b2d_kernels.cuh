@@ -168,25 +168,14 @@ __global__ void k_bp_free_list(Dev d) {
     }
 }
 
-#ifndef B2D_MORTON_CELLS
-#define B2D_MORTON_CELLS 0       // measured: Z-order cells are no better for the solver and slower for the pair search
-#endif
 B2D_D unsigned long long cell_key_of(int cx, int cy, int cz) {
-    const int OFF = 1 << 20, MX = (1 << 21) - 1;
+    // 16 bits per axis (radix sort passes are paid per key byte).  Cells beyond the range share the boundary key, which
+    // only makes the candidate lists there longer: the exact AABB tests decide.  All-ones is reserved for "no cell".
+    const int OFF = 1 << 15, MX = (1 << 16) - 2;
     unsigned long long x = (unsigned long long)min(max(cx + OFF, 0), MX);
     unsigned long long y = (unsigned long long)min(max(cy + OFF, 0), MX);
     unsigned long long z = (unsigned long long)min(max(cz + OFF, 0), MX);
-#if B2D_MORTON_CELLS
-    // Z-order: bodies that are neighbours in the sorted cell list are neighbours in space (the colour sort reuses the rank)
-    auto spread = [](unsigned long long v) {
-        v = (v | (v << 32)) & 0x1F00000000FFFFULL; v = (v | (v << 16)) & 0x1F0000FF0000FFULL;
-        v = (v | (v << 8)) & 0x100F00F00F00F00FULL; v = (v | (v << 4)) & 0x10C30C30C30C30C3ULL;
-        v = (v | (v << 2)) & 0x1249249249249249ULL; return v;
-    };
-    return (spread(x) << 2) | (spread(y) << 1) | spread(z);
-#else
-    return (x << 42) | (y << 21) | z;
-#endif
+    return (x << 32) | (y << 16) | z;
 }
 B2D_D void cell_of(const Dev &d, uint32_t i, int &cx, int &cy, int &cz) {
     float4 a = d.bbmin[i], b = d.bbmax[i];
@@ -269,7 +258,7 @@ __global__ void k_bp_pairs(Dev d) {
             if (d.newcount[A] == 0) continue;
             // newpairs holds max_manifolds entries: a body whose range would run past it (and therefore every body behind
             // it in the scan) is dropped, the append below stops in front of the first hole
-            if ((unsigned long long)d.newoff[A] + d.newcount[A] > d.NM) { atomicMin(&d.cnt->nnew, d.newoff[A]); atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
+            if ((unsigned long long)d.newoff[A] + d.newcount[A] > d.NM) { atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
             out = d.newpairs + d.newoff[A];
         }
         if (is_dynamic(fA) && shape_of(fA) != SH_NONE) {
@@ -292,15 +281,21 @@ __global__ void k_bp_pairs(Dev d) {
         if (!FILL) d.newcount[A] = count;
     }
 }
-__global__ void k_bp_total(Dev d) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        uint32_t n = d.nbodies;
-        d.cnt->nnew = n ? d.newoff[n - 1] + d.newcount[n - 1] : 0;
-    }
+// Number of new pairs this step.  newpairs holds max_manifolds entries: a body whose range would run past it (and
+// therefore every body behind it in the scan) is dropped by the fill pass, so the usable prefix ends where the first
+// such range starts (found by bisection on the monotone prefix sums; only on overflow).
+B2D_D uint32_t bp_nnew(const Dev &d) {
+    const uint32_t n = d.nbodies;
+    if (!n) return 0;
+    const unsigned long long total = (unsigned long long)d.newoff[n - 1] + d.newcount[n - 1];
+    if (total <= d.NM) return (uint32_t)total;
+    uint32_t lo = 0, hi = n - 1;                       // first body whose range ends beyond the buffer
+    while (lo < hi) { const uint32_t mid = (lo + hi) / 2; if ((unsigned long long)d.newoff[mid] + d.newcount[mid] > d.NM) hi = mid; else lo = mid + 1; }
+    return d.newoff[lo];
 }
 // make_contact_manifold (util/constraint_util.cpp:67-102): slots come from the free list first.
 __global__ void k_bp_append(Dev d) {
-    const uint32_t nnew = d.cnt->nnew, nfree = d.cnt->nfree, hwm = d.cnt->hwm;
+    const uint32_t nnew = bp_nnew(d), nfree = d.cnt->nfree, hwm = d.cnt->hwm;
     GRID_STRIDE(k, nnew) {
         uint32_t slot = k < nfree ? d.free_list[k] : hwm + (k - nfree);
         if (slot >= d.NM) { atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
@@ -311,6 +306,7 @@ __global__ void k_bp_append(Dev d) {
 __global__ void k_bp_finish(Dev d) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Counters &c = *d.cnt;
+        c.nnew = bp_nnew(d);
         if (c.nnew > c.nfree) c.hwm = min(d.NM, c.hwm + (c.nnew - c.nfree));
     }
 }
@@ -419,7 +415,7 @@ __global__ void k_np_fixup(Dev d) {
 }
 
 template<int FN>
-__global__ void __launch_bounds__(128) k_np_detect(Dev d) {
+B2D_D void np_detect_range(const Dev &d) {
     const uint32_t b = d.cnt->npoff[FN], e = d.cnt->npoff[FN + 1];
     for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
         const uint32_t m = d.cidx_s[i];
@@ -447,6 +443,13 @@ __global__ void __launch_bounds__(128) k_np_detect(Dev d) {
             d.R2[ri] = f4(res.pt[s].normal, 0);
         }
     }
+}
+// the two heavy overloads (box-box, capsule-box) get a launch each, the seven light ones share one
+template<int FN>
+__global__ void __launch_bounds__(128) k_np_detect(Dev d) { np_detect_range<FN>(d); }
+__global__ void __launch_bounds__(128) k_np_detect_light(Dev d) {
+    np_detect_range<1>(d); np_detect_range<2>(d); np_detect_range<3>(d); np_detect_range<4>(d);
+    np_detect_range<6>(d); np_detect_range<7>(d); np_detect_range<8>(d);
 }
 
 __global__ void __launch_bounds__(128) k_np_merge(Dev d) {
@@ -667,7 +670,13 @@ __global__ void k_wake_bodies(Dev d, const uint32_t *ids, uint32_t n) {
 
 // apply_gravity, sys/apply_gravity.hpp:12-17
 __global__ void k_gravity(Dev d) {
+    // also resets what the colouring and the tile packing accumulate into (they run after this kernel)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Counters &c = *d.cnt;
+        c.remaining[0] = c.remaining[1] = 0; c.nlist = 0; c.bar = 0; c.tile_wmax = 0; c.ncolors_all = 0; c.nhcolors_all = 0;
+    }
     GRID_STRIDE(i, d.nbodies) {
+        d.bmask[i] = 0ULL; d.jmask[i] = 0ULL; d.prop[i] = ~0ULL; d.jprop[i] = ~0ULL;
         if (!is_dynamic(d.flags[i])) continue;
         v3 v = mk3(d.linvel[i]); v += mk3(d.grav[i]) * d.dt;
         d.linvel[i] = f4(v, 0);
@@ -1322,7 +1331,10 @@ B2D_D void hinge_pass(const Dev &d, uint32_t i, bool warm, int pass, uint32_t ma
 // solved.  Impulses are private to the owning thread and stored as soon as they are final.
 B2D_D void prefetch_L2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 struct NRow { float4 r0, r1, r2, im; };
-B2D_D NRow load_nrow(const Dev &d, size_t ri) { NRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.im = d.IMP[ri]; return r; }
+#ifndef B2D_ROW_LD
+#define B2D_ROW_LD(p) __ldcs(p)       // rows stream past L1 (evict-first): the per-body data keeps it
+#endif
+B2D_D NRow load_nrow(const Dev &d, size_t ri) { NRow r; r.r0 = B2D_ROW_LD(&d.R0[ri]); r.r1 = B2D_ROW_LD(&d.R1[ri]); r.r2 = B2D_ROW_LD(&d.R2[ri]); r.im = B2D_ROW_LD(&d.IMP[ri]); return r; }
 B2D_D void solve_nrow(const Dev &d, NRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
     nrow_solve(r.r0, r.r1, r.r2, r.im, A, B, warm);
     if (!warm) d.IMP[ri] = r.im;
@@ -1355,7 +1367,7 @@ B2D_D void normal_pass(const Dev &d, uint32_t i, const uint4 hd, const uint2 tk2
 }
 
 struct FRow { float4 r0, r1, r2, r3, im; };
-B2D_D FRow load_frow(const Dev &d, size_t ri) { FRow r; r.r0 = d.R0[ri]; r.r1 = d.R1[ri]; r.r2 = d.R2[ri]; r.r3 = d.R3[ri]; r.im = d.IMP[ri]; return r; }
+B2D_D FRow load_frow(const Dev &d, size_t ri) { FRow r; r.r0 = B2D_ROW_LD(&d.R0[ri]); r.r1 = B2D_ROW_LD(&d.R1[ri]); r.r2 = B2D_ROW_LD(&d.R2[ri]); r.r3 = B2D_ROW_LD(&d.R3[ri]); r.im = B2D_ROW_LD(&d.IMP[ri]); return r; }
 B2D_D void solve_frow(const Dev &d, FRow &r, size_t ri, VBody &A, VBody &B, bool warm) {
     frow_solve(r.r0, r.r1, r.r2, r.r3, r.im, A, B, warm);
     if (!warm) d.IMP[ri] = r.im;
@@ -1471,6 +1483,7 @@ __global__ void k_store_impulses(Dev d) {
 // integrate_velocities (island_solver.cpp:358-376); with refresh != 0 also update_aabbs + update_inertias
 // (solver.cpp:453-465) fused in, used when no position iterations run in between.
 __global__ void __launch_bounds__(256) k_integrate(Dev d, int refresh) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.cnt->bar = 0;       // grid barrier counter of k_position_df
     GRID_STRIDE(i, d.nbodies) {
         uint32_t f = d.flags[i];
         if (!is_dynamic(f)) continue;
@@ -1902,24 +1915,31 @@ B2D_D int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x
 B2D_D float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 __global__ void k_bounds_init(Dev d) {
     if (blockIdx.x == 0 && threadIdx.x < 6) d.cnt->bounds[threadIdx.x] = threadIdx.x < 3 ? f2ord(INFINITY) : f2ord(-INFINITY);
+    if (blockIdx.x == 0 && threadIdx.x == 6) d.cnt->speed = 0;
 }
+// + the largest distance any point of any body can travel per second at its current velocity (|v| + |w| r, r = half
+// diagonal of the AABB): lets the host look one step ahead when it overlaps the exchange with the next step
 __global__ void k_bounds_reduce(Dev d) {
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, sp = 0.0f;
     GRID_STRIDE(i, d.nbodies) {
         uint32_t f = d.flags[i];
         if (!is_procedural(f) || shape_of(f) == SH_NONE) continue;
         float4 a = d.bbmin[i], b = d.bbmax[i];
         mn[0] = fminf(mn[0], a.x); mn[1] = fminf(mn[1], a.y); mn[2] = fminf(mn[2], a.z);
         mx[0] = fmaxf(mx[0], b.x); mx[1] = fmaxf(mx[1], b.y); mx[2] = fmaxf(mx[2], b.z);
+        if (is_dynamic(f)) sp = fmaxf(sp, length(mk3(d.linvel[i])) + length(mk3(d.angvel[i])) * 0.5f * length(mk3(b) - mk3(a)));
     }
     #pragma unroll
     for (int k = 0; k < 3; ++k) {
         for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
         if ((threadIdx.x & 31) == 0) { atomicMin(&d.cnt->bounds[k], f2ord(mn[k])); atomicMax(&d.cnt->bounds[3 + k], f2ord(mx[k])); }
     }
+    for (int o = 16; o > 0; o >>= 1) sp = fmaxf(sp, __shfl_xor_sync(0xffffffffu, sp, o));
+    if ((threadIdx.x & 31) == 0 && sp > 0.0f) atomicMax(&d.cnt->speed, __float_as_uint(sp));      // non-negative floats order like their bits
 }
-__global__ void k_bounds_final(Dev d, float *out6) {
-    if (blockIdx.x == 0 && threadIdx.x < 6) out6[threadIdx.x] = ord2f(d.cnt->bounds[threadIdx.x]);
+__global__ void k_bounds_final(Dev d, float *out8) {
+    if (blockIdx.x == 0 && threadIdx.x < 6) out8[threadIdx.x] = ord2f(d.cnt->bounds[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 6) { out8[6] = __uint_as_float(d.cnt->speed); out8[7] = 0.0f; }
 }
 
 // ====================================================================== statistics

@@ -31,12 +31,12 @@ constexpr int TILE_CAP = 256;                  // threads per tile CTA = capacit
 constexpr int TILE_ISLAND_MAX = 128;           // an island is tiled if it has at most this many bodies, manifolds and joints
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint32_t SLOT_NONE = 0xFFFFu;
-// sort keys.  tiled: tile(20) | colour(6); dataflow: DF | colour(6) | points-1 (2) | spatial rank(16); no rows: INACTIVE
-constexpr int KEY_TILE_BITS = 20;
+// sort keys.  tiled: tile(16) | colour(6); dataflow: DF | colour(6) | points-1 (2) | spatial rank(14); no rows: INACTIVE
+constexpr int KEY_TILE_BITS = 16;                                   // 24-bit keys: three radix passes
 constexpr uint32_t KEY_DF = 1u << (KEY_TILE_BITS + 6);
 constexpr uint32_t KEY_INACTIVE = 1u << (KEY_TILE_BITS + 7);
 constexpr int COLOR_KEY_BITS = KEY_TILE_BITS + 8;
-constexpr int KEY_DF_SPATIAL_BITS = 16;
+constexpr int KEY_DF_SPATIAL_BITS = 14;
 constexpr int KEY_DF_COLOR_SHIFT = KEY_DF_SPATIAL_BITS + 2;
 
 constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
@@ -59,6 +59,7 @@ struct Counters {
     uint32_t nlist;          // colouring work list length
     uint32_t bar;            // grid barrier counter (zeroed by the host before each persistent kernel)
     int bounds[6];           // order-preserving int encoding of the min/max of all dynamic AABBs (multi-GPU exchange)
+    uint32_t speed;          // float bits: fastest point of any dynamic body, m/s (multi-GPU exchange)
     uint32_t nhactive;               // hinges with rows this step
     uint32_t ntiles;                 // island tiles this step
     uint32_t tile_wmax;              // heaviest tiled island (zeroed by the host, like the next two)
@@ -77,6 +78,7 @@ struct Dev {
     uint32_t nbodies, nhinges, nlarge;   // host-known counts
     float dt;
     float cell, inv_cell;          // broadphase grid pitch
+    float halo_margin;             // multi-GPU: islands closer than this to a peer's box / island are boundary islands
 
     // ---- bodies
     float4 *pos;       // xyz position, w inv_mass

@@ -385,9 +385,14 @@ class TorchComm:
         so a hand-over inside a timed region pays for the transfer only."""
         import torch
         sent = self.bytes_sent
-        send = {p: torch.zeros(16, dtype=torch.uint8, device=device) for p in range(self.world_size) if p != self.rank}
-        self.exchange(send, {p: 16 for p in send}, device)
+        # a small and a blob-sized message: NCCL connects further channels the first time a pair moves megabytes
+        for nbytes in (16, 8 << 20):
+            send = {p: torch.zeros(nbytes, dtype=torch.uint8, device=device) for p in range(self.world_size) if p != self.rank}
+            self.exchange(send, {p: nbytes for p in send}, device)
+            torch.cuda.synchronize()
         self.all_gather(torch.zeros(8, dtype=torch.float32, device=device))
+        self.all_gather(torch.zeros((4096, 8), dtype=torch.float32, device=device))
+        self.all_gather(torch.zeros(1, dtype=torch.int32, device=device))
         torch.cuda.synchronize()
         self.bytes_sent = sent
 
@@ -464,7 +469,7 @@ class DeviceShardedWorld:
     send / recv, sizes having been all-gathered first; b2d_handover_unpack appends them.  The check repeats until no
     island moves (an island arriving at rank r may itself touch an island of a still lower rank)."""
 
-    def __init__(self, scene, rank, world_size, comm, device=0, owner=None, labels=None, slack=0.25, **kw):
+    def __init__(self, scene, rank, world_size, comm, device=0, owner=None, labels=None, slack=0.25, pipeline=False, **kw):
         import torch
         from .scenes import build_world
         self.torch = torch
@@ -483,7 +488,16 @@ class DeviceShardedWorld:
         self.ext = torch.cuda.ExternalStream(self.world.stream, device=device)
         dev = torch.device("cuda", device)
         self.dev = dev
-        self.bounds = torch.zeros(6, dtype=torch.float32, device=dev)
+        self.bounds = torch.zeros(8, dtype=torch.float32, device=dev)          # min xyz, max xyz, speed, 0
+        # pipeline: the boxes of step k are read while step k + 1 already runs (no host round trip on the GPU's critical
+        # path); the decision they trigger takes effect one step later, so every margin is widened by what two bodies
+        # can travel towards each other in a step (speeds may double in a collision; gravity adds g dt)
+        self.pipeline = bool(pipeline)
+        self.dt = float(self.world.fixed_dt)
+        self.pending = None                                                  # (pinned host copy of the gathered boxes, event)
+        self.host_boxes = [torch.zeros((world_size, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.host_events = [torch.cuda.Event() for _ in range(2)]
+        self.flip = 0
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.rec_cap = kw["max_bodies"]
         self.records = torch.zeros((self.rec_cap, 8), dtype=torch.float32, device=dev)
@@ -503,24 +517,56 @@ class DeviceShardedWorld:
     def _gather_bounds(self):
         self.world.device_bounds(self.bounds.data_ptr())
         g = self.comm.all_gather(self.bounds)
-        return g, g.cpu().numpy()                            # the one per-step host read: N x 6 floats
+        return g, g.cpu().numpy()                            # the one per-step host read: N x 8 floats
+
+    def _margin(self, gh, lookahead):
+        """Broadphase margin, widened by `lookahead` steps of closing travel at the fastest speeds seen on any rank."""
+        if not lookahead:
+            return MARGIN
+        vmax = float(np.nanmax(gh[:, 6])) if len(gh) else 0.0
+        return MARGIN + lookahead * self.dt * (4.0 * vmax + 2.0 * 9.8 * self.dt)
+
+    def _resolve(self, g, gh, lookahead):
+        """Hand islands over until no two rank boxes are within the margin of each other (blocking)."""
+        margin = self._margin(gh, lookahead)
+        pairs = overlapping_ranks(gh[:, :6], margin)
+        while pairs:
+            self.halo_checks += 1
+            t0 = time.perf_counter()
+            self.world.set_halo_margin(margin)
+            moved = self._handover(pairs, g[:, :6].contiguous())
+            if moved == 0:
+                break
+            self.handover_rounds += 1
+            self.handover_ms.append((time.perf_counter() - t0) * 1e3)
+            g, gh = self._gather_bounds()
+            margin = self._margin(gh, lookahead)
+            pairs = overlapping_ranks(gh[:, :6], margin)
+        return pairs
 
     def exchange(self):
         """After a step: rank boxes, and a hand-over if any two came within the broadphase margin of each other."""
         torch = self.torch
         with torch.cuda.stream(self.ext):
-            g, gh = self._gather_bounds()
-            pairs = overlapping_ranks(gh)
-            while pairs:
-                self.halo_checks += 1
-                t0 = time.perf_counter()
-                moved = self._handover(pairs, g)
-                if moved == 0:
-                    break
-                self.handover_rounds += 1
-                self.handover_ms.append((time.perf_counter() - t0) * 1e3)
+            if not self.pipeline:
                 g, gh = self._gather_bounds()
-                pairs = overlapping_ranks(gh)
+                pairs = self._resolve(g, gh, 0)
+            else:
+                # enqueue this step's boxes (reduction, all-gather, copy to pinned memory), then look at the PREVIOUS step's
+                self.world.device_bounds(self.bounds.data_ptr())
+                g = self.comm.all_gather(self.bounds)
+                k = self.flip
+                self.host_boxes[k].copy_(g, non_blocking=True)
+                self.host_events[k].record(self.ext)
+                prev, self.pending, self.flip = self.pending, k, 1 - k
+                pairs = []
+                if prev is not None:
+                    self.host_events[prev].synchronize()         # a step old: long done
+                    gh = self.host_boxes[prev].numpy()
+                    if overlapping_ranks(gh[:, :6], self._margin(gh, 1)):
+                        g, gh = self._gather_bounds()            # blocking path, on the current state
+                        pairs = self._resolve(g, gh, 1)
+                        self.pending = None                      # the boxes in flight predate the hand-over
         self.last_pairs = pairs
         return pairs
 

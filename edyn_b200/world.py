@@ -262,10 +262,13 @@ class World:
         return imp[:self.num_hinges]
 
     def device_bounds(self, device_ptr):
-        """Enqueue the dynamic-AABB bounds reduction into 6 floats at `device_ptr` (an int device address)."""
+        """Enqueue the dynamic-AABB bounds reduction into 8 floats (min, max, speed, 0) at `device_ptr` (an int device address)."""
         self._check(self.l.b2d_device_bounds(self.h, C.c_void_p(device_ptr)))
 
     # -- multi-GPU hand-over (device buffers are passed as integer addresses; the transport belongs to the caller)
+    def set_halo_margin(self, margin):
+        self._check(self.l.b2d_set_halo_margin(self.h, C.c_float(margin)))
+
     def set_entities(self, first, entity):
         e = _c(entity, u32)
         self._check(self.l.b2d_set_entities(self.h, C.c_uint32(first), C.c_uint32(len(e)), _p(e)))

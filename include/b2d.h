@@ -182,16 +182,20 @@ int b2d_download_hinge_impulses(b2d_world *w, float *imp5);
 int b2d_get_stats(b2d_world *w, b2d_stats *out);
 /* Restart the per-kernel timing averages reported by b2d_get_stats. */
 int b2d_reset_timers(b2d_world *w);
-/* Development aid: raw copy of the device-side counter block (layout private to the library; used by
- * tools/solver_profile.py with a -DB2D_DF_PROFILE build).  Not part of the reference-facing surface. */
+/* Development aid: raw copy of the device-side counter block (layout private to the library).  Not part of the reference-facing surface. */
 int b2d_debug_counters(b2d_world *w, void *out, uint32_t bytes);
 /* Development aid: the island tiles of the last step: out6 = tiles, manifolds / hinges solved in
  * tiles, manifolds / hinges with rows, most bodies in one tile. */
 int b2d_debug_tiles(b2d_world *w, uint32_t *out6);
 /* Multi-GPU exchange: enqueue, on the world's stream, the reduction of all dynamic AABBs into
- * device_out6 = {min xyz, max xyz} -- a DEVICE pointer (e.g. a buffer owned by the host framework) the adapter then all-gathers over
- * NCCL to detect island groups of different ranks coming within the broadphase margin of each other. */
-int b2d_device_bounds(b2d_world *w, float *device_out6);
+ * device_out8 = {min xyz, max xyz, speed, 0} -- a DEVICE pointer (e.g. a buffer owned by the host framework) the adapter
+ * then all-gathers over NCCL to detect island groups of different ranks coming within the broadphase margin of each
+ * other.  speed = the fastest any point of any dynamic body moves (|v| + |w| r, m/s): an adapter that overlaps the
+ * exchange with the next step widens its margins by what the bodies can travel in that step. */
+int b2d_device_bounds(b2d_world *w, float *device_out8);
+/* Distance below which an island counts as touching a peer's box / island in b2d_island_halo and b2d_handover_plan
+ * (never below the manifold separation threshold 0.026, broadphase.hpp:18, which is the default). */
+int b2d_set_halo_margin(b2d_world *w, float margin);
 /* ---- Island hand-over between the worlds of different GPUs.  The host framework owns the
  * transport (NCCL send/recv of DEVICE buffers); every payload is produced and consumed on the device.
  *   b2d_set_entities   scene-global name per body (the entt::entity of the EnTT binding); default = local id.

@@ -669,13 +669,22 @@ void World::solve() {
     if (use_order) {
         for (uint32_t h : hinge_order)
             if (bodies[hinges[h].a].awake() || bodies[hinges[h].b].awake()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
+        std::vector<char> seen(manifolds.size(), 0);
         for (uint64_t k : manifold_order) {
             auto it = manifold_map.find(k);
             if (it == manifold_map.end()) continue;
+            seen[it->second] = 1;
             const Manifold &m = manifolds[it->second];
             if (!bodies[m.a].awake() && !bodies[m.b].awake()) continue;
             IslandWork &w = island_of(m.a, m.b);
             for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(it->second, p);
+        }
+        // manifolds the injected order does not name (the two sides drifted apart in a free run): natural order, at the end
+        for (uint32_t mi = uint32_t(manifolds.size()); mi-- > 0;) {
+            const Manifold &m = manifolds[mi];
+            if (seen[mi] || m.num == 0 || (!bodies[m.a].awake() && !bodies[m.b].awake())) continue;
+            IslandWork &w = island_of(m.a, m.b);
+            for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(mi, p);
         }
     } else {
         // Natural order: constraint-type major (hinge before contact, constraints/constraint.hpp:23-34),

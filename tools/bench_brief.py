@@ -10,4 +10,4 @@ for k, r in j.get("workloads", {}).items():
     row(k, r)
 h = j["config"].get("handover")
 if h:
-    print("handover:", {k: h[k] for k in ("bodies_in_per_rank", "rank0_handover_round_ms", "rank0_handover_phases_ms", "rank0_host_ms_each_step") if k in h})
+    print("handover:", {k: h[k] for k in ("bodies_in_per_rank", "rank0_handover_round_ms", "rank0_handover_phases_ms", "rank0_host_ms_each_step", "rank0_last_step_device_ms") if k in h})
