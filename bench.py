@@ -416,6 +416,7 @@ def run_sharded(args, world_size, rank, local_rank):
 
     if st["error_flags"]:
         raise SystemExit(f"rank {rank}: device error flags {st['error_flags']}")
+    print(f"[rank {rank}] hand-over rounds (ms): {sw.handover_phases}; host ms per timed step: {[round(x, 2) for x in step_ms]}", file=sys.stderr, flush=True)
     if rank == 0:
         local_scene = dict(scene, dynamic=sw.dynamic)
         roofline = solver_roofline(st, local_scene, ms / args.steps)

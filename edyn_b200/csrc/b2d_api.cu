@@ -13,6 +13,8 @@
 #include <string>
 #include <unordered_set>
 #include <vector>
+#include <chrono>
+#include <unistd.h>
 
 using namespace b2d;
 
@@ -27,6 +29,7 @@ struct b2d_world {
     int num_sms = 0;
     int coop_blocks_color = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
     int tile_blocks = 0, tile_pos_blocks = 0;       // grids of the island-tile kernels (CTAs loop over the tiles)
+    uint32_t bp_warp_max = 100000;                  // neighbourhood search: warp per body up to this many bodies (B2D_BP_WARP_MAX)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
     uint64_t launches = 0, steps = 0;
@@ -64,6 +67,16 @@ struct b2d_world {
 // The captured step no longer matches the world (counts, table pointers, grid pitch changed): re-capture before the next
 // replay.  The executable graphs are kept so that the re-capture can patch them in place (capture()).
 static void drop_graphs(b2d_world *w) { w->graph_valid = false; }
+// B2D_TRACE=1: wall-clock marks of the hand-over entry points on stderr (development aid)
+struct Trace {
+    const char *what; bool on; std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char *w_) : what(w_), on(getenv("B2D_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *label) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[b2d trace pid %d] %s: %s at %.3f ms\n", (int)getpid(), what, label, ms);
+    }
+};
 static void destroy_graphs(b2d_world *w) {
     for (cudaGraphExec_t *g : {&w->gx_pre, &w->gx_solve, &w->gx_post, &w->gx_all}) if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
     w->graph_valid = false;
@@ -201,6 +214,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, TILE_CAP, TILE_SOLVE_SMEM); w->tile_blocks = std::max(1, per_sm) * w->num_sms;
     cudaFuncSetAttribute(k_position_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_POS_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_tiles, TILE_CAP, TILE_POS_SMEM); w->tile_pos_blocks = std::max(1, per_sm) * w->num_sms;
+    if (const char *e = getenv("B2D_BP_WARP_MAX")) w->bp_warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("B2D_TILES")) if (atoi(e) == 0) d.max_tiles = 0;          // development: everything through the dataflow path
     if (const char *e = getenv("B2D_GRAPH")) w->use_graph = atoi(e) != 0;
 
@@ -353,14 +367,13 @@ int b2d_remove_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
     for (uint32_t k = 0; k < n; ++k) if (ids[k] >= d.nbodies) { w->error = "b2d_remove_bodies: body id out of range"; return B2D_ERR_ARGUMENT; }
     if (!n) return B2D_OK;
     cudaStream_t s = w->stream;
-    uint32_t *dev_ids = nullptr;
-    CK(cudaMallocAsync(&dev_ids, n * sizeof(uint32_t), s));
+    if ((size_t)n > w->stage_floats) { w->error = "b2d_remove_bodies: more ids than the staging buffer holds"; return B2D_ERR_CAPACITY; }
+    uint32_t *dev_ids = (uint32_t *)w->stage;          // the staging buffer doubles as scratch: every user synchronises before it returns
     CK(cudaMemcpyAsync(dev_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     LAUNCH(k_remove_bodies, n, 256, d, dev_ids, n);
     if (d.nhinges) LAUNCH(k_remove_hinges, d.nhinges, 256, d);
     // destroying a node queues its island for wake-up (island_manager.cpp:74-97); restated coarsely: everybody wakes
     if (d.sleeping) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies);
-    CK(cudaFreeAsync(dev_ids, s));
     CK(cudaStreamSynchronize(s));
     for (uint32_t k = 0; k < n; ++k) class_forget(w, ids[k]);
     w->contacts_dirty = true; w->class_dirty = true; w->ehash_dirty = true;
@@ -376,11 +389,10 @@ int b2d_wake_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
     if (!ids) { if (d.nbodies) LAUNCH(k_wake_bodies, d.nbodies, 256, d, (const uint32_t *)nullptr, d.nbodies); CK(cudaStreamSynchronize(s)); return B2D_OK; }
     for (uint32_t k = 0; k < n; ++k) if (ids[k] >= d.nbodies) { w->error = "b2d_wake_bodies: body id out of range"; return B2D_ERR_ARGUMENT; }
     if (!n) return B2D_OK;
-    uint32_t *dev_ids = nullptr;
-    CK(cudaMallocAsync(&dev_ids, n * sizeof(uint32_t), s));
+    if ((size_t)n > w->stage_floats) { w->error = "b2d_wake_bodies: more ids than the staging buffer holds"; return B2D_ERR_CAPACITY; }
+    uint32_t *dev_ids = (uint32_t *)w->stage;
     CK(cudaMemcpyAsync(dev_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     LAUNCH(k_wake_bodies, n, 256, d, (const uint32_t *)dev_ids, n);
-    CK(cudaFreeAsync(dev_ids, s));
     CK(cudaStreamSynchronize(s));
     return B2D_OK;
 }
@@ -517,10 +529,12 @@ static int enqueue_broadphase(b2d_world *w) {
         t = w->cub_tmp_bytes;
         CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, 48, s)); w->launches += 4;
         LAUNCH(k_bp_cell_starts, d.nbodies, 256, d);
-        LAUNCH(k_bp_pairs<false>, d.nbodies, 128, d);
+        // a warp per query body while that still fills the machine with few bodies, a thread per body beyond
+        const bool bp_warp = d.nbodies <= w->bp_warp_max;
+        if (bp_warp) LAUNCH(k_bp_pairs_warp<false>, (uint64_t)d.nbodies * 32, 256, d); else LAUNCH(k_bp_pairs<false>, d.nbodies, 128, d);
         t = w->cub_tmp_bytes;
         CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.newcount, d.newoff, (int)d.nbodies, s)); ++w->launches;
-        LAUNCH(k_bp_pairs<true>, d.nbodies, 128, d);
+        if (bp_warp) LAUNCH(k_bp_pairs_warp<true>, (uint64_t)d.nbodies * 32, 256, d); else LAUNCH(k_bp_pairs<true>, d.nbodies, 128, d);
         LAUNCH(k_bp_append, d.NM, 256, d);
         LAUNCH(k_bp_finish, 1, 32, d);
     }
@@ -528,11 +542,9 @@ static int enqueue_broadphase(b2d_world *w) {
 }
 static int enqueue_narrowphase(b2d_world *w) {
     Dev &d = w->d; cudaStream_t s = w->stream;
+    CK(cudaMemsetAsync(d.cnt->npcount, 0, 32 * sizeof(uint32_t), s));        // histogram + cursors
     LAUNCH(k_np_keys, d.NM, 256, d);
-    size_t t = w->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.ckey, d.ckey_s, d.cidx, d.cidx_s, (int)d.NM, 0, 8, s)); w->launches += 3;
-    LAUNCH(k_np_offsets, d.NM, 256, d);
-    LAUNCH(k_np_fixup, 1, 32, d);
+    LAUNCH(k_np_scatter, d.NM, 256, d);           // CTAs of exactly 256 threads (window size)
     LAUNCH(k_np_detect_light, d.NM, 128, d);
     launch_detect<5>(w); launch_detect<9>(w);
     LAUNCH(k_np_merge, d.NM, 128, d);
@@ -1092,6 +1104,7 @@ int b2d_handover_plan(b2d_world *w, const void *device_records, uint32_t my_begi
     if (!w || !counts || nranks == 0 || nranks > 64 || my_end < my_begin || (my_end > my_begin && !device_records)) return B2D_ERR_ARGUMENT;
     cudaSetDevice(w->cfg.device);
     Dev &d = w->d; cudaStream_t s = w->stream;
+    Trace tr("plan");
     CK(cudaMemsetAsync(w->dev_counts, 0, 4 * 64 * sizeof(uint32_t), s));
     if (my_end > my_begin && my_begin > 0)
         LAUNCH(k_plan_islands, (uint64_t)(my_end - my_begin) * my_begin, 256, d, (const HaloRec *)device_records, my_begin, my_end);
@@ -1110,6 +1123,7 @@ int b2d_handover_plan(b2d_world *w, const void *device_records, uint32_t my_begi
         if (a < d.nbodies && b < d.nbodies && w->host_bdst[a] != NO_RANK && w->host_bdst[a] == w->host_bdst[b] && w->host_bdst[a] < nranks) ++w->plan_counts[4 * w->host_bdst[a] + 3];
     }
     w->plan_ranks = nranks;
+    tr.mark("done");
     std::memcpy(counts, w->plan_counts.data(), 4 * nranks * sizeof(uint32_t));
     return B2D_OK;
 }
@@ -1125,6 +1139,7 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
     cudaSetDevice(w->cfg.device);
     Dev &d = w->d; cudaStream_t s = w->stream;
     const uint32_t *c = &w->plan_counts[4 * dst];
+    Trace tr("pack");
     if (capacity < b2d_handover_bytes(c)) { w->error = "b2d_handover_pack: blob too small"; return B2D_ERR_CAPACITY; }
     std::vector<uint32_t> ids; ids.reserve(c[0]);
     for (uint32_t i = 0; i < d.nbodies; ++i) if (w->host_bdst[i] == dst) ids.push_back(i);
@@ -1145,9 +1160,9 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
     float4 *ob = (float4 *)(blob + sizeof(BlobHeader)), *om = ob + (size_t)BLOB_BODY_F4 * c[0], *oh = om + (size_t)BLOB_MANIFOLD_F4 * c[1];
     uint2 *ox = (uint2 *)(oh + (size_t)BLOB_HINGE_F4 * c[2]);
     k_pack_header<<<1, 32, 0, s>>>(hdr, c[0], c[1], c[2], c[3]); ++w->launches;
-    uint32_t *dev_ids = nullptr; uint2 *dev_ex = nullptr;
+    if ((size_t)c[0] + 2 * (size_t)c[3] + 4 > w->stage_floats) { w->error = "b2d_handover_pack: plan larger than the staging buffer"; return B2D_ERR_CAPACITY; }
+    uint32_t *dev_ids = (uint32_t *)w->stage; uint2 *dev_ex = (uint2 *)(w->stage + ((c[0] + 1u) & ~1u));      // scratch inside the staging buffer
     if (c[0]) {
-        CK(cudaMallocAsync(&dev_ids, c[0] * sizeof(uint32_t), s));
         CK(cudaMemcpyAsync(dev_ids, ids.data(), c[0] * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         LAUNCH(k_pack_bodies, c[0], 256, d, (const uint32_t *)dev_ids, c[0], ob);
     }
@@ -1165,7 +1180,6 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
         LAUNCH(k_pack_hinges, d.nhinges, 256, d, oh);
     }
     if (c[3]) {
-        CK(cudaMallocAsync(&dev_ex, c[3] * sizeof(uint2), s));
         CK(cudaMemcpyAsync(dev_ex, ex.data(), c[3] * sizeof(uint2), cudaMemcpyHostToDevice, s));
         LAUNCH(k_pack_exclusions, c[3], 256, d, (const uint2 *)dev_ex, c[3], ox);
     }
@@ -1173,10 +1187,10 @@ int b2d_handover_pack(b2d_world *w, uint32_t dst, void *device_blob, uint64_t ca
     if (c[0]) {
         LAUNCH(k_remove_bodies, c[0], 256, d, (const uint32_t *)dev_ids, c[0]);
         if (d.nhinges) LAUNCH(k_remove_hinges, d.nhinges, 256, d);
-        CK(cudaFreeAsync(dev_ids, s));
     }
-    if (dev_ex) CK(cudaFreeAsync(dev_ex, s));
+    tr.mark("enqueued");
     CK(cudaStreamSynchronize(s));
+    tr.mark("synced");
     for (uint32_t i : ids) { class_forget(w, i); w->host_bdst[i] = NO_RANK; }
     w->class_removed = true; w->ehash_dirty = true; w->labels_stale = true;
     drop_graphs(w);
@@ -1188,8 +1202,10 @@ int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, u
     cudaSetDevice(w->cfg.device);
     Dev &d = w->d; cudaStream_t s = w->stream;
     BlobHeader h;
+    Trace tr("unpack");
     CK(cudaMemcpyAsync(&h, device_blob, sizeof(h), cudaMemcpyDeviceToHost, s));
     Counters cn; { int rc = fetch_counters(w, cn); if (rc) return rc; }
+    tr.mark("blob header on the host (the receive has landed)");
     if (h.magic != BLOB_MAGIC) { w->error = "b2d_handover_unpack: not a hand-over blob"; return B2D_ERR_ARGUMENT; }
     const uint32_t c[4] = {h.nb, h.nm, h.nh, h.nx};
     if (bytes < b2d_handover_bytes(c)) { w->error = "b2d_handover_unpack: blob truncated"; return B2D_ERR_ARGUMENT; }
@@ -1222,12 +1238,11 @@ int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, u
     if (h.nm) { LAUNCH(k_unpack_manifolds, h.nm, 256, d, h.nm, im, cn.hwm); LAUNCH(k_bump_hwm, 1, 32, d, h.nm); }
     if (h.nh) { LAUNCH(k_unpack_hinges, h.nh, 256, d, d.nhinges, h.nh, ih); d.nhinges += h.nh; }
     if (h.nx) {
-        uint2 *loc = nullptr;
-        CK(cudaMallocAsync(&loc, h.nx * sizeof(uint2), s));
+        if (2 * (size_t)h.nx > w->stage_floats) { w->error = "b2d_handover_unpack: more exclusions than the staging buffer holds"; return B2D_ERR_CAPACITY; }
+        uint2 *loc = (uint2 *)w->stage;
         LAUNCH(k_unpack_exclusions, h.nx, 256, d, ix, h.nx, loc);
         std::vector<uint2> host(h.nx);
         CK(cudaMemcpyAsync(host.data(), loc, h.nx * sizeof(uint2), cudaMemcpyDeviceToHost, s));
-        CK(cudaFreeAsync(loc, s));
         CK(cudaStreamSynchronize(s));
         std::vector<uint64_t> keys; keys.reserve(h.nx);     // both ends are newcomers with fresh local ids: the pairs cannot exist yet
         for (const uint2 &e : host) {
@@ -1235,9 +1250,11 @@ int b2d_handover_unpack(b2d_world *w, const void *device_blob, uint64_t bytes, u
             const uint64_t lo = std::min(e.x, e.y), hi = std::max(e.x, e.y);
             keys.push_back((lo << 32) | hi);
         }
+        tr.mark("exclusions translated");
         int rc = insert_exclusions(w, keys); if (rc) return rc;
     }
     CK(cudaStreamSynchronize(s));
+    tr.mark("done");
     w->labels_stale = true;
     drop_graphs(w);
     if (counts_out) std::memcpy(counts_out, c, sizeof(c));

@@ -281,6 +281,57 @@ __global__ void k_bp_pairs(Dev d) {
         if (!FILL) d.newcount[A] = count;
     }
 }
+// The same search with one WARP per query body: lane c < 27 takes cell c of the neighbourhood (in the loop order of
+// the thread-per-body kernel), lane 27 the brute-force list, and a warp prefix sum of the lane counts puts the pairs in
+// exactly the order the serial walk produces.  27 hash probes and cell walks in flight per body instead of one after
+// the other: the search is latency-bound at small body counts (100 us for 4 096 bodies with a thread per body).
+template<bool FILL>
+__global__ void k_bp_pairs_warp(Dev d) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = wid; t < d.nbodies; t += nw) {
+        const uint32_t A = d.cellbody_s[t];
+        const uint32_t fA = d.flags[A];
+        uint2 *out = nullptr;
+        if (FILL) {
+            if (d.newcount[A] == 0) continue;
+            if ((unsigned long long)d.newoff[A] + d.newcount[A] > d.NM) { if (lane == 0) atomicOr(&d.cnt->err, ERR_MANIFOLD_CAPACITY); continue; }
+            out = d.newpairs + d.newoff[A];
+        }
+        uint32_t total = 0;
+        if (is_dynamic(fA) && shape_of(fA) != SH_NONE) {
+            const box3 bbA = body_box(d, A);
+            const box3 qA = inset(bbA, BP_OFFSET);
+            // this lane's share of the candidates, walked once to count and (FILL) once more to write
+            uint32_t start = 0, end = 0; unsigned long long key = EMPTY_KEY; int mode = 0;      // 0 nothing, 1 one cell, 2 a range of body ids, 3 the large list
+            if (!(fA & F_LARGE)) {
+                if (lane < 27u) {
+                    int cx, cy, cz; cell_of(d, A, cx, cy, cz);
+                    key = cell_key_of(cx + (int)(lane / 9u) - 1, cy + (int)((lane / 3u) % 3u) - 1, cz + (int)(lane % 3u) - 1);
+                    if (hash_find(d.chash_key, d.chash_val, d.chash_size, key, start)) mode = 1;
+                }
+            } else if (lane < 27u) {
+                const uint32_t chunk = (d.nbodies + 26u) / 27u;
+                start = min(lane * chunk, d.nbodies); end = min(start + chunk, d.nbodies); mode = 2;
+            }
+            if (lane == 27u) mode = 3;
+            auto walk = [&](uint2 *o) {
+                uint32_t c = 0;
+                if (mode == 1) { for (uint32_t k = start; k < d.nbodies && d.cellkey_s[k] == key; ++k) bp_candidate(d, A, fA, bbA, qA, d.cellbody_s[k], c, o); }
+                else if (mode == 2) { for (uint32_t j = start; j < end; ++j) if (!(d.flags[j] & F_LARGE)) bp_candidate(d, A, fA, bbA, qA, j, c, o); }
+                else if (mode == 3) { for (uint32_t k = 0; k < d.nlarge; ++k) bp_candidate(d, A, fA, bbA, qA, d.large_list[k], c, o); }
+                return c;
+            };
+            const uint32_t mine = walk(nullptr);
+            uint32_t incl = mine;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            if (FILL && mine) walk(out + (incl - mine));
+        }
+        if (!FILL && lane == 0) d.newcount[A] = total;
+    }
+}
 // Number of new pairs this step.  newpairs holds max_manifolds entries: a body whose range would run past it (and
 // therefore every body behind it in the scan) is dropped by the fill pass, so the usable prefix ends where the first
 // such range starts (found by bisection on the monotone prefix sums; only on overflow).
@@ -379,7 +430,7 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
 }
 
 // Narrowphase in three kernels:
-//   k_np_keys     pair-type key per manifold slot (static per slot), radix-sorted on the host side so that
+//   k_np_keys     pair-type key per manifold slot + histogram, k_np_scatter the counting sort by type, so that
 //   k_np_detect<FN> runs ONE collide() overload per launch over a contiguous range of the sorted list
 //                 (no intra-warp divergence between sphere/box/capsule code paths); the <= 4 result points go to
 //                 the solver-row arrays R0/R1/R2, which are idle in this phase;
@@ -387,31 +438,55 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
 //                 (collision_util.hpp:105-276, sequential flavour of narrowphase.hpp:62-84) per manifold.
 __global__ void k_np_keys(Dev d) {
     const uint32_t hwm = d.cnt->hwm;
-    GRID_STRIDE(m, d.NM) {
+    GRID_STRIDE(m, hwm) {
         uint32_t key = 0xFF;
-        if (m < hwm && (d.mstate[m] & MS_ALIVE)) {
+        if (d.mstate[m] & MS_ALIVE) {
             uint2 pr = d.mpair[m];
-            if (!is_dynamic(d.flags[pr.x]) && !is_dynamic(d.flags[pr.y])) { d.ckey[m] = key; d.cidx[m] = m; continue; }   // sleeping manifold (narrowphase.cpp:31)
-            int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
-            int fn = pair_fn(ka, kb);
-            if (!fn) fn = pair_fn(kb, ka);
-            key = (uint32_t)fn;
+            if (is_dynamic(d.flags[pr.x]) || is_dynamic(d.flags[pr.y])) {      // else: sleeping manifold (narrowphase.cpp:31)
+                int ka = shape_of(d.flags[pr.x]), kb = shape_of(d.flags[pr.y]);
+                int fn = pair_fn(ka, kb);
+                if (!fn) fn = pair_fn(kb, ka);
+                key = (uint32_t)fn;
+            }
         }
-        d.ckey[m] = key; d.cidx[m] = m;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 16) d.cnt->npoff[threadIdx.x] = 0xFFFFFFFFu;
-}
-__global__ void k_np_offsets(Dev d) {
-    GRID_STRIDE(i, d.NM) {
-        uint32_t k = d.ckey_s[i];
-        if (i == 0 || d.ckey_s[i - 1] != k) d.cnt->npoff[k == 0xFF ? 10 : k] = i;
+        d.ckey[m] = key;
+        if (key != 0xFF) {          // histogram of the pair types, one atomic per type per warp
+            const uint32_t grp = __match_any_sync(__activemask(), key);
+            if ((threadIdx.x & 31u) == (uint32_t)(__ffs(grp) - 1)) atomicAdd(&d.cnt->npcount[key & 15u], (uint32_t)__popc(grp));
+        }
     }
 }
-__global__ void k_np_fixup(Dev d) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Counting sort by pair type: manifold slots of one type become a contiguous range of cidx_s.  Every CTA takes windows
+// of 256 consecutive slots, keeps their order inside a type (manifold slots are spatially coherent, the detect kernels
+// gather body data through them) and claims the window's share of each range with one atomic per type; which window
+// comes first is first come first served -- it only decides which thread runs which manifold.
+__global__ void __launch_bounds__(256) k_np_scatter(Dev d) {
+    __shared__ uint32_t s_off[16], s_base[16], s_wcount[8][16];
     Counters &c = *d.cnt;
-    if (c.npoff[10] == 0xFFFFFFFFu) c.npoff[10] = d.NM;
-    for (int k = 9; k >= 0; --k) if (c.npoff[k] == 0xFFFFFFFFu) c.npoff[k] = c.npoff[k + 1];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int k = 0; k < 16; ++k) { s_off[k] = acc; acc += c.npcount[k]; }
+        if (blockIdx.x == 0) for (int k = 0; k < 16; ++k) c.npoff[k] = s_off[k];
+    }
+    const uint32_t hwm = c.hwm, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t w0 = blockIdx.x * 256u; w0 < hwm; w0 += gridDim.x * 256u) {
+        if (threadIdx.x < 128) s_wcount[threadIdx.x >> 4][threadIdx.x & 15u] = 0;
+        __syncthreads();
+        const uint32_t m = w0 + threadIdx.x;
+        const uint32_t key = m < hwm ? d.ckey[m] : 0xFFu;
+        const uint32_t grp = __match_any_sync(0xffffffffu, key);
+        const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+        if (key != 0xFFu && rank == 0) s_wcount[warp][key & 15u] = __popc(grp);
+        __syncthreads();
+        if (threadIdx.x < 16) {          // exclusive prefix over the warps, then the window's claim on the type's range
+            uint32_t acc = 0;
+            for (int w = 0; w < 8; ++w) { const uint32_t n = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = acc; acc += n; }
+            s_base[threadIdx.x] = acc ? atomicAdd(&c.npcursor[threadIdx.x], acc) : 0u;
+        }
+        __syncthreads();
+        if (key != 0xFFu) d.cidx_s[s_off[key & 15u] + s_base[key & 15u] + s_wcount[warp][key & 15u] + rank] = m;
+        __syncthreads();
+    }
 }
 
 template<int FN>

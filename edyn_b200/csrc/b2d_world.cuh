@@ -70,6 +70,7 @@ struct Counters {
     uint32_t cchunk[MAX_COLORS + 2]; // prefix sum of ceil(colour size / 32): warp-sized chunks never span two colours
     uint32_t hchunk[MAX_COLORS + 2];
     uint32_t npoff[16];              // narrowphase: start of each pair-type range in the type-sorted list
+    uint32_t npcount[16], npcursor[16];      // its histogram and scatter cursors (zeroed by the host)
     unsigned long long dbg[16];  // development counters (B2D_DF_PROFILE builds only)
 };
 

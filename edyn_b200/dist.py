@@ -512,6 +512,10 @@ class DeviceShardedWorld:
             comm.warmup(dev)
 
     def close(self):
+        # pinned buffers and events must go before the CUDA context does (interpreter teardown order is not ours)
+        self.torch.cuda.synchronize()
+        self.host_boxes = self.host_events = None
+        self.pending = None
         self.world.close()
 
     def _gather_bounds(self):

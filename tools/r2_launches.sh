@@ -3,7 +3,7 @@
 TAG=$1; shift
 mkdir -p gpurun_out/$TAG
 for wl in "$@"; do
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 9650 -c 450 --csv --log-file gpurun_out/$TAG/launches_$wl.csv python bench.py --workload $wl --only --steps 2 --warmup 1 --no-cpu > gpurun_out/$TAG/ncu_$wl.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-6000} -c 400 --csv --log-file gpurun_out/$TAG/launches_$wl.csv python bench.py --workload $wl --only --steps 2 --warmup 1 --no-cpu > gpurun_out/$TAG/ncu_$wl.log 2>&1
   python tools/launch_summary.py gpurun_out/$TAG/launches_$wl.csv > gpurun_out/$TAG/summary_$wl.txt 2>&1
   cat gpurun_out/$TAG/summary_$wl.txt
 done
