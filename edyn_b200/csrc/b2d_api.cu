@@ -135,6 +135,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     if (!prop.cooperativeLaunch) { g_create_error = "b2d_create: device lacks cooperative launch"; delete w; return nullptr; }
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream"; delete w; return nullptr; }
     cudaEventCreate(&w->ev_step0); cudaEventCreate(&w->ev_step1);
+
     for (int i = 0; i < b2d_world::RING; ++i) { cudaEventCreate(&w->ev_solve0[i]); cudaEventCreate(&w->ev_solve1[i]); cudaEventCreate(&w->ev_int0[i]); cudaEventCreate(&w->ev_int1[i]); }
 
     Dev &d = w->d;
@@ -614,7 +615,8 @@ static int enqueue_solver_a(b2d_world *w, int recolor) {
 static int enqueue_solver_b(b2d_world *w) {
     Dev &d = w->d;
     const int vi = (int)w->cfg.velocity_iterations;
-    // the two schedules work on disjoint islands
+    // The two schedules work on disjoint islands.  (Forking the tile kernel onto a second stream was measured: no gain --
+    // the cooperative launch wants the whole machine and waits for the tiles, or the tiles wait for it.)
     if (d.max_tiles) { k_solve_tiles<<<w->tile_blocks, TILE_CAP, TILE_SOLVE_SMEM, w->stream>>>(d, vi); ++w->launches; }
     CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
     return B2D_OK;

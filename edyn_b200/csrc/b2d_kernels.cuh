@@ -437,6 +437,9 @@ B2D_D MPoint create_point(const CPoint &rp, q4 ornA, q4 ornB, float2 matA, float
 //   k_np_merge    update_contact_distances (collision_util.cpp:28-45) + process_collision
 //                 (collision_util.hpp:105-276, sequential flavour of narrowphase.hpp:62-84) per manifold.
 __global__ void k_np_keys(Dev d) {
+    __shared__ uint32_t s_hist[16];
+    if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t hwm = d.cnt->hwm;
     GRID_STRIDE(m, hwm) {
         uint32_t key = 0xFF;
@@ -450,11 +453,10 @@ __global__ void k_np_keys(Dev d) {
             }
         }
         d.ckey[m] = key;
-        if (key != 0xFF) {          // histogram of the pair types, one atomic per type per warp
-            const uint32_t grp = __match_any_sync(__activemask(), key);
-            if ((threadIdx.x & 31u) == (uint32_t)(__ffs(grp) - 1)) atomicAdd(&d.cnt->npcount[key & 15u], (uint32_t)__popc(grp));
-        }
+        if (key != 0xFF) atomicAdd(&s_hist[key & 15u], 1u);       // histogram of the pair types, per CTA first
     }
+    __syncthreads();
+    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&d.cnt->npcount[threadIdx.x], s_hist[threadIdx.x]);
 }
 // Counting sort by pair type: manifold slots of one type become a contiguous range of cidx_s.  Every CTA takes windows
 // of 256 consecutive slots, keeps their order inside a type (manifold slots are spatially coherent, the detect kernels
@@ -878,8 +880,11 @@ __global__ void k_tile_assign(Dev d) {
             const uint32_t r = d.parent[i];
             if (d.swgt[r]) {
                 tile = d.swsum[r] / g;
-                if (tile < d.max_tiles) {
-                    slot = atomicAdd(&d.tile_nb[tile], 1u);         // order within the tile is immaterial
+                if (tile < d.max_tiles) {                           // order within the tile is immaterial; one atomic per tile per warp
+                    const uint32_t grp = __match_any_sync(__activemask(), tile), lane = threadIdx.x & 31u, leader = (uint32_t)(__ffs(grp) - 1);
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&d.tile_nb[tile], (uint32_t)__popc(grp));
+                    slot = __shfl_sync(grp, base, leader) + __popc(grp & ((1u << lane) - 1u));
                     d.tile_body[(size_t)tile * TILE_CAP + slot] = i;
                 } else tile = TILE_NONE;
             }
@@ -1929,6 +1934,7 @@ __global__ void __launch_bounds__(B2D_POS_THREADS, B2D_POS_MIN_BLOCKS) k_positio
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const uint32_t hchunks = s_hchunk[nh], cchunks = s_cchunk[nc];
+    if (hchunks + cchunks == 0) return;               // every island is tiled (the whole grid takes this exit together)
     GRID_STRIDE(i, d.nbodies) {
         d.isl_err[i] = 0; d.isl_done[i] = 0;
         if (is_dynamic(d.flags[i])) {

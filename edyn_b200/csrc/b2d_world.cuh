@@ -27,8 +27,11 @@ constexpr int MAX_COLORS = 64;
 // constraint rows in registers for all iterations, __syncthreads between colours, no global synchronisation at all --
 // are packed into tiles of up to TILE_CAP bodies / contact manifolds / joints; everything else (a pile is one island)
 // goes through the global dataflow kernels.
-constexpr int TILE_CAP = 256;                  // threads per tile CTA = capacity in bodies, manifolds and joints
-constexpr int TILE_ISLAND_MAX = 128;           // an island is tiled if it has at most this many bodies, manifolds and joints
+#ifndef B2D_TILE_CAP
+#define B2D_TILE_CAP 256
+#endif
+constexpr int TILE_CAP = B2D_TILE_CAP;         // threads per tile CTA = capacity in bodies, manifolds and joints
+constexpr int TILE_ISLAND_MAX = TILE_CAP / 2;  // an island is tiled if it has at most this many bodies, manifolds and joints
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint32_t SLOT_NONE = 0xFFFFu;
 // sort keys.  tiled: tile(16) | colour(6); dataflow: DF | colour(6) | points-1 (2) | spatial rank(14); no rows: INACTIVE
