@@ -28,7 +28,9 @@ struct b2d_world {
     std::string error;
     int num_sms = 0;
     int coop_blocks_color = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
-    int tile_blocks = 0, tile_pos_blocks = 0;       // grids of the island-tile kernels (CTAs loop over the tiles)
+    int tile_blocks = 0, tile_pos_blocks = 0, tile_fused_blocks = 0;       // grids of the island-tile kernels (CTAs loop over the tiles)
+    bool fuse_tiles = true;                         // one kernel for the tiled islands' whole solver.update (B2D_FUSE_TILES=0: separate kernels)
+    int cell_key_bits = 48;                         // sum of d.cell_bits: end bit of the cell sort
     uint32_t bp_warp_max = 100000;                  // neighbourhood search: warp per body up to this many bodies (B2D_BP_WARP_MAX)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     float *stage = nullptr; size_t stage_floats = 0;        // device staging for packed host arrays
@@ -48,7 +50,7 @@ struct b2d_world {
     uint64_t updates = 0;             // island updates so far (sleep timestamps)
     // broadphase classes: bounding diameter and kind per body (host mirror), re-derived lazily before the next step
     std::vector<float> diam; std::vector<unsigned char> isdyn;
-    bool class_dirty = false, ehash_dirty = true, labels_stale = true;
+    bool class_dirty = false, ehash_dirty = true, labels_stale = true, cells_dirty = true;
     // running figures of the classification so that a hand-over (a few arrivals / departures) does not re-walk every body
     double class_sum = 0; uint64_t class_cnt = 0; float class_big = 1e30f; uint32_t class_new_first = 0; bool class_removed = false;
     std::vector<uint32_t> plan_counts;   // nranks x 4 of the current plan (bodies, manifolds, hinges, exclusions)
@@ -66,7 +68,7 @@ struct b2d_world {
 
 // The captured step no longer matches the world (counts, table pointers, grid pitch changed): re-capture before the next
 // replay.  The executable graphs are kept so that the re-capture can patch them in place (capture()).
-static void drop_graphs(b2d_world *w) { w->graph_valid = false; }
+static void drop_graphs(b2d_world *w) { w->graph_valid = false; w->cells_dirty = true; }
 // B2D_TRACE=1: wall-clock marks of the hand-over entry points on stderr (development aid)
 struct Trace {
     const char *what; bool on; std::chrono::steady_clock::time_point t0;
@@ -142,6 +144,7 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     const uint32_t NB = cfg->max_bodies, NM = cfg->max_manifolds, NH = std::max<uint32_t>(cfg->max_hinges, 1);
     d.NB = NB; d.NM = NM; d.NH = NH; d.dt = w->cfg.fixed_dt;
     d.nbodies = 0; d.nhinges = 0; d.nlarge = 0; d.cell = 1.0f; d.inv_cell = 1.0f; d.halo_margin = HALO_MARGIN;
+    for (int k = 0; k < 3; ++k) { d.cell_org[k] = -(1 << 15); d.cell_bits[k] = 16; }
     bool ok = true;
     ok = ok && dalloc(w, d.pos, NB) && dalloc(w, d.orn, NB) && dalloc(w, d.linvel, NB) && dalloc(w, d.angvel, NB);
     ok = ok && dalloc(w, d.dvw, 2 * (size_t)NB) && dalloc(w, d.invI, 3 * (size_t)NB) && dalloc(w, d.invIW, 3 * (size_t)NB);
@@ -215,6 +218,9 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, TILE_CAP, TILE_SOLVE_SMEM); w->tile_blocks = std::max(1, per_sm) * w->num_sms;
     cudaFuncSetAttribute(k_position_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_POS_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_tiles, TILE_CAP, TILE_POS_SMEM); w->tile_pos_blocks = std::max(1, per_sm) * w->num_sms;
+    cudaFuncSetAttribute(k_island_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_FUSED_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_island_tiles, TILE_CAP, TILE_FUSED_SMEM); w->tile_fused_blocks = std::max(1, per_sm) * w->num_sms;
+    if (const char *e = getenv("B2D_FUSE_TILES")) w->fuse_tiles = atoi(e) != 0;
     if (const char *e = getenv("B2D_BP_WARP_MAX")) w->bp_warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("B2D_TILES")) if (atoi(e) == 0) d.max_tiles = 0;          // development: everything through the dataflow path
     if (const char *e = getenv("B2D_GRAPH")) w->use_graph = atoi(e) != 0;
@@ -528,7 +534,7 @@ static int enqueue_broadphase(b2d_world *w) {
     if (d.nbodies) {
         LAUNCH(k_bp_cells, d.nbodies, 256, d);
         t = w->cub_tmp_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, 48, s)); w->launches += 4;
+        CK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, t, d.cellkey, d.cellkey_s, d.cellbody, d.cellbody_s, (int)d.nbodies, 0, w->cell_key_bits, s)); w->launches += 4;
         LAUNCH(k_bp_cell_starts, d.nbodies, 256, d);
         // a warp per query body while that still fills the machine with few bodies, a thread per body beyond
         const bool bp_warp = d.nbodies <= w->bp_warp_max;
@@ -617,21 +623,27 @@ static int enqueue_solver_b(b2d_world *w) {
     const int vi = (int)w->cfg.velocity_iterations;
     // The two schedules work on disjoint islands.  (Forking the tile kernel onto a second stream was measured: no gain --
     // the cooperative launch wants the whole machine and waits for the tiles, or the tiles wait for it.)
-    if (d.max_tiles) { k_solve_tiles<<<w->tile_blocks, TILE_CAP, TILE_SOLVE_SMEM, w->stream>>>(d, vi); ++w->launches; }
+    const int pi = (int)w->cfg.position_iterations;
+    if (d.max_tiles) {
+        if (w->fuse_tiles && pi > 0) { k_island_tiles<<<w->tile_fused_blocks, TILE_CAP, TILE_FUSED_SMEM, w->stream>>>(d, vi, pi); ++w->launches; }
+        else { k_solve_tiles<<<w->tile_blocks, TILE_CAP, TILE_SOLVE_SMEM, w->stream>>>(d, vi); ++w->launches; }
+    }
     CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
     return B2D_OK;
 }
 static int enqueue_integrate(b2d_world *w) {
     Dev &d = w->d;
-    LAUNCH(k_integrate, d.nbodies, 256, d, w->cfg.position_iterations == 0 ? 1 : 0);
+    const int fused = (d.max_tiles && w->fuse_tiles && w->cfg.position_iterations > 0) ? 1 : 0;
+    LAUNCH(k_integrate, d.nbodies, 256, d, w->cfg.position_iterations == 0 ? 1 : 0, fused);
     return B2D_OK;
 }
 static int enqueue_solver_c(b2d_world *w) {
     Dev &d = w->d; cudaStream_t s = w->stream;
     const int pi = (int)w->cfg.position_iterations;
-    LAUNCH(k_store_impulses, d.NM, 256, d);
+    const int fused = (d.max_tiles && w->fuse_tiles && pi > 0) ? 1 : 0;
+    LAUNCH(k_store_impulses, d.NM, 256, d, fused);
     if (pi > 0) {
-        if (d.max_tiles) { k_position_tiles<<<w->tile_pos_blocks, TILE_CAP, TILE_POS_SMEM, s>>>(d, pi); ++w->launches; }
+        if (d.max_tiles && !fused) { k_position_tiles<<<w->tile_pos_blocks, TILE_CAP, TILE_POS_SMEM, s>>>(d, pi); ++w->launches; }
         CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }
@@ -669,10 +681,38 @@ static int classify_arrivals(b2d_world *w) {
     w->class_new_first = d.nbodies; w->class_removed = false;
     return B2D_OK;
 }
-static int prepare_step(b2d_world *w) {
-    if (w->class_dirty) return reclassify(w);
-    if (w->class_new_first < w->d.nbodies || w->class_removed) return classify_arrivals(w);
+// Size the fields of the broadphase cell key to the world as it is now (with room to grow: half the extent again on
+// every side, at least 16 cells); runs when the step sequence is (re)captured, i.e. when the population changed.
+static int measure_cells(b2d_world *w) {
+    Dev &d = w->d;
+    if (!d.nbodies) return B2D_OK;
+    int *dev6 = (int *)w->stage;
+    const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, -0x7FFFFFFF, -0x7FFFFFFF, -0x7FFFFFFF};
+    int ext[6];
+    CK(cudaMemcpyAsync(dev6, init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
+    LAUNCH(k_cell_extent, d.nbodies, 256, d, dev6);
+    CK(cudaMemcpyAsync(ext, dev6, sizeof(ext), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    int total = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (ext[k] > ext[3 + k]) { d.cell_org[k] = -(1 << 15); d.cell_bits[k] = 16; total += 16; continue; }
+        const long long span = (long long)ext[3 + k] - ext[k] + 1, room = std::max<long long>(16, span / 2);
+        int bits = 1;
+        while ((1LL << bits) < span + 2 * room + 2 && bits < 16) ++bits;
+        d.cell_bits[k] = bits;
+        d.cell_org[k] = (int)std::max<long long>(ext[k] - room, -(1LL << 30));
+        total += bits;
+    }
+    w->cell_key_bits = total;
     return B2D_OK;
+}
+static int prepare_step(b2d_world *w) {
+    int rc = B2D_OK;
+    if (w->class_dirty) rc = reclassify(w);
+    else if (w->class_new_first < w->d.nbodies || w->class_removed) rc = classify_arrivals(w);
+    if (rc) return rc;
+    if (w->cells_dirty) { rc = measure_cells(w); w->cells_dirty = false; }
+    return rc;
 }
 
 int b2d_run_phases(b2d_world *w, uint32_t mask) {

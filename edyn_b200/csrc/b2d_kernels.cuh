@@ -168,14 +168,15 @@ __global__ void k_bp_free_list(Dev d) {
     }
 }
 
-B2D_D unsigned long long cell_key_of(int cx, int cy, int cz) {
-    // 16 bits per axis (radix sort passes are paid per key byte).  Cells beyond the range share the boundary key, which
-    // only makes the candidate lists there longer: the exact AABB tests decide.  All-ones is reserved for "no cell".
-    const int OFF = 1 << 15, MX = (1 << 16) - 2;
-    unsigned long long x = (unsigned long long)min(max(cx + OFF, 0), MX);
-    unsigned long long y = (unsigned long long)min(max(cy + OFF, 0), MX);
-    unsigned long long z = (unsigned long long)min(max(cz + OFF, 0), MX);
-    return (x << 32) | (y << 16) | z;
+// Cell key: the three cell coordinates relative to d.cell_org, packed into d.cell_bits[0..2] bits each (radix sort
+// passes are paid per key byte, so the host sizes the fields to the extent the world had when the step was captured).
+// Cells beyond the range share the boundary key, which only makes the candidate lists there longer: every pair still
+// goes through the exact AABB tests.  All-ones is reserved for "no cell".
+B2D_D unsigned long long cell_key_of(const Dev &d, int cx, int cy, int cz) {
+    const unsigned long long x = (unsigned long long)min(max(cx - d.cell_org[0], 0), (1 << d.cell_bits[0]) - 2);
+    const unsigned long long y = (unsigned long long)min(max(cy - d.cell_org[1], 0), (1 << d.cell_bits[1]) - 1);
+    const unsigned long long z = (unsigned long long)min(max(cz - d.cell_org[2], 0), (1 << d.cell_bits[2]) - 1);
+    return (x << (d.cell_bits[1] + d.cell_bits[2])) | (y << d.cell_bits[2]) | z;
 }
 B2D_D void cell_of(const Dev &d, uint32_t i, int &cx, int &cy, int &cz) {
     float4 a = d.bbmin[i], b = d.bbmax[i];
@@ -189,8 +190,24 @@ __global__ void k_bp_cells(Dev d) {
     GRID_STRIDE(i, d.nbodies) {
         uint32_t f = d.flags[i];
         unsigned long long key = EMPTY_KEY;
-        if (shape_of(f) != SH_NONE && !(f & F_LARGE)) { int cx, cy, cz; cell_of(d, i, cx, cy, cz); key = cell_key_of(cx, cy, cz); }
+        if (shape_of(f) != SH_NONE && !(f & F_LARGE)) { int cx, cy, cz; cell_of(d, i, cx, cy, cz); key = cell_key_of(d, cx, cy, cz); }
         d.cellkey[i] = key; d.cellbody[i] = i;
+    }
+}
+// Cells occupied by the bodies that go into the grid (host: sizes the key fields, b2d_api.cu measure_cells)
+__global__ void k_cell_extent(Dev d, int *out6) {
+    int mn[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[3] = {-0x7FFFFFFF, -0x7FFFFFFF, -0x7FFFFFFF};
+    GRID_STRIDE(i, d.nbodies) {
+        const uint32_t f = d.flags[i];
+        if (shape_of(f) == SH_NONE || (f & F_LARGE)) continue;
+        int c[3]; cell_of(d, i, c[0], c[1], c[2]);
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) { mn[k] = min(mn[k], c[k]); mx[k] = max(mx[k], c[k]); }
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = __reduce_min_sync(0xffffffffu, mn[k]); mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+        if ((threadIdx.x & 31) == 0 && mn[k] <= mx[k]) { atomicMin(&out6[k], mn[k]); atomicMax(&out6[3 + k], mx[k]); }
     }
 }
 // First sorted index of every occupied cell -> hash table.
@@ -267,7 +284,7 @@ __global__ void k_bp_pairs(Dev d) {
             if (!(fA & F_LARGE)) {
                 int cx, cy, cz; cell_of(d, A, cx, cy, cz);
                 for (int dx = -1; dx <= 1; ++dx) for (int dy = -1; dy <= 1; ++dy) for (int dz = -1; dz <= 1; ++dz) {
-                    unsigned long long key = cell_key_of(cx + dx, cy + dy, cz + dz);
+                    unsigned long long key = cell_key_of(d, cx + dx, cy + dy, cz + dz);
                     uint32_t start;
                     if (!hash_find(d.chash_key, d.chash_val, d.chash_size, key, start)) continue;
                     for (uint32_t k = start; k < d.nbodies && d.cellkey_s[k] == key; ++k)
@@ -307,7 +324,7 @@ __global__ void k_bp_pairs_warp(Dev d) {
             if (!(fA & F_LARGE)) {
                 if (lane < 27u) {
                     int cx, cy, cz; cell_of(d, A, cx, cy, cz);
-                    key = cell_key_of(cx + (int)(lane / 9u) - 1, cy + (int)((lane / 3u) % 3u) - 1, cz + (int)(lane % 3u) - 1);
+                    key = cell_key_of(d, cx + (int)(lane / 9u) - 1, cy + (int)((lane / 3u) % 3u) - 1, cz + (int)(lane % 3u) - 1);
                     if (hash_find(d.chash_key, d.chash_val, d.chash_size, key, start)) mode = 1;
                 }
             } else if (lane < 27u) {
@@ -1543,13 +1560,16 @@ __global__ void __launch_bounds__(B2D_SOLVE_THREADS, 2) k_solve_df(Dev d, int it
 }
 
 // assign_applied_impulses (island_solver.cpp:232-248): rows -> warm-start cache of the constraints.
-__global__ void k_store_impulses(Dev d) {
+__global__ void k_store_impulses(Dev d, int fused) {
     const uint32_t n = d.cnt->nactive, nh = d.cnt->nhactive;
-    GRID_STRIDE(i, n) {
+    const uint32_t first = fused ? d.cnt->ntiled : 0u, hfirst = fused ? d.cnt->nhtiled : 0u;       // k_island_tiles stored its own
+    GRID_STRIDE(k, n - first) {
+        const uint32_t i = first + k;
         const uint32_t npts = d.hdr[i].z, m = d.cidx_s[i];
         for (uint32_t s = 0; s < npts; ++s) d.pI[(size_t)s * d.NM + m] = d.IMP[(size_t)s * d.NM + i];
     }
-    GRID_STRIDE(i, nh) {
+    GRID_STRIDE(k, nh - hfirst) {
+        const uint32_t i = hfirst + k;
         uint4 hd = d.hhdr[i];
         const float4 *R = d.HR + 7 * (size_t)i;
         float4 r5 = R[5], r6 = R[6];
@@ -1562,11 +1582,12 @@ __global__ void k_store_impulses(Dev d) {
 
 // integrate_velocities (island_solver.cpp:358-376); with refresh != 0 also update_aabbs + update_inertias
 // (solver.cpp:453-465) fused in, used when no position iterations run in between.
-__global__ void __launch_bounds__(256) k_integrate(Dev d, int refresh) {
+__global__ void __launch_bounds__(256) k_integrate(Dev d, int refresh, int fused) {
     if (blockIdx.x == 0 && threadIdx.x == 0) d.cnt->bar = 0;       // grid barrier counter of k_position_df
     GRID_STRIDE(i, d.nbodies) {
         uint32_t f = d.flags[i];
         if (!is_dynamic(f)) continue;
+        if (fused && d.btile[i] != TILE_NONE) continue;             // integrated by k_island_tiles
         float4 p4 = d.pos[i];
         v3 v = mk3(d.linvel[i]), w = mk3(d.angvel[i]);
         v += mk3(d.dvw[2 * i]); w += mk3(d.dvw[2 * i + 1]);
@@ -1782,6 +1803,254 @@ __global__ void __launch_bounds__(TILE_CAP, 2) k_position_tiles(Dev d, int iters
         if (t < nb && s_fresh[t]) {
             const float4 p = s_body[8 * t], o = s_body[8 * t + 1];
             d.pos[mybody] = make_float4(p.x, p.y, p.z, d.pos[mybody].w); d.orn[mybody] = o;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------- island tiles: the whole solver.update on chip
+// k_solve_tiles + integrate_velocities + assign_applied_impulses + k_position_tiles for the tiled islands in ONE
+// kernel: a tile's bodies, joints and manifolds are loaded once, the velocity iterations run, the bodies are integrated
+// where they sit (shared memory), the impulses go straight to the warm-start cache, the position iterations run on
+// the same records, and positions / orientations / velocities are written once.  Same arithmetic in the same order as
+// the separate kernels (k_integrate, k_store_impulses skip what this kernel has done).
+// shared memory of a tile, float4 x TILE_CAP each: body records [0..7] -- velocity phase: dv, dw, inv_IW rows (| inv_m);
+// position phase: pos | inv_m, orn, inv_IW rows, inv_I rows --, joint rows [8..14], contact points 3-4 [15..24]
+// (solver rows, then pA pB pN pL)
+constexpr size_t TILE_FUSED_SMEM = (8 + 7 + 10) * TILE_CAP * sizeof(float4);
+B2D_D void tf_load(const float4 *sb, uint32_t tag, uint32_t slot, VBody &b) {           // velocity phase: SoA records
+    b.proc = !(tag & 0x80000000u); b.id = tag & 0x7FFFFFFFu;
+    if (b.proc) {
+        const float4 a = sb[slot], w = sb[TILE_CAP + slot], r0 = sb[2 * TILE_CAP + slot], r1 = sb[3 * TILE_CAP + slot], r2 = sb[4 * TILE_CAP + slot];
+        b.dv = mk3(a); b.dw = mk3(w); b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(r1); b.inv_I.r2 = mk3(r2);
+    } else { b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); b.inv_m = 0; b.inv_I = m3_zero(); }
+}
+B2D_D void tf_store(float4 *sb, uint32_t slot, const VBody &b) {
+    if (b.proc) { sb[slot] = f4(b.dv, 0); sb[TILE_CAP + slot] = f4(b.dw, 0); }
+}
+// position phase; a non-procedural partner (static / kinematic) is read from the thread's own copy
+B2D_D void tq_load(const float4 *sb, uint32_t tag, uint32_t slot, const float4 &spos, const float4 &sorn, PBody &b) {
+    b.id = tag & 0x7FFFFFFFu; b.proc = !(tag >> 31); b.fresh = false;
+    if (b.proc) {
+        const float4 p = sb[slot];
+        b.pos = mk3(p); b.inv_m = p.w; b.orn = mkq(sb[TILE_CAP + slot]);
+        b.inv_IW.r0 = mk3(sb[2 * TILE_CAP + slot]); b.inv_IW.r1 = mk3(sb[3 * TILE_CAP + slot]); b.inv_IW.r2 = mk3(sb[4 * TILE_CAP + slot]);
+        b.inv_I.r0 = mk3(sb[5 * TILE_CAP + slot]); b.inv_I.r1 = mk3(sb[6 * TILE_CAP + slot]); b.inv_I.r2 = mk3(sb[7 * TILE_CAP + slot]);
+    } else { b.pos = mk3(spos); b.orn = mkq(sorn); b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero(); }
+}
+B2D_D void tq_store(float4 *sb, uint32_t slot, const PBody &b) {
+    if (!b.proc || !b.fresh) return;
+    sb[slot] = f4(b.pos, b.inv_m); sb[TILE_CAP + slot] = f4(b.orn);
+    sb[2 * TILE_CAP + slot] = f4(b.inv_IW.r0, 0); sb[3 * TILE_CAP + slot] = f4(b.inv_IW.r1, 0); sb[4 * TILE_CAP + slot] = f4(b.inv_IW.r2, 0);
+}
+__global__ void __launch_bounds__(TILE_CAP, 2) k_island_tiles(Dev d, int vel_iters, int pos_iters) {
+    extern __shared__ float4 s_tile[];
+    float4 *s_body = s_tile, *s_hr = s_tile + 8 * TILE_CAP, *s_row = s_tile + 15 * TILE_CAP;
+    __shared__ uint32_t s_err[TILE_CAP], s_done[TILE_CAP], s_root[TILE_CAP];
+    __shared__ uint32_t s_ncol[2];
+    const uint32_t ntiles = d.cnt->ntiles, t = threadIdx.x;
+    const size_t NM = d.NM;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t nb = min(d.tile_nb[tile], (uint32_t)TILE_CAP);
+        const uint32_t c0 = d.tile_c0[tile], c1 = min(d.tile_c1[tile], c0 + TILE_CAP), h0 = d.tile_h0[tile], h1 = min(d.tile_h1[tile], h0 + TILE_CAP);
+        if (t < 2) s_ncol[t] = 0;
+        uint32_t mybody = 0;
+        if (t < nb) {
+            mybody = d.tile_body[(size_t)tile * TILE_CAP + t];
+            s_body[t] = make_float4(0, 0, 0, 0); s_body[TILE_CAP + t] = make_float4(0, 0, 0, 0);
+            s_body[2 * TILE_CAP + t] = d.invIW[3 * mybody]; s_body[3 * TILE_CAP + t] = d.invIW[3 * mybody + 1]; s_body[4 * TILE_CAP + t] = d.invIW[3 * mybody + 2];
+            s_err[t] = 0; s_done[t] = 0; s_root[t] = d.parent[mybody] == mybody ? 1u : 0u;
+        }
+        __syncthreads();
+        const bool hasH = h0 + t < h1, hasC = c0 + t < c1;
+        const uint32_t hi = h0 + t, ci = c0 + t;
+        uint4 hh = make_uint4(0, 0, 0, 0), ch = make_uint4(0, 0, 0, 0);
+        uint32_t hcol = 0xFFu, ccol = 0xFFu;
+        float4 a0, a1, a2, a3, aim, b0, b1, b2, b3, bim;      // rows of contact points 1 and 2
+        a0 = a1 = a2 = a3 = aim = b0 = b1 = b2 = b3 = bim = make_float4(0, 0, 0, 0);
+        if (hasH) {
+            hh = d.hhdr[hi]; hcol = d.hkey_s[hi] & 63u;
+            const float4 *R = d.HR + 7 * (size_t)hi;
+            #pragma unroll
+            for (int k = 0; k < 7; ++k) s_hr[k * TILE_CAP + t] = R[k];
+            atomicMax(&s_ncol[0], hcol + 1u);
+        }
+        if (hasC) {
+            ch = d.hdr[ci]; ccol = d.ckey_s[ci] & 63u;
+            a0 = d.R0[ci]; a1 = d.R1[ci]; a2 = d.R2[ci]; a3 = d.R3[ci]; aim = d.IMP[ci];
+            if (ch.z > 1) { b0 = d.R0[NM + ci]; b1 = d.R1[NM + ci]; b2 = d.R2[NM + ci]; b3 = d.R3[NM + ci]; bim = d.IMP[NM + ci]; }
+            for (uint32_t s = 2; s < ch.z; ++s) {
+                const size_t ri = s * NM + ci;
+                float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                r[0] = d.R0[ri]; r[TILE_CAP] = d.R1[ri]; r[2 * TILE_CAP] = d.R2[ri]; r[3 * TILE_CAP] = d.R3[ri]; r[4 * TILE_CAP] = d.IMP[ri];
+            }
+            atomicMax(&s_ncol[1], ccol + 1u);
+        }
+        __syncthreads();
+        const uint32_t nhc = s_ncol[0], ncc = s_ncol[1];
+        // ---- velocity iterations (k_solve_tiles)
+        for (int it = -1; it < vel_iters; ++it) {
+            const bool warm = it < 0;
+            for (uint32_t c = 0; c < nhc; ++c) {
+                if (hcol == c) {
+                    const float4 r0 = s_hr[t], r1 = s_hr[TILE_CAP + t], r2 = s_hr[2 * TILE_CAP + t], r3 = s_hr[3 * TILE_CAP + t],
+                                 r4 = s_hr[4 * TILE_CAP + t], r5 = s_hr[5 * TILE_CAP + t], r6 = s_hr[6 * TILE_CAP + t];
+                    const float em[5] = {r0.w, r1.w, r2.w, r3.w, r4.x}, rhs[5] = {r4.y, r4.z, r4.w, r5.x, r5.y};
+                    float imp[5] = {r5.z, r5.w, r6.x, r6.y, r6.z};
+                    VBody A, B; tf_load(s_body, hh.x, hh.w & 0xFFFFu, A); tf_load(s_body, hh.y, hh.w >> 16, B);
+                    hinge_solve(mk3(r0), mk3(r1), mk3(r2), mk3(r3), em, rhs, imp, A, B, warm);
+                    tf_store(s_body, hh.w & 0xFFFFu, A); tf_store(s_body, hh.w >> 16, B);
+                    if (!warm) { s_hr[5 * TILE_CAP + t] = make_float4(r5.x, r5.y, imp[0], imp[1]); s_hr[6 * TILE_CAP + t] = make_float4(imp[2], imp[3], imp[4], 0); }
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                if (ccol == c) {
+                    VBody A, B; tf_load(s_body, ch.x, ch.w & 0xFFFFu, A); tf_load(s_body, ch.y, ch.w >> 16, B);
+                    nrow_solve(a0, a1, a2, aim, A, B, warm);
+                    if (ch.z > 1) nrow_solve(b0, b1, b2, bim, A, B, warm);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                        float4 im = r[4 * TILE_CAP];
+                        nrow_solve(r[0], r[TILE_CAP], r[2 * TILE_CAP], im, A, B, warm);
+                        r[4 * TILE_CAP] = im;
+                    }
+                    tf_store(s_body, ch.w & 0xFFFFu, A); tf_store(s_body, ch.w >> 16, B);
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                if (ccol == c) {
+                    VBody A, B; tf_load(s_body, ch.x, ch.w & 0xFFFFu, A); tf_load(s_body, ch.y, ch.w >> 16, B);
+                    frow_solve(a0, a1, a2, a3, aim, A, B, warm);
+                    if (ch.z > 1) frow_solve(b0, b1, b2, b3, bim, A, B, warm);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_row + (s - 2) * 5 * TILE_CAP + t;
+                        float4 im = r[4 * TILE_CAP];
+                        frow_solve(r[0], r[TILE_CAP], r[2 * TILE_CAP], r[3 * TILE_CAP], im, A, B, warm);
+                        r[4 * TILE_CAP] = im;
+                    }
+                    tf_store(s_body, ch.w & 0xFFFFu, A); tf_store(s_body, ch.w >> 16, B);
+                }
+                __syncthreads();
+            }
+        }
+        // ---- assign_applied_impulses (k_store_impulses): rows -> warm-start cache of the constraints
+        uint32_t m = 0;
+        if (hasC) {
+            m = d.cidx_s[ci];
+            d.pI[m] = aim; if (ch.z > 1) d.pI[NM + m] = bim;
+            for (uint32_t s = 2; s < ch.z; ++s) d.pI[s * NM + m] = s_row[((s - 2) * 5 + 4) * TILE_CAP + t];
+        }
+        if (hasH) {
+            const float4 r5 = s_hr[5 * TILE_CAP + t], r6 = s_hr[6 * TILE_CAP + t];
+            float *imp = d.himp + 5 * (size_t)hh.z;
+            imp[0] = r5.z; imp[1] = r5.w; imp[2] = r6.x; imp[3] = r6.y; imp[4] = r6.z;
+        }
+        // ---- what the position iterations need from global memory is requested before the integration below
+        uint32_t hisl = 0, cisl = 0;
+        v3 fA0 = mk3(0, 0, 0), fB0 = fA0, pvA = fA0, pvB = fA0;
+        float4 a40, b40, n40, l40, a41, b41, n41, l41;         // contact points 1 and 2
+        a40 = b40 = n40 = l40 = a41 = b41 = n41 = l41 = make_float4(0, 0, 0, 0);
+        float4 spos = make_float4(0, 0, 0, 0), sorn = make_float4(0, 0, 0, 1);      // this thread's non-procedural partner (contact, else joint)
+        if (hasH) {
+            hisl = d.bslot[d.hisl[hi]];
+            const uint32_t h = hh.z;
+            fA0 = mk3(d.hfA0[h]); fB0 = mk3(d.hfB0[h]); pvA = mk3(d.hpivA[h]); pvB = mk3(d.hpivB[h]);
+        }
+        if (hasC) {
+            cisl = d.bslot[d.pisl[ci]];
+            a40 = d.pA[m]; b40 = d.pB[m]; n40 = d.pN[m]; l40 = d.pL[m];
+            if (ch.z > 1) { a41 = d.pA[NM + m]; b41 = d.pB[NM + m]; n41 = d.pN[NM + m]; l41 = d.pL[NM + m]; }
+        }
+        float4 hpos = spos, horn = sorn;                        // a joint to a static / kinematic body
+        if (hasC && ((ch.x | ch.y) >> 31)) { const uint32_t sbody = ((ch.x >> 31) ? ch.x : ch.y) & 0x7FFFFFFFu; spos = d.pos[sbody]; sorn = d.orn[sbody]; }
+        if (hasH && ((hh.x | hh.y) >> 31)) { const uint32_t sbody = ((hh.x >> 31) ? hh.x : hh.y) & 0x7FFFFFFFu; hpos = d.pos[sbody]; horn = d.orn[sbody]; }
+        __syncthreads();                                         // the rows in s_row are dead from here on
+        if (hasC) for (uint32_t s = 2; s < ch.z; ++s) {
+            const size_t mi = s * NM + m;
+            float4 *r = s_row + (s - 2) * 4 * TILE_CAP + t;
+            r[0] = d.pA[mi]; r[TILE_CAP] = d.pB[mi]; r[2 * TILE_CAP] = d.pN[mi]; r[3 * TILE_CAP] = d.pL[mi];
+        }
+        // ---- integrate_velocities (k_integrate) for the tile's bodies; the records turn into position records
+        if (t < nb) {
+            const float4 p4 = d.pos[mybody];
+            v3 v = mk3(d.linvel[mybody]), w = mk3(d.angvel[mybody]);
+            v += mk3(s_body[t]); w += mk3(s_body[TILE_CAP + t]);
+            v3 pos = mk3(p4); pos += v * d.dt;
+            const q4 orn = integrate(mkq(d.orn[mybody]), w, d.dt);
+            d.linvel[mybody] = f4(v, 0); d.angvel[mybody] = f4(w, 0);
+            s_body[t] = f4(pos, s_body[2 * TILE_CAP + t].w);     // inverse mass as the solvers see it
+            s_body[TILE_CAP + t] = f4(orn);
+            s_body[5 * TILE_CAP + t] = d.invI[3 * mybody]; s_body[6 * TILE_CAP + t] = d.invI[3 * mybody + 1]; s_body[7 * TILE_CAP + t] = d.invI[3 * mybody + 2];
+        }
+        __syncthreads();
+        // ---- position iterations (k_position_tiles)
+        for (int it = 0; it < pos_iters; ++it) {
+            for (uint32_t c = 0; c < nhc; ++c) {
+                if (hcol == c && !s_done[hisl]) {
+                    PBody A, B; tq_load(s_body, hh.x, hh.w & 0xFFFFu, hpos, horn, A); tq_load(s_body, hh.y, hh.w >> 16, hpos, horn, B);
+                    float max_error = 0.0f;
+                    v3 axisA = rotate(A.orn, fA0), axisB = rotate(B.orn, fB0);
+                    v3 p, q; plane_space(axisA, p, q);
+                    v3 u = cross(axisA, axisB);
+                    const v3 z = mk3(0, 0, 0);
+                    { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
+                    { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
+                    v3 pivotA = to_world(pvA, A.pos, A.orn), pivotB = to_world(pvB, B.pos, B.orn);
+                    v3 dir = pivotA - pivotB;
+                    float e = length(dir);
+                    if (e > EPS) {
+                        dir /= e;
+                        v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+                        position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
+                    }
+                    tq_store(s_body, hh.w & 0xFFFFu, A); tq_store(s_body, hh.w >> 16, B);
+                    tile_error_max(s_err, hisl, max_error);
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < ncc; ++c) {
+                if (ccol == c && !s_done[cisl]) {
+                    PBody A, B; tq_load(s_body, ch.x, ch.w & 0xFFFFu, spos, sorn, A); tq_load(s_body, ch.y, ch.w >> 16, spos, sorn, B);
+                    float max_error = 0.0f;
+                    auto point = [&](float4 &pa, const float4 &pb, float4 &pn, const float4 &pl) {
+                        v3 pAw = to_world(mk3(pa), A.pos, A.orn), pBw = to_world(mk3(pb), B.pos, B.orn);
+                        unsigned att = __float_as_uint(pl.w) & 3u;
+                        v3 normal = mk3(pn);
+                        if (att == ATT_A) normal = rotate(A.orn, mk3(pl)); else if (att == ATT_B) normal = rotate(B.orn, mk3(pl));
+                        float dist = dot(pAw - pBw, normal);
+                        v3 rA = pAw - A.pos, rB = pBw - B.pos;
+                        pn = f4(normal, pn.w); pa = f4(mk3(pa), dist);
+                        if (dist > -EPS) return;
+                        position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
+                    };
+                    point(a40, b40, n40, l40);
+                    if (ch.z > 1) point(a41, b41, n41, l41);
+                    for (uint32_t s = 2; s < ch.z; ++s) {
+                        float4 *r = s_row + (s - 2) * 4 * TILE_CAP + t;
+                        float4 pa = r[0], pn = r[2 * TILE_CAP];
+                        point(pa, r[TILE_CAP], pn, r[3 * TILE_CAP]);
+                        r[0] = pa; r[2 * TILE_CAP] = pn;
+                    }
+                    tq_store(s_body, ch.w & 0xFFFFu, A); tq_store(s_body, ch.w >> 16, B);
+                    tile_error_max(s_err, cisl, max_error);
+                }
+                __syncthreads();
+            }
+            if (it + 1 < pos_iters) {
+                if (t < nb && s_root[t]) { if (__uint_as_float(s_err[t]) < 0.005f) s_done[t] = 1; s_err[t] = 0; }
+                __syncthreads();
+            }
+        }
+        if (hasC) {
+            d.pN[m] = n40; d.pA[m] = a40;
+            if (ch.z > 1) { d.pN[NM + m] = n41; d.pA[NM + m] = a41; }
+            for (uint32_t s = 2; s < ch.z; ++s) { const float4 *r = s_row + (s - 2) * 4 * TILE_CAP + t; d.pA[s * NM + m] = r[0]; d.pN[s * NM + m] = r[2 * TILE_CAP]; }
+        }
+        if (t < nb) {
+            const float4 p = s_body[t];
+            d.pos[mybody] = make_float4(p.x, p.y, p.z, d.pos[mybody].w); d.orn[mybody] = s_body[TILE_CAP + t];
         }
         __syncthreads();
     }

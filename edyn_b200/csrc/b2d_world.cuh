@@ -83,6 +83,7 @@ struct Dev {
     float dt;
     float cell, inv_cell;          // broadphase grid pitch
     float halo_margin;             // multi-GPU: islands closer than this to a peer's box / island are boundary islands
+    int cell_org[3]; int cell_bits[3];     // broadphase cell key: origin and field widths (bits) per axis
 
     // ---- bodies
     float4 *pos;       // xyz position, w inv_mass
