@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2: `ncu --set full` of the solver kernels, one launch each, after the settle steps (bench.py --only --steps 2).
-# usage: bash tools/r2_ncu_full.sh TAG     -> gpurun_out/TAG/{tiles_chains,df_mixed,postiles_chains}.ncu-rep
+# usage: bash tools/r2_ncu_full.sh TAG     -> gpurun_out/TAG/{tiles_chains,df_mixed,posdf_mixed}.ncu-rep
 TAG=${1:-ncu}
 mkdir -p gpurun_out/$TAG
 run() {  # name kernel-regex workload
@@ -19,6 +19,6 @@ for k in want:
     if k in h: print(f"{name}: {k} = {v[h.index(k)]} {rows[1][h.index(k)] if len(rows) > 2 else ''}")
 PY
 }
-run tiles_chains k_solve_tiles chains_1048576
-run postiles_chains k_position_tiles chains_1048576
+run tiles_chains k_island_tiles chains_1048576
 run df_mixed k_solve_df mixed_262144
+run posdf_mixed k_position_df mixed_262144
