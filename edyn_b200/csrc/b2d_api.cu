@@ -28,8 +28,7 @@ struct b2d_world {
     std::string error;
     int num_sms = 0;
     int coop_blocks_color = 0, coop_blocks_df = 0, coop_blocks_pos_df = 0;
-    int tile_blocks = 0, tile_pos_blocks = 0, tile_fused_blocks = 0;       // grids of the island-tile kernels (CTAs loop over the tiles)
-    bool fuse_tiles = true;                         // one kernel for the tiled islands' whole solver.update (B2D_FUSE_TILES=0: separate kernels)
+    int tile_blocks = 0, tile_fused_blocks = 0;     // grids of the island-tile kernels (CTAs loop over the tiles)
     int cell_key_bits = 48;                         // sum of d.cell_bits: end bit of the cell sort
     uint32_t bp_warp_max = 100000;                  // neighbourhood search: warp per body up to this many bodies (B2D_BP_WARP_MAX)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
@@ -216,11 +215,8 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_df, B2D_POS_THREADS, 0); w->coop_blocks_pos_df = std::max(1, per_sm) * w->num_sms;
     cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SOLVE_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tiles, TILE_CAP, TILE_SOLVE_SMEM); w->tile_blocks = std::max(1, per_sm) * w->num_sms;
-    cudaFuncSetAttribute(k_position_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_POS_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_position_tiles, TILE_CAP, TILE_POS_SMEM); w->tile_pos_blocks = std::max(1, per_sm) * w->num_sms;
     cudaFuncSetAttribute(k_island_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_FUSED_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_island_tiles, TILE_CAP, TILE_FUSED_SMEM); w->tile_fused_blocks = std::max(1, per_sm) * w->num_sms;
-    if (const char *e = getenv("B2D_FUSE_TILES")) w->fuse_tiles = atoi(e) != 0;
     if (const char *e = getenv("B2D_BP_WARP_MAX")) w->bp_warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("B2D_TILES")) if (atoi(e) == 0) d.max_tiles = 0;          // development: everything through the dataflow path
     if (const char *e = getenv("B2D_GRAPH")) w->use_graph = atoi(e) != 0;
@@ -625,7 +621,8 @@ static int enqueue_solver_b(b2d_world *w) {
     // the cooperative launch wants the whole machine and waits for the tiles, or the tiles wait for it.)
     const int pi = (int)w->cfg.position_iterations;
     if (d.max_tiles) {
-        if (w->fuse_tiles && pi > 0) { k_island_tiles<<<w->tile_fused_blocks, TILE_CAP, TILE_FUSED_SMEM, w->stream>>>(d, vi, pi); ++w->launches; }
+        // with position iterations: the tiled islands' whole solver.update in one launch; without: the velocity part alone
+        if (pi > 0) { k_island_tiles<<<w->tile_fused_blocks, TILE_CAP, TILE_FUSED_SMEM, w->stream>>>(d, vi, pi); ++w->launches; }
         else { k_solve_tiles<<<w->tile_blocks, TILE_CAP, TILE_SOLVE_SMEM, w->stream>>>(d, vi); ++w->launches; }
     }
     CK(coop_launch(w, k_solve_df, w->coop_blocks_df, B2D_SOLVE_THREADS, d, vi));
@@ -633,17 +630,16 @@ static int enqueue_solver_b(b2d_world *w) {
 }
 static int enqueue_integrate(b2d_world *w) {
     Dev &d = w->d;
-    const int fused = (d.max_tiles && w->fuse_tiles && w->cfg.position_iterations > 0) ? 1 : 0;
+    const int fused = (d.max_tiles && w->cfg.position_iterations > 0) ? 1 : 0;      // k_island_tiles has integrated the tiled bodies
     LAUNCH(k_integrate, d.nbodies, 256, d, w->cfg.position_iterations == 0 ? 1 : 0, fused);
     return B2D_OK;
 }
 static int enqueue_solver_c(b2d_world *w) {
-    Dev &d = w->d; cudaStream_t s = w->stream;
+    Dev &d = w->d;
     const int pi = (int)w->cfg.position_iterations;
-    const int fused = (d.max_tiles && w->fuse_tiles && pi > 0) ? 1 : 0;
+    const int fused = (d.max_tiles && pi > 0) ? 1 : 0;
     LAUNCH(k_store_impulses, d.NM, 256, d, fused);
     if (pi > 0) {
-        if (d.max_tiles && !fused) { k_position_tiles<<<w->tile_pos_blocks, TILE_CAP, TILE_POS_SMEM, s>>>(d, pi); ++w->launches; }
         CK(coop_launch(w, k_position_df, w->coop_blocks_pos_df, B2D_POS_THREADS, d, pi));
         LAUNCH(k_finalize, d.nbodies, 256, d);
     }

@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256) k_color(Dev d) {
 }
 
 // ---- island tiles.  An island with at most TILE_ISLAND_MAX dynamic bodies, manifolds with points and joints is solved
-// inside one CTA (k_solve_tiles, k_position_tiles).  Islands are packed into tiles in root-id order: with weight
+// inside one CTA (k_island_tiles; k_solve_tiles when there are no position iterations).  Islands are packed into tiles in root-id order: with weight
 // w = max(bodies, manifolds, joints) <= TILE_ISLAND_MAX per island and P the exclusive prefix sum of the weights, island
 // -> tile P / g with g = TILE_CAP + 1 - (heaviest tiled island) puts at most TILE_CAP of each into every tile.  Which islands
 // are tiled changes speed, never results: the per-body constraint order is fixed by the colours alone.
@@ -1652,165 +1652,11 @@ B2D_D void island_error_max(const Dev &d, uint32_t isl, float err) {
 B2D_D uint32_t island_of(const Dev &d, uint32_t a, uint32_t b) { uint32_t l = d.parent[a]; return l != 0xFFFFFFFFu ? l : d.parent[b]; }
 
 
-// ---------------------------------------------------------------------- island tiles: position iterations on chip
-// <= N position iterations, each island stopping once its max error drops below 0.005 (island_solver.cpp:263-353,
-// :538-543).  Same tiles and colours as k_solve_tiles: thread t owns joint t and contact manifold t of the tile, the
-// body transforms (position, orientation, world inverse inertia) live in shared memory together with the per-island
-// error / done words (kept at the slot of the island's root body), colours are separated by __syncthreads.  The
-// contact points of the first two slots stay in registers; their refreshed normal and distance
-// (contact_constraint.cpp:72-76) are written back once at the end.
-// shared memory of a tile: per body pos | inverse mass, orn, world and body inverse inertia (8 float4); contact points 3 and 4
-constexpr size_t TILE_POS_SMEM = (8 + 8) * TILE_CAP * sizeof(float4);
-B2D_D void tp_load(const float4 *sb, const Dev &d, uint32_t tag, uint32_t slot, PBody &b) {
-    b.id = tag & 0x7FFFFFFFu; b.proc = !(tag >> 31); b.fresh = false;
-    if (b.proc) {
-        const float4 *r = sb + 8 * slot;
-        const float4 p = r[0];
-        b.pos = mk3(p); b.inv_m = p.w; b.orn = mkq(r[1]);
-        b.inv_IW.r0 = mk3(r[2]); b.inv_IW.r1 = mk3(r[3]); b.inv_IW.r2 = mk3(r[4]);
-        b.inv_I.r0 = mk3(r[5]); b.inv_I.r1 = mk3(r[6]); b.inv_I.r2 = mk3(r[7]);
-    } else {
-        b.pos = mk3(d.pos[b.id]); b.orn = mkq(d.orn[b.id]);
-        b.inv_m = 0; b.inv_IW = m3_zero(); b.inv_I = m3_zero();
-    }
-}
-B2D_D void tp_store(float4 *sb, uint32_t *fresh, uint32_t slot, const PBody &b) {
-    if (!b.proc || !b.fresh) return;
-    float4 *r = sb + 8 * slot;
-    r[0] = f4(b.pos, b.inv_m); r[1] = f4(b.orn);
-    r[2] = f4(b.inv_IW.r0, 0); r[3] = f4(b.inv_IW.r1, 0); r[4] = f4(b.inv_IW.r2, 0);
-    fresh[slot] = 1u;
-}
+// per-island max error of a tile, kept at the shared-memory slot of the island's root body
 B2D_D void tile_error_max(uint32_t *s_err, uint32_t islot, float err) { if (err != 0.0f) atomicMax(&s_err[islot], __float_as_uint(err)); }
-__global__ void __launch_bounds__(TILE_CAP, 2) k_position_tiles(Dev d, int iters) {
-    extern __shared__ float4 s_tile[];                     // TILE_POS_SMEM bytes
-    float4 *s_body = s_tile;                               // 8 float4 per body
-    float4 *s_pt = s_tile + 8 * TILE_CAP;                  // contact points 3 and 4: (pA pB pN pL) x 2, row-major over the tile's manifolds
-    __shared__ uint32_t s_err[TILE_CAP], s_done[TILE_CAP], s_fresh[TILE_CAP], s_root[TILE_CAP];
-    __shared__ uint32_t s_ncol[2];
-    const uint32_t ntiles = d.cnt->ntiles, t = threadIdx.x;
-    const size_t NM = d.NM;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t nb = min(d.tile_nb[tile], (uint32_t)TILE_CAP);
-        const uint32_t c0 = d.tile_c0[tile], c1 = min(d.tile_c1[tile], c0 + TILE_CAP), h0 = d.tile_h0[tile], h1 = min(d.tile_h1[tile], h0 + TILE_CAP);
-        if (t < 2) s_ncol[t] = 0;
-        uint32_t mybody = 0;
-        if (t < nb) {
-            const uint32_t b = d.tile_body[(size_t)tile * TILE_CAP + t];
-            mybody = b;
-            float4 *r = s_body + 8 * t;
-            r[0] = d.pos[b]; r[1] = d.orn[b];
-            const float4 w0 = d.invIW[3 * b];
-            r[0].w = w0.w;                                       // inverse mass as the solvers see it (0 unless dynamic)
-            r[2] = w0; r[3] = d.invIW[3 * b + 1]; r[4] = d.invIW[3 * b + 2];
-            r[5] = d.invI[3 * b]; r[6] = d.invI[3 * b + 1]; r[7] = d.invI[3 * b + 2];
-            s_err[t] = 0; s_done[t] = 0; s_fresh[t] = 0; s_root[t] = d.parent[b] == b ? 1u : 0u;
-        }
-        __syncthreads();
-        const bool hasH = h0 + t < h1, hasC = c0 + t < c1;
-        const uint32_t hi = h0 + t, ci = c0 + t;
-        uint4 hh = make_uint4(0, 0, 0, 0), ch = make_uint4(0, 0, 0, 0);
-        uint32_t hcol = 0xFFu, ccol = 0xFFu, hisl = 0, cisl = 0, m = 0;
-        v3 fA0 = mk3(0, 0, 0), fB0 = fA0, pvA = fA0, pvB = fA0;
-        float4 a40, b40, n40, l40, a41, b41, n41, l41;         // contact points 1 and 2
-        a40 = b40 = n40 = l40 = a41 = b41 = n41 = l41 = make_float4(0, 0, 0, 0);
-        bool touched = false;
-        if (hasH) {
-            hh = d.hhdr[hi]; hcol = d.hkey_s[hi] & 63u; hisl = d.bslot[d.hisl[hi]];
-            const uint32_t h = hh.z;
-            fA0 = mk3(d.hfA0[h]); fB0 = mk3(d.hfB0[h]); pvA = mk3(d.hpivA[h]); pvB = mk3(d.hpivB[h]);
-            atomicMax(&s_ncol[0], hcol + 1u);
-        }
-        if (hasC) {
-            ch = d.hdr[ci]; ccol = d.ckey_s[ci] & 63u; cisl = d.bslot[d.pisl[ci]]; m = d.cidx_s[ci];
-            a40 = d.pA[m]; b40 = d.pB[m]; n40 = d.pN[m]; l40 = d.pL[m];
-            if (ch.z > 1) { a41 = d.pA[NM + m]; b41 = d.pB[NM + m]; n41 = d.pN[NM + m]; l41 = d.pL[NM + m]; }
-            for (uint32_t s = 2; s < ch.z; ++s) {
-                const size_t mi = s * NM + m;
-                float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t;
-                r[0] = d.pA[mi]; r[TILE_CAP] = d.pB[mi]; r[2 * TILE_CAP] = d.pN[mi]; r[3 * TILE_CAP] = d.pL[mi];
-            }
-            atomicMax(&s_ncol[1], ccol + 1u);
-        }
-        __syncthreads();
-        const uint32_t nhc = s_ncol[0], ncc = s_ncol[1];
-        for (int it = 0; it < iters; ++it) {
-            for (uint32_t c = 0; c < nhc; ++c) {
-                // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
-                if (hcol == c && !s_done[hisl]) {
-                    PBody A, B; tp_load(s_body, d, hh.x, hh.w & 0xFFFFu, A); tp_load(s_body, d, hh.y, hh.w >> 16, B);
-                    float max_error = 0.0f;
-                    v3 axisA = rotate(A.orn, fA0), axisB = rotate(B.orn, fB0);
-                    v3 p, q; plane_space(axisA, p, q);
-                    v3 u = cross(axisA, axisB);
-                    const v3 z = mk3(0, 0, 0);
-                    { float e = dot(u, p); if (fabsf(e) > EPS) position_solve(A, B, z, p, z, -p, e, max_error); }
-                    { float e = dot(u, q); if (fabsf(e) > EPS) position_solve(A, B, z, q, z, -q, e, max_error); }
-                    v3 pivotA = to_world(pvA, A.pos, A.orn), pivotB = to_world(pvB, B.pos, B.orn);
-                    v3 dir = pivotA - pivotB;
-                    float e = length(dir);
-                    if (e > EPS) {
-                        dir /= e;
-                        v3 rA = pivotA - A.pos, rB = pivotB - B.pos;
-                        position_solve(A, B, dir, cross(rA, dir), -dir, -cross(rB, dir), -e, max_error);
-                    }
-                    tp_store(s_body, s_fresh, hh.w & 0xFFFFu, A); tp_store(s_body, s_fresh, hh.w >> 16, B);
-                    tile_error_max(s_err, hisl, max_error);
-                }
-                __syncthreads();
-            }
-            for (uint32_t c = 0; c < ncc; ++c) {
-                // contact_constraint::solve_position, contact_constraint.cpp:58-90
-                if (ccol == c && !s_done[cisl]) {
-                    PBody A, B; tp_load(s_body, d, ch.x, ch.w & 0xFFFFu, A); tp_load(s_body, d, ch.y, ch.w >> 16, B);
-                    float max_error = 0.0f;
-                    touched = true;
-                    // one contact point: refreshes its normal and distance in place, corrects the bodies if it penetrates
-                    auto point = [&](float4 &pa, const float4 &pb, float4 &pn, const float4 &pl) {
-                        v3 pAw = to_world(mk3(pa), A.pos, A.orn), pBw = to_world(mk3(pb), B.pos, B.orn);
-                        unsigned att = __float_as_uint(pl.w) & 3u;
-                        v3 normal = mk3(pn);
-                        if (att == ATT_A) normal = rotate(A.orn, mk3(pl)); else if (att == ATT_B) normal = rotate(B.orn, mk3(pl));
-                        float dist = dot(pAw - pBw, normal);
-                        v3 rA = pAw - A.pos, rB = pBw - B.pos;
-                        pn = f4(normal, pn.w); pa = f4(mk3(pa), dist);
-                        if (dist > -EPS) return;
-                        position_solve(A, B, normal, cross(rA, normal), -normal, -cross(rB, normal), -dist, max_error);
-                    };
-                    point(a40, b40, n40, l40);
-                    if (ch.z > 1) point(a41, b41, n41, l41);
-                    for (uint32_t s = 2; s < ch.z; ++s) {
-                        float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t;
-                        float4 pa = r[0], pn = r[2 * TILE_CAP];
-                        point(pa, r[TILE_CAP], pn, r[3 * TILE_CAP]);
-                        r[0] = pa; r[2 * TILE_CAP] = pn;
-                    }
-                    tp_store(s_body, s_fresh, ch.w & 0xFFFFu, A); tp_store(s_body, s_fresh, ch.w >> 16, B);
-                    tile_error_max(s_err, cisl, max_error);
-                }
-                __syncthreads();
-            }
-            if (it + 1 < iters) {
-                if (t < nb && s_root[t]) { if (__uint_as_float(s_err[t]) < 0.005f) s_done[t] = 1; s_err[t] = 0; }
-                __syncthreads();
-            }
-        }
-        if (hasC && touched) {
-            d.pN[m] = n40; d.pA[m] = a40;
-            if (ch.z > 1) { d.pN[NM + m] = n41; d.pA[NM + m] = a41; }
-            for (uint32_t s = 2; s < ch.z; ++s) { const float4 *r = s_pt + (s - 2) * 4 * TILE_CAP + t; d.pA[s * NM + m] = r[0]; d.pN[s * NM + m] = r[2 * TILE_CAP]; }
-        }
-        if (t < nb && s_fresh[t]) {
-            const float4 p = s_body[8 * t], o = s_body[8 * t + 1];
-            d.pos[mybody] = make_float4(p.x, p.y, p.z, d.pos[mybody].w); d.orn[mybody] = o;
-        }
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------------- island tiles: the whole solver.update on chip
-// k_solve_tiles + integrate_velocities + assign_applied_impulses + k_position_tiles for the tiled islands in ONE
-// kernel: a tile's bodies, joints and manifolds are loaded once, the velocity iterations run, the bodies are integrated
+// velocity iterations + integrate_velocities + assign_applied_impulses + position iterations of the tiled islands in
+// ONE kernel: a tile's bodies, joints and manifolds are loaded once, the velocity iterations run, the bodies are integrated
 // where they sit (shared memory), the impulses go straight to the warm-start cache, the position iterations run on
 // the same records, and positions / orientations / velocities are written once.  Same arithmetic in the same order as
 // the separate kernels (k_integrate, k_store_impulses skip what this kernel has done).
@@ -1888,7 +1734,7 @@ __global__ void __launch_bounds__(TILE_CAP, 2) k_island_tiles(Dev d, int vel_ite
         }
         __syncthreads();
         const uint32_t nhc = s_ncol[0], ncc = s_ncol[1];
-        // ---- velocity iterations (k_solve_tiles)
+        // ---- velocity iterations (as in k_solve_tiles)
         for (int it = -1; it < vel_iters; ++it) {
             const bool warm = it < 0;
             for (uint32_t c = 0; c < nhc; ++c) {
@@ -1985,7 +1831,9 @@ __global__ void __launch_bounds__(TILE_CAP, 2) k_island_tiles(Dev d, int vel_ite
             s_body[5 * TILE_CAP + t] = d.invI[3 * mybody]; s_body[6 * TILE_CAP + t] = d.invI[3 * mybody + 1]; s_body[7 * TILE_CAP + t] = d.invI[3 * mybody + 2];
         }
         __syncthreads();
-        // ---- position iterations (k_position_tiles)
+        // ---- position iterations: <= N, each island stopping once its max error drops below 0.005 (island_solver.cpp:263-353,
+        // :538-543); per-island error / done words sit at the slot of the island's root body; the contact points of the first two
+        // slots stay in registers, their refreshed normal and distance (contact_constraint.cpp:72-76) are written back at the end
         for (int it = 0; it < pos_iters; ++it) {
             for (uint32_t c = 0; c < nhc; ++c) {
                 if (hcol == c && !s_done[hisl]) {
