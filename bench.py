@@ -21,11 +21,18 @@ Keys beyond the base contract:
   roofline      velocity-solve kernel: algorithmic bytes (388 B per contact point per velocity iteration, 544 B per hinge
                 per iteration, + 0.75 pass for the warm start) / mean CUDA-event duration of that
                 kernel over the timed steps, against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline  the oracle port timed on this box's host cores (rank 0, N = 1 only) on the same settled state.
+  cpu_baseline  rank 0, N = 1 only.  kind "reference": the reference's OWN stepper (oracle/_ref/libedyn_stepper.so =
+                /root/reference/src/edyn compiled unmodified against oracle/entt_lite), execution_mode
+                sequential_multithreaded on all host threads, on a bounded SLICE of the workload (same generator, fewer
+                chains / a smaller pile: REF_SLICE) -- the full chain scene cannot be run by the reference in bounded
+                time (entity_graph::insert_edge walks the plane's adjacency list for every new contact: quadratic in the
+                bodies touching one static body).  `cpu_port` next to it: the oracle port (oracle/liboracle.so) on the
+                FULL workload from the device's settled state, all threads -- the faster of the two CPU paths.
+                Where the stepper library is absent the port is the cpu_baseline (kind "port").
   e2e           same metric through the C ABI with HOST buffers: every step uploads the body state from pinned
                 host memory (b2d_upload_state), steps, and downloads it again (b2d_download_state).
---impl reference times the reference's CPU path (the oracle port: the reference stepper itself needs EnTT,
-which this image lacks -- DESIGN.md section 6) on the SAME workload with all host threads.
+--impl reference times the reference's CPU path: the real stepper on the slice above when oracle/_ref holds it (the line
+also carries `port`, the oracle port on the full workload), else the oracle port on the full workload.
 """
 import argparse
 import json
@@ -137,6 +144,55 @@ def oracle_from_device(scene, w, threads):
 
 # ---------------------------------------------------------------------------------------------------------- CPU arm
 
+# fraction of the workload's bodies the REAL reference stepper is timed on (it is 10-30x slower per body than the port and
+# has a quadratic contact-creation step on scenes where everything touches one plane); throughput is per body-step
+REF_SLICE = {"chains_1048576": 1.0 / 16, "mixed_262144": 1.0 / 8, "spheres_65536": 1.0, "boxes_4096": 1.0}
+
+
+def have_real_reference():
+    from oracle import oracle as O
+    return O.ref_stepper() is not None
+
+
+def make_ref_world(scene, threads):
+    from oracle import oracle as O
+    st = scene["settings"]
+    r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"], threads=threads)
+    r.add_bodies(scene["bodies"])
+    if scene["hinges"]:
+        h = scene["hinges"]
+        r.add_hinges(h["a"], h["b"], h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
+    if scene["exclusions"] is not None:
+        r.add_exclusions(*scene["exclusions"])
+    return r
+
+
+def reference_real(args, name, steps, warmup, settle, budget_s):
+    """The reference's own stepper_sequential (sequential_multithreaded, all host threads) on a slice of workload `name`.
+    Settles as far as the time budget allows (the line says how far), then times `steps` steps."""
+    cores = os.cpu_count() or 1
+    scene = make_scene(name, args.scale * REF_SLICE.get(name, 1.0))
+    r = make_ref_world(scene, cores)
+    t_start = time.perf_counter()
+    n_settle, took = 0, []
+    while n_settle < settle:
+        t0 = time.perf_counter()
+        r.step(1)
+        took.append(time.perf_counter() - t0)
+        n_settle += 1
+        est = min(took[-2:])                                    # the step that creates all the contacts is an outlier
+        if time.perf_counter() - t_start + 1.5 * est * (warmup + steps + 1) > budget_s:
+            break
+    r.step(warmup)
+    t0 = time.perf_counter()
+    r.step(steps)
+    dt = time.perf_counter() - t0
+    value = scene["dynamic"] * steps / dt
+    sample = f"{scene['name']}: {scene['dynamic']} of the workload's dynamic bodies (same generator and settings), the reference's own " \
+             f"stepper_sequential compiled from /root/reference against oracle/entt_lite, execution_mode sequential_multithreaded with " \
+             f"{cores} workers, {n_settle} untimed settle steps, {steps} timed steps"
+    return scene, value, dt, sample, cores
+
 def reference_one(args, name, steps, warmup, settle, budget_s):
     """The CPU path (oracle port, all host threads) on the full workload `name`.  If the untimed settle would blow the
     time budget the settled state is approached with fewer settle steps and the line says so."""
@@ -165,14 +221,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene, value, dt, sample, cores = reference_one(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget)
+    port = None
+    if have_real_reference():
+        kind = "reference"
+        scene, value, dt, sample, cores = reference_real(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget / 2)
+        _, pv, pdt, psample, pcores = reference_one(args, args.workload, min(args.steps, 10), min(args.warmup, 3), args.ref_settle, args.ref_budget / 2)
+        port = {"value": pv, "unit": "body-steps/s", "cores": pcores, "kind": "port", "sample": psample}
+    else:
+        kind = "port"
+        scene, value, dt, sample, cores = reference_one(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget)
     line = {"impl": "reference", "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}", "scene": scene["name"],
                        "dynamic_bodies": scene["dynamic"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if port:
+        line["port"] = port
     print(json.dumps(line), flush=True)
 
 
@@ -204,7 +270,7 @@ def traffic_for(name):
     return None
 
 
-def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_clocks):
+def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_clocks, real_reference=False):
     """One workload, whole scene on one GPU: device-resident value, e2e through host buffers, roofline, CPU baseline."""
     import torch
     import edyn_b200 as E
@@ -276,6 +342,10 @@ def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_cl
         cpu = {"value": n_dyn * nsteps / dt, "unit": "body-steps/s", "cores": cores, "kind": "port",
                "sample": f"{nsteps} steps of the same settled {scene['name']} state downloaded from the device "
                          f"(oracle/ CPU restatement of stepper_sequential; broadphase queries, narrowphase and per-island solve on {cores} threads)"}
+    cpu_port = None
+    if cpu and real_reference and have_real_reference():
+        _, rv, _, rsample, rcores = reference_real(args, name, 5, 2, min(args.ref_settle, 60), args.ref_real_seconds)
+        cpu_port, cpu = cpu, {"value": rv, "unit": "body-steps/s", "cores": rcores, "kind": "reference", "sample": rsample}
     if st["error_flags"]:
         raise SystemExit(f"{name}: device error flags {st['error_flags']}")
     res = {"value": value, "unit": "body-steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
@@ -290,6 +360,8 @@ def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_cl
            "roofline": roofline}
     if cpu:
         res["cpu_baseline"] = cpu
+    if cpu_port:
+        res["cpu_port"] = cpu_port
     if clocks:
         res["clocks"] = clocks
     w.close()
@@ -297,13 +369,14 @@ def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_cl
 
 
 def run_single(args, local_rank):
-    top = measure_single(args, args.workload, local_rank, args.steps, args.warmup, 0 if args.no_cpu else args.cpu_seconds, True)
+    top = measure_single(args, args.workload, local_rank, args.steps, args.warmup, 0 if args.no_cpu else args.cpu_seconds, True, real_reference=True)
     line = {"metric": "body-steps/sec", "value": top["value"], "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(top["config"], parallelism="1 GPU: whole scene in one device world"),
             "clocks": top.get("clocks"), "gpu_launches": top["gpu_launches"], "e2e": top["e2e"], "roofline": top["roofline"]}
-    if "cpu_baseline" in top:
-        line["cpu_baseline"] = top["cpu_baseline"]
+    for k in ("cpu_baseline", "cpu_port"):
+        if k in top:
+            line[k] = top[k]
     if args.workload == DEFAULT_WORKLOAD and args.scale == 1.0 and not args.only:
         subs = {}
         for name in OTHER_WORKLOADS:
@@ -482,6 +555,7 @@ def main():
     ap.add_argument("--ref-settle", type=int, default=SETTLE_STEPS)
     ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: seconds the untimed settle + timed steps may take")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-real-seconds", type=float, default=75.0, help="device arm: budget of the real reference stepper's cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exact-exchange", action="store_true", help="N > 1: read every step's rank boxes before the next step starts (no look-ahead margin)")
     args = ap.parse_args()

@@ -1,0 +1,2 @@
+#pragma once
+#include "../entt_lite.hpp"

@@ -206,10 +206,19 @@ void ora_set_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32_t nm,
     World &w = *static_cast<World *>(h);
     w.use_order = true;
     w.hinge_order.assign(hinge_idx, hinge_idx + nh);
-    w.manifold_order.resize(nm);
+    w.manifold_order.resize(nm); w.point_order.clear();
     for (uint32_t i = 0; i < nm; ++i) w.manifold_order[i] = World::key(pairs[2 * i], pairs[2 * i + 1]);
 }
-void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; }
+// The same with one entry per contact ROW: (body pair, index of the point in the manifold's list) -- the granularity at
+// which the reference orders rows (every contact point is a constraint entity of its own, island_solver.cpp:113-160).
+void ora_set_point_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32_t nc, const uint32_t *contact3) {
+    World &w = *static_cast<World *>(h);
+    w.use_order = true;
+    w.hinge_order.assign(hinge_idx, hinge_idx + nh);
+    w.manifold_order.resize(nc); w.point_order.resize(nc);
+    for (uint32_t i = 0; i < nc; ++i) { w.manifold_order[i] = World::key(contact3[3 * i], contact3[3 * i + 1]); w.point_order[i] = contact3[3 * i + 2]; }
+}
+void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; static_cast<World *>(h)->point_order.clear(); }
 
 int ora_should_collide(void *h, uint32_t a, uint32_t b) { return static_cast<World *>(h)->should_collide(a, b) ? 1 : 0; }
 

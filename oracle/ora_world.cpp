@@ -670,14 +670,17 @@ void World::solve() {
         for (uint32_t h : hinge_order)
             if (bodies[hinges[h].a].awake() || bodies[hinges[h].b].awake()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
         std::vector<char> seen(manifolds.size(), 0);
-        for (uint64_t k : manifold_order) {
+        for (size_t oi = 0; oi < manifold_order.size(); ++oi) {
+            const uint64_t k = manifold_order[oi];
             auto it = manifold_map.find(k);
             if (it == manifold_map.end()) continue;
             seen[it->second] = 1;
             const Manifold &m = manifolds[it->second];
             if (!bodies[m.a].awake() && !bodies[m.b].awake()) continue;
             IslandWork &w = island_of(m.a, m.b);
-            for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(it->second, p);
+            const uint32_t one = oi < point_order.size() ? point_order[oi] : 0xFFFFFFFFu;       // rows point by point (the reference's own order)
+            if (one != 0xFFFFFFFFu) { if (one < m.num) w.pts.emplace_back(it->second, one); }
+            else for (uint32_t p = 0; p < m.num; ++p) w.pts.emplace_back(it->second, p);
         }
         // manifolds the injected order does not name (the two sides drifted apart in a free run): natural order, at the end
         for (uint32_t mi = uint32_t(manifolds.size()); mi-- > 0;) {

@@ -7,6 +7,9 @@
 // Not restated (out of scope): restitution_solver (run both sides with
 // restitution iterations = 0 so restitution goes through the row rhs), sleeping (benchmarks set
 // sleeping_disabled), center_of_mass/origin offsets, contact_extras.
+// PINNED: leaf functions against the reference's object code (tests/test_oracle_fixtures.py), whole steps bit for bit
+// against the reference's real stepper_sequential (oracle/_ref/libedyn_stepper.so, tests/test_ref_stepper.py and
+// tests/golden/whole_step.npz) with the reference's row order replayed through set_point_order().
 #pragma once
 #include "ora_collide.hpp"
 #include <unordered_map>
@@ -80,6 +83,8 @@ struct World {
     bool use_order = false;
     std::vector<uint32_t> hinge_order;
     std::vector<uint64_t> manifold_order;                   // pair keys
+    std::vector<uint32_t> point_order;                      // optional, one per entry of manifold_order: which point of the manifold's list
+                                                            // the row is (0xFFFFFFFF = all its points, in list order)
     int threads = 1;                                        // island-parallel solve (run_island_solver_seq_mt analogue)
 
     static uint64_t key(uint32_t a, uint32_t b) { return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a; }

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libedyn_ref.so")
+STEPPER_SO = os.path.join(HERE, "_ref", "libedyn_stepper.so")
 
 SH_SPHERE, SH_CAPSULE, SH_BOX, SH_PLANE, SH_NONE = 0, 2, 3, 6, 255
 DYNAMIC, KINEMATIC, STATIC = 0, 1, 2
@@ -26,6 +27,9 @@ def build(force=False):
     """Compile the restatement (always) and oracle/_ref (only where /root/reference exists)."""
     if force or not os.path.exists(ORACLE_SO) or os.path.isdir("/root/reference/src/edyn"):
         subprocess.run(["make", "-s", "-C", HERE], check=True)
+    # the reference's whole sequential stepper (about a minute on 8 cores the first time, a no-op make afterwards)
+    if os.path.isdir("/root/reference/src/edyn"):
+        subprocess.run(["make", "-s", "-j", str(os.cpu_count() or 4), "-C", HERE, "stepper"], check=True)
 
 
 def _ptr(a):
@@ -404,5 +408,112 @@ class OracleWorld:
         p = _arr(pairs, _u, (-1, 2))
         self.l.ora_set_order(self.h, C.c_uint32(len(h)), _ptr(h), C.c_uint32(len(p)), _ptr(p))
 
+    def set_point_order(self, hinge_idx, contact3):
+        """Row order with one entry per contact ROW: (body0, body1, index of the point in the manifold's list)."""
+        hinge_idx = _arr(hinge_idx, _u)
+        contact3 = _arr(contact3, _u, (-1, 3))
+        self.l.ora_set_point_order(self.h, C.c_uint32(len(hinge_idx)), _ptr(hinge_idx), C.c_uint32(len(contact3)), _ptr(contact3))
+
     def clear_order(self):
         self.l.ora_clear_order(self.h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference itself: edyn::attach / make_rigidbody / make_constraint<hinge_constraint> / exclude_collision /
+# step_simulation compiled in place from /root/reference against oracle/entt_lite (oracle/ref_stepper.cpp, `make stepper`).
+
+_stepper = None
+
+
+def ref_stepper():
+    """The library, or None where it was neither built here nor shipped (it needs /root/reference at build time)."""
+    global _stepper
+    if _stepper is None and os.path.exists(STEPPER_SO):
+        l = C.CDLL(STEPPER_SO, mode=os.RTLD_NOW)
+        l.refs_create.restype = C.c_void_p
+        l.refs_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        for name in ("refs_num_bodies", "refs_num_manifolds", "refs_get_contacts"):
+            getattr(l, name).restype = C.c_uint32
+        _stepper = l
+    return _stepper
+
+
+class RefWorld:
+    """One registry stepped by the reference's own stepper_sequential.  threads = 0: execution_mode::sequential;
+    threads > 0: sequential_multithreaded with that many workers (edyn.cpp:85-89)."""
+
+    def __init__(self, dt=1.0 / 60, vel_iters=8, pos_iters=3, restitution_iters=0, threads=0):
+        self.l = ref_stepper()
+        if self.l is None:
+            raise RuntimeError("oracle/_ref/libedyn_stepper.so is not available")
+        self.h = C.c_void_p(self.l.refs_create(C.c_float(dt), vel_iters, pos_iters, restitution_iters, threads))
+        self.num_hinges = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.l.refs_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def num_bodies(self):
+        return int(self.l.refs_num_bodies(self.h))
+
+    def add_bodies(self, b, sleeping_disabled=True):
+        n = len(b["kind"])
+        a = [_arr(b["pos"], _f, (n, 3)), _arr(b["orn"], _f, (n, 4)), _arr(b["linvel"], _f, (n, 3)), _arr(b["angvel"], _f, (n, 3)),
+             _arr(b["inv_mass"], _f, (n,)), _arr(b["gravity"], _f, (n, 3)), _arr(b["kind"], _u, (n,)), _arr(b["shape_kind"], _u, (n,)),
+             _arr(b["shape_params"], _f, (n, 4)), _arr(b["friction"], _f, (n,)), _arr(b["restitution"], _f, (n,))]
+        grp = _arr(b["group"], np.uint64, (n,)) if b.get("group") is not None else None
+        msk = _arr(b["mask"], np.uint64, (n,)) if b.get("mask") is not None else None
+        rc = self.l.refs_add_bodies(self.h, C.c_uint32(n), *[_ptr(x) for x in a], _ptr(grp), _ptr(msk), C.c_int(1 if sleeping_disabled else 0))
+        if rc:
+            raise RuntimeError("refs_add_bodies: unsupported shape kind")
+
+    def add_hinges(self, a, b, pivotA, pivotB, axisA, axisB):
+        n = len(a)
+        arrs = [_arr(a, _u), _arr(b, _u), _arr(pivotA, _f, (n, 3)), _arr(pivotB, _f, (n, 3)), _arr(axisA, _f, (n, 3)), _arr(axisB, _f, (n, 3))]
+        self.num_hinges += n
+        return self.l.refs_add_hinges(self.h, C.c_uint32(n), *[_ptr(x) for x in arrs])
+
+    def add_exclusions(self, a, b):
+        a, b = _arr(a, _u), _arr(b, _u)
+        self.l.refs_add_exclusions(self.h, C.c_uint32(len(a)), _ptr(a), _ptr(b))
+
+    def step(self, n=1):
+        self.l.refs_step(self.h, C.c_uint32(n))
+
+    def state(self):
+        n = self.num_bodies
+        pos, orn, lv, av, bb = np.zeros((n, 3), _f), np.zeros((n, 4), _f), np.zeros((n, 3), _f), np.zeros((n, 3), _f), np.zeros((n, 6), _f)
+        self.l.refs_get_state(self.h, _ptr(pos), _ptr(orn), _ptr(lv), _ptr(av), _ptr(bb))
+        return dict(pos=pos, orn=orn, linvel=lv, angvel=av, aabb=bb)
+
+    def inertia_inv(self):
+        inv = np.zeros((self.num_bodies, 9), _f)
+        self.l.refs_get_inertia_inv(self.h, _ptr(inv))
+        return inv
+
+    def contacts(self):
+        """pairs (ordered: body[0], body[1]), num, pts (m, 4, 14): pivotA pivotB normal distance impulse_n impulse_t0 impulse_t1 lifetime."""
+        m = int(self.l.refs_num_manifolds(self.h))
+        pairs, num, pts = np.zeros((max(m, 1), 2), _u), np.zeros(max(m, 1), _u), np.zeros((max(m, 1), 4, 14), _f)
+        got = int(self.l.refs_get_contacts(self.h, C.c_uint32(m), _ptr(pairs), _ptr(num), _ptr(pts)))
+        return dict(pairs=pairs[:got], num=num[:got], pts=pts[:got])
+
+    def islands(self):
+        lab = np.zeros(self.num_bodies, _u)
+        self.l.refs_get_islands(self.h, _ptr(lab))
+        return lab
+
+    def solver_order(self, max_contacts=None):
+        """(hinge indices, (n, 3) contact rows as body0, body1, point index) of the last step, in the reference's row order."""
+        cap_c = int(max_contacts or 4 * max(1, int(self.l.refs_num_manifolds(self.h))))
+        cap_h = max(1, self.num_hinges)
+        hi, ct = np.zeros(cap_h, _u), np.zeros((cap_c, 3), _u)
+        nh, nc = C.c_uint32(0), C.c_uint32(0)
+        if self.l.refs_get_solver_order(self.h, C.c_uint32(cap_h), _ptr(hi), C.byref(nh), C.c_uint32(cap_c), _ptr(ct), C.byref(nc)):
+            raise RuntimeError("refs_get_solver_order: buffer too small")
+        return hi[:nh.value].copy(), ct[:nc.value].copy()
