@@ -178,6 +178,14 @@ void ora_set_contacts(void *h, uint32_t n, const uint32_t *pairs, const uint32_t
     }
 }
 
+// Replaces the partition the next PH_SOLVE groups its rows by (the per-island position-iteration early-out is the one
+// place where it matters).  Tests use it to follow the reference's island BOOKKEEPING, which can lag the connected
+// components: a split pending on an island is lost when that island is merged into a bigger one the same step
+// (island_manager.cpp:352-357 after :297-350).
+void ora_set_islands(void *h, const uint32_t *label) {
+    World &w = *static_cast<World *>(h);
+    w.island.assign(label, label + w.bodies.size());
+}
 void ora_get_islands(void *h, uint32_t *label) {
     World &w = *static_cast<World *>(h);
     if (w.island.size() != w.bodies.size()) w.islands();
@@ -218,6 +226,8 @@ void ora_set_point_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32
     w.manifold_order.resize(nc); w.point_order.resize(nc);
     for (uint32_t i = 0; i < nc; ++i) { w.manifold_order[i] = World::key(contact3[3 * i], contact3[3 * i + 1]); w.point_order[i] = contact3[3 * i + 2]; }
 }
+void ora_set_position_type_order(void *h, int contacts_first) { static_cast<World *>(h)->position_contacts_first = contacts_first != 0; }
+void ora_set_position_renormalize_all(int on) { position_renormalize_all = on != 0; }
 void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; static_cast<World *>(h)->point_order.clear(); }
 
 int ora_should_collide(void *h, uint32_t a, uint32_t b) { return static_cast<World *>(h)->should_collide(a, b) ? 1 : 0; }

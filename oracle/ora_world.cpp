@@ -622,6 +622,7 @@ static SBody solver_body(const Body &b) {
     return s;
 }
 
+bool position_renormalize_all = false;
 // position_solver::solve, dynamics/position_solver.hpp:16-51
 void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error) {
     const bool pA = A.awake(), pB = B.awake();
@@ -632,7 +633,9 @@ void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max
     scalar eff_mass = effective_mass(J, inv_mA, inv_IA, inv_mB, inv_IB);
     scalar correction = error * scalar(0.2) * eff_mass;
     // The reference also runs these updates for non-procedural bodies with zero mass/inertia, which only
-    // re-normalises their (unit) orientation; skipped here so islands sharing a static body can run in parallel.
+    // re-normalises their (unit) orientation -- a no-op unless the quaternion is an ulp off unit length; skipped by
+    // default (and on the device) so islands sharing a static body can run in parallel, reproduced on request
+    // (position_renormalize_all) to match the reference to the last bit on arbitrarily oriented static bodies.
     if (pA) {
         A.pos += inv_mA * J[0] * correction;
         vec3 acA = inv_IA * J[1] * correction;
@@ -644,6 +647,10 @@ void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max
         vec3 acB = inv_IB * J[3] * correction;
         B.orn = B.orn + quat_derivative(B.orn, acB);
         B.orn = normalize(B.orn);
+    }
+    if (position_renormalize_all) {
+        if (!pA) A.orn = normalize(A.orn);
+        if (!pB) B.orn = normalize(B.orn);
     }
     if (pA) { mat3 basis = to_mat3(A.orn); A.inv_IW = basis * A.inv_I * transpose(basis); }
     if (pB) { mat3 basis = to_mat3(B.orn); B.inv_IW = basis * B.inv_I * transpose(basis); }
@@ -812,15 +819,15 @@ void World::solve() {
         // ---- position iterations (island_solver.cpp:263-353, :538-543)
         for (int it = 0; it < pi; ++it) {
             scalar max_error = 0;
-            {
+            auto joints = [&] {
                 scalar type_err = 0;
                 for (uint32_t h : W.hinges) {                // hinge_constraint::solve_position, hinge_constraint.cpp:180-213
                     Hinge &hc = hinges[h];
                     hinge_solve_position(hc, bodies[hc.a], bodies[hc.b], type_err);
                 }
                 max_error = std::max(max_error, type_err);
-            }
-            {
+            };
+            auto contacts = [&] {
                 scalar type_err = 0;
                 for (auto [mi, p] : W.pts) {                 // contact_constraint::solve_position, contact_constraint.cpp:58-90
                     Manifold &m = manifolds[mi];
@@ -829,7 +836,12 @@ void World::solve() {
                     contact_solve_position(cp, A, B, type_err);
                 }
                 max_error = std::max(max_error, type_err);
-            }
+            };
+            // island_solver.cpp:340 expands the constraint types as ARGUMENTS of max_variadic(...): the order in which
+            // the types are swept is the compiler's argument evaluation order -- tuple order (hinge before contact) with
+            // clang / MSVC, reversed with GCC.  Default: tuple order (what the device does); the GCC order is selectable
+            // so that a GCC-built reference can be matched bit for bit.
+            if (position_contacts_first) { contacts(); joints(); } else { joints(); contacts(); }
             if (max_error < scalar(0.005)) break;            // island_solver.cpp:350-353
         }
     });

@@ -83,6 +83,7 @@ struct World {
     bool use_order = false;
     std::vector<uint32_t> hinge_order;
     std::vector<uint64_t> manifold_order;                   // pair keys
+    bool position_contacts_first = false;                   // position iterations: sweep contacts before joints (GCC argument order, see step())
     std::vector<uint32_t> point_order;                      // optional, one per entry of manifold_order: which point of the manifold's list
                                                             // the row is (0xFFFFFFFF = all its points, in list order)
     int threads = 1;                                        // island-parallel solve (run_island_solver_seq_mt analogue)
@@ -124,6 +125,7 @@ void prepare_contact(const Point &cp, scalar dt, vec3 posA, quat ornA, vec3 posB
                      Row &normal_row, scalar &error, FrictionPair &f);
 // position_solver::solve (dynamics/position_solver.hpp:16-51) and contact_constraint::solve_position
 // (contact_constraint.cpp:58-90) on two bodies; returns false when the point is not penetrating (nothing solved)
+extern bool position_renormalize_all;   // position_solver.hpp:26-32 also normalises non-procedural bodies' orientation: off by default
 void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max_error);
 bool contact_solve_position(Point &cp, Body &A, Body &B, scalar &max_error);
 void hinge_solve_position(const Hinge &hc, Body &A, Body &B, scalar &max_error);   // hinge_constraint.cpp:180-213

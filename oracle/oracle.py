@@ -389,6 +389,11 @@ class OracleWorld:
         self.l.ora_get_islands(self.h, _ptr(lab))
         return lab
 
+    def set_islands(self, labels):
+        """Partition used by the next PH_SOLVE instead of the connected components computed by PH_ISLANDS."""
+        lab = _arr(labels, _u, (self.num_bodies,))
+        self.l.ora_set_islands(self.h, _ptr(lab))
+
     def should_collide(self, a, b):
         self.l.ora_should_collide.restype = C.c_int
         return bool(self.l.ora_should_collide(self.h, C.c_uint32(a), C.c_uint32(b)))
@@ -413,6 +418,16 @@ class OracleWorld:
         hinge_idx = _arr(hinge_idx, _u)
         contact3 = _arr(contact3, _u, (-1, 3))
         self.l.ora_set_point_order(self.h, C.c_uint32(len(hinge_idx)), _ptr(hinge_idx), C.c_uint32(len(contact3)), _ptr(contact3))
+
+    def set_position_type_order(self, contacts_first):
+        """Position iterations sweep the constraint types in the compiler's argument evaluation order
+        (island_solver.cpp:340): tuple order (joints, then contacts; default) or GCC's (contacts first)."""
+        self.l.ora_set_position_type_order(self.h, C.c_int(1 if contacts_first else 0))
+
+    def set_position_renormalize_all(self, on):
+        """Process-wide: position_solver::solve's in-place normalisation of NON-procedural bodies' orientation too
+        (position_solver.hpp:26-32); only matters for static bodies whose quaternion is an ulp off unit length."""
+        self.l.ora_set_position_renormalize_all(C.c_int(1 if on else 0))
 
     def clear_order(self):
         self.l.ora_clear_order(self.h)
