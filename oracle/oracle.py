@@ -440,16 +440,21 @@ class OracleWorld:
 _stepper = None
 
 
+def load_refs_library(path):
+    """dlopen a library exporting the refs_* interface of oracle/ref_stepper.cpp and declare the non-int signatures."""
+    l = C.CDLL(path, mode=os.RTLD_NOW)
+    l.refs_create.restype = C.c_void_p
+    l.refs_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+    for name in ("refs_num_bodies", "refs_num_manifolds", "refs_get_contacts"):
+        getattr(l, name).restype = C.c_uint32
+    return l
+
+
 def ref_stepper():
     """The library, or None where it was neither built here nor shipped (it needs /root/reference at build time)."""
     global _stepper
     if _stepper is None and os.path.exists(STEPPER_SO):
-        l = C.CDLL(STEPPER_SO, mode=os.RTLD_NOW)
-        l.refs_create.restype = C.c_void_p
-        l.refs_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
-        for name in ("refs_num_bodies", "refs_num_manifolds", "refs_get_contacts"):
-            getattr(l, name).restype = C.c_uint32
-        _stepper = l
+        _stepper = load_refs_library(STEPPER_SO)
     return _stepper
 
 
@@ -457,8 +462,8 @@ class RefWorld:
     """One registry stepped by the reference's own stepper_sequential.  threads = 0: execution_mode::sequential;
     threads > 0: sequential_multithreaded with that many workers (edyn.cpp:85-89)."""
 
-    def __init__(self, dt=1.0 / 60, vel_iters=8, pos_iters=3, restitution_iters=0, threads=0):
-        self.l = ref_stepper()
+    def __init__(self, dt=1.0 / 60, vel_iters=8, pos_iters=3, restitution_iters=0, threads=0, library=None):
+        self.l = library if library is not None else ref_stepper()
         if self.l is None:
             raise RuntimeError("oracle/_ref/libedyn_stepper.so is not available")
         self.h = C.c_void_p(self.l.refs_create(C.c_float(dt), vel_iters, pos_iters, restitution_iters, threads))

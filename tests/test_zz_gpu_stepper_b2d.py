@@ -1,0 +1,61 @@
+"""The reference-side binding on the device: a REAL Edyn registry (edyn::attach, make_rigidbody,
+make_constraint<hinge_constraint>, exclude_collision) stepped by edyn::stepper_b2d
+(edyn_b200/csrc/host/stepper_b2d.hpp) over edyn_b200/libb2d.so must give exactly what the same scene gives when its
+arrays are handed to the C ABI directly (edyn_b200.World) -- same library, same capacities, so bit for bit -- and must
+follow the reference's own CPU stepper on the same user code.  tests/integration/_build/libedyn_b2d_dev.so is built where
+the reference is (tests/integration/Makefile) and shipped; the CPU suite exercises the same harness over a mock
+(tests/test_stepper_b2d.py).  Named to run after the parity suites."""
+import numpy as np
+import pytest
+
+from tests.golden import make_whole_step as G
+from tests.test_stepper_b2d import EdynB2dWorld, build_integration, load
+
+pytestmark = pytest.mark.gpu
+MAX_MANIFOLDS = 1 << 16
+
+
+@pytest.fixture(scope="module")
+def dev(gpu, O):
+    build_integration()
+    lib = load(O, "dev")
+    if lib is None:
+        pytest.skip("tests/integration/_build/libedyn_b2d_dev.so not shipped (needs the reference at build time)")
+    return lib
+
+
+@pytest.mark.parametrize("name", ["boxes_27", "mixed_125", "chains_16"])
+def test_registry_through_the_binding_equals_arrays_through_the_abi_on_device(dev, E, O, name):
+    scene = G.build_scene(E, name)
+    n = len(scene["bodies"]["kind"])
+    nh = len(scene["hinges"]["a"]) if scene["hinges"] else 0
+    w = EdynB2dWorld(O, dev, scene, max_manifolds=MAX_MANIFOLDS)
+    d = E.scenes.build_world(scene, max_manifolds=MAX_MANIFOLDS, max_bodies=n + 8, max_hinges=max(nh, 1))
+    for s in range(60):
+        w.step(1); d.step(1)
+        if s % 10 == 9:
+            a, b = w.state(), d.download_state(aabb=True)
+            for k in ("pos", "orn", "linvel", "angvel", "aabb"):
+                assert np.array_equal(a[k], b[k][:n]), f"{name} step {s}: {k} differs by {np.abs(a[k] - b[k][:n]).max():.3e}"
+    assert d.stats()["error_flags"] == 0
+    w.close(); d.close()
+
+
+def test_device_binding_follows_the_real_cpu_stepper(dev, E, O):
+    """Same user code, the reference's stepper_sequential on the CPU and stepper_b2d on the GPU: identical in free fall
+    (no row order involved; sinf / cosf may differ from glibc by an ulp), the same resting pile afterwards."""
+    if O.ref_stepper() is None:
+        pytest.skip("oracle/_ref/libedyn_stepper.so not shipped")
+    scene = G.build_scene(E, "boxes_27")
+    st = scene["settings"]
+    w = EdynB2dWorld(O, dev, scene, max_manifolds=MAX_MANIFOLDS)
+    r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    G.populate(r, scene)
+    w.step(5); r.step(5)
+    a, b = w.state(), r.state()
+    for k in ("pos", "orn", "linvel", "angvel"):
+        assert np.abs(a[k] - b[k]).max() <= 1e-6, k
+    w.step(175); r.step(175)
+    a, b = w.state(), r.state()
+    assert np.abs(a["pos"] - b["pos"]).max() < 1e-2 and np.abs(a["linvel"]).max() < 0.05
+    w.close()
