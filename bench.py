@@ -167,12 +167,49 @@ def make_ref_world(scene, threads):
     return r
 
 
+def reference_real_isolated(args, name, steps, warmup, settle, budget_s):
+    """reference_real in a child process: a fault inside the reference library (or a hang: the child is given the budget
+    plus a margin) costs this leg, not the bench line.  Returns reference_real's tuple without the scene, or None."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--ref-child", json.dumps([name, steps, warmup, settle, budget_s, args.scale])]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=2.0 * budget_s + 120.0)
+        if out.returncode != 0:
+            raise RuntimeError(f"exit code {out.returncode}: {out.stderr[-300:]}")
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        return d["scene"], d["dynamic"], d["value"], d["dt"], d["sample"], d["cores"]
+    except Exception as e:          # noqa: BLE001 -- whatever happened, the port still gives a CPU number
+        print(f"bench: real reference stepper leg failed ({e}); reporting the port only", file=sys.stderr, flush=True)
+        return None
+
+
+def ref_child(spec):
+    name, steps, warmup, settle, budget_s, scale = json.loads(spec)
+    args = argparse.Namespace(scale=scale)
+    scene, value, dt, sample, cores = reference_real(args, name, int(steps), int(warmup), int(settle), float(budget_s))
+    print(json.dumps({"scene": scene["name"], "dynamic": scene["dynamic"], "value": value, "dt": dt, "sample": sample, "cores": cores}), flush=True)
+
+
 def reference_real(args, name, steps, warmup, settle, budget_s):
     """The reference's own stepper_sequential (sequential_multithreaded, all host threads) on a slice of workload `name`.
     Settles as far as the time budget allows (the line says how far), then times `steps` steps."""
     cores = os.cpu_count() or 1
     scene = make_scene(name, args.scale * REF_SLICE.get(name, 1.0))
-    r = make_ref_world(scene, cores)
+    threads, calib = cores, ""
+    if cores > 16:
+        # "all the host threads it can use": on a many-core host the reference's per-island tasks and parallel_for may run
+        # better on fewer workers than hardware threads -- try both on a quarter-size scene and keep the faster
+        small = make_scene(name, args.scale * REF_SLICE.get(name, 1.0) / 4)
+        rates = {}
+        for t in (cores, 16):
+            w = make_ref_world(small, t)
+            w.step(12)
+            t0 = time.perf_counter()
+            w.step(6)
+            rates[t] = 6.0 / (time.perf_counter() - t0)
+            del w
+        threads = max(rates, key=rates.get)
+        calib = f" (calibrated: {cores} workers {rates[cores]:.1f} steps/s, 16 workers {rates[16]:.1f} steps/s on {small['name']})"
+    r = make_ref_world(scene, threads)
     t_start = time.perf_counter()
     n_settle, took = 0, []
     while n_settle < settle:
@@ -190,8 +227,8 @@ def reference_real(args, name, steps, warmup, settle, budget_s):
     value = scene["dynamic"] * steps / dt
     sample = f"{scene['name']}: {scene['dynamic']} of the workload's dynamic bodies (same generator and settings), the reference's own " \
              f"stepper_sequential compiled from /root/reference against oracle/entt_lite, execution_mode sequential_multithreaded with " \
-             f"{cores} workers, {n_settle} untimed settle steps, {steps} timed steps"
-    return scene, value, dt, sample, cores
+             f"{threads} workers{calib}, {n_settle} untimed settle steps, {steps} timed steps"
+    return scene, value, dt, sample, threads
 
 def reference_one(args, name, steps, warmup, settle, budget_s):
     """The CPU path (oracle port, all host threads) on the full workload `name`.  If the untimed settle would blow the
@@ -222,19 +259,21 @@ def run_reference(args):
     if rank != 0:
         return
     port = None
-    if have_real_reference():
+    real = reference_real_isolated(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget / 2) if have_real_reference() else None
+    if real:
         kind = "reference"
-        scene, value, dt, sample, cores = reference_real(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget / 2)
+        scene_name, n_dyn, value, dt, sample, cores = real
         _, pv, pdt, psample, pcores = reference_one(args, args.workload, min(args.steps, 10), min(args.warmup, 3), args.ref_settle, args.ref_budget / 2)
         port = {"value": pv, "unit": "body-steps/s", "cores": pcores, "kind": "port", "sample": psample}
     else:
         kind = "port"
         scene, value, dt, sample, cores = reference_one(args, args.workload, args.steps, args.warmup, args.ref_settle, args.ref_budget)
+        scene_name, n_dyn = scene["name"], scene["dynamic"]
     line = {"impl": "reference", "metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}", "scene": scene["name"],
-                       "dynamic_bodies": scene["dynamic"], "sample": sample},
+            "config": {"workload": args.workload if args.scale == 1.0 else f"{args.workload} x{args.scale}", "scene": scene_name,
+                       "dynamic_bodies": n_dyn, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if port:
@@ -344,8 +383,10 @@ def measure_single(args, name, local_rank, steps, warmup, cpu_seconds, sample_cl
                          f"(oracle/ CPU restatement of stepper_sequential; broadphase queries, narrowphase and per-island solve on {cores} threads)"}
     cpu_port = None
     if cpu and real_reference and have_real_reference():
-        _, rv, _, rsample, rcores = reference_real(args, name, 5, 2, min(args.ref_settle, 60), args.ref_real_seconds)
-        cpu_port, cpu = cpu, {"value": rv, "unit": "body-steps/s", "cores": rcores, "kind": "reference", "sample": rsample}
+        real = reference_real_isolated(args, name, 5, 2, min(args.ref_settle, 60), args.ref_real_seconds)
+        if real:
+            _, _, rv, _, rsample, rcores = real
+            cpu_port, cpu = cpu, {"value": rv, "unit": "body-steps/s", "cores": rcores, "kind": "reference", "sample": rsample}
     if st["error_flags"]:
         raise SystemExit(f"{name}: device error flags {st['error_flags']}")
     res = {"value": value, "unit": "body-steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
@@ -557,8 +598,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-real-seconds", type=float, default=75.0, help="device arm: budget of the real reference stepper's cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-child", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--exact-exchange", action="store_true", help="N > 1: read every step's rank boxes before the next step starts (no look-ahead margin)")
     args = ap.parse_args()
+    if args.ref_child:
+        ref_child(args.ref_child)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

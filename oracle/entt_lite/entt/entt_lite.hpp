@@ -8,6 +8,8 @@
 // Not EnTT: no groups, no sorting, no runtime views, no meta reflection beyond the names some headers mention.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -54,7 +56,8 @@ public:
 inline namespace literals { constexpr hashed_string operator"" _hs(const char *str, std::size_t n) noexcept { return hashed_string{str, n}; } }
 
 namespace internal {
-inline id_type next_type_index() { static id_type v = 0; return v++; }
+inline id_type next_type_index() { static std::atomic<id_type> v{0}; return v++; }
+inline std::uint64_t next_registry_uid() { static std::atomic<std::uint64_t> v{0}; return ++v; }
 template<typename T> constexpr std::string_view pretty() { return __PRETTY_FUNCTION__; }
 }
 template<typename T> struct type_index { static id_type value() noexcept { static const id_type v = internal::next_type_index(); return v; } };
@@ -531,8 +534,15 @@ public:
     // ---- pools
     template<typename T> storage_for_type<std::remove_const_t<T>> &storage() { return assure<std::remove_const_t<T>>(); }
     template<typename T> const storage_for_type<std::remove_const_t<T>> *storage() const {
+        using pool_type = storage_impl<std::remove_const_t<T>, registry>;
+        static thread_local std::uint64_t cached_owner = 0;
+        static thread_local const pool_type *cached = nullptr;
+        if (cached_owner == uid) return cached;
+        std::lock_guard<std::mutex> lock(pools_mutex);
         auto it = pools.find(type_hash<std::remove_const_t<T>>::value());
-        return it == pools.end() ? nullptr : static_cast<const storage_for_type<std::remove_const_t<T>> *>(it->second.get());
+        if (it == pools.end()) return nullptr;
+        cached = static_cast<const pool_type *>(it->second.get()); cached_owner = uid;
+        return cached;
     }
     template<typename T, typename... A> decltype(auto) emplace(entity e, A &&...args) { return assure<T>().emplace(e, std::forward<A>(args)...); }
     template<typename T, typename It> void insert(It first, It last, const T &value = {}) { assure<T>().insert(first, last, value); }
@@ -598,6 +608,13 @@ private:
     template<typename T> bool has(entity e) const noexcept { auto *p = storage<T>(); return p && p->contains(e); }
     template<typename T> storage_impl<T, registry> &assure() {
         static_assert(!std::is_const_v<T>);
+        // Pools are created on first use and never removed.  The sequential_multithreaded mode calls registry.view<...>()
+        // from worker threads: the lookup goes through a per-thread cache keyed by the registry's unique id, creation and
+        // map access sit behind a mutex (EnTT itself leaves this to the caller).
+        static thread_local std::uint64_t cached_owner = 0;
+        static thread_local storage_impl<T, registry> *cached = nullptr;
+        if (cached_owner == uid) return *cached;
+        std::lock_guard<std::mutex> lock(pools_mutex);
         const id_type id = type_hash<T>::value();
         auto it = pools.find(id);
         if (it == pools.end()) {
@@ -606,8 +623,11 @@ private:
             order.push_back(p.get());
             it = pools.emplace(id, std::move(p)).first;
         }
-        return static_cast<storage_impl<T, registry> &>(*it->second);
+        cached = static_cast<storage_impl<T, registry> *>(it->second.get()); cached_owner = uid;
+        return *cached;
     }
+    const std::uint64_t uid = internal::next_registry_uid();
+    mutable std::mutex pools_mutex;
     std::vector<entity> ids; std::vector<std::uint32_t> where; size_type alive{};
     std::unordered_map<id_type, std::unique_ptr<pool_base>> pools;
     std::vector<pool_base *> order;
