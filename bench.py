@@ -93,7 +93,38 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.t = index, [], False, None
 
+    def _nvml(self):
+        """In-process NVML handle of CUDA device `index` (by UUID, so CUDA_VISIBLE_DEVICES cannot misalign them), or None."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None
+
     def _run(self):
+        # NVML in process: a sample every 2 ms, so that a timed region of a few tens of milliseconds is covered by many
+        # samples; nvidia-smi (one process launch per sample, ~100 ms) only where NVML cannot be loaded
+        nv = self._nvml()
+        if nv is not None:
+            pynvml, h = nv
+            try:
+                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                        pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+                while not self.stop_flag:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    why = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append([str(int(sm)), str(int(mx))] + ["Active" if why & b else "Not Active" for b in bits])
+                    time.sleep(0.002)
+                return
+            except Exception:
+                pass                                    # fall through to nvidia-smi with whatever was sampled so far
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
