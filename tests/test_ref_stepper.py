@@ -182,6 +182,56 @@ def test_random_scenes_lockstep_with_real_stepper(refstep, E, seeds):
     assert coarser <= 15 * len(seeds)            # the lagging bookkeeping is the exception, not the rule
 
 
+MEDIUM = {
+    "boxes_512": (lambda E: E.scenes.boxes_on_plane(8), 90),
+    "mixed_1000": (lambda E: E.scenes.mixed_pile(10), 90),
+    "spheres_2048": (lambda E: E.scenes.spheres_in_box(16, 8, 16), 90),
+    "chains_4096": (lambda E: E.scenes.hinge_chains(32, 32), 40),
+}
+
+
+def lockstep(O, scene, steps, threads=1):
+    """Free-running lock step of the real stepper and the oracle (row order and island bookkeeping follow the reference);
+    returns (first step with any difference or None, steps on which the reference's partition was coarser, contact points)."""
+    st = scene["settings"]
+    r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    o = O.OracleWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"], threads=threads)
+    G.populate(r, scene); G.populate(o, scene)
+    o.set_position_type_order(contacts_first=True)
+    dyn = np.asarray(scene["bodies"]["kind"]) == 0
+    first_bad, coarser, points = None, 0, 0
+    for s in range(steps):
+        r.step(1)
+        hi, ct = r.solver_order()
+        o.run_phases(O.PH_BROAD | O.PH_NARROW | O.PH_ISLANDS)
+        ref_islands = r.islands()
+        refines, equal = _refines(o.islands()[dyn], ref_islands[dyn])
+        assert refines, f"step {s}: the oracle's islands are not a refinement of the reference's"
+        coarser += not equal
+        o.set_islands(ref_islands)
+        o.set_point_order(hi, ct)
+        o.run_phases(O.PH_SOLVE)
+        a, b = r.state(), o.state()
+        rc, oc = r.contacts(), o.contacts()
+        same = all(np.array_equal(a[k], b[k]) for k in ("pos", "orn", "linvel", "angvel", "aabb")) and \
+            np.array_equal(np.sort(_keys(rc["pairs"])), np.sort(_keys(oc["pairs"]))) and int(rc["num"].sum()) == int(oc["num"].sum())
+        if not same and first_bad is None:
+            first_bad = s
+        points = int(rc["num"].sum())
+    return first_bad, coarser, points
+
+
+@pytest.mark.parametrize("name", list(MEDIUM))
+def test_oracle_lockstep_with_real_stepper_medium_scenes(refstep, E, name):
+    """Hundreds to thousands of bodies, thousands of contact points, the oracle on all host threads (its per-island solve
+    is threaded like run_island_solver_seq_mt): still bit for bit.  tools/ref_lockstep.py runs the same at benchmark sizes
+    (config 2 and config 3 at full size, 1/16 of config 5, 1/64 of config 4); results in DESIGN.md section 6."""
+    make, steps = MEDIUM[name]
+    first_bad, _, points = lockstep(refstep, make(E), steps, threads=os.cpu_count() or 1)
+    assert first_bad is None, f"{name}: first difference at step {first_bad}"
+    assert points > 1000
+
+
 def test_real_stepper_multithreaded_matches_sequential(refstep, E):
     """execution_mode::sequential_multithreaded (what bench.py's reference arm times) gives the sequential mode's results."""
     O = refstep
