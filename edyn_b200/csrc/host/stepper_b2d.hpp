@@ -10,6 +10,8 @@
 // cannot be created the constructor throws.
 #pragma once
 #include <entt/entity/registry.hpp>
+#include <edyn/collision/contact_manifold.hpp>
+#include <edyn/collision/contact_point.hpp>
 #include <edyn/comp/aabb.hpp>
 #include <edyn/comp/angvel.hpp>
 #include <edyn/comp/collision_exclusion.hpp>
@@ -32,6 +34,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -54,6 +57,8 @@ class stepper_b2d {
     std::vector<std::vector<uint32_t>> m_excluded;           // body id -> ids it is staged as excluded from
     std::vector<uint8_t> m_is_dirty;
     std::vector<float> m_pos, m_orn, m_lv, m_av, m_aabb;     // download buffers
+    std::unordered_map<uint64_t, entt::entity> m_manifold_of;   // (body id 0 << 32 | body id 1) -> mirrored contact_manifold entity
+    uint64_t m_steps {0}, m_mirror_step {0};
     double m_last_time;
     bool m_paused {false};
     bool m_scattering {false};                               // our own component writes are not "dirty"
@@ -321,6 +326,7 @@ public:
         upload_dirty();
         if (s.pre_step_callback) (*s.pre_step_callback)(*m_registry);
         check(b2d_step(m_world, 1), "b2d_step");
+        ++m_steps;
         scatter_state();                                               // blocks until the step's results are on the host
         if (s.post_step_callback) (*s.post_step_callback)(*m_registry);
         m_last_time = time;
@@ -337,6 +343,106 @@ public:
         m_last_time = start + double(num_steps) * fixed_dt;
     }
 
+    // ---- contacts, on demand.  The device keeps manifolds and points resident; creating and
+    // destroying an entity with five components per contact point per step on the host is the cost this design removes.
+    // A user who observes contacts calls mirror_contacts() when they want to look: afterwards the registry holds what
+    // the CPU stepper would hold -- one contact_manifold + contact_manifold_state entity per touching (AABB-overlapping)
+    // pair, and per contact point an entity with contact_point, contact_point_list, contact_point_geometry,
+    // contact_point_material and contact_point_impulse, linked newest first (collision_util.cpp:319-395).  A point keeps
+    // its entity for as long as it persists on the device (matched through its lifetime counter and its place in the
+    // list); new points get contact_started_tag after their components, like narrowphase::patch_new_contacts
+    // (narrowphase.cpp:111-130); vanished points and manifolds are destroyed, so on_destroy<contact_point> fires.
+    // Not mirrored: the contact_constraint / graph edge of each point (the CPU solver is not running).
+    struct mirror_stats { uint32_t manifolds, points, points_created, points_destroyed; };
+
+    mirror_stats mirror_contacts() {
+        auto &reg = *m_registry;
+        uint32_t n = 0, got = 0;
+        check(b2d_num_manifolds(m_world, &n), "b2d_num_manifolds");
+        std::vector<uint32_t> pairs(2 * size_t(n) + 2), num(size_t(n) + 1), u2(8 * size_t(n) + 8);
+        std::vector<float> pt(72 * size_t(n) + 72);                            // 4 slots x 18 floats per manifold
+        if (n) check(b2d_download_contacts(m_world, n, pairs.data(), num.data(), pt.data(), u2.data(), &got), "b2d_download_contacts");
+        const uint32_t elapsed = uint32_t(m_steps - m_mirror_step);
+        mirror_stats st {};
+        std::unordered_map<uint64_t, entt::entity> next;
+        next.reserve(got);
+        for (uint32_t i = 0; i < got; ++i) {
+            const uint32_t a = pairs[2 * i], b = pairs[2 * i + 1];
+            if (a >= m_entities.size() || b >= m_entities.size() || m_entities[a] == entt::null || m_entities[b] == entt::null) continue;
+            const uint64_t key = (uint64_t(a) << 32) | b;
+            entt::entity me;
+            if (auto it = m_manifold_of.find(key); it != m_manifold_of.end()) { me = it->second; m_manifold_of.erase(it); }
+            else {
+                me = reg.create();
+                reg.emplace<contact_manifold>(me, contact_manifold{{m_entities[a], m_entities[b]}});
+                reg.emplace<contact_manifold_state>(me);
+            }
+            next.emplace(key, me);
+            sync_points(me, std::min<uint32_t>(num[i], 4u), &pt[72 * size_t(i)], &u2[8 * size_t(i)], elapsed, st);
+            ++st.manifolds;
+        }
+        for (auto &gone : m_manifold_of) {                                     // pairs that separated since the last look
+            if (!reg.valid(gone.second)) continue;
+            sync_points(gone.second, 0, nullptr, nullptr, elapsed, st);
+            reg.destroy(gone.second);
+        }
+        m_manifold_of.swap(next);
+        m_mirror_step = m_steps;
+        return st;
+    }
+
+private:
+    void sync_points(entt::entity me, uint32_t np, const float *p18, const uint32_t *u2, uint32_t elapsed, mirror_stats &st) {
+        auto &reg = *m_registry;
+        std::vector<entt::entity> old, now(np, entt::entity{entt::null}), fresh;
+        for (auto e = reg.get<contact_manifold_state>(me).contact_entity; e != entt::null; e = reg.get<contact_point_list>(e).next) old.push_back(e);
+        size_t j = 0;
+        for (uint32_t s = 0; s < np; ++s) {
+            const float *p = p18 + 18 * s;
+            const uint32_t lifetime = u2[2 * s + 1];
+            entt::entity e = entt::null;
+            if (lifetime >= elapsed) {                                         // older than the last look: find its entity, in list order
+                size_t k = j;
+                while (k < old.size() && reg.get<contact_point>(old[k]).lifetime + elapsed != lifetime) ++k;
+                if (k < old.size()) {
+                    for (; j < k; ++j) { reg.destroy(old[j]); ++st.points_destroyed; }
+                    e = old[k]; j = k + 1;
+                }
+            }
+            if (e == entt::null) {
+                e = reg.create();
+                reg.emplace<contact_point_material>(e);
+                reg.emplace<contact_point_impulse>(e);
+                reg.emplace<contact_point_geometry>(e);
+                reg.emplace<contact_point_list>(e);
+                reg.emplace<contact_point>(e);
+                fresh.push_back(e);
+                ++st.points_created;
+            }
+            auto &cp = reg.get<contact_point>(e);
+            cp.pivotA = {p[0], p[1], p[2]}; cp.pivotB = {p[3], p[4], p[5]}; cp.normal = {p[6], p[7], p[8]}; cp.lifetime = lifetime;
+            auto &geom = reg.get<contact_point_geometry>(e);
+            geom.local_normal = {p[9], p[10], p[11]}; geom.distance = p[12];
+            geom.normal_attachment = static_cast<contact_normal_attachment>(u2[2 * s]);
+            auto &mat = reg.get<contact_point_material>(e);
+            mat.friction = p[13]; mat.restitution = p[14]; mat.spin_friction = 0; mat.roll_friction = 0;
+            auto &imp = reg.get<contact_point_impulse>(e);
+            imp.normal_impulse = p[15]; imp.friction_impulse = {p[16], p[17]};
+            now[s] = e;
+            ++st.points;
+        }
+        for (; j < old.size(); ++j) { reg.destroy(old[j]); ++st.points_destroyed; }
+        for (uint32_t s = 0; s < np; ++s) {
+            auto &link = reg.get<contact_point_list>(now[s]);
+            link.parent = me; link.next = s + 1 < np ? now[s + 1] : entt::entity{entt::null};
+        }
+        auto &state = reg.get<contact_manifold_state>(me);
+        state.num_points = uint8_t(np);
+        state.contact_entity = np ? now[0] : entt::entity{entt::null};
+        for (auto e : fresh) reg.emplace<contact_started_tag>(e);
+    }
+
+public:
     void set_paused(bool paused) { m_paused = paused; }
     bool is_paused() const { return m_paused; }
 };

@@ -21,6 +21,9 @@ void ora_step(void *h, int n);
 uint32_t ora_num_bodies(void *h);
 void ora_get_state(void *h, float *pos, float *orn, float *linvel, float *angvel, float *aabb6, float *inv_IW9);
 void ora_set_state(void *h, const float *pos, const float *orn, const float *linvel, const float *angvel);
+uint32_t ora_num_manifolds(void *h);
+void ora_get_pairs(void *h, uint32_t *pairs);
+void ora_get_contacts(void *h, uint32_t *num, float *pt18, uint32_t *pt_u2);
 }
 
 struct b2d_world { void *ora; std::string err; uint32_t patched = 0; };
@@ -74,6 +77,15 @@ int b2d_upload_bodies(b2d_world *w, uint32_t n, const uint32_t *ids, const b2d_b
 int b2d_upload_state(b2d_world *w, const float *pos, const float *orn, const float *lv, const float *av) { ora_set_state(w->ora, pos, orn, lv, av); return B2D_OK; }
 int b2d_step(b2d_world *w, uint32_t n) { ora_step(w->ora, int(n)); return B2D_OK; }
 int b2d_download_state(b2d_world *w, float *pos, float *orn, float *lv, float *av, float *aabb, float *iw) { ora_get_state(w->ora, pos, orn, lv, av, aabb, iw); return B2D_OK; }
+int b2d_num_manifolds(b2d_world *w, uint32_t *n) { *n = ora_num_manifolds(w->ora); return B2D_OK; }
+int b2d_download_contacts(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint32_t *num, float *pt18, uint32_t *pt_u2, uint32_t *n) {
+    const uint32_t m = ora_num_manifolds(w->ora);
+    if (m > capacity) { w->err = "capacity"; return B2D_ERR_CAPACITY; }
+    ora_get_pairs(w->ora, pairs);
+    ora_get_contacts(w->ora, num, pt18, pt_u2);
+    *n = m;
+    return B2D_OK;
+}
 int b2d_sync(b2d_world *) { return B2D_OK; }
 // test hook (not in b2d.h): how many bodies travelled through b2d_upload_bodies so far
 __attribute__((visibility("default"))) uint32_t b2d_mock_patched(b2d_world *w) { return w->patched; }

@@ -12,6 +12,12 @@
 #include <memory>
 
 namespace {
+struct contact_observer {                      // what a user of the reference connects to see contacts come and go
+    uint32_t started = 0, ended = 0;
+    void on_started(entt::registry &, entt::entity) { ++started; }
+    void on_ended(entt::registry &, entt::entity) { ++ended; }
+};
+std::map<void *, std::unique_ptr<contact_observer>> g_observers;
 std::map<void *, std::unique_ptr<edyn::stepper_b2d>> g_steppers;
 edyn::stepper_b2d &stepper(void *h) { return *g_steppers.at(h); }
 }
@@ -26,7 +32,43 @@ REFS_API int eb2d_attach(void *h, int device, uint32_t max_bodies, uint32_t max_
     } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_attach: %s\n", e.what()); return -1; }
     return 0;
 }
-REFS_API void eb2d_detach(void *h) { g_steppers.erase(h); }
+REFS_API void eb2d_detach(void *h) {
+    if (auto it = g_observers.find(h); it != g_observers.end()) {
+        auto &r = static_cast<World *>(h)->registry;
+        r.on_construct<edyn::contact_started_tag>().disconnect<&contact_observer::on_started>(*it->second);
+        r.on_destroy<edyn::contact_point>().disconnect<&contact_observer::on_ended>(*it->second);
+        g_observers.erase(it);
+    }
+    g_steppers.erase(h);
+}
+// out4 = manifolds, points, points created, points destroyed by this call; observed2 = running totals of
+// on_construct<contact_started_tag> and on_destroy<contact_point> as a user's listeners see them
+REFS_API int eb2d_mirror_contacts(void *h, uint32_t *out4, uint32_t *observed2) {
+    auto *w = static_cast<World *>(h);
+    if (!g_observers.count(h)) {
+        auto obs = std::make_unique<contact_observer>();
+        w->registry.on_construct<edyn::contact_started_tag>().connect<&contact_observer::on_started>(*obs);
+        w->registry.on_destroy<edyn::contact_point>().connect<&contact_observer::on_ended>(*obs);
+        g_observers[h] = std::move(obs);
+    }
+    try {
+        const auto st = stepper(h).mirror_contacts();
+        out4[0] = st.manifolds; out4[1] = st.points; out4[2] = st.points_created; out4[3] = st.points_destroyed;
+    } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_mirror_contacts: %s\n", e.what()); return -1; }
+    observed2[0] = g_observers[h]->started; observed2[1] = g_observers[h]->ended;
+    return 0;
+}
+// the contact point entities in the order refs_get_contacts reports the points (manifold by manifold, list order)
+REFS_API uint32_t eb2d_contact_entities(void *h, uint32_t capacity, uint32_t *entities, uint32_t *lifetime) {
+    auto &r = static_cast<World *>(h)->registry;
+    uint32_t k = 0;
+    for (auto [me, manifold, state] : r.view<edyn::contact_manifold, edyn::contact_manifold_state>().each()) {
+        for (auto e = state.contact_entity; e != entt::null && k < capacity; e = r.get<edyn::contact_point_list>(e).next) {
+            entities[k] = entt::to_integral(e); lifetime[k] = r.get<edyn::contact_point>(e).lifetime; ++k;
+        }
+    }
+    return k;
+}
 REFS_API int eb2d_step(void *h, uint32_t n) {
     auto *w = static_cast<World *>(h);
     try {

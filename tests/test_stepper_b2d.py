@@ -83,6 +83,19 @@ class EdynB2dWorld:
     def remove_exclusion(self, a, b):
         self.lib.eb2d_remove_exclusion(self.r.h, _u(a), _u(b))
 
+    def mirror_contacts(self):
+        """stepper_b2d::mirror_contacts; returns (manifolds, points, created, destroyed) of this call and the running totals
+        a user's on_construct<contact_started_tag> / on_destroy<contact_point> listeners have seen."""
+        out, seen = (C.c_uint32 * 4)(), (C.c_uint32 * 2)()
+        assert self.lib.eb2d_mirror_contacts(self.r.h, out, seen) == 0
+        return tuple(out), tuple(seen)
+
+    def contact_entities(self, capacity=1 << 16):
+        ent, life = np.zeros(capacity, np.uint32), np.zeros(capacity, np.uint32)
+        self.lib.eb2d_contact_entities.restype = C.c_uint32
+        k = self.lib.eb2d_contact_entities(self.r.h, _u(capacity), ent.ctypes.data_as(C.c_void_p), life.ctypes.data_as(C.c_void_p))
+        return ent[:k].copy(), life[:k].copy()
+
     def close(self):
         if self.r is not None:
             self.lib.eb2d_detach(self.r.h)          # the stepper disconnects from the registry before the registry goes
@@ -189,4 +202,57 @@ def test_exclusions_and_destroyed_bodies(mock, O, E):
     for k in ("pos", "orn", "linvel", "angvel"):
         assert np.array_equal(got[k][keep], want[k][keep]), k
         assert not got[k][victim].any()                      # the entity is gone from the registry
+    w.close()
+
+
+def _contacts_by_pair(c, cols):
+    """{(body0, body1): (points in list order restricted to `cols`)} of a contacts() dictionary."""
+    out = {}
+    for i, (a, b) in enumerate(np.asarray(c["pairs"]).reshape(-1, 2).tolist()):
+        out[(a, b)] = np.asarray(c["pts"][i, :c["num"][i]][:, cols], np.float32)
+    return out
+
+
+@pytest.mark.parametrize("name", ["boxes_27", "mixed_125", "chains_16"])
+def test_contacts_mirrored_into_the_registry_on_demand(mock, O, E, name):
+    """mirror_contacts(): afterwards the registry reads -- through the reference's own component layout, walked the way user
+    code walks it (contact_manifold_state.contact_entity -> contact_point_list.next) -- exactly like the device's manifolds:
+    ordered pairs incl. those without points, points in list order, pivots / normal / distance / applied impulses /
+    lifetime bit for bit.  Points keep their entity while they persist; new ones raise contact_started_tag, vanished
+    ones on_destroy<contact_point>."""
+    scene = G.build_scene(E, name)
+    w = EdynB2dWorld(O, mock, scene)
+    o = _plain_oracle(O, scene)
+    PT18 = [0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 15, 16, 17]      # pivotA pivotB normal distance impulses of the 18-float device point
+    PT14 = list(range(13))                                   # the same fields as refs_get_contacts lays them out
+    seen_started = seen_ended = 0
+    before = {}
+    for stage, steps in enumerate((45, 1, 7, 40)):
+        w.step(steps); o.step(steps)
+        (manifolds, points, created, destroyed), (started, ended) = w.mirror_contacts()
+        got, want = w.r.contacts(), o.contacts()
+        assert manifolds == len(want["pairs"]) and points == int(want["num"].sum())
+        g, t = _contacts_by_pair(got, PT14), _contacts_by_pair(want, PT18)
+        assert g.keys() == t.keys(), f"{name} stage {stage}: manifold sets differ"
+        for k in t:
+            assert np.array_equal(g[k], t[k]), f"{name} stage {stage}: points of manifold {k} differ"
+        life = {k: want["lifetime"][i, :want["num"][i]] for i, k in enumerate(map(tuple, want["pairs"].tolist()))}
+        got_life = _contacts_by_pair(got, [13])
+        for k in life:
+            assert np.array_equal(got_life[k][:, 0].astype(np.uint32), life[k])
+        # events as a user's listeners saw them
+        assert started - seen_started == created and ended - seen_ended == destroyed
+        seen_started, seen_ended = started, ended
+        # identity: a point that is `steps` older than at the last look lives in the same entity
+        ent, lt = w.contact_entities()
+        assert len(ent) == points and len(set(ent.tolist())) == points
+        now = dict(zip(ent.tolist(), lt.tolist()))
+        if stage:
+            kept = [e for e, l in now.items() if l >= steps]
+            assert all(e in before and before[e] + steps == now[e] for e in kept), f"{name} stage {stage}: a persisting point changed entity"
+            assert created == len(now) - len(kept)
+        else:
+            assert created == points and destroyed == 0
+        before = now
+    assert seen_started > 0
     w.close()

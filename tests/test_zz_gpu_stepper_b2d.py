@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from tests.golden import make_whole_step as G
-from tests.test_stepper_b2d import EdynB2dWorld, build_integration, load
+from tests.test_stepper_b2d import EdynB2dWorld, _contacts_by_pair, build_integration, load
 
 pytestmark = pytest.mark.gpu
 MAX_MANIFOLDS = 1 << 16
@@ -40,6 +40,29 @@ def test_registry_through_the_binding_equals_arrays_through_the_abi_on_device(de
             moving = np.asarray(scene["bodies"]["kind"]) != 2        # static bodies keep the AABB make_rigidbody gave them
             assert np.array_equal(a["aabb"][moving], b["aabb"][:n][moving]), f"{name} step {s}: AABBs differ"
     assert d.stats()["error_flags"] == 0
+    w.close(); d.close()
+
+
+def test_device_contacts_mirrored_into_the_registry(dev, E, O):
+    """stepper_b2d::mirror_contacts on the device: the registry's contact_manifold / contact_point entities, walked like
+    user code walks them, hold exactly the device's manifolds (twin world fed the arrays directly)."""
+    scene = G.build_scene(E, "mixed_125")
+    n = len(scene["bodies"]["kind"])
+    w = EdynB2dWorld(O, dev, scene, max_manifolds=MAX_MANIFOLDS)
+    d = E.scenes.build_world(scene, max_manifolds=MAX_MANIFOLDS, max_bodies=n + 8, max_hinges=1)
+    seen = 0
+    for steps in (45, 5):
+        w.step(steps); d.step(steps)
+        (manifolds, points, created, destroyed), (started, ended) = w.mirror_contacts()
+        got, want = w.r.contacts(), d.contacts()
+        assert manifolds == len(want["pairs"]) and points == int(want["num"].sum()) and points > 100
+        g = _contacts_by_pair(got, list(range(13)))
+        t = _contacts_by_pair(want, [0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 15, 16, 17])
+        assert g.keys() == t.keys()
+        for k in t:
+            assert np.array_equal(g[k], t[k]), f"points of manifold {k} differ"
+        assert started - seen == created
+        seen = started
     w.close(); d.close()
 
 
