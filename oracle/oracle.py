@@ -511,6 +511,11 @@ class RefWorld:
         self.l.refs_get_state(self.h, _ptr(pos), _ptr(orn), _ptr(lv), _ptr(av), _ptr(bb))
         return dict(pos=pos, orn=orn, linvel=lv, angvel=av, aabb=bb)
 
+    def sleeping(self):
+        out = np.zeros(self.num_bodies, _u)
+        self.l.refs_get_sleeping(self.h, _ptr(out))
+        return out.astype(bool)
+
     def inertia_inv(self):
         inv = np.zeros((self.num_bodies, 9), _f)
         self.l.refs_get_inertia_inv(self.h, _ptr(inv))

@@ -130,7 +130,9 @@ REFS_API int refs_add_exclusions(void *h, uint32_t n, const uint32_t *a, const u
 }
 REFS_API void refs_step(void *h, uint32_t n) {
     auto *w = static_cast<World *>(h);
-    for (uint32_t i = 0; i < n; ++i) { w->time = double(++w->steps) * w->dt; edyn::step_simulation(w->registry, w->time); }
+    // step j carries the time stepper_sequential::update would give it: sim_time + fixed_dt * i, i.e. j * fixed_dt counted
+    // from the attach time 0 (stepper_sequential.cpp:71-75); only island sleeping looks at it (island_manager.cpp:605-623)
+    for (uint32_t i = 0; i < n; ++i) { w->time = double(w->steps++) * w->dt; edyn::step_simulation(w->registry, w->time); }
 }
 REFS_API uint32_t refs_num_bodies(void *h) { return uint32_t(static_cast<World *>(h)->bodies.size()); }
 REFS_API void refs_get_state(void *h, float *pos, float *orn, float *lv, float *av, float *aabb) {
@@ -182,6 +184,11 @@ REFS_API uint32_t refs_get_contacts(void *h, uint32_t capacity, uint32_t *pairs,
         ++n;
     }
     return n;
+}
+// 1 per body that carries sleeping_tag (island_manager::put_to_sleep, island_manager.cpp:541-566)
+REFS_API void refs_get_sleeping(void *h, uint32_t *asleep) {
+    auto *w = static_cast<World *>(h);
+    for (size_t i = 0; i < w->bodies.size(); ++i) asleep[i] = w->registry.valid(w->bodies[i]) && w->registry.all_of<edyn::sleeping_tag>(w->bodies[i]) ? 1u : 0u;
 }
 // island label per body: entity index of the island entity for procedural bodies, 0xFFFFFFFF otherwise
 REFS_API void refs_get_islands(void *h, uint32_t *label) {

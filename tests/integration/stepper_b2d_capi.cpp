@@ -72,7 +72,7 @@ REFS_API uint32_t eb2d_contact_entities(void *h, uint32_t capacity, uint32_t *en
 REFS_API int eb2d_step(void *h, uint32_t n) {
     auto *w = static_cast<World *>(h);
     try {
-        for (uint32_t i = 0; i < n; ++i) { w->time = double(++w->steps) * w->dt; stepper(h).step_simulation(w->time); }
+        for (uint32_t i = 0; i < n; ++i) { w->time = double(w->steps++) * w->dt; stepper(h).step_simulation(w->time); }
     } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_step: %s\n", e.what()); return -1; }
     return 0;
 }

@@ -232,6 +232,44 @@ def test_oracle_lockstep_with_real_stepper_medium_scenes(refstep, E, name):
     assert points > 1000
 
 
+SLEEPY = {
+    "sleep_and_wake": (lambda E: E.scenes.sleep_and_wake(), 500, 3),        # sleeps, is woken by an impact, both sleep again
+    "boxes_27": (lambda E: E.scenes.boxes_on_plane(3), 400, 1),
+    "approaching_stacks": (lambda E: E.scenes.approaching_stacks(), 500, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(SLEEPY))
+def test_island_sleeping_matches_real_stepper(refstep, E, name):
+    """Bodies created WITHOUT sleeping_disabled: island sleep timestamps, put_to_sleep after island_time_to_sleep = 2 s,
+    wake-up when a new edge joins a sleeping island (island_manager.cpp:257-295, :541-623) -- sleeping_tag per body and the
+    whole state identical to the restatement's every step.  Step j is given the time stepper_sequential::update gives it
+    (j * fixed_dt from attach time 0), which is also the restatement's and the device's clock."""
+    O = refstep
+    make, steps, min_events = SLEEPY[name]
+    scene = make(E)
+    st = scene["settings"]
+    r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    o = O.OracleWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    r.add_bodies(scene["bodies"], sleeping_disabled=False)
+    o.add_bodies(scene["bodies"])
+    o.set_sleeping(True)
+    o.set_position_type_order(contacts_first=True)
+    events, prev = 0, np.zeros(len(scene["bodies"]["kind"]), bool)
+    for s in range(steps):
+        r.step(1)
+        hi, ct = r.solver_order()
+        _oracle_step(O, o, hi, ct)
+        asleep = r.sleeping()
+        assert np.array_equal(asleep, o.sleeping().astype(bool)), f"{name} step {s}: sleeping flags differ"
+        a, b = r.state(), o.state()
+        for k in ("pos", "orn", "linvel", "angvel"):
+            assert np.array_equal(a[k], b[k]), f"{name} step {s}: {k} differs"
+        events += not np.array_equal(asleep, prev)
+        prev = asleep
+    assert events >= min_events and prev.any()
+
+
 def test_real_stepper_multithreaded_matches_sequential(refstep, E):
     """execution_mode::sequential_multithreaded (what bench.py's reference arm times) gives the sequential mode's results."""
     O = refstep
