@@ -56,6 +56,8 @@ class stepper_b2d {
     std::vector<entt::entity> m_dirty, m_exclusion_dirty;    // entities the user patched since the last step
     std::vector<std::vector<uint32_t>> m_excluded;           // body id -> ids it is staged as excluded from
     std::vector<uint8_t> m_is_dirty;
+    std::vector<uint32_t> m_asleep, m_was_asleep;            // B2D_FLAG_SLEEPING: sleeping_tag per body, this step / last step
+    bool m_sleeping {false};
     std::vector<float> m_pos, m_orn, m_lv, m_av, m_aabb;     // download buffers
     std::unordered_map<uint64_t, entt::entity> m_manifold_of;   // (body id 0 << 32 | body id 1) -> mirrored contact_manifold entity
     uint64_t m_steps {0}, m_mirror_step {0};
@@ -81,6 +83,7 @@ public:
         c.velocity_iterations = s.num_solver_velocity_iterations;
         c.position_iterations = s.num_solver_position_iterations;
         c.flags = cap.sleeping ? B2D_FLAG_SLEEPING : 0u;
+        m_sleeping = cap.sleeping;
         m_world = b2d_create(&c);
         if (!m_world) throw std::runtime_error(std::string("b2d_create: ") + b2d_last_error(nullptr));
         // make_rigidbody emplaces rigidbody_tag LAST (util/rigidbody.cpp:184): every other component exists by then
@@ -317,6 +320,29 @@ public:
         m_scattering = false;
     }
 
+    // sleeping_tag on the bodies as island_manager::put_to_sleep / wake_up_island leave it (island_manager.cpp:541-566,
+    // :257-295); islands fall asleep and wake up on the device
+    void sync_sleeping() {
+        auto &reg = *m_registry;
+        const auto n = m_entities.size();
+        m_asleep.resize(n); m_was_asleep.resize(n, 0u);
+        check(b2d_download_sleeping(m_world, m_asleep.data()), "b2d_download_sleeping");
+        for (size_t i = 0; i < n; ++i) {
+            if (m_asleep[i] == m_was_asleep[i] || m_entities[i] == entt::null) continue;
+            if (m_asleep[i]) reg.emplace_or_replace<sleeping_tag>(m_entities[i]); else reg.remove<sleeping_tag>(m_entities[i]);
+        }
+        m_was_asleep = m_asleep;
+    }
+
+    // edyn::wake_up_entity for a body of the device world (util/island_util.cpp): its island follows at the next step
+    void wake_up(entt::entity e) {
+        const uint32_t id = id_of(e);
+        if (id == no_id) return;
+        check(b2d_wake_bodies(m_world, &id, 1), "b2d_wake_bodies");
+        m_registry->remove<sleeping_tag>(e);
+        if (id < m_was_asleep.size()) m_was_asleep[id] = 0;
+    }
+
     // ---- stepper_sequential's public surface
     void step_simulation(double time) {                                // stepper_sequential.cpp:121-147 (one fixed step)
         auto &s = m_registry->ctx().get<settings>();
@@ -328,6 +354,7 @@ public:
         check(b2d_step(m_world, 1), "b2d_step");
         ++m_steps;
         scatter_state();                                               // blocks until the step's results are on the host
+        if (m_sleeping) sync_sleeping();
         if (s.post_step_callback) (*s.post_step_callback)(*m_registry);
         m_last_time = time;
     }

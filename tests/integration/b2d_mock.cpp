@@ -22,6 +22,9 @@ uint32_t ora_num_bodies(void *h);
 void ora_get_state(void *h, float *pos, float *orn, float *linvel, float *angvel, float *aabb6, float *inv_IW9);
 void ora_set_state(void *h, const float *pos, const float *orn, const float *linvel, const float *angvel);
 uint32_t ora_num_manifolds(void *h);
+void ora_set_sleeping(void *h, int enabled);
+void ora_wake_bodies(void *h, uint32_t n, const uint32_t *ids);
+void ora_get_sleeping(void *h, uint32_t *asleep);
 void ora_get_pairs(void *h, uint32_t *pairs);
 void ora_get_contacts(void *h, uint32_t *num, float *pt18, uint32_t *pt_u2);
 }
@@ -34,6 +37,7 @@ b2d_world *b2d_create(const b2d_config *c) {
     if (!c || c->max_bodies == 0) { g_create_error = "mock: bad configuration"; return nullptr; }
     auto *w = new b2d_world();
     w->ora = ora_create(c->fixed_dt, int(c->velocity_iterations), int(c->position_iterations), 1);
+    if (c->flags & B2D_FLAG_SLEEPING) ora_set_sleeping(w->ora, 1);
     return w;
 }
 void b2d_destroy(b2d_world *w) { if (w) { ora_destroy(w->ora); delete w; } }
@@ -84,6 +88,12 @@ int b2d_download_contacts(b2d_world *w, uint32_t capacity, uint32_t *pairs, uint
     ora_get_pairs(w->ora, pairs);
     ora_get_contacts(w->ora, num, pt18, pt_u2);
     *n = m;
+    return B2D_OK;
+}
+int b2d_download_sleeping(b2d_world *w, uint32_t *asleep) { ora_get_sleeping(w->ora, asleep); return B2D_OK; }
+int b2d_wake_bodies(b2d_world *w, const uint32_t *ids, uint32_t n) {
+    if (!ids) { w->err = "mock: wake-all is not supported"; return B2D_ERR_UNSUPPORTED; }
+    ora_wake_bodies(w->ora, n, ids);
     return B2D_OK;
 }
 int b2d_sync(b2d_world *) { return B2D_OK; }

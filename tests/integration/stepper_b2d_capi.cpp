@@ -23,11 +23,12 @@ edyn::stepper_b2d &stepper(void *h) { return *g_steppers.at(h); }
 }
 
 // attaches the device stepper to a world made by refs_create(); bodies added before or after are both picked up
-REFS_API int eb2d_attach(void *h, int device, uint32_t max_bodies, uint32_t max_manifolds, uint32_t max_hinges) {
+REFS_API int eb2d_attach(void *h, int device, uint32_t max_bodies, uint32_t max_manifolds, uint32_t max_hinges, int sleeping) {
     auto *w = static_cast<World *>(h);
     try {
         edyn::b2d_capacities cap;
         cap.device = device; cap.max_bodies = max_bodies; cap.max_manifolds = max_manifolds; cap.max_hinges = max_hinges;
+        cap.sleeping = sleeping != 0;
         g_steppers[h] = std::make_unique<edyn::stepper_b2d>(w->registry, w->time, cap);
     } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_attach: %s\n", e.what()); return -1; }
     return 0;
@@ -79,6 +80,10 @@ REFS_API int eb2d_step(void *h, uint32_t n) {
 // edyn::update semantics: as many fixed steps as fit in `time - last time` (stepper_sequential.cpp:28-69)
 REFS_API int eb2d_update(void *h, double time) {
     try { stepper(h).update(time); } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_update: %s\n", e.what()); return -1; }
+    return 0;
+}
+REFS_API int eb2d_wake_up(void *h, uint32_t body) {
+    try { stepper(h).wake_up(static_cast<World *>(h)->bodies[body]); } catch (const std::exception &e) { std::fprintf(stderr, "eb2d_wake_up: %s\n", e.what()); return -1; }
     return 0;
 }
 REFS_API uint32_t eb2d_body_id(void *h, uint32_t body) { return stepper(h).body_id(static_cast<World *>(h)->bodies[body]); }

@@ -45,20 +45,24 @@ def load(O, variant):
 class EdynB2dWorld:
     """A real Edyn registry (O.RefWorld's construction path) stepped by edyn::stepper_b2d."""
 
-    def __init__(self, O, lib, scene, attach_first=False, max_manifolds=1 << 16, **kw):
+    def __init__(self, O, lib, scene, attach_first=False, max_manifolds=1 << 16, sleeping=False, **kw):
         st = scene["settings"]
-        self.lib = lib
+        self.lib, self.sleeping = lib, sleeping
         self.r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"], library=lib, **kw)
         n = len(scene["bodies"]["kind"])
         nh = len(scene["hinges"]["a"]) if scene["hinges"] else 0
         if attach_first:
             self._attach(n, max_manifolds, nh)
-        G.populate(self.r, scene)
+        if sleeping:                                    # bodies without sleeping_disabled_tag on the registry side as well
+            assert not scene["hinges"] and scene["exclusions"] is None
+            self.r.add_bodies(scene["bodies"], sleeping_disabled=False)
+        else:
+            G.populate(self.r, scene)
         if not attach_first:
             self._attach(n, max_manifolds, nh)
 
     def _attach(self, n, max_manifolds, nh):
-        rc = self.lib.eb2d_attach(self.r.h, 0, _u(n + 8), _u(max_manifolds), _u(max(nh, 1)))
+        rc = self.lib.eb2d_attach(self.r.h, 0, _u(n + 8), _u(max_manifolds), _u(max(nh, 1)), C.c_int(1 if self.sleeping else 0))
         assert rc == 0, "stepper_b2d could not be created"
 
     def step(self, n=1):
@@ -82,6 +86,9 @@ class EdynB2dWorld:
 
     def remove_exclusion(self, a, b):
         self.lib.eb2d_remove_exclusion(self.r.h, _u(a), _u(b))
+
+    def wake_up(self, body):
+        assert self.lib.eb2d_wake_up(self.r.h, _u(body)) == 0
 
     def mirror_contacts(self):
         """stepper_b2d::mirror_contacts; returns (manifolds, points, created, destroyed) of this call and the running totals
@@ -255,4 +262,28 @@ def test_contacts_mirrored_into_the_registry_on_demand(mock, O, E, name):
             assert created == points and destroyed == 0
         before = now
     assert seen_started > 0
+    w.close()
+
+
+def test_sleeping_tags_follow_the_device(mock, O, E):
+    """B2D_FLAG_SLEEPING: sleeping_tag on the registry's bodies after every step == the device's flags (the box falls
+    asleep after 2 s, is woken by the second box landing on it, both sleep again), and stepper_b2d::wake_up."""
+    scene = E.scenes.sleep_and_wake()
+    w = EdynB2dWorld(O, mock, scene, sleeping=True)
+    o = _plain_oracle(O, scene)
+    o.set_sleeping(True)
+    changes, prev = 0, np.zeros(3, bool)
+    for s in range(460):
+        w.step(1); o.step(1)
+        tags = w.r.sleeping()
+        assert np.array_equal(tags, o.sleeping().astype(bool)), f"step {s}"
+        changes += not np.array_equal(tags, prev)
+        prev = tags
+    assert changes >= 3 and prev[:2].all()
+    _assert_same(w.state(), o.state(), "after sleeping", keys=("pos", "orn", "linvel", "angvel"))
+    w.wake_up(0)
+    o.wake_bodies([0])
+    assert not w.r.sleeping()[0]
+    w.step(3); o.step(3)
+    assert np.array_equal(w.r.sleeping(), o.sleeping().astype(bool))
     w.close()
