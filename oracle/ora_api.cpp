@@ -228,6 +228,20 @@ void ora_set_point_order(void *h, uint32_t nh, const uint32_t *hinge_idx, uint32
 }
 void ora_set_position_type_order(void *h, int contacts_first) { static_cast<World *>(h)->position_contacts_first = contacts_first != 0; }
 void ora_set_position_renormalize_all(int on) { position_renormalize_all = on != 0; }
+// Restitution solver: iterations (0 = off) and, per step, the entity graph's orders it depends on (see ora_world.hpp)
+void ora_set_restitution_iterations(void *h, int iters, int individual) {
+    World &w = *static_cast<World *>(h);
+    w.restitution_iters = iters; w.individual_restitution_iters = individual;
+}
+void ora_set_graph_order(void *h, const uint32_t *adj_off, const uint32_t *adj_nbr, uint32_t n_tagged, const uint32_t *tagged_pairs) {
+    World &w = *static_cast<World *>(h);
+    const uint32_t nb = uint32_t(w.bodies.size());
+    w.adj_off.assign(adj_off, adj_off + nb + 1);
+    w.adj_nbr.assign(adj_nbr, adj_nbr + adj_off[nb]);
+    w.rest_edge_order.resize(n_tagged);
+    for (uint32_t i = 0; i < n_tagged; ++i) w.rest_edge_order[i] = World::key(tagged_pairs[2 * i], tagged_pairs[2 * i + 1]);
+    w.graph_order_set = true;
+}
 void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; static_cast<World *>(h)->point_order.clear(); }
 
 int ora_should_collide(void *h, uint32_t a, uint32_t b) { return static_cast<World *>(h)->should_collide(a, b) ? 1 : 0; }

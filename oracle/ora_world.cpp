@@ -657,9 +657,156 @@ void position_solve(Body &A, Body &B, const vec3 J[4], scalar error, scalar &max
     max_error = std::max(std::abs(error), max_error);
 }
 
+// ------------------------------------------------------------------ restitution solver
+// get_manifold_min_relvel, restitution_solver.cpp:32-83
+scalar World::manifold_min_relvel(const Manifold &m) const {
+    const Body &A = bodies[m.a], &B = bodies[m.b];
+    const vec3 z{0, 0, 0};
+    const vec3 lvA = A.kind == BK_STATIC ? z : A.linvel, avA = A.kind == BK_STATIC ? z : A.angvel;
+    const vec3 lvB = B.kind == BK_STATIC ? z : B.linvel, avB = B.kind == BK_STATIC ? z : B.angvel;
+    scalar min_relvel = SCALAR_MAX;
+    for (uint32_t p = 0; p < m.num; ++p) {
+        const Point &cp = m.pt[p];
+        vec3 pivotA = to_world(cp.pivotA, A.pos, A.orn), pivotB = to_world(cp.pivotB, B.pos, B.orn);
+        vec3 rA = pivotA - A.pos, rB = pivotB - B.pos;
+        vec3 vA = lvA + cross(avA, rA), vB = lvB + cross(avB, rB);
+        vec3 relvel = vA - vB;
+        min_relvel = std::min(dot(relvel, cp.normal), min_relvel);
+    }
+    return min_relvel;
+}
+
+// the solve_manifolds lambda, restitution_solver.cpp:146-310: rows of all points of the group from the CURRENT velocities,
+// a few Gauss-Seidel sweeps (normal row, then its friction pair), then the delta velocities are applied at once
+void World::solve_restitution_group(const std::vector<uint32_t> &group) {
+    struct GRow { Row r; FrictionPair f; uint32_t a, b; scalar inv_mA, inv_mB; mat3 inv_IA, inv_IB; };
+    std::vector<GRow> rows;
+    for (uint32_t mi : group) {
+        const Manifold &m = manifolds[mi];
+        const Body &A = bodies[m.a], &B = bodies[m.b];
+        SBody sA = solver_body(A), sB = solver_body(B);
+        for (uint32_t p = 0; p < m.num; ++p) {
+            Point cp = m.pt[p];
+            cp.imp_n = 0; cp.imp_t[0] = cp.imp_t[1] = 0; cp.distance = 0;             // impulse 0, constraint_row_options{}.error == 0
+            GRow g{}; g.a = m.a; g.b = m.b; g.inv_mA = sA.inv_m; g.inv_mB = sB.inv_m; g.inv_IA = sA.inv_I; g.inv_IB = sB.inv_I;
+            scalar error;
+            prepare_contact(cp, dt, A.pos, A.orn, B.pos, B.orn, sA.v, sA.w, sA.inv_m, sA.inv_I, sB.v, sB.w, sB.inv_m, sB.inv_I, g.r, error, g.f);
+            prepare_row(g.r, sA.inv_m, sA.inv_I, sB.inv_m, sB.inv_I, 0, scalar(0.2), cp.restitution, sA.v, sA.w, sB.v, sB.w);
+            rows.push_back(g);
+        }
+    }
+    vec3 dummy_dv{0, 0, 0}, dummy_dw{0, 0, 0};                                          // non-procedural bodies (restitution_solver.cpp:85-86)
+    auto DV = [&](uint32_t i) -> vec3 & { return bodies[i].awake() ? bodies[i].dv : dummy_dv; };
+    auto DW = [&](uint32_t i) -> vec3 & { return bodies[i].awake() ? bodies[i].dw : dummy_dw; };
+    for (int it = 0; it < individual_restitution_iters; ++it) {
+        for (GRow &g : rows) {
+            vec3 &dvA = DV(g.a), &dwA = DW(g.a), &dvB = DV(g.b), &dwB = DW(g.b);
+            scalar delta = solve_row(g.r, dvA, dwA, dvB, dwB);
+            dvA += g.inv_mA * g.r.J[0] * delta; dwA += g.inv_IA * g.r.J[1] * delta;     // apply_row_impulse, constraint_row.cpp:24-32
+            dvB += g.inv_mB * g.r.J[2] * delta; dwB += g.inv_IB * g.r.J[3] * delta;
+            solve_friction(g.f, g.r.impulse, g.inv_mA, g.inv_IA, g.inv_mB, g.inv_IB, dvA, dwA, dvB, dwB);
+        }
+    }
+    for (uint32_t mi : group) {
+        for (uint32_t i : {manifolds[mi].a, manifolds[mi].b}) {
+            Body &b = bodies[i];
+            if (b.kind == BK_STATIC) continue;
+            b.linvel += b.dv; b.angvel += b.dw;
+            b.dv = b.dw = vec3{0, 0, 0};
+        }
+    }
+}
+
+// solve_restitution_iteration, restitution_solver.cpp:88-384, for one island; `tagged` = its manifolds with
+// contact_manifold_with_restitution in island.edges order
+bool World::restitution_iteration(const std::vector<uint32_t> &tagged) {
+    scalar min_relvel = SCALAR_MAX;
+    int64_t fastest = -1;
+    for (uint32_t mi : tagged) {
+        scalar local = manifold_min_relvel(manifolds[mi]);
+        if (local < min_relvel) { min_relvel = local; fastest = mi; }
+    }
+    if (fastest < 0) return true;
+    const scalar relvel_threshold = scalar(-0.005);
+    if (min_relvel > relvel_threshold) return true;
+    const Manifold &fm = manifolds[size_t(fastest)];
+    auto connecting = [&](uint32_t i) { return bodies[i].kind == BK_DYNAMIC; };
+    scalar speedA = 0, speedB = 0;
+    if (bodies[fm.a].kind != BK_STATIC) speedA = length_sqr(bodies[fm.a].linvel);
+    if (bodies[fm.b].kind != BK_STATIC) speedB = length_sqr(bodies[fm.b].linvel);
+    uint32_t start;
+    if (speedA > speedB) start = connecting(fm.a) ? fm.a : fm.b;
+    else start = connecting(fm.b) ? fm.b : fm.a;
+    // entity_graph::traverse, core/entity_graph.hpp:357-426: breadth first over the adjacency lists
+    const uint32_t nb = uint32_t(bodies.size());
+    std::vector<uint8_t> visited(nb, 0);
+    std::vector<uint32_t> to_visit{start}, group;
+    while (!to_visit.empty()) {
+        const uint32_t node = to_visit.back();
+        to_visit.pop_back();
+        visited[node] = 1;
+        if (!connecting(node)) continue;
+        const uint32_t a0 = adj_off[node], a1 = adj_off[node + 1];
+        group.clear();
+        for (uint32_t k = a0; k < a1; ++k) {                       // visit_edges: the manifolds of this node, fast enough
+            if (!(adj_nbr[k] >> 31)) continue;
+            auto it = manifold_map.find(key(node, adj_nbr[k] & 0x7FFFFFFFu));
+            if (it == manifold_map.end()) continue;
+            if (manifold_min_relvel(manifolds[it->second]) < relvel_threshold) group.push_back(it->second);
+        }
+        if (!group.empty()) solve_restitution_group(group);
+        for (uint32_t k = a0; k < a1; ++k) {
+            const uint32_t nbr = adj_nbr[k] & 0x7FFFFFFFu;
+            if (!visited[nbr]) { to_visit.insert(to_visit.begin(), nbr); visited[nbr] = 1; }
+        }
+    }
+    return false;
+}
+
+// solve_restitution, restitution_solver.cpp:386-408; called first thing in solver::update, before gravity (solver.cpp:397)
+void World::solve_restitution() {
+    const uint32_t nb = uint32_t(bodies.size());
+    if (!graph_order_set) {                                        // no graph supplied: ascending neighbour ids, manifold order
+        std::vector<std::vector<uint32_t>> nbrs(nb);
+        for (const Manifold &m : manifolds) { nbrs[m.a].push_back(m.b | 0x80000000u); nbrs[m.b].push_back(m.a | 0x80000000u); }
+        for (const Hinge &h : hinges) if (h.a != h.b) { nbrs[h.a].push_back(h.b); nbrs[h.b].push_back(h.a); }
+        adj_off.assign(nb + 1, 0); adj_nbr.clear();
+        for (uint32_t i = 0; i < nb; ++i) {
+            auto &v = nbrs[i];
+            std::sort(v.begin(), v.end(), [](uint32_t x, uint32_t y) { return (x & 0x7FFFFFFFu) < (y & 0x7FFFFFFFu) || ((x & 0x7FFFFFFFu) == (y & 0x7FFFFFFFu) && x > y); });
+            v.erase(std::unique(v.begin(), v.end(), [](uint32_t x, uint32_t y) { return (x & 0x7FFFFFFFu) == (y & 0x7FFFFFFFu); }), v.end());
+            adj_nbr.insert(adj_nbr.end(), v.begin(), v.end());
+            adj_off[i + 1] = uint32_t(adj_nbr.size());
+        }
+        rest_edge_order.clear();
+        for (const Manifold &m : manifolds) rest_edge_order.push_back(key(m.a, m.b));
+    }
+    // the tagged manifolds per island (make_contact_manifold, constraint_util.cpp:86-101: mixed restitution > EPSILON)
+    std::unordered_map<uint32_t, std::vector<uint32_t>> per_island;
+    std::vector<uint32_t> labels;
+    for (uint64_t k : rest_edge_order) {
+        auto it = manifold_map.find(k);
+        if (it == manifold_map.end()) continue;
+        const Manifold &m = manifolds[it->second];
+        if (!(material_mix_restitution(bodies[m.a].restitution, bodies[m.b].restitution) > EPS)) continue;
+        if (!bodies[m.a].awake() && !bodies[m.b].awake()) continue;             // island_view(exclude_sleeping_disabled)
+        const uint32_t lab = bodies[m.a].awake() ? island[m.a] : island[m.b];
+        auto &v = per_island[lab];
+        if (v.empty()) labels.push_back(lab);
+        v.push_back(it->second);
+    }
+    for (int i = 0; i < restitution_iters; ++i) {
+        bool all_solved = true;
+        for (uint32_t lab : labels) all_solved &= restitution_iteration(per_island[lab]);
+        if (all_solved) break;
+    }
+    graph_order_set = false;                                       // the order belongs to one step
+}
+
 void World::solve() {
     const uint32_t nb = uint32_t(bodies.size());
     if (island.size() != bodies.size()) islands();
+    if (restitution_iters > 0) solve_restitution();               // solver.cpp:397
     // apply_gravity, sys/apply_gravity.hpp:12-17
     for (Body &b : bodies) if (b.awake()) b.linvel += b.gravity * dt;
 
@@ -756,7 +903,8 @@ void World::solve() {
             SFric f{}; f.normal_row = uint32_t(rows.size());
             scalar error;
             prepare_contact(cp, dt, A.pos, A.orn, B.pos, B.orn, sA.v, sA.w, sA.inv_m, sA.inv_I, sB.v, sB.w, sB.inv_m, sB.inv_I, sr.r, error, f);
-            prepare_row(sr.r, sA.inv_m, sA.inv_I, sB.inv_m, sB.inv_I, error, scalar(0.2), cp.restitution, sA.v, sA.w, sB.v, sB.w);
+            // solver.cpp:217-236: the rows carry no restitution when the restitution solver runs
+            prepare_row(sr.r, sA.inv_m, sA.inv_I, sB.inv_m, sB.inv_I, error, scalar(0.2), restitution_iters > 0 ? scalar(0) : cp.restitution, sA.v, sA.w, sB.v, sB.w);
             rows.push_back(sr); fric.push_back(f);
         }
         (void)first_contact_row;

@@ -4,9 +4,10 @@
 //   src/edyn/collision/broadphase.cpp:119-195, src/edyn/collision/narrowphase.cpp:21-40,
 //   include/edyn/util/collision_util.hpp:105-276, src/edyn/dynamics/solver.cpp:387-468,
 //   src/edyn/dynamics/island_solver.cpp:76-111,263-376,521-543.
-// Not restated (out of scope): restitution_solver (run both sides with
-// restitution iterations = 0 so restitution goes through the row rhs), sleeping (benchmarks set
-// sleeping_disabled), center_of_mass/origin offsets, contact_extras.
+// Also restated: island sleeping (island_manager.cpp:541-623) and the restitution solver
+// (dynamics/restitution_solver.cpp:86-408; off unless restitution_iters > 0 -- the device path and the benchmark
+// configurations run with restitution iterations = 0, restitution through the row rhs).
+// Not restated (out of scope): center_of_mass/origin offsets, contact_extras.
 // PINNED: leaf functions against the reference's object code (tests/test_oracle_fixtures.py), whole steps bit for bit
 // against the reference's real stepper_sequential (oracle/_ref/libedyn_stepper.so, tests/test_ref_stepper.py and
 // tests/golden/whole_step.npz) with the reference's row order replayed through set_point_order().
@@ -87,6 +88,20 @@ struct World {
     std::vector<uint32_t> point_order;                      // optional, one per entry of manifold_order: which point of the manifold's list
                                                             // the row is (0xFFFFFFFF = all its points, in list order)
     int threads = 1;                                        // island-parallel solve (run_island_solver_seq_mt analogue)
+    // Restitution solver (dynamics/restitution_solver.cpp:86-408; settings.hpp:29-30: 8 iterations by default in the
+    // reference, 0 here = restitution goes through the row rhs).  It walks the entity graph breadth first, so its result
+    // depends on the graph's adjacency order and on island.edges order; both are supplied by the caller
+    // (ora_set_graph_order): adj_off / adj_nbr = per body the neighbours in adjacency-list order, bit 31 set when the
+    // adjacency holds a contact manifold; rest_edge_order = the manifolds tagged contact_manifold_with_restitution in
+    // island.edges iteration order (pair keys).  Without them: ascending neighbour id / manifold order.
+    int restitution_iters = 0, individual_restitution_iters = 3;
+    std::vector<uint32_t> adj_off, adj_nbr;
+    std::vector<uint64_t> rest_edge_order;
+    bool graph_order_set = false;
+    void solve_restitution();
+    scalar manifold_min_relvel(const Manifold &m) const;
+    void solve_restitution_group(const std::vector<uint32_t> &group);
+    bool restitution_iteration(const std::vector<uint32_t> &tagged);
 
     static uint64_t key(uint32_t a, uint32_t b) { return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a; }
 

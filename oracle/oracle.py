@@ -429,6 +429,15 @@ class OracleWorld:
         (position_solver.hpp:26-32); only matters for static bodies whose quaternion is an ulp off unit length."""
         self.l.ora_set_position_renormalize_all(C.c_int(1 if on else 0))
 
+    def set_restitution_iterations(self, iterations, individual=3):
+        """settings.num_restitution_iterations / num_individual_restitution_iterations (reference defaults 8 / 3; 0 = the
+        restitution solver is off and restitution goes through the row rhs)."""
+        self.l.ora_set_restitution_iterations(self.h, C.c_int(iterations), C.c_int(individual))
+
+    def set_graph_order(self, adj_off, adj_nbr, tagged_pairs):
+        off, nbr, tag = _arr(adj_off, _u), _arr(adj_nbr, _u), _arr(tagged_pairs, _u, (-1, 2))
+        self.l.ora_set_graph_order(self.h, _ptr(off), _ptr(nbr), C.c_uint32(len(tag)), _ptr(tag))
+
     def clear_order(self):
         self.l.ora_clear_order(self.h)
 
@@ -510,6 +519,24 @@ class RefWorld:
         pos, orn, lv, av, bb = np.zeros((n, 3), _f), np.zeros((n, 4), _f), np.zeros((n, 3), _f), np.zeros((n, 3), _f), np.zeros((n, 6), _f)
         self.l.refs_get_state(self.h, _ptr(pos), _ptr(orn), _ptr(lv), _ptr(av), _ptr(bb))
         return dict(pos=pos, orn=orn, linvel=lv, angvel=av, aabb=bb)
+
+    def step_begin(self):
+        """First half of step_simulation: broadphase, narrowphase, island manager (see refs_step_begin)."""
+        self.l.refs_step_begin(self.h)
+
+    def step_end(self):
+        self.l.refs_step_end(self.h)
+
+    def graph_order(self, max_adjacencies=None, max_tagged=None):
+        """(adj_off, adj_nbr, tagged_pairs) as the restitution solver will walk them in the coming solver.update."""
+        n = self.num_bodies
+        cap_a = max_adjacencies or max(64, 32 * n)
+        cap_t = max_tagged or max(64, 16 * n)
+        off, nbr, tag, nt = np.zeros(n + 1, _u), np.zeros(cap_a, _u), np.zeros((cap_t, 2), _u), C.c_uint32(0)
+        rc = self.l.refs_get_graph_order(self.h, _ptr(off), C.c_uint32(cap_a), _ptr(nbr), C.c_uint32(cap_t), _ptr(tag), C.byref(nt))
+        if rc:
+            raise RuntimeError("refs_get_graph_order: capacity")
+        return off, nbr[:off[n]].copy(), tag[:nt.value].copy()
 
     def sleeping(self):
         out = np.zeros(self.num_bodies, _u)

@@ -3,6 +3,12 @@
 // under /root/reference -- behind a small C interface, built against oracle/entt_lite (a from-scratch stand-in for the
 // EnTT 3.15 dependency, which this image does not have).  Used as the whole-step oracle for oracle/ (tests/) and as the
 // CPU baseline "reference" arm of bench.py.  Nothing under edyn_b200/ links or loads it.
+// The restitution solver's result depends on orders inside the entity graph at the moment solver::update starts, so
+// refs_step_begin / refs_step_end run stepper_sequential::step_simulation (stepper_sequential.cpp:121-147) in two halves;
+// that needs its three members, hence the access hack on this ONE header (object layout is unaffected).
+#define private public
+#include <edyn/simulation/stepper_sequential.hpp>
+#undef private
 #include <edyn/edyn.hpp>
 #include <edyn/util/rigidbody.hpp>
 #include <edyn/util/constraint_util.hpp>
@@ -18,6 +24,10 @@
 #include <edyn/comp/aabb.hpp>
 #include <edyn/comp/inertia.hpp>
 #include <edyn/comp/island.hpp>
+#include <edyn/comp/graph_node.hpp>
+#include <edyn/core/entity_graph.hpp>
+#include <edyn/collision/broadphase.hpp>
+#include <edyn/collision/narrowphase.hpp>
 #include <edyn/comp/tag.hpp>
 #include <edyn/context/settings.hpp>
 #include <edyn/dynamics/island_constraint_entities.hpp>
@@ -133,6 +143,67 @@ REFS_API void refs_step(void *h, uint32_t n) {
     // step j carries the time stepper_sequential::update would give it: sim_time + fixed_dt * i, i.e. j * fixed_dt counted
     // from the attach time 0 (stepper_sequential.cpp:71-75); only island sleeping looks at it (island_manager.cpp:605-623)
     for (uint32_t i = 0; i < n; ++i) { w->time = double(w->steps++) * w->dt; edyn::step_simulation(w->registry, w->time); }
+}
+// step_simulation in two halves: everything up to and including island_manager.update, then solver.update and the callbacks
+REFS_API void refs_step_begin(void *h) {
+    auto *w = static_cast<World *>(h);
+    auto &r = w->registry;
+    auto &stepper = r.ctx().get<edyn::stepper_sequential>();
+    w->time = double(w->steps++) * w->dt;
+    stepper.m_last_time = w->time;
+    auto &settings = r.ctx().get<edyn::settings>();
+    if (settings.pre_step_callback) (*settings.pre_step_callback)(r);
+    stepper.m_poly_initializer.init_new_shapes();
+    r.ctx().get<edyn::broadphase>().update(stepper.m_multithreaded);
+    r.ctx().get<edyn::narrowphase>().update(stepper.m_multithreaded);
+    stepper.m_island_manager.update(stepper.m_last_time);
+}
+REFS_API void refs_step_end(void *h) {
+    auto *w = static_cast<World *>(h);
+    auto &r = w->registry;
+    auto &stepper = r.ctx().get<edyn::stepper_sequential>();
+    auto &settings = r.ctx().get<edyn::settings>();
+    stepper.m_solver.update(stepper.m_multithreaded);
+    if (settings.clear_actions_func) (*settings.clear_actions_func)(r);
+    if (settings.post_step_callback) (*settings.post_step_callback)(r);
+}
+// The orders the restitution solver walks (restitution_solver.cpp:108-124, :352-381): adj_off / adj_nbr = per body its
+// neighbours in the entity graph's adjacency-list order (bit 31: the adjacency holds a contact manifold); tagged = the
+// manifolds with contact_manifold_with_restitution in island.edges iteration order, island after island, as ordered pairs.
+REFS_API int refs_get_graph_order(void *h, uint32_t *adj_off, uint32_t cap_adj, uint32_t *adj_nbr, uint32_t cap_tagged, uint32_t *tagged_pairs, uint32_t *n_tagged) {
+    auto *w = static_cast<World *>(h);
+    auto &r = w->registry;
+    auto &graph = r.ctx().get<edyn::entity_graph>();
+    std::vector<uint32_t> body_of;
+    for (size_t i = 0; i < w->bodies.size(); ++i) { const auto k = entt::to_entity(w->bodies[i]); if (k >= body_of.size()) body_of.resize(k + 1, 0xFFFFFFFFu); body_of[k] = uint32_t(i); }
+    uint32_t n = 0;
+    for (size_t i = 0; i < w->bodies.size(); ++i) {
+        adj_off[i] = n;
+        if (!r.valid(w->bodies[i])) continue;
+        const auto node0 = r.get<edyn::graph_node>(w->bodies[i]).node_index;
+        bool overflow = false;
+        graph.visit_neighbors(node0, [&](entt::entity other) {
+            if (n >= cap_adj) { overflow = true; return; }
+            const auto node1 = r.get<edyn::graph_node>(other).node_index;
+            bool has_manifold = false;
+            graph.visit_edges(node0, node1, [&](auto edge_index) { if (r.all_of<edyn::contact_manifold>(graph.edge_entity(edge_index))) has_manifold = true; });
+            adj_nbr[n++] = body_of[entt::to_entity(other)] | (has_manifold ? 0x80000000u : 0u);
+        });
+        if (overflow) return -1;
+    }
+    adj_off[w->bodies.size()] = n;
+    uint32_t t = 0;
+    for (auto [island_entity, island] : r.view<edyn::island>().each()) {
+        for (auto e : island.edges) {
+            if (!r.all_of<edyn::contact_manifold_with_restitution>(e)) continue;
+            if (t >= cap_tagged) return -1;
+            const auto &m = r.get<edyn::contact_manifold>(e);
+            tagged_pairs[2 * t] = body_of[entt::to_entity(m.body[0])]; tagged_pairs[2 * t + 1] = body_of[entt::to_entity(m.body[1])];
+            ++t;
+        }
+    }
+    *n_tagged = t;
+    return 0;
 }
 REFS_API uint32_t refs_num_bodies(void *h) { return uint32_t(static_cast<World *>(h)->bodies.size()); }
 REFS_API void refs_get_state(void *h, float *pos, float *orn, float *lv, float *av, float *aabb) {
