@@ -242,6 +242,7 @@ void ora_set_graph_order(void *h, const uint32_t *adj_off, const uint32_t *adj_n
     for (uint32_t i = 0; i < n_tagged; ++i) w.rest_edge_order[i] = World::key(tagged_pairs[2 * i], tagged_pairs[2 * i + 1]);
     w.graph_order_set = true;
 }
+void ora_set_pool_order(void *h, int on) { static_cast<World *>(h)->emulate_pool_order = on != 0; }
 void ora_clear_order(void *h) { static_cast<World *>(h)->use_order = false; static_cast<World *>(h)->point_order.clear(); }
 
 int ora_should_collide(void *h, uint32_t a, uint32_t b) { return static_cast<World *>(h)->should_collide(a, b) ? 1 : 0; }

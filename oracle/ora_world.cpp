@@ -102,6 +102,7 @@ uint32_t World::add_body(const Body &b) {
     uint32_t i = uint32_t(bodies.size() - 1);
     bodies[i].dv = bodies[i].dw = vec3{0, 0, 0};
     refresh_body(i);
+    if (bodies[i].kind == BK_DYNAMIC) proc_pool.push_back(i);
     return i;
 }
 
@@ -142,6 +143,7 @@ static inline uint64_t cell_key(int64_t x, int64_t y, int64_t z) {
 // loses a body is parked on the dead slot (neither end procedural: it is never prepared or solved again).
 void World::remove_body(uint32_t i) {
     Body &b = bodies[i];
+    if (auto it = std::find(proc_pool.begin(), proc_pool.end(), i); it != proc_pool.end()) { *it = proc_pool.back(); proc_pool.pop_back(); }   // swap and pop
     b.kind = BK_STATIC; b.sh.kind = SH_NONE;
     b.linvel = b.angvel = b.dv = b.dw = vec3{0, 0, 0};
     b.inv_m = 0; b.inv_I = b.inv_IW = mat3_zero();
@@ -256,14 +258,16 @@ void World::broadphase() {
             return x < y;
         });
     });
-    for (uint32_t ii = n; ii-- > 0;) {
+    auto create_for = [&](uint32_t ii) {
         for (uint32_t j : hits[ii]) {                   // make_contact_manifold, util/constraint_util.cpp:67-102
             if (manifold_map.count(key(ii, j))) continue;        // made a moment ago by the partner's (earlier) query
             Manifold m{}; m.a = ii; m.b = j; m.num = 0;
             manifold_map[key(ii, j)] = uint32_t(manifolds.size());
             manifolds.push_back(m);
         }
-    }
+    };
+    if (emulate_pool_order) { for (size_t k = proc_pool.size(); k-- > 0;) create_for(proc_pool[k]); }
+    else for (uint32_t ii = n; ii-- > 0;) create_for(ii);
 }
 
 // ------------------------------------------------------------------ narrowphase

@@ -88,6 +88,13 @@ struct World {
     std::vector<uint32_t> point_order;                      // optional, one per entry of manifold_order: which point of the manifold's list
                                                             // the row is (0xFFFFFFFF = all its points, in list order)
     int threads = 1;                                        // island-parallel solve (run_island_solver_seq_mt analogue)
+    // Which body of a new pair becomes body[0] = which of the two issues its broadphase query first = iteration order of
+    // view<AABB, procedural_tag> (broadphase.cpp:183), i.e. of the procedural_tag pool: newest first.  Without removals
+    // that is descending body index (default, and what the device does).  registry.destroy(body) is a swap-and-pop in
+    // the pool -- the newest body takes the removed one's place in the iteration -- which proc_pool reproduces when
+    // emulate_pool_order is on (comparisons with the real stepper after bodies were destroyed).
+    bool emulate_pool_order = false;
+    std::vector<uint32_t> proc_pool;                        // packed array of the procedural_tag pool
     // Restitution solver (dynamics/restitution_solver.cpp:86-408; settings.hpp:29-30: 8 iterations by default in the
     // reference, 0 here = restitution goes through the row rhs).  It walks the entity graph breadth first, so its result
     // depends on the graph's adjacency order and on island.edges order; both are supplied by the caller

@@ -429,6 +429,11 @@ class OracleWorld:
         (position_solver.hpp:26-32); only matters for static bodies whose quaternion is an ulp off unit length."""
         self.l.ora_set_position_renormalize_all(C.c_int(1 if on else 0))
 
+    def set_pool_order(self, on):
+        """Broadphase queries in the procedural_tag pool's order, swap-and-pop on removal included (which body of a new
+        pair is body[0] after bodies were destroyed); off = descending index, the device's rule."""
+        self.l.ora_set_pool_order(self.h, C.c_int(1 if on else 0))
+
     def set_restitution_iterations(self, iterations, individual=3):
         """settings.num_restitution_iterations / num_individual_restitution_iterations (reference defaults 8 / 3; 0 = the
         restitution solver is off and restitution goes through the row rhs)."""
@@ -519,6 +524,16 @@ class RefWorld:
         pos, orn, lv, av, bb = np.zeros((n, 3), _f), np.zeros((n, 4), _f), np.zeros((n, 3), _f), np.zeros((n, 3), _f), np.zeros((n, 6), _f)
         self.l.refs_get_state(self.h, _ptr(pos), _ptr(orn), _ptr(lv), _ptr(av), _ptr(bb))
         return dict(pos=pos, orn=orn, linvel=lv, angvel=av, aabb=bb)
+
+    def destroy_body(self, body):
+        self.l.refs_destroy_body(self.h, C.c_uint32(body))
+
+    def remove_exclusion(self, a, b):
+        self.l.refs_remove_exclusion(self.h, C.c_uint32(a), C.c_uint32(b))
+
+    def set_velocity(self, body, linvel, angvel):
+        lv, av = _arr(linvel, _f), _arr(angvel, _f)
+        self.l.refs_set_velocity(self.h, C.c_uint32(body), _ptr(lv), _ptr(av))
 
     def step_begin(self):
         """First half of step_simulation: broadphase, narrowphase, island manager (see refs_step_begin)."""

@@ -211,6 +211,12 @@ REFS_API void refs_get_state(void *h, float *pos, float *orn, float *lv, float *
     auto &r = w->registry;
     for (size_t i = 0; i < w->bodies.size(); ++i) {
         const auto e = w->bodies[i];
+        if (!r.valid(e)) {                                  // destroyed by refs_destroy_body: the slot reads as zeros
+            for (int k = 0; k < 3; ++k) pos[3 * i + k] = lv[3 * i + k] = av[3 * i + k] = 0;
+            for (int k = 0; k < 4; ++k) orn[4 * i + k] = 0;
+            if (aabb) for (int k = 0; k < 6; ++k) aabb[6 * i + k] = 0;
+            continue;
+        }
         const auto &p = r.get<edyn::position>(e); const auto &q = r.get<edyn::orientation>(e);
         pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
         orn[4 * i] = q.x; orn[4 * i + 1] = q.y; orn[4 * i + 2] = q.z; orn[4 * i + 3] = q.w;
@@ -255,6 +261,20 @@ REFS_API uint32_t refs_get_contacts(void *h, uint32_t capacity, uint32_t *pairs,
         ++n;
     }
     return n;
+}
+// ---- what user code does between steps (plain registry / public API calls)
+REFS_API void refs_destroy_body(void *h, uint32_t body) {                      // registry.destroy(entity)
+    auto *w = static_cast<World *>(h);
+    if (w->registry.valid(w->bodies[body])) w->registry.destroy(w->bodies[body]);
+}
+REFS_API void refs_remove_exclusion(void *h, uint32_t a, uint32_t b) {
+    auto *w = static_cast<World *>(h);
+    edyn::remove_collision_exclusion(w->registry, w->bodies[a], w->bodies[b]);
+}
+REFS_API void refs_set_velocity(void *h, uint32_t body, const float *lv, const float *av) {
+    auto *w = static_cast<World *>(h);
+    w->registry.patch<edyn::linvel>(w->bodies[body], [&](edyn::linvel &v) { v.x = lv[0]; v.y = lv[1]; v.z = lv[2]; });
+    w->registry.patch<edyn::angvel>(w->bodies[body], [&](edyn::angvel &v) { v.x = av[0]; v.y = av[1]; v.z = av[2]; });
 }
 // 1 per body that carries sleeping_tag (island_manager::put_to_sleep, island_manager.cpp:541-566)
 REFS_API void refs_get_sleeping(void *h, uint32_t *asleep) {
