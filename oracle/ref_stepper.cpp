@@ -269,6 +269,7 @@ REFS_API void refs_destroy_body(void *h, uint32_t body) {                      /
 }
 REFS_API void refs_remove_exclusion(void *h, uint32_t a, uint32_t b) {
     auto *w = static_cast<World *>(h);
+    if (!w->registry.valid(w->bodies[a]) || !w->registry.valid(w->bodies[b])) return;      // one of them was destroyed
     edyn::remove_collision_exclusion(w->registry, w->bodies[a], w->bodies[b]);
 }
 REFS_API void refs_set_velocity(void *h, uint32_t body, const float *lv, const float *av) {

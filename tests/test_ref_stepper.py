@@ -363,7 +363,8 @@ def _lockstep_with_mutations(O, scene, steps, seed):
                 r.destroy_body(b); o.remove_bodies([b]); alive[b] = False
             elif what == 1 and excluded:
                 a, b = excluded.pop()
-                r.remove_exclusion(a, b); o.remove_exclusions([a], [b])
+                if alive[a] and alive[b]:
+                    r.remove_exclusion(a, b); o.remove_exclusions([a], [b])
             else:
                 b = int(rng.choice(np.where(alive[:n])[0]))
                 lv, av = rng.uniform(-3, 3, 3).astype(np.float32), rng.uniform(-3, 3, 3).astype(np.float32)
