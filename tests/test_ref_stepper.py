@@ -343,7 +343,9 @@ def test_wide_random_scenes_lockstep_with_real_stepper(refstep, E, seeds):
 
 
 def _lockstep_with_mutations(O, scene, steps, seed):
-    """Every 17th step user code interferes: registry.destroy(body), remove_collision_exclusion, or a patched velocity."""
+    from edyn_b200 import rigidbody as E_rigidbody
+    """Every 17th step user code interferes: registry.destroy(body), remove_collision_exclusion, a patched velocity, or
+    make_rigidbody of a new body (which recycles the identifier of a destroyed entity)."""
     rng = np.random.default_rng(seed)
     st = scene["settings"]
     r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
@@ -351,22 +353,31 @@ def _lockstep_with_mutations(O, scene, steps, seed):
     G.populate(r, scene); G.populate(o, scene)
     o.set_position_type_order(contacts_first=True)
     o.set_pool_order(True)               # destroying a body reorders the pool the broadphase iterates (swap and pop)
-    kind, n = np.asarray(scene["bodies"]["kind"]), scene["dynamic"]
+    kind = np.asarray(scene["bodies"]["kind"]).copy()
     alive = np.ones(len(kind), bool)
     excluded = list(zip(*[x.tolist() for x in scene["exclusions"]])) if scene["exclusions"] is not None else []
     events = 0
     for s in range(steps):
         if s and s % 17 == 0:
-            what = rng.integers(3)
-            if what == 0 and alive[:n].sum() > 4:
-                b = int(rng.choice(np.where(alive[:n])[0]))
+            what = rng.integers(4)
+            movable = np.where(alive & (kind == 0))[0]
+            if what == 0 and len(movable) > 4:
+                b = int(rng.choice(movable))
                 r.destroy_body(b); o.remove_bodies([b]); alive[b] = False
+            elif what == 3:
+                R = E_rigidbody
+                d = R.RigidBodyDef(position=tuple(rng.uniform([-1, 2, -1], [1, 4, 1])), mass=float(rng.choice([0.5, 1.0, 2.0])),
+                                   linvel=tuple(rng.uniform(-2, 2, 3)),
+                                   shape=[R.sphere_shape(0.3), R.box_shape((0.3, 0.2, 0.25)), R.capsule_shape(0.15, 0.3, 1)][rng.integers(3)])
+                soa = R.bodies_soa([d])
+                r.add_bodies(soa); o.add_bodies(soa)
+                kind, alive = np.append(kind, 0), np.append(alive, True)
             elif what == 1 and excluded:
                 a, b = excluded.pop()
                 if alive[a] and alive[b]:
                     r.remove_exclusion(a, b); o.remove_exclusions([a], [b])
             else:
-                b = int(rng.choice(np.where(alive[:n])[0]))
+                b = int(rng.choice(movable))
                 lv, av = rng.uniform(-3, 3, 3).astype(np.float32), rng.uniform(-3, 3, 3).astype(np.float32)
                 r.set_velocity(b, lv, av)
                 x = o.state()
