@@ -154,6 +154,21 @@ def test_registry_through_the_binding_equals_arrays_through_the_abi(mock, O, E, 
     w.close()
 
 
+def test_random_registries_through_the_binding(mock, O, E):
+    """The staging on broad content: random scenes (all shape kinds on dynamic, kinematic and static bodies, filters, bodies
+    with their own gravity, materials, tilted planes, hinges with random axes, exclusions) built in a real registry and
+    staged by stepper_b2d == the same arrays handed to the ABI directly, bit for bit."""
+    from tests.test_ref_stepper import random_scene_wide
+    for seed in range(12):
+        scene = random_scene_wide(E, O, seed)
+        w = EdynB2dWorld(O, mock, scene, attach_first=bool(seed & 1))
+        o = _plain_oracle(O, scene)
+        for s in range(6):
+            w.step(10); o.step(10)
+            _assert_same(w.state(), o.state(), f"seed {seed} step {10 * s + 9}")
+        w.close()
+
+
 def test_binding_follows_the_real_stepper(mock, O, E):
     """Same user code, two steppers: the reference's stepper_sequential and stepper_b2d (over the mock).  Identical while
     nothing touches (no row order involved), and the same resting pile afterwards."""
