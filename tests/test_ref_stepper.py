@@ -439,6 +439,28 @@ def test_restitution_solver_matches_real_stepper(refstep, E):
     assert np.abs(ends[0] - ends[1]).max() > 0.1
 
 
+def test_python_make_rigidbody_mirror_matches_real_make_rigidbody(refstep, E):
+    """edyn_b200.rigidbody (what bench.py and the Python adapter stage) vs util/rigidbody.cpp:47-185 on 600 random bodies:
+    inverse inertia of spheres / boxes / capsules (all three axes) identical to the last bit.  Masses are drawn so that
+    1 / (1 / m) == m in float, because the harness hands the reference 1 / inv_mass."""
+    O, R = refstep, E.rigidbody
+    rng, f = np.random.default_rng(7), np.float32
+    defs = []
+    while len(defs) < 600:
+        m = f(rng.uniform(0.05, 50))
+        if f(1) / (f(1) / m) != m:
+            continue
+        shape = [R.sphere_shape(float(rng.uniform(0.05, 2))), R.box_shape(tuple(rng.uniform(0.05, 2, 3))),
+                 R.capsule_shape(float(rng.uniform(0.05, 1)), float(rng.uniform(0.05, 2)), int(rng.integers(3)))][rng.integers(3)]
+        defs.append(R.RigidBodyDef(position=(10.0 * len(defs), 5, 0), mass=float(m), shape=shape))
+    soa = R.bodies_soa(defs)
+    r = O.RefWorld()
+    r.add_bodies(soa)
+    assert np.array_equal(r.inertia_inv(), soa["inv_inertia"].reshape(-1, 9))
+    r.step(1)
+    assert np.array_equal(r.state()["aabb"][:, :3] <= r.state()["pos"], np.ones((600, 3), bool))
+
+
 def test_real_stepper_multithreaded_matches_sequential(refstep, E):
     """execution_mode::sequential_multithreaded (what bench.py's reference arm times) gives the sequential mode's results."""
     O = refstep
