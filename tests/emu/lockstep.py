@@ -1,0 +1,78 @@
+"""TEST INFRASTRUCTURE.  The library's CUDA kernels, executed by the CPU emulation (tests/emu), in lock step with the
+oracle through the normal Python adapter and C ABI -- the same comparison tests/test_gpu_parity.py makes on a B200: ordered
+pair lists identical, post-solve state within 1e-5 (here: identical, glibc's sinf / cosf on both sides) with the oracle
+replaying the device's Gauss-Seidel order, manifolds and joint impulses re-synchronised every step.
+
+    python tests/emu/lockstep.py fixed|narrow|wide FIRST LAST [--tiles 0|1] [--steps N]     -> one JSON line
+Runs in its own process because B2D_LIB has to be set before edyn_b200 is imported."""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def lockstep(E, O, scene, steps):
+    import numpy as np
+    w = E.scenes.build_world(scene)
+    st = scene["settings"]
+    o = O.OracleWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    o.add_bodies(scene["bodies"])
+    if scene["hinges"]:
+        h = scene["hinges"]
+        o.add_hinges(h["a"], h["b"], h["pivot_a"], h["pivot_b"], h["axis_a"], h["axis_b"])
+    if scene["exclusions"] is not None:
+        o.add_exclusions(*scene["exclusions"])
+    worst = 0.0
+    for s in range(steps):
+        w.step(1)
+        hi, pr = w.solver_order()
+        o.run_phases(O.PH_BROAD | O.PH_NARROW | O.PH_ISLANDS)
+        o.set_order(hi, pr)
+        o.run_phases(O.PH_SOLVE)
+        g, c = w.download_state(), o.state()
+        if {tuple(p) for p in w.pairs().tolist()} != {tuple(p) for p in o.pairs().tolist()}:
+            return dict(ok=False, step=s, why="ordered broadphase pair lists differ")
+        if not np.array_equal(w.islands(), o.islands()):
+            return dict(ok=False, step=s, why="island labels differ")
+        err = max(float(np.abs(g[k] - c[k]).max()) for k in ("pos", "orn", "linvel", "angvel", "aabb"))
+        worst = max(worst, err)
+        if err > 1e-5:
+            return dict(ok=False, step=s, why=f"state differs by {err:.3e}")
+        o.set_state(g["pos"], g["orn"], g["linvel"], g["angvel"])
+        gc = w.contacts()
+        o.set_contacts(gc["pairs"], gc["num"], gc["pts"], gc["att"], gc["lifetime"])
+        if scene["hinges"]:
+            o.set_hinge_impulses(w.hinge_impulses())
+    stats = w.stats()
+    w.close()
+    return dict(ok=stats["error_flags"] == 0, worst=worst, points=int(stats["contact_points"]), flags=int(stats["error_flags"]))
+
+
+def main():
+    kind, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    tiles = sys.argv[sys.argv.index("--tiles") + 1] if "--tiles" in sys.argv else "1"
+    steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 100
+    from tests.emu import build
+    os.environ["B2D_LIB"] = build.build()
+    os.environ["B2D_GRAPH"] = "0"
+    os.environ["B2D_TILES"] = tiles
+    import edyn_b200 as E
+    from oracle import oracle as O
+    from tests.test_ref_stepper import random_scene, random_scene_wide
+    fixed = [lambda: E.scenes.hello_world(), lambda: E.scenes.boxes_on_plane(3), lambda: E.scenes.spheres_in_box(4, 6, 4),
+             lambda: E.scenes.mixed_pile(5, jitter=0.01), lambda: E.scenes.hinge_chains(2, 2)]
+    out, t0 = [], time.time()
+    for i in range(first, last):
+        scene = fixed[i]() if kind == "fixed" else (random_scene_wide if kind == "wide" else random_scene)(E, O, i)
+        res = lockstep(E, O, scene, steps)
+        res["scene"] = scene["name"]
+        out.append(res)
+    print(json.dumps(dict(results=out, seconds=time.time() - t0)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,37 @@
+"""The library's CUDA kernels on a machine without a GPU: edyn_b200/csrc compiled against tests/emu (a CPU emulation of
+blocks, __syncthreads, warp collectives, cooperative launches and the ticket polls -- see tests/emu/include/cuda_runtime.h
+for what it is and is not) and driven through the real C ABI and Python adapter, in lock step with the oracle.
+
+It complements the -m gpu suite, it does not replace it: it executes the same C++ on the same data layout, so logic
+errors show up; memory ordering, occupancy and speed do not exist here.  What it adds is CONTENT the GPU suite has not
+seen: arbitrarily oriented static boxes, static / kinematic spheres and capsules, rotating kinematic bodies, hinges with
+non-parallel axes and pivots that start apart, tilted ground planes, restitution up to 1, friction 0-2, 1-20 velocity and
+0-6 position iterations -- through both solver schedules (island tiles and ticket dataflow)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(kind, first, last, tiles="1", steps=80):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu", "lockstep.py"), kind, str(first), str(last), "--tiles", tiles, "--steps", str(steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=1500)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])["results"]
+
+
+def test_emulated_kernels_on_the_benchmark_scene_families(O):
+    """Validates the emulation itself: these five are green on a real B200 (tests/test_gpu_parity.py)."""
+    for res in _run("fixed", 0, 5, steps=60):
+        assert res["ok"] and res["worst"] <= 1e-5, res
+    assert sum(r["points"] for r in _run("fixed", 1, 2, steps=60)) > 50
+
+
+@pytest.mark.parametrize("kind,first,last,tiles", [("narrow", 0, 3, "1"), ("wide", 0, 5, "1"), ("wide", 5, 8, "0"), ("narrow", 3, 5, "0")])
+def test_emulated_kernels_on_random_scenes(O, kind, first, last, tiles):
+    for res in _run(kind, first, last, tiles=tiles):
+        assert res["ok"] and res["worst"] <= 1e-5, res
