@@ -179,6 +179,11 @@ b2d_world *b2d_create(const b2d_config *cfg) {
     d.ehash_size = pow2_at_least(2ull * NB);
     ok = ok && dalloc(w, d.entity, NB) && dalloc(w, d.ehash, d.ehash_size, 0xFF) && dalloc(w, d.ibox, 6 * (size_t)NB) && dalloc(w, d.isl_dst, NB, 0xFF) && dalloc(w, d.bdst, NB, 0xFF);
     ok = ok && dalloc(w, w->dev_counts, 4 * 64);
+    if (cfg->flags & B2D_FLAG_RESTITUTION_SOLVER) {
+        d.rest_iters = 8; d.rest_individual = 3;                  // context/settings.hpp:29-30
+        ok = ok && dalloc(w, d.rcnt, NB) && dalloc(w, d.roff, NB) && dalloc(w, d.rcur, NB) && dalloc(w, d.rstamp, NB) && dalloc(w, d.rnext, NB)
+                && dalloc(w, d.radj, 2 * ((size_t)NM + NH)) && dalloc(w, d.radj_m, 2 * ((size_t)NM + NH));
+    }
     d.sleeping = (cfg->flags & B2D_FLAG_SLEEPING) ? 1u : 0u;
     if (d.sleeping) {
         ok = ok && dalloc(w, d.prev_label, NB, 0xFF) && dalloc(w, d.isl_size, NB) && dalloc(w, d.size_new, NB) && dalloc(w, d.isl_flags, NB)
@@ -589,8 +594,24 @@ static int enqueue_islands(b2d_world *w) {
 }
 // solver.update in three segments so that the velocity solve can be bracketed by timing events between two graphs:
 // A gravity .. row preparation, B the velocity iterations, C integration .. refresh.
+// solve_restitution, first thing in solver::update (solver.cpp:397): the entity graph as adjacency lists, then one thread per island
+static int enqueue_restitution(b2d_world *w) {
+    Dev &d = w->d; cudaStream_t s = w->stream;
+    if (!d.rest_iters || !d.nbodies) return B2D_OK;
+    CK(cudaMemsetAsync(d.rcnt, 0, d.nbodies * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(d.rcur, 0, d.nbodies * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(d.rstamp, 0, d.nbodies * sizeof(uint32_t), s));
+    LAUNCH(k_rest_count, (uint64_t)d.NM + d.nhinges, 256, d);
+    size_t t = w->cub_tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, t, d.rcnt, d.roff, (int)d.nbodies, s)); ++w->launches;
+    LAUNCH(k_rest_fill, (uint64_t)d.NM + d.nhinges, 256, d);
+    LAUNCH(k_rest_sort, d.nbodies, 128, d);
+    LAUNCH(k_rest_solve, d.nbodies, 64, d);
+    return B2D_OK;
+}
 static int enqueue_solver_a(b2d_world *w, int recolor) {
     Dev &d = w->d; cudaStream_t s = w->stream;
+    { int rc = enqueue_restitution(w); if (rc) return rc; }
     CK(cudaMemsetAsync(d.isl_nb, 0, 3 * (size_t)d.NB * sizeof(uint32_t), s));             // island census: bodies, manifolds, joints
     CK(cudaMemsetAsync(d.tile_nb, 0, 5 * (size_t)d.max_tiles * sizeof(uint32_t), s));      // tile body counts and (empty) ranges
     LAUNCH(k_gravity, std::max<uint32_t>(d.nbodies, 1), 256, d);                             // + resets of the colouring / packing accumulators
@@ -773,8 +794,9 @@ int b2d_step(b2d_world *w, uint32_t num_steps) {
     cudaEventRecord(w->ev_step0, w->stream);
     for (uint32_t i = 0; i < num_steps; ++i) {
         // graphs replay a fixed sequence: island sleeping passes a fresh timestamp every step and a recolouring step
-        // runs a different colouring kernel argument, both go the plain way
-        const bool plain = !w->use_graph || w->d.sleeping || w->contacts_dirty || (w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->d.nbodies == 0;
+        // runs a different colouring kernel argument, both go the plain way; so does the restitution solver (first version: its
+        // per-island thread carries a large local frame, kept out of graph capture)
+        const bool plain = !w->use_graph || w->d.sleeping || w->d.rest_iters || w->contacts_dirty || (w->cfg.flags & B2D_FLAG_RECOLOR_EACH_STEP) || w->d.nbodies == 0;
         if (!plain && !w->graph_valid) build_graphs(w);
         if (plain || !w->graph_valid) {
             rc = b2d_run_phases(w, B2D_PHASE_ALL);

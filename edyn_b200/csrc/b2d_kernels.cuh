@@ -1061,7 +1061,7 @@ __global__ void __launch_bounds__(256) k_prepare_contacts(Dev d) {
             float error = 0.0f;
             if (a4.w > 0) error = a4.w / d.dt;
             float relvel = rel_speed(normal, J1, J2, J3, A.v, A.w, B.v, B.w);
-            float rhs = -(error * 0.2f + relvel * (1.0f + n4.w));
+            float rhs = -(error * 0.2f + relvel * (1.0f + (d.rest_iters ? 0.0f : n4.w)));     // solver.cpp:217-236
             v3 t, u; plane_space(normal, t, u);
             v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
             v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
@@ -2147,6 +2147,218 @@ __global__ void k_count_points(Dev d) {
     GRID_STRIDE(m, hwm) { uint32_t st = d.mstate[m]; if (st & MS_ALIVE) local += st & MS_NPTS_MASK; }
     for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&d.cnt->npoints, local);
+}
+
+// ====================================================================== restitution solver
+// dynamics/restitution_solver.cpp:86-408 (settings: 8 rounds x 3 sweeps by default).  Before gravity is applied, per island
+// and per round: the manifold with contact_manifold_with_restitution that closes fastest; if it closes faster than 0.005 m/s,
+// a breadth-first walk of the entity graph from the faster of its two bodies; at every dynamic body visited, the manifolds
+// of that body still closing faster than the threshold are solved together -- rows from the CURRENT velocities with the
+// points' restitution, a few Gauss-Seidel sweeps (normal row, then its friction pair), then the delta velocities are added
+// to the velocities at once.  Afterwards the ordinary rows carry no restitution (solver.cpp:217-236).
+// The walk is serial by construction, so is this: ONE THREAD PER ISLAND (islands are independent; a scene of many small
+// islands parallelises over them, a single pile does not -- DESIGN.md section 8).  Orders the reference takes from EnTT and
+// the graph's history are fixed here: neighbours in ascending body id, ties of the fastest manifold to the smaller pair key.
+constexpr int REST_MAX_MANIFOLDS = 32;      // manifolds of one body solved as a group
+constexpr int REST_MAX_ROWS = 96;           // their contact points
+
+// the entity graph as adjacency lists: manifolds (with or without points) and joints are edges
+__global__ void k_rest_count(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(k, hwm + d.nhinges) {
+        uint2 p;
+        if (k < hwm) { if (!(d.mstate[k] & MS_ALIVE)) continue; p = d.mpair[k]; }
+        else { p = d.hpair[k - hwm]; if (p.x == p.y) continue; }
+        if (is_dynamic(d.flags[p.x])) atomicAdd(&d.rcnt[p.x], 1u);
+        if (is_dynamic(d.flags[p.y])) atomicAdd(&d.rcnt[p.y], 1u);
+    }
+}
+__global__ void k_rest_fill(Dev d) {
+    const uint32_t hwm = d.cnt->hwm;
+    GRID_STRIDE(k, hwm + d.nhinges) {
+        uint2 p; uint32_t tag = 0, slot = 0;
+        if (k < hwm) { if (!(d.mstate[k] & MS_ALIVE)) continue; p = d.mpair[k]; tag = 0x80000000u; slot = k; }
+        else { p = d.hpair[k - hwm]; if (p.x == p.y) continue; }
+        if (is_dynamic(d.flags[p.x])) { const uint32_t at = d.roff[p.x] + atomicAdd(&d.rcur[p.x], 1u); d.radj[at] = p.y | tag; d.radj_m[at] = slot; }
+        if (is_dynamic(d.flags[p.y])) { const uint32_t at = d.roff[p.y] + atomicAdd(&d.rcur[p.y], 1u); d.radj[at] = p.x | tag; d.radj_m[at] = slot; }
+    }
+}
+// ascending neighbour id, one entry per neighbour (a joint and a manifold between the same two bodies share an adjacency)
+__global__ void k_rest_sort(Dev d) {
+    GRID_STRIDE(b, d.nbodies) {
+        const uint32_t n = d.rcnt[b], o = d.roff[b];
+        if (n == 0) continue;
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint32_t e = d.radj[o + i], m = d.radj_m[o + i];
+            uint32_t j = i;
+            while (j > 0 && (d.radj[o + j - 1] & 0x7FFFFFFFu) > (e & 0x7FFFFFFFu)) { d.radj[o + j] = d.radj[o + j - 1]; d.radj_m[o + j] = d.radj_m[o + j - 1]; --j; }
+            d.radj[o + j] = e; d.radj_m[o + j] = m;
+        }
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t e = d.radj[o + i], m = d.radj_m[o + i];
+            if (w && (d.radj[o + w - 1] & 0x7FFFFFFFu) == (e & 0x7FFFFFFFu)) { if (e >> 31) { d.radj[o + w - 1] |= 0x80000000u; d.radj_m[o + w - 1] = m; } }
+            else { d.radj[o + w] = e; d.radj_m[o + w] = m; ++w; }
+        }
+        d.rcnt[b] = w;
+    }
+}
+// get_manifold_min_relvel, restitution_solver.cpp:32-83
+B2D_D float rest_min_relvel(const Dev &d, uint32_t m) {
+    const uint2 pr = d.mpair[m];
+    const uint32_t npts = d.mstate[m] & MS_NPTS_MASK;
+    const uint32_t fa = d.flags[pr.x], fb = d.flags[pr.y];
+    const v3 z = mk3(0, 0, 0);
+    const v3 lvA = kind_of(fa) == 2u ? z : mk3(d.linvel[pr.x]), avA = kind_of(fa) == 2u ? z : mk3(d.angvel[pr.x]);
+    const v3 lvB = kind_of(fb) == 2u ? z : mk3(d.linvel[pr.y]), avB = kind_of(fb) == 2u ? z : mk3(d.angvel[pr.y]);
+    const v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
+    const q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
+    float min_relvel = SCALAR_MAX;
+    for (uint32_t s = 0; s < npts; ++s) {
+        const size_t mi = (size_t)s * d.NM + m;
+        const v3 pivotA = to_world(mk3(d.pA[mi]), posA, ornA), pivotB = to_world(mk3(d.pB[mi]), posB, ornB);
+        const v3 rA = pivotA - posA, rB = pivotB - posB;
+        const v3 vA = lvA + cross(avA, rA), vB = lvB + cross(avB, rB);
+        const v3 relvel = vA - vB;
+        min_relvel = fminf(dot(relvel, mk3(d.pN[mi])), min_relvel);
+    }
+    return min_relvel;
+}
+B2D_D void rest_body_load(const Dev &d, uint32_t i, VBody &b) {
+    b.id = i; b.proc = is_dynamic(d.flags[i]);
+    if (b.proc) {
+        const float4 r0 = d.invIW[3 * i];
+        b.inv_m = r0.w; b.inv_I.r0 = mk3(r0); b.inv_I.r1 = mk3(d.invIW[3 * i + 1]); b.inv_I.r2 = mk3(d.invIW[3 * i + 2]);
+        b.dv = mk3(d.dvw[2 * i]); b.dw = mk3(d.dvw[2 * i + 1]);
+    } else { b.inv_m = 0; b.inv_I = m3_zero(); b.dv = mk3(0, 0, 0); b.dw = mk3(0, 0, 0); }
+}
+B2D_D void rest_body_store(const Dev &d, const VBody &b) {
+    if (b.proc) { d.dvw[2 * b.id] = f4(b.dv, 0.0f); d.dvw[2 * b.id + 1] = f4(b.dw, 0.0f); }
+}
+// the solve_manifolds lambda, restitution_solver.cpp:146-310
+B2D_D void rest_solve_group(const Dev &d, const uint32_t *group, int ng) {
+    float4 r0[REST_MAX_ROWS], r1[REST_MAX_ROWS], r2[REST_MAX_ROWS], r3[REST_MAX_ROWS], im[REST_MAX_ROWS];
+    uint32_t ra[REST_MAX_ROWS], rb[REST_MAX_ROWS];
+    int nr = 0;
+    for (int g = 0; g < ng; ++g) {
+        const uint32_t m = group[g];
+        const uint2 pr = d.mpair[m];
+        const uint32_t npts = d.mstate[m] & MS_NPTS_MASK;
+        const SBody A = solver_body(d, pr.x, d.flags[pr.x]), B = solver_body(d, pr.y, d.flags[pr.y]);
+        const v3 posA = mk3(d.pos[pr.x]), posB = mk3(d.pos[pr.y]);
+        const q4 ornA = mkq(d.orn[pr.x]), ornB = mkq(d.orn[pr.y]);
+        for (uint32_t s = 0; s < npts; ++s) {
+            if (nr == REST_MAX_ROWS) { atomicOr(&d.cnt->err, ERR_RESTITUTION_GROUP); break; }
+            const size_t mi = (size_t)s * d.NM + m;
+            const float4 a4 = d.pA[mi], b4 = d.pB[mi], n4 = d.pN[mi];
+            const v3 normal = mk3(n4);
+            const v3 pAw = to_world(mk3(a4), posA, ornA), pBw = to_world(mk3(b4), posB, ornB);
+            const v3 rA = pAw - posA, rB = pBw - posB;
+            const v3 J1 = cross(rA, normal), J2 = -normal, J3 = -cross(rB, normal);
+            const float em = eff_mass(normal, J1, J2, J3, A, B);
+            const float relvel = rel_speed(normal, J1, J2, J3, A.v, A.w, B.v, B.w);
+            const float rhs = -(0.0f * 0.2f + relvel * (1.0f + n4.w));              // constraint_row_options{}: error 0, the point's restitution
+            v3 t, u; plane_space(normal, t, u);
+            const v3 T1 = cross(rA, t), T2 = -t, T3 = -cross(rB, t);
+            const v3 U1 = cross(rA, u), U2 = -u, U3 = -cross(rB, u);
+            r0[nr] = f4(normal, rhs); r1[nr] = f4(rA, em); r2[nr] = f4(rB, b4.w);
+            r3[nr] = make_float4(eff_mass(t, T1, T2, T3, A, B), eff_mass(u, U1, U2, U3, A, B),
+                                 -rel_speed(t, T1, T2, T3, A.v, A.w, B.v, B.w), -rel_speed(u, U1, U2, U3, A.v, A.w, B.v, B.w));
+            im[nr] = make_float4(0, 0, 0, 0);
+            ra[nr] = pr.x; rb[nr] = pr.y;
+            ++nr;
+        }
+    }
+    for (uint32_t it = 0; it < d.rest_individual; ++it) {
+        for (int k = 0; k < nr; ++k) {
+            VBody A, B;
+            rest_body_load(d, ra[k], A); rest_body_load(d, rb[k], B);
+            nrow_solve(r0[k], r1[k], r2[k], im[k], A, B, false);
+            frow_solve(r0[k], r1[k], r2[k], r3[k], im[k], A, B, false);
+            rest_body_store(d, A); rest_body_store(d, B);
+        }
+    }
+    for (int g = 0; g < ng; ++g) {                             // apply the delta velocities (idempotent for shared bodies)
+        const uint2 pr = d.mpair[group[g]];
+        const uint32_t ids[2] = {pr.x, pr.y};
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = ids[k];
+            if (!is_dynamic(d.flags[i])) continue;                 // static: skipped; kinematic: its deltas are the dummy zeros
+            d.linvel[i] = f4(mk3(d.linvel[i]) + mk3(d.dvw[2 * i]), 0.0f);
+            d.angvel[i] = f4(mk3(d.angvel[i]) + mk3(d.dvw[2 * i + 1]), 0.0f);
+            d.dvw[2 * i] = make_float4(0, 0, 0, 0); d.dvw[2 * i + 1] = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+__global__ void k_rest_solve(Dev d) {
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    const float threshold = -0.005f;
+    GRID_STRIDE(root, d.nbodies) {
+        if (d.parent[root] != root || !is_dynamic(d.flags[root])) continue;       // one thread per awake island
+        uint32_t stamp = 0;
+        for (uint32_t round = 0; round < d.rest_iters; ++round) {
+            // ---- the manifold with restitution that closes fastest (walk over the island)
+            float best = SCALAR_MAX; uint32_t best_m = NONE; unsigned long long best_key = ~0ULL;
+            ++stamp;
+            uint32_t head = root, tail = root;
+            d.rstamp[root] = stamp; d.rnext[root] = NONE;
+            while (head != NONE) {
+                const uint32_t b = head; head = d.rnext[b];
+                const uint32_t o = d.roff[b], n = d.rcnt[b];
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint32_t e = d.radj[o + k], nbr = e & 0x7FFFFFFFu;
+                    if (e >> 31) {
+                        const uint32_t m = d.radj_m[o + k];
+                        const uint2 pr = d.mpair[m];
+                        if (fminf(d.mat[pr.x].y, d.mat[pr.y].y) > EPS) {            // contact_manifold_with_restitution, constraint_util.cpp:86-101
+                            const float rel = rest_min_relvel(d, m);
+                            const unsigned long long key = pair_key(pr.x, pr.y);
+                            if (rel < best || (rel == best && best_m != NONE && key < best_key)) { best = rel; best_m = m; best_key = key; }
+                        }
+                    }
+                    if (is_dynamic(d.flags[nbr]) && d.rstamp[nbr] != stamp) {
+                        d.rstamp[nbr] = stamp; d.rnext[nbr] = NONE;
+                        if (head == NONE) head = nbr; else d.rnext[tail] = nbr;
+                        tail = nbr;
+                    }
+                }
+            }
+            if (best_m == NONE || best > threshold) break;                          // nothing (left) to bounce in this island
+            // ---- start at the faster body of that manifold (a dynamic one)
+            const uint2 fp = d.mpair[best_m];
+            const uint32_t fa = d.flags[fp.x], fb = d.flags[fp.y];
+            const float speedA = kind_of(fa) == 2u ? 0.0f : length_sqr(mk3(d.linvel[fp.x]));
+            const float speedB = kind_of(fb) == 2u ? 0.0f : length_sqr(mk3(d.linvel[fp.y]));
+            uint32_t start;
+            if (speedA > speedB) start = is_dynamic(fa) ? fp.x : fp.y; else start = is_dynamic(fb) ? fp.y : fp.x;
+            // ---- breadth-first: at every body the manifolds still closing fast enough, solved as a group
+            ++stamp;
+            head = start; tail = start;
+            d.rstamp[start] = stamp; d.rnext[start] = NONE;
+            while (head != NONE) {
+                const uint32_t b = head; head = d.rnext[b];
+                const uint32_t o = d.roff[b], n = d.rcnt[b];
+                uint32_t group[REST_MAX_MANIFOLDS]; int ng = 0;
+                for (uint32_t k = 0; k < n; ++k) {
+                    if (!(d.radj[o + k] >> 31)) continue;
+                    const uint32_t m = d.radj_m[o + k];
+                    if (rest_min_relvel(d, m) < threshold) {
+                        if (ng == REST_MAX_MANIFOLDS) { atomicOr(&d.cnt->err, ERR_RESTITUTION_GROUP); break; }
+                        group[ng++] = m;
+                    }
+                }
+                if (ng) rest_solve_group(d, group, ng);
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint32_t nbr = d.radj[o + k] & 0x7FFFFFFFu;
+                    if (is_dynamic(d.flags[nbr]) && d.rstamp[nbr] != stamp) {
+                        d.rstamp[nbr] = stamp; d.rnext[nbr] = NONE;
+                        if (head == NONE) head = nbr; else d.rnext[tail] = nbr;
+                        tail = nbr;
+                    }
+                }
+            }
+        }
+    }
 }
 
 } // namespace b2d

@@ -46,6 +46,7 @@ constexpr uint32_t ERR_MANIFOLD_CAPACITY = 1u;
 constexpr uint32_t ERR_COLOR_OVERFLOW = 2u;
 constexpr uint32_t ERR_LARGE_CAPACITY = 4u;
 constexpr uint32_t ERR_UNKNOWN_ENTITY = 16u;    // a hand-over blob names a body this world does not hold
+constexpr uint32_t ERR_RESTITUTION_GROUP = 32u; // restitution solver: one body touches more manifolds / points than a group holds
 constexpr uint32_t ERR_SOLVER_TIMEOUT = 8u;     // a dataflow wait exceeded its spin budget (would have been a hang)
 
 struct Counters {
@@ -172,6 +173,12 @@ struct Dev {
     uint32_t *isl_dst, *bdst;            // destination rank per island root / per body (0xFFFFFFFF = stays)
 
     Counters *cnt;
+
+    // ---- restitution solver (B2D_FLAG_RESTITUTION_SOLVER; appended last so that the other fields keep their offsets)
+    uint32_t rest_iters, rest_individual;    // settings.num_restitution_iterations / num_individual_restitution_iterations; 0 = off
+    uint32_t *rcnt, *roff, *rcur;            // per body: neighbours in the entity graph, start of its list, fill cursor
+    uint32_t *radj, *radj_m;                 // neighbour id | 0x80000000 if the adjacency holds a contact manifold; its manifold slot
+    uint32_t *rstamp, *rnext;                // breadth-first walk: visit stamp and queue link per body
 };
 
 } // namespace b2d

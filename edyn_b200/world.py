@@ -23,6 +23,7 @@ f32, u32 = np.float32, np.uint32
 
 PH_BROAD, PH_NARROW, PH_ISLANDS, PH_SOLVE, PH_ALL = 1, 2, 4, 8, 15
 FLAG_RECOLOR_EACH_STEP = 1
+FLAG_RESTITUTION_SOLVER = 4     # the reference's default restitution solver (8 x 3 iterations) instead of restitution through the row rhs
 FLAG_SLEEPING = 2                # island sleeping; off = every body is sleeping_disabled (benchmark configurations)
 
 

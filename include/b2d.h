@@ -74,6 +74,10 @@ typedef struct b2d_config {
 } b2d_config;
 
 #define B2D_FLAG_RECOLOR_EACH_STEP 1u  /* recompute the constraint colouring from scratch every step */
+#define B2D_FLAG_RESTITUTION_SOLVER 4u /* settings.num_restitution_iterations = 8, num_individual_restitution_iterations = 3 (the
+                                          reference's defaults, include/edyn/context/settings.hpp:29-30): the restitution solver
+                                          (src/edyn/dynamics/restitution_solver.cpp:86-408) runs before gravity, the rows then carry no
+                                          restitution.  Off = set_solver_restitution_iterations(0): restitution through the row rhs */
 #define B2D_FLAG_SLEEPING 2u           /* island sleeping (src/edyn/simulation/island_manager.cpp:541-623).  Off = every
                                           body carries sleeping_disabled_tag, as the benchmark configurations prescribe */
 

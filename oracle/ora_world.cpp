@@ -770,7 +770,7 @@ bool World::restitution_iteration(const std::vector<uint32_t> &tagged) {
 // solve_restitution, restitution_solver.cpp:386-408; called first thing in solver::update, before gravity (solver.cpp:397)
 void World::solve_restitution() {
     const uint32_t nb = uint32_t(bodies.size());
-    if (!graph_order_set) {                                        // no graph supplied: ascending neighbour ids, manifold order
+    if (!graph_order_set) {                                        // no graph supplied: ascending neighbour ids, pair-key order (= the device's conventions)
         std::vector<std::vector<uint32_t>> nbrs(nb);
         for (const Manifold &m : manifolds) { nbrs[m.a].push_back(m.b | 0x80000000u); nbrs[m.b].push_back(m.a | 0x80000000u); }
         for (const Hinge &h : hinges) if (h.a != h.b) { nbrs[h.a].push_back(h.b); nbrs[h.b].push_back(h.a); }
@@ -784,6 +784,7 @@ void World::solve_restitution() {
         }
         rest_edge_order.clear();
         for (const Manifold &m : manifolds) rest_edge_order.push_back(key(m.a, m.b));
+        std::sort(rest_edge_order.begin(), rest_edge_order.end());    // ties of the fastest manifold go to the smaller pair key (the device's rule)
     }
     // the tagged manifolds per island (make_contact_manifold, constraint_util.cpp:86-101: mixed restitution > EPSILON)
     std::unordered_map<uint32_t, std::vector<uint32_t>> per_island;

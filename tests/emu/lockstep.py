@@ -3,7 +3,7 @@ oracle through the normal Python adapter and C ABI -- the same comparison tests/
 pair lists identical, post-solve state within 1e-5 (here: identical, glibc's sinf / cosf on both sides) with the oracle
 replaying the device's Gauss-Seidel order, manifolds and joint impulses re-synchronised every step.
 
-    python tests/emu/lockstep.py fixed|narrow|wide FIRST LAST [--tiles 0|1] [--steps N]     -> one JSON line
+    python tests/emu/lockstep.py fixed|narrow|wide FIRST LAST [--tiles 0|1] [--steps N] [--restitution]     -> one JSON line
 Runs in its own process because B2D_LIB has to be set before edyn_b200 is imported."""
 import json
 import os
@@ -15,11 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 
-def lockstep(E, O, scene, steps):
+def lockstep(E, O, scene, steps, restitution_solver=False):
     import numpy as np
-    w = E.scenes.build_world(scene)
+    w = E.scenes.build_world(scene, flags=E.world.FLAG_RESTITUTION_SOLVER if restitution_solver else 0)
     st = scene["settings"]
     o = O.OracleWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+    if restitution_solver:
+        o.set_restitution_iterations(8, 3)          # no graph order handed over: the oracle's defaults are the device's conventions
     o.add_bodies(scene["bodies"])
     if scene["hinges"]:
         h = scene["hinges"]
@@ -56,6 +58,7 @@ def main():
     kind, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     tiles = sys.argv[sys.argv.index("--tiles") + 1] if "--tiles" in sys.argv else "1"
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 100
+    restitution = "--restitution" in sys.argv
     from tests.emu import build
     os.environ["B2D_LIB"] = build.build()
     os.environ["B2D_GRAPH"] = "0"
@@ -68,7 +71,7 @@ def main():
     out, t0 = [], time.time()
     for i in range(first, last):
         scene = fixed[i]() if kind == "fixed" else (random_scene_wide if kind == "wide" else random_scene)(E, O, i)
-        res = lockstep(E, O, scene, steps)
+        res = lockstep(E, O, scene, steps, restitution)
         res["scene"] = scene["name"]
         out.append(res)
     print(json.dumps(dict(results=out, seconds=time.time() - t0)))

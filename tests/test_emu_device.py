@@ -17,8 +17,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(kind, first, last, tiles="1", steps=80):
+def _run(kind, first, last, tiles="1", steps=80, restitution=False):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emu", "lockstep.py"), kind, str(first), str(last), "--tiles", tiles, "--steps", str(steps)]
+    if restitution:
+        cmd.append("--restitution")
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     return json.loads(r.stdout.strip().splitlines()[-1])["results"]
@@ -31,7 +33,16 @@ def test_emulated_kernels_on_the_benchmark_scene_families(O):
     assert sum(r["points"] for r in _run("fixed", 1, 2, steps=60)) > 50
 
 
-@pytest.mark.parametrize("kind,first,last,tiles", [("narrow", 0, 3, "1"), ("wide", 0, 5, "1"), ("wide", 5, 8, "0"), ("narrow", 3, 5, "0")])
+@pytest.mark.parametrize("kind,first,last,tiles", [("narrow", 0, 2, "1"), ("wide", 0, 4, "1"), ("wide", 4, 6, "0"), ("narrow", 2, 3, "0")])
 def test_emulated_kernels_on_random_scenes(O, kind, first, last, tiles):
     for res in _run(kind, first, last, tiles=tiles):
+        assert res["ok"] and res["worst"] <= 1e-5, res
+
+
+def test_emulated_restitution_solver(O):
+    """B2D_FLAG_RESTITUTION_SOLVER (k_rest_* in b2d_kernels.cuh: the entity graph as adjacency lists, one thread per island
+    walking it breadth first) against the oracle's restatement of restitution_solver.cpp -- which is bit-identical to the
+    real stepper (tests/test_ref_stepper.py).  The device fixes the orders the reference inherits from EnTT (neighbours in
+    ascending body id, ties of the fastest manifold to the smaller pair key); the oracle's defaults are those conventions."""
+    for res in _run("fixed", 3, 4, restitution=True) + _run("narrow", 0, 2, restitution=True) + _run("wide", 0, 3, restitution=True):
         assert res["ok"] and res["worst"] <= 1e-5, res

@@ -84,3 +84,15 @@ def test_device_binding_follows_the_real_cpu_stepper(dev, E, O):
     a, b = w.state(), r.state()
     assert np.abs(a["pos"] - b["pos"]).max() < 1e-2 and np.abs(a["linvel"]).max() < 0.05
     w.close()
+
+
+@pytest.mark.xfail(strict=False, reason="first run on hardware: the restitution solver was written after the round's GPU budget ended and is "
+                                        "verified under the CPU emulation only (tests/test_emu_device.py::test_emulated_restitution_solver)")
+def test_device_restitution_solver_matches_oracle(gpu, E, O):
+    """B2D_FLAG_RESTITUTION_SOLVER on the B200 in lock step with the oracle's restatement of restitution_solver.cpp (the
+    reference's default settings), mixed pile with e = 0.2 and a random scene with e up to 0.8."""
+    from tests.emu.lockstep import lockstep
+    from tests.test_ref_stepper import random_scene
+    for scene in (E.scenes.mixed_pile(5, jitter=0.01), random_scene(E, O, 3)):
+        res = lockstep(E, O, scene, 100, restitution_solver=True)
+        assert res["ok"] and res["worst"] <= 1e-5, (scene["name"], res)
