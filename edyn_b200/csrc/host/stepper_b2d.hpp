@@ -84,6 +84,11 @@ public:
         c.position_iterations = s.num_solver_position_iterations;
         c.flags = cap.sleeping ? B2D_FLAG_SLEEPING : 0u;
         m_sleeping = cap.sleeping;
+        if (s.num_restitution_iterations > 0) {              // the reference's default is 8 x 3 (context/settings.hpp:29-30)
+            if (s.num_restitution_iterations != 8 || s.num_individual_restitution_iterations != 3)
+                throw std::runtime_error("stepper_b2d: restitution iterations other than the defaults (8 x 3) or 0 are not supported");
+            c.flags |= B2D_FLAG_RESTITUTION_SOLVER;
+        }
         m_world = b2d_create(&c);
         if (!m_world) throw std::runtime_error(std::string("b2d_create: ") + b2d_last_error(nullptr));
         // make_rigidbody emplaces rigidbody_tag LAST (util/rigidbody.cpp:184): every other component exists by then

@@ -23,6 +23,7 @@ void ora_get_state(void *h, float *pos, float *orn, float *linvel, float *angvel
 void ora_set_state(void *h, const float *pos, const float *orn, const float *linvel, const float *angvel);
 uint32_t ora_num_manifolds(void *h);
 void ora_set_sleeping(void *h, int enabled);
+void ora_set_restitution_iterations(void *h, int iters, int individual);
 void ora_wake_bodies(void *h, uint32_t n, const uint32_t *ids);
 void ora_get_sleeping(void *h, uint32_t *asleep);
 void ora_get_pairs(void *h, uint32_t *pairs);
@@ -38,6 +39,7 @@ b2d_world *b2d_create(const b2d_config *c) {
     auto *w = new b2d_world();
     w->ora = ora_create(c->fixed_dt, int(c->velocity_iterations), int(c->position_iterations), 1);
     if (c->flags & B2D_FLAG_SLEEPING) ora_set_sleeping(w->ora, 1);
+    if (c->flags & B2D_FLAG_RESTITUTION_SOLVER) ora_set_restitution_iterations(w->ora, 8, 3);
     return w;
 }
 void b2d_destroy(b2d_world *w) { if (w) { ora_destroy(w->ora); delete w; } }

@@ -302,3 +302,19 @@ def test_sleeping_tags_follow_the_device(mock, O, E):
     w.step(3); o.step(3)
     assert np.array_equal(w.r.sleeping(), o.sleeping().astype(bool))
     w.close()
+
+
+def test_default_restitution_settings_select_the_restitution_solver(mock, O, E):
+    """settings.num_restitution_iterations = 8 (the reference's default) -> B2D_FLAG_RESTITUTION_SOLVER; 0 -> restitution
+    through the row rhs.  Seen from the registry the two give different trajectories, each equal to the oracle's."""
+    scene = G.build_scene(E, "mixed_125")           # e = 0.2
+    ends = []
+    for iters in (0, 8):
+        w = EdynB2dWorld(O, mock, scene, restitution_iters=iters)
+        o = _plain_oracle(O, scene)
+        o.set_restitution_iterations(iters)
+        w.step(60); o.step(60)
+        _assert_same(w.state(), o.state(), f"restitution iterations {iters}")
+        ends.append(w.state()["pos"])
+        w.close()
+    assert np.abs(ends[0] - ends[1]).max() > 1e-3
