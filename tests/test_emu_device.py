@@ -17,10 +17,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(kind, first, last, tiles="1", steps=80, restitution=False):
+def _run(kind, first, last, tiles="1", steps=80, restitution=False, mutate=False):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emu", "lockstep.py"), kind, str(first), str(last), "--tiles", tiles, "--steps", str(steps)]
     if restitution:
         cmd.append("--restitution")
+    if mutate:
+        cmd.append("--mutate")
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     return json.loads(r.stdout.strip().splitlines()[-1])["results"]
@@ -46,3 +48,9 @@ def test_emulated_restitution_solver(O):
     ascending body id, ties of the fastest manifold to the smaller pair key); the oracle's defaults are those conventions."""
     for res in _run("fixed", 3, 4, restitution=True) + _run("narrow", 0, 2, restitution=True) + _run("wide", 0, 3, restitution=True):
         assert res["ok"] and res["worst"] <= 1e-5, res
+
+
+def test_emulated_kernels_under_user_interference(O):
+    """b2d_remove_bodies, b2d_add_bodies, b2d_remove_exclusions and b2d_upload_bodies every 13th step of random scenes."""
+    for res in _run("narrow", 0, 2, steps=100, mutate=True):
+        assert res["ok"] and res["points"] >= 6, res
