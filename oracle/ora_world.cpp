@@ -222,8 +222,9 @@ void World::broadphase() {
     }
 
     const vec3 off = vec3{1, 1, 1} * -BREAKING_THRESHOLD;      // m_aabb_offset, broadphase.hpp:15
-    // Awake procedural bodies issue the queries (broadphase.cpp:183).  EnTT views are believed to iterate
-    // newest-first: descending index.  This fixes which body becomes body[0].
+    // Awake procedural bodies issue the queries (broadphase.cpp:183) in the order of view<AABB, procedural_tag>: newest
+    // first = descending index (confirmed against the real stepper, tests/test_ref_stepper.py; after removals see
+    // emulate_pool_order).  This fixes which body becomes body[0].
     // The queries themselves are independent and run on all threads (collide_tree_async, broadphase.cpp:157-175, stores the
     // hits per entity); the manifolds are then created serially in view order (finish_async_update, :197-214), because
     // a pair found by an earlier query must not be created again by its partner's.
@@ -850,7 +851,8 @@ void World::solve() {
         }
     } else {
         // Natural order: constraint-type major (hinge before contact, constraints/constraint.hpp:23-34),
-        // newest-first inside a type (assumed EnTT order), list order inside a manifold.
+        // newest-first inside a type, list order inside a manifold (the reference's actual order is island.edges order, which
+        // tests replay through set_point_order).
         for (uint32_t h = uint32_t(hinges.size()); h-- > 0;)
             if (bodies[hinges[h].a].awake() || bodies[hinges[h].b].awake()) island_of(hinges[h].a, hinges[h].b).hinges.push_back(h);
         for (uint32_t mi = uint32_t(manifolds.size()); mi-- > 0;) {
