@@ -28,6 +28,20 @@ def _run(kind, first, last, tiles="1", steps=80, restitution=False, mutate=False
     return json.loads(r.stdout.strip().splitlines()[-1])["results"]
 
 
+def test_emulation_primitives(tmp_path):
+    """The emulation itself: barriers, warp collectives with full / partial masks and exited lanes, atomics, shared memory,
+    the cub stand-ins, warps of one block waiting for each other through polled flags (tests/emu/selftest.cpp)."""
+    import shutil
+    cxx = shutil.which("g++")
+    assert cxx
+    exe = str(tmp_path / "emu_selftest")
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I" + os.path.join(emu, "include"), "-o", exe, os.path.join(emu, "selftest.cpp"),
+                    os.path.join(emu, "emu_runtime.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "emu selftest ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_emulated_kernels_on_the_benchmark_scene_families(O):
     """Validates the emulation itself: these five are green on a real B200 (tests/test_gpu_parity.py)."""
     for res in _run("fixed", 0, 5, steps=60):
