@@ -119,6 +119,27 @@ def lockstep_with_mutations(E, O, scene, steps, seed):
     return dict(ok=flags == 0, worst=0.0, points=events, flags=flags)
 
 
+def free_run_against_real_stepper(E, O):
+    """No oracle in between: the kernels (emulated) and the reference's real stepper, both free-running from the same scene.
+    Hinge chains are insensitive to the sweep order (tiny islands at rest), so the two must simply agree; hello_world must be
+    identical while the box falls."""
+    import numpy as np
+    from tests.golden import make_whole_step as G
+    out = []
+    for name, scene, marks in (("chains_64", E.scenes.hinge_chains(4, 4), (60, 300)), ("hello_world", E.scenes.hello_world(), (24,))):
+        st = scene["settings"]
+        w = E.scenes.build_world(scene)
+        r = O.RefWorld(vel_iters=st["velocity_iterations"], pos_iters=st["position_iterations"])
+        G.populate(r, scene)
+        n, done = scene["dynamic"], 0
+        for m in marks:
+            w.step(m - done); r.step(m - done); done = m
+            g, c = w.download_state(), r.state()
+            out.append(dict(scene=name, step=m, dpos=float(np.abs(g["pos"][:n] - c["pos"][:n]).max()), dvel=float(np.abs(g["linvel"][:n] - c["linvel"][:n]).max())))
+        w.close()
+    return out
+
+
 def main():
     kind, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     tiles = sys.argv[sys.argv.index("--tiles") + 1] if "--tiles" in sys.argv else "1"
@@ -134,6 +155,9 @@ def main():
     fixed = [lambda: E.scenes.hello_world(), lambda: E.scenes.boxes_on_plane(3), lambda: E.scenes.spheres_in_box(4, 6, 4),
              lambda: E.scenes.mixed_pile(5, jitter=0.01), lambda: E.scenes.hinge_chains(2, 2)]
     out, t0 = [], time.time()
+    if kind == "vsref":
+        print(json.dumps(dict(results=free_run_against_real_stepper(E, O), seconds=0.0)))
+        return
     for i in range(first, last):
         scene = fixed[i]() if kind == "fixed" else (random_scene_wide if kind == "wide" else random_scene)(E, O, i)
         res = lockstep_with_mutations(E, O, scene, steps, i) if "--mutate" in sys.argv else lockstep(E, O, scene, steps, restitution)
